@@ -1,0 +1,141 @@
+/*
+ * syntex_b200 — C ABI of the B200-native SynTex hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types. The reference (swift-n-brutal/syntex)
+ * has no FFI of its own — its boundary is the Python surface of texture_utils / gatys.Synthesizer / po.model,
+ * which builds TensorFlow graph ops. Each entry point below replaces the arithmetic of one of those call sites
+ * (cited as path:line relative to the reference root). The Python mirror of the reference interface lives in
+ * syntex_b200/{texture_utils,gatys,po}.py and calls these through ctypes.
+ *
+ * Conventions
+ *   - All tensors are dense NHWC. Images/gradients are fp32, feature maps are bf16 on the device, Gram matrices
+ *     and losses are fp32.
+ *   - Every function returns 0 on success and a negative code on failure; stx_last_error() returns the message
+ *     for the calling thread. Nothing falls back to a CPU path: without a CUDA device every compute call fails.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream). Calls are asynchronous on that stream
+ *     unless documented as synchronous (the *_host variants).
+ *   - Layer indices follow texture_utils/vgg19.py:11-30 (PARAM_SHAPE order up to pool4):
+ *       0 conv1_1  1 conv1_2  2 pool1  3 conv2_1  4 conv2_2  5 pool2  6 conv3_1  7 conv3_2  8 conv3_3  9 conv3_4
+ *       10 pool3  11 conv4_1  12 conv4_2  13 conv4_3  14 conv4_4  15 pool4
+ */
+#ifndef SYNTEX_B200_H_
+#define SYNTEX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STX_NUM_LAYERS 16
+#define STX_NUM_CONVS 12
+
+#define STX_OK 0
+#define STX_ERR_INVALID (-1)
+#define STX_ERR_CUDA (-2)
+#define STX_ERR_UNSUPPORTED (-3)
+#define STX_ERR_STATE (-4)
+
+typedef struct stx_vgg stx_vgg;     /* VGG19 weights up to pool4, packed for the tensor-core kernels */
+typedef struct stx_plan stx_plan;   /* one f/g evaluation pipeline for a fixed (batch, height, width) */
+typedef struct stx_lbfgs stx_lbfgs; /* device-resident L-BFGS(-B) state bound to a plan */
+
+const char* stx_last_error(void);
+int stx_abi_version(void);
+/* Bring-up knobs (descriptor strides etc.); key/value meanings are internal. */
+int stx_debug_set(int key, int value);
+
+/* ---- weights: texture_utils/vgg19.py:97-130 (Vgg19.__init__) and :192-206 (get_var, constants) ------------
+ * weights_hwio[i] / biases[i]: host fp32 arrays for conv layer i in network order (conv1_1 .. conv4_4), laid out
+ * (3,3,Cin,Cout) and (Cout,) as stored by texture_utils/caffe2npz.py:16-18. The conv1_1 input-channel flip for
+ * RGB input (vgg19.py:124-127) is the caller's job, as it is the loader's job in the reference.
+ * mean3: per-channel mean subtracted after the x255 scaling (vgg19.py:142-146), in the channel order of the input. */
+int stx_vgg_create(stx_vgg** out, const float* const* weights_hwio, const float* const* biases, int num_convs,
+                   const float* mean3, void* stream);
+void stx_vgg_destroy(stx_vgg* vgg);
+
+/* ---- plan: the graph that gatys/synthesizer.py:54-107 (Synthesizer.build) and po/model.py:51-69 construct ----
+ * topmost: last layer index to compute (15 = pool4, the Vgg19Extractor default, vgg19_extractor.py:5-6).
+ * loss_layers/coefs: the Gram layers and weights (Synthesizer.DEFAULT_COEFS, synthesizer.py:17-23). */
+int stx_plan_create(stx_plan** out, const stx_vgg* vgg, int batch, int height, int width, int topmost,
+                    int num_loss_layers, const int* loss_layers, const float* coefs);
+void stx_plan_destroy(stx_plan* plan);
+size_t stx_plan_device_bytes(const stx_plan* plan);
+
+/* Vgg19.build (vgg19.py:132-169): image [batch,H,W,3] fp32 device, values in [0,1] (or a pre-image that is passed
+ * through a sigmoid first, synthesizer.py:59). Computes every layer up to topmost; with_grams != 0 also computes
+ * the Gram matrices of the loss layers (build_gram, utils.py:8-21). */
+int stx_plan_forward(stx_plan* plan, const float* image, int is_preimage, int with_grams, void* stream);
+/* Copy one recorded layer out as fp32 [batch,h,w,c] (device). */
+int stx_plan_layer_shape(const stx_plan* plan, int layer, int* h, int* w, int* c);
+int stx_plan_copy_feature_f32(stx_plan* plan, int layer, float* out, void* stream);
+/* Copy the Gram matrix of loss layer k (index into loss_layers) as fp32 [batch,C,C] (device). */
+int stx_plan_copy_gram(stx_plan* plan, int k, float* out, void* stream);
+/* Target Grams: the buf/gram_* variables and their assign ops (synthesizer.py:66-74). Either assign the Grams of
+ * the last forward, or set them from a device array [batch,C,C] (per_image = 1) / [1,C,C] (broadcast). */
+int stx_plan_update_target_from_forward(stx_plan* plan, void* stream);
+int stx_plan_set_target_gram(stx_plan* plan, int k, const float* gram, int per_image, void* stream);
+
+/* Synthesizer.step (synthesizer.py:119-125): one f/g evaluation.
+ *   func [batch]         = loss_overall  (build_texture_loss, utils.py:44-49)
+ *   grad [batch,H,W,3]   = d sum(loss_overall) / d x   (tf.gradients, synthesizer.py:79), w.r.t. the pre-image
+ *                          when is_preimage.
+ * x, func, grad are device pointers. layer_loss (nullable) receives the unweighted per-layer losses
+ * [num_loss_layers][batch]. */
+int stx_plan_step(stx_plan* plan, const float* x, int is_preimage, float* func, float* grad, float* layer_loss,
+                  void* stream);
+/* Same through host buffers (what sess.run does for the reference): H2D of x, f/g, D2H of func and grad.
+ * Synchronous. */
+int stx_plan_step_host(stx_plan* plan, const float* x_host, int is_preimage, float* func_host, float* grad_host,
+                       void* stream);
+/* Per-layer gradients of build_texture_loss(calc_grad=True) (utils.py:50-55): d loss_layer[k] / d feat[k],
+ * fp32 [batch,h,w,c] device, for the features of the last forward and the current targets. */
+int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream);
+
+/* ---- device-resident L-BFGS with box bounds: the optimiser loop of synthesizer.py:127-151 ----------------
+ * Replaces scipy.optimize.minimize(method="L-BFGS-B", jac=True, bounds=[0,1]^n, options={maxiter, maxcor,
+ * ftol=0, gtol=0}) with a projected L-BFGS whose state (x, history, line search) never leaves the GPU.
+ * Each of the `batch` images of the plan is an independent problem with its own history and line search. */
+int stx_lbfgs_create(stx_lbfgs** out, stx_plan* plan, int maxcor, int bounded, float lower, float upper);
+void stx_lbfgs_destroy(stx_lbfgs* opt);
+/* x0: device [batch,H,W,3]. Resets the history. */
+int stx_lbfgs_reset(stx_lbfgs* opt, const float* x0, int is_preimage, void* stream);
+/* Run f/g evaluations until every problem has completed `maxiter` iterations (or `max_evals` evaluations were
+ * spent, 0 = 3*maxiter). Asynchronous; no host round trip inside. */
+int stx_lbfgs_run(stx_lbfgs* opt, int maxiter, int max_evals, void* stream);
+/* Results (device -> caller's device buffers): x [batch,H,W,3], fun [batch], iterations and evaluations [batch]. */
+int stx_lbfgs_result(stx_lbfgs* opt, float* x, float* fun, int* nit, int* nfev, void* stream);
+/* Whole optimisation through host buffers: H2D of x0, run, D2H of x and fun. Synchronous. */
+int stx_lbfgs_minimize_host(stx_lbfgs* opt, const float* x0_host, int is_preimage, int maxiter, float* x_host,
+                            float* fun_host, int* nit_host, int* nfev_host, void* stream);
+
+/* ---- stand-alone operators (building blocks; used by the Python texture_utils mirror and the tests) --------- */
+/* HWIO fp32 (3,3,cin,cout) -> bf16 forward pack [9][cout][cin] and dgrad pack [9][cin][cout] (device pointers). */
+int stx_pack_conv_weights(const float* w_hwio, int cin, int cout, void* w_fwd_bf16, void* w_dgrad_bf16,
+                          void* stream);
+/* out = epilogue(conv(x, w)) with x [n,H,W,cin] bf16, w packed [taps][cout][cin] bf16, taps in {9, 1}.
+ * epilogue: (+ bias[cout] fp32) (+ addend bf16) (relu) (zero where mask <= 0); any of them may be NULL/0.
+ * force_bn: 0 = automatic N tile, else 64 or 128. */
+int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_packed, int cout, int taps,
+                  const float* bias, const void* addend, const void* mask, int relu, void* out, int force_bn,
+                  void* stream);
+/* conv1_1 (+preprocessing) forward and input-gradient. w27x64/b64 fp32 device. */
+int stx_conv1_1_fwd(const float* image, int n, int H, int W, int is_preimage, const float* mean3_host,
+                    const float* w27x64, const float* b64, void* out_bf16, void* stream);
+int stx_conv1_1_bwd(const void* g_bf16, const float* image, int n, int H, int W, int is_preimage,
+                    const float* w27x64, float* grad_out, void* stream);
+int stx_avgpool2_fwd(const void* x_bf16, int n, int H, int W, int C, void* out_bf16, void* stream);
+int stx_avgpool2_bwd(const void* g_bf16, const void* act_bf16_or_null, int n, int H, int W, int C, void* out_bf16,
+                     void* stream);
+/* build_gram (utils.py:8-21) on a bf16 feature map [n,H*W,C]: G [n,C,C] fp32. workspace: stx_gram_workspace_bytes. */
+size_t stx_gram_workspace_bytes(int n, int HW, int C);
+int stx_gram_bf16(const void* feat_bf16, int n, int HW, int C, float eps, float* G_out, void* workspace,
+                  void* stream);
+int stx_f32_to_bf16(const float* x, size_t count, void* out_bf16, void* stream);
+int stx_bf16_to_f32(const void* x_bf16, size_t count, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYNTEX_B200_H_ */

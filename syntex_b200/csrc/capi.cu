@@ -1,0 +1,266 @@
+// extern "C" surface declared in include/syntex_b200.h. Thin: argument checks + calls into plan.cu / ops.
+#include "../../include/syntex_b200.h"
+
+#include "lbfgs.h"
+#include "ops.h"
+#include "plan.h"
+
+using namespace stx;
+
+namespace stx {
+extern int g_debug_gram_lbo;
+extern int g_debug_gram_sbo;
+}  // namespace stx
+
+struct stx_vgg {
+  Vgg* v;
+};
+struct stx_plan {
+  Plan* p;
+};
+struct stx_lbfgs {
+  Lbfgs* o;
+};
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* stx_last_error(void) { return last_error().c_str(); }
+int stx_abi_version(void) { return 1; }
+
+int stx_debug_set(int key, int value) {
+  switch (key) {
+    case 1: g_debug_gram_lbo = value; return STX_OK;
+    case 2: g_debug_gram_sbo = value; return STX_OK;
+    default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+int stx_vgg_create(stx_vgg** out, const float* const* weights_hwio, const float* const* biases, int num_convs,
+                   const float* mean3, void* stream) {
+  STX_REQUIRE(out, "stx_vgg_create: null out");
+  Vgg* v = nullptr;
+  STX_TRY(vgg_create(&v, weights_hwio, biases, num_convs, mean3, S(stream)));
+  *out = new stx_vgg{v};
+  return STX_OK;
+}
+void stx_vgg_destroy(stx_vgg* vgg) {
+  if (!vgg) return;
+  delete vgg->v;
+  delete vgg;
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+int stx_plan_create(stx_plan** out, const stx_vgg* vgg, int batch, int height, int width, int topmost,
+                    int num_loss_layers, const int* loss_layers, const float* coefs) {
+  STX_REQUIRE(out && vgg, "stx_plan_create: null argument");
+  Plan* p = nullptr;
+  STX_TRY(plan_create(&p, vgg->v, batch, height, width, topmost, num_loss_layers, loss_layers, coefs));
+  *out = new stx_plan{p};
+  return STX_OK;
+}
+void stx_plan_destroy(stx_plan* plan) {
+  if (!plan) return;
+  delete plan->p;
+  delete plan;
+}
+size_t stx_plan_device_bytes(const stx_plan* plan) { return plan ? plan->p->arena_bytes : 0; }
+
+int stx_plan_forward(stx_plan* plan, const float* image, int is_preimage, int with_grams, void* stream) {
+  STX_REQUIRE(plan, "stx_plan_forward: null plan");
+  return plan->p->forward(image, is_preimage, with_grams, false, S(stream));
+}
+
+int stx_plan_layer_shape(const stx_plan* plan, int layer, int* h, int* w, int* c) {
+  STX_REQUIRE(plan, "stx_plan_layer_shape: null plan");
+  STX_REQUIRE(layer >= 0 && layer <= plan->p->topmost, "layer index out of range for this plan");
+  if (h) *h = plan->p->lh[layer];
+  if (w) *w = plan->p->lw[layer];
+  if (c) *c = plan->p->lc[layer];
+  return STX_OK;
+}
+
+int stx_plan_copy_feature_f32(stx_plan* plan, int layer, float* out, void* stream) {
+  STX_REQUIRE(plan && out, "stx_plan_copy_feature_f32: null argument");
+  Plan* p = plan->p;
+  STX_REQUIRE(layer >= 0 && layer <= p->topmost, "layer index out of range for this plan");
+  const size_t n = static_cast<size_t>(p->B) * p->lh[layer] * p->lw[layer] * p->lc[layer];
+  return bf16_to_f32_launch(p->act[layer], n, out, S(stream));
+}
+
+int stx_plan_copy_gram(stx_plan* plan, int k, float* out, void* stream) {
+  STX_REQUIRE(plan && out, "stx_plan_copy_gram: null argument");
+  Plan* p = plan->p;
+  STX_REQUIRE(k >= 0 && k < static_cast<int>(p->loss.size()), "loss-layer index out of range");
+  if (!p->have_grams) return fail(STX_ERR_STATE, "stx_plan_copy_gram: no forward with Grams has run");
+  const LossLayer& ll = p->loss[k];
+  STX_CUDA(cudaMemcpyAsync(out, ll.G, static_cast<size_t>(p->B) * ll.C * ll.C * sizeof(float),
+                           cudaMemcpyDeviceToDevice, S(stream)));
+  return STX_OK;
+}
+
+int stx_plan_update_target_from_forward(stx_plan* plan, void* stream) {
+  STX_REQUIRE(plan, "stx_plan_update_target_from_forward: null plan");
+  Plan* p = plan->p;
+  if (!p->have_grams) return fail(STX_ERR_STATE, "update_target: no forward with Grams has run");
+  for (LossLayer& ll : p->loss) {
+    STX_CUDA(cudaMemcpyAsync(ll.target, ll.G, static_cast<size_t>(p->B) * ll.C * ll.C * sizeof(float),
+                             cudaMemcpyDeviceToDevice, S(stream)));
+    ll.target_stride = static_cast<long long>(ll.C) * ll.C;
+  }
+  p->have_target = true;
+  return STX_OK;
+}
+
+int stx_plan_set_target_gram(stx_plan* plan, int k, const float* gram, int per_image, void* stream) {
+  STX_REQUIRE(plan && gram, "stx_plan_set_target_gram: null argument");
+  Plan* p = plan->p;
+  STX_REQUIRE(k >= 0 && k < static_cast<int>(p->loss.size()), "loss-layer index out of range");
+  LossLayer& ll = p->loss[k];
+  const size_t cc = static_cast<size_t>(ll.C) * ll.C;
+  STX_CUDA(cudaMemcpyAsync(ll.target, gram, (per_image ? p->B : 1) * cc * sizeof(float), cudaMemcpyDeviceToDevice,
+                           S(stream)));
+  ll.target_stride = per_image ? static_cast<long long>(cc) : 0;
+  bool all = true;
+  p->have_target = all;
+  return STX_OK;
+}
+
+int stx_plan_step(stx_plan* plan, const float* x, int is_preimage, float* func, float* grad, float* layer_loss,
+                  void* stream) {
+  STX_REQUIRE(plan, "stx_plan_step: null plan");
+  return plan->p->step(x, is_preimage, func, grad, layer_loss, S(stream));
+}
+
+int stx_plan_step_host(stx_plan* plan, const float* x_host, int is_preimage, float* func_host, float* grad_host,
+                       void* stream) {
+  STX_REQUIRE(plan && x_host && func_host && grad_host, "stx_plan_step_host: null argument");
+  Plan* p = plan->p;
+  const size_t n = p->image_elems();
+  float* px = p->pinned;
+  float* pg = p->pinned + n;
+  float* pf = p->pinned + 2 * n;
+  memcpy(px, x_host, n * sizeof(float));
+  STX_CUDA(cudaMemcpyAsync(p->x_dev, px, n * sizeof(float), cudaMemcpyHostToDevice, S(stream)));
+  STX_TRY(p->step(p->x_dev, is_preimage, p->func_dev, p->grad_dev, nullptr, S(stream)));
+  STX_CUDA(cudaMemcpyAsync(pg, p->grad_dev, n * sizeof(float), cudaMemcpyDeviceToHost, S(stream)));
+  STX_CUDA(cudaMemcpyAsync(pf, p->func_dev, p->B * sizeof(float), cudaMemcpyDeviceToHost, S(stream)));
+  STX_CUDA(cudaStreamSynchronize(S(stream)));
+  memcpy(grad_host, pg, n * sizeof(float));
+  memcpy(func_host, pf, p->B * sizeof(float));
+  return STX_OK;
+}
+
+int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream) {
+  STX_REQUIRE(plan && out, "stx_plan_layer_grad: null argument");
+  Plan* p = plan->p;
+  STX_REQUIRE(k >= 0 && k < static_cast<int>(p->loss.size()), "loss-layer index out of range");
+  if (!p->have_grams || !p->have_target)
+    return fail(STX_ERR_STATE, "stx_plan_layer_grad: needs a forward with Grams and target Grams");
+  LossLayer& ll = p->loss[k];
+  // d loss_layer / dF = 4/(C^2 n) * F (G - T)   (utils.py:46-48, :54): re-scale the difference, then one 1x1 GEMM.
+  const float norm = static_cast<float>(ll.HW) + 1e-6f;
+  const float dscale = 4.0f / (static_cast<float>(ll.C) * static_cast<float>(ll.C) * norm);
+  STX_TRY(gram_finish_launch(ll.gram, 1e-6f, nullptr, ll.target, ll.target_stride, dscale, ll.dscaled, 0.0f, nullptr, 0,
+                             S(stream)));
+  STX_TRY(conv_launch(ll.layer_grad_op, S(stream)));
+  const size_t n = static_cast<size_t>(p->B) * ll.HW * ll.C;
+  return bf16_to_f32_launch(p->gbuf[0], n, out, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ L-BFGS
+int stx_lbfgs_create(stx_lbfgs** out, stx_plan* plan, int maxcor, int bounded, float lower, float upper) {
+  STX_REQUIRE(out && plan, "stx_lbfgs_create: null argument");
+  Lbfgs* o = nullptr;
+  STX_TRY(lbfgs_create(&o, plan->p, maxcor, bounded, lower, upper));
+  *out = new stx_lbfgs{o};
+  return STX_OK;
+}
+void stx_lbfgs_destroy(stx_lbfgs* opt) {
+  if (!opt) return;
+  delete opt->o;
+  delete opt;
+}
+int stx_lbfgs_reset(stx_lbfgs* opt, const float* x0, int is_preimage, void* stream) {
+  STX_REQUIRE(opt && x0, "stx_lbfgs_reset: null argument");
+  return opt->o->reset(x0, is_preimage, S(stream));
+}
+int stx_lbfgs_run(stx_lbfgs* opt, int maxiter, int max_evals, void* stream) {
+  STX_REQUIRE(opt, "stx_lbfgs_run: null optimizer");
+  return opt->o->run(maxiter, max_evals, S(stream));
+}
+int stx_lbfgs_result(stx_lbfgs* opt, float* x, float* fun, int* nit, int* nfev, void* stream) {
+  STX_REQUIRE(opt, "stx_lbfgs_result: null optimizer");
+  return opt->o->result(x, fun, nit, nfev, S(stream));
+}
+int stx_lbfgs_minimize_host(stx_lbfgs* opt, const float* x0_host, int is_preimage, int maxiter, float* x_host,
+                            float* fun_host, int* nit_host, int* nfev_host, void* stream) {
+  STX_REQUIRE(opt && x0_host && x_host && fun_host, "stx_lbfgs_minimize_host: null argument");
+  return opt->o->minimize_host(x0_host, is_preimage, maxiter, x_host, fun_host, nit_host, nfev_host, S(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ stand-alone ops
+int stx_pack_conv_weights(const float* w_hwio, int cin, int cout, void* w_fwd_bf16, void* w_dgrad_bf16,
+                          void* stream) {
+  return pack_weights_launch(w_hwio, cin, cout, static_cast<bf16*>(w_fwd_bf16), static_cast<bf16*>(w_dgrad_bf16),
+                             S(stream));
+}
+
+int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_packed, int cout, int taps,
+                  const float* bias, const void* addend, const void* mask, int relu, void* out, int force_bn,
+                  void* stream) {
+  STX_REQUIRE(out, "stx_conv_bf16: null output");
+  ConvOp op;
+  STX_TRY(conv_prepare(&op, static_cast<const bf16*>(x), n, H, W, cin, static_cast<const bf16*>(w_packed), cout, taps,
+                       0, force_bn));
+  op.bias = bias;
+  op.addend = static_cast<const bf16*>(addend);
+  op.mask = static_cast<const bf16*>(mask);
+  op.relu = relu;
+  op.out = static_cast<bf16*>(out);
+  return conv_launch(op, S(stream));
+}
+
+int stx_conv1_1_fwd(const float* image, int n, int H, int W, int is_preimage, const float* mean3_host,
+                    const float* w27x64, const float* b64, void* out_bf16, void* stream) {
+  return conv1_1_fwd_launch(image, n, H, W, is_preimage, mean3_host, w27x64, b64, static_cast<bf16*>(out_bf16),
+                            S(stream));
+}
+int stx_conv1_1_bwd(const void* g_bf16, const float* image, int n, int H, int W, int is_preimage,
+                    const float* w27x64, float* grad_out, void* stream) {
+  return conv1_1_bwd_launch(static_cast<const bf16*>(g_bf16), image, n, H, W, is_preimage, w27x64, grad_out,
+                            S(stream));
+}
+int stx_avgpool2_fwd(const void* x_bf16, int n, int H, int W, int C, void* out_bf16, void* stream) {
+  return avgpool2_fwd_launch(static_cast<const bf16*>(x_bf16), n, H, W, C, static_cast<bf16*>(out_bf16), S(stream));
+}
+int stx_avgpool2_bwd(const void* g_bf16, const void* act, int n, int H, int W, int C, void* out_bf16, void* stream) {
+  return avgpool2_bwd_mask_launch(static_cast<const bf16*>(g_bf16), static_cast<const bf16*>(act), n, H, W, C,
+                                  static_cast<bf16*>(out_bf16), S(stream));
+}
+
+size_t stx_gram_workspace_bytes(int n, int HW, int C) {
+  if (n <= 0 || HW <= 0 || C <= 0) return 0;
+  return gram_partial_bytes(n, HW, C);
+}
+int stx_gram_bf16(const void* feat_bf16, int n, int HW, int C, float eps, float* G_out, void* workspace,
+                  void* stream) {
+  STX_REQUIRE(G_out, "stx_gram_bf16: null output");
+  GramOp op;
+  STX_TRY(gram_prepare(&op, static_cast<const bf16*>(feat_bf16), n, HW, C, static_cast<float*>(workspace)));
+  STX_TRY(gram_launch(op, S(stream)));
+  return gram_finish_launch(op, eps, G_out, nullptr, 0, 0.0f, nullptr, 0.0f, nullptr, 0, S(stream));
+}
+
+int stx_f32_to_bf16(const float* x, size_t count, void* out_bf16, void* stream) {
+  STX_REQUIRE(count == 0 || (x && out_bf16), "stx_f32_to_bf16: null argument");
+  return f32_to_bf16_launch(x, count, static_cast<bf16*>(out_bf16), S(stream));
+}
+int stx_bf16_to_f32(const void* x_bf16, size_t count, float* out, void* stream) {
+  STX_REQUIRE(count == 0 || (x_bf16 && out), "stx_bf16_to_f32: null argument");
+  return bf16_to_f32_launch(static_cast<const bf16*>(x_bf16), count, out, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+#include "common.h"
+
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+namespace stx {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error() { return g_last_error; }
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return STX_ERR_CUDA;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The driver entry point is resolved through the runtime so the library has no link-time libcuda dependency
+// (it must load on the GPU-less build box for the symbol-export test).
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(STX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(STX_ERR_INVALID, "tensor map base not 16B aligned");
+  cuuint64_t gdim[5];
+  cuuint64_t gstride[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estride[5];
+  uint64_t stride = sizeof(bf16);
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estride[i] = 1;
+    stride *= dims[i];
+    if (i < rank - 1) gstride[i] = stride;
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                  gdim, gstride, bdim, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d), rank %d dims [%llu %llu %llu %llu] box [%u %u %u %u]",
+             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+             rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return fail(STX_ERR_CUDA, buf);
+  }
+  return STX_OK;
+}
+
+}  // namespace stx

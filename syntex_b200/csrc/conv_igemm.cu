@@ -1,0 +1,320 @@
+// 3x3 (and 1x1) convolution over NHWC bf16 activations as an implicit GEMM on tcgen05 tensor cores.
+//
+//   D[M = 128 output pixels, N = BN output channels] = sum over (tap, 64-channel chunk) A_tap * W_tap^T
+//
+// * A tile  : a BNI x BH x BW patch of pixels (BNI*BH*BW = 128) x 64 input channels, fetched by ONE 4-D TMA box
+//             whose (w, h) coordinates are shifted by the tap offset. Halo pixels are out of range for the
+//             tensor map and arrive as zeros, which is exactly TF's SAME padding (reference:
+//             texture_utils/vgg19.py:176, tf.nn.conv2d(..., padding="SAME")).
+// * W tile  : BN x 64 slice of the pre-packed weights [tap][C_out][C_in] (K-major), one 3-D TMA box.
+// * Both operands land in shared memory with the 128-byte swizzle and are consumed directly by
+//   tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) through shared-memory descriptors; accumulators live in TMEM.
+// * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM -> registers ->
+//   bias / addend / ReLU / ReLU-mask -> bf16 -> global).
+//
+// The same kernel serves
+//   forward      relu(conv(x, W) + b)                          (vgg19.py:171-179)
+//   dgrad        (conv(dy, rot180(W)^T) [+ addend]) * [a > 0]   (Conv2DBackpropInput + ReluGrad of tf.gradients,
+//                                                               gatys/synthesizer.py:79)
+//   Gram dF      F * Dscaled as a 1x1 convolution with per-image weights (utils.py:54), accumulated in place.
+#include "common.h"
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace stx {
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;                       // bf16 elements per 128-byte swizzle row
+constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB per stage
+constexpr int kThreads = 192;
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int kBBytes = BN * kChunkK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarrierOffset + 128 /*barriers + tmem slot*/ + 1024 /*alignment slack*/;
+};
+
+struct ConvKernelParams {
+  int H, W, nimg;
+  int cout;            // total output channels (row pitch of out/addend/mask)
+  int cchunks;         // C_in / 64
+  int taps;            // 9 or 1
+  int bw_log2, bh_log2;
+  int tiles_w, tiles_h;
+  int n_step;          // images advanced per tile along the batch axis
+  int per_image_w;     // weight "tap" index = image index (Gram dF mode); only rows of the first image are stored
+  int relu;
+  const float* bias;   // [cout] or null
+  const bf16* addend;  // [nimg,H,W,cout] or null (may alias out)
+  const bf16* mask;    // [nimg,H,W,cout] or null: result is zeroed where mask <= 0
+  bf16* out;           // [nimg,H,W,cout]
+};
+
+union Pack8 {
+  uint4 u;
+  __nv_bfloat162 h2[4];
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 2)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const ConvKernelParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* accum_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // Tile coordinates.
+  const int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w;
+  const int th = (tile / p.tiles_w) % p.tiles_h;
+  const int tn = tile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw << p.bw_log2;
+  const int h0 = th << p.bh_log2;
+  const int n0 = tn * p.n_step;
+  const int nblk = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int iters = p.taps * p.cchunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
+        const int tap = it / p.cchunks;
+        const int cc = it - tap * p.cchunks;
+        int dy = 0, dx = 0;
+        if (p.taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        uint8_t* a_dst = smem + s * L::kStageBytes;
+        uint8_t* b_dst = a_dst + kABytes;
+        mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
+        tma_load_4d(a_dst, &tmA, &full_bar[s], cc * kChunkK, w0 + dx, h0 + dy, n0);
+        tma_load_3d(b_dst, &tmB, &full_bar[s], cc * kChunkK, nblk * BN, p.per_image_w ? n0 : tap);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_bar[s], ph, 200 + s);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+        const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kChunkK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(accum_bar);         // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;      // accumulator row = pixel index inside the tile
+    const int ww = r & ((1 << p.bw_log2) - 1);
+    const int hh = (r >> p.bw_log2) & ((1 << p.bh_log2) - 1);
+    const int nn = r >> (p.bw_log2 + p.bh_log2);
+    const int n = n0 + nn, h = h0 + hh, w = w0 + ww;
+    const bool valid = (n < p.nimg) && (h < p.H) && (w < p.W) && (!p.per_image_w || nn == 0);
+    const size_t row_off = ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.cout + nblk * BN;
+
+    mbar_wait(accum_bar, 0, 300);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nblk * BN + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
+          }
+        }
+        if (p.addend) {
+          const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + row_off + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            Pack8 pk;
+            pk.u = a4[j];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(pk.h2[e]);
+              v[8 * j + 2 * e] += f.x;
+              v[8 * j + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (p.mask) {
+          const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + row_off + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            Pack8 pk;
+            pk.u = __ldg(m4 + j);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(pk.h2[e]);
+              if (!(f.x > 0.0f)) v[8 * j + 2 * e] = 0.0f;
+              if (!(f.y > 0.0f)) v[8 * j + 2 * e + 1] = 0.0f;
+            }
+          }
+        }
+        uint4* o4 = reinterpret_cast<uint4*>(p.out + row_off + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          Pack8 pk;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pk.h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+          o4[j] = pk.u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BN);
+}
+
+template <int BN>
+int launch_bn(const ConvOp& op, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    STX_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  ConvKernelParams p;
+  p.H = op.H;
+  p.W = op.W;
+  p.nimg = op.nimg;
+  p.cout = op.cout;
+  p.cchunks = op.cin / kChunkK;
+  p.taps = op.taps;
+  p.bw_log2 = op.bw_log2;
+  p.bh_log2 = op.bh_log2;
+  p.tiles_w = op.tiles_w;
+  p.tiles_h = op.tiles_h;
+  p.n_step = op.n_step;
+  p.per_image_w = op.per_image_w;
+  p.relu = op.relu;
+  p.bias = op.bias;
+  p.addend = op.addend;
+  p.mask = op.mask;
+  p.out = op.out;
+  dim3 grid(op.tiles_w * op.tiles_h * op.tiles_n, op.cout / BN, 1);
+  conv_igemm_kernel<BN><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, p);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+}  // namespace
+
+int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
+                 int taps, int per_image_w, int force_bn) {
+  STX_REQUIRE(x && wpacked, "conv: null operand");
+  STX_REQUIRE(nimg > 0 && H > 0 && W > 0, "conv: empty tensor");
+  STX_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv: channels must be multiples of 64");
+  STX_REQUIRE(taps == 9 || taps == 1, "conv: taps must be 9 (3x3) or 1 (1x1)");
+  op->nimg = nimg;
+  op->H = H;
+  op->W = W;
+  op->cin = cin;
+  op->cout = cout;
+  op->taps = taps;
+  op->per_image_w = per_image_w;
+  // Tile geometry: BW x BH x BNI pixels = 128 accumulator rows.
+  int bw = 16;
+  while (bw > 1 && (bw >> 1) >= W) bw >>= 1;       // smallest power of two >= W, capped at 16
+  int bh = kTileM / bw;
+  while (bh > 1 && (bh >> 1) >= H) bh >>= 1;
+  int bni = kTileM / (bw * bh);
+  op->bw_log2 = ilog2(bw);
+  op->bh_log2 = ilog2(bh);
+  op->tiles_w = (W + bw - 1) / bw;
+  op->tiles_h = (H + bh - 1) / bh;
+  op->n_step = per_image_w ? 1 : bni;
+  op->tiles_n = (nimg + op->n_step - 1) / op->n_step;
+  // N tile: 128 when that still fills the machine, otherwise 64 (more CTAs for the small deep layers).
+  const int tiles_m = op->tiles_w * op->tiles_h * op->tiles_n;
+  int bn = 64;
+  if (cout % 128 == 0 && tiles_m * (cout / 128) >= 148) bn = 128;
+  if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0)) bn = force_bn;
+  op->bn = bn;
+
+  const uint64_t adims[4] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                             static_cast<uint64_t>(nimg)};
+  const uint32_t abox[4] = {64u, static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), static_cast<uint32_t>(bni)};
+  STX_TRY(encode_tmap_bf16(&op->tmA, x, 4, adims, abox));
+  const uint64_t bdims[3] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(cout),
+                             static_cast<uint64_t>(per_image_w ? nimg : taps)};
+  const uint32_t bbox[3] = {64u, static_cast<uint32_t>(bn), 1u};
+  STX_TRY(encode_tmap_bf16(&op->tmB, wpacked, 3, bdims, bbox));
+  op->bias = nullptr;
+  op->addend = nullptr;
+  op->mask = nullptr;
+  op->out = nullptr;
+  op->relu = 0;
+  return STX_OK;
+}
+
+int conv_launch(const ConvOp& op, cudaStream_t stream) {
+  STX_REQUIRE(op.out != nullptr, "conv: output not set");
+  if (op.bn == 128) return launch_bn<128>(op, stream);
+  return launch_bn<64>(op, stream);
+}
+
+}  // namespace stx

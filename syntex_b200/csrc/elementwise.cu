@@ -1,0 +1,327 @@
+// Bandwidth-bound pieces of the VGG19 path: the 3-channel first layer (fused with preprocessing), 2x2 average
+// pooling forward / backward (+ReLU mask), weight packing and dtype conversion. All are simple coalesced
+// 16-byte-vector kernels; none has data reuse worth staging.
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace stx {
+
+namespace {
+
+union Pack8 {
+  uint4 u;
+  __nv_bfloat162 h2[4];
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// conv1_1 forward. Reference: vgg19.py:142-146 (x*255 - mean) and :171-179 (conv + bias + relu), optional
+// sigmoid pre-image (gatys/synthesizer.py:59). Two threads per pixel, 32 output channels each.
+// Zero padding applies to the *preprocessed* image, as in the TF graph.
+__global__ void __launch_bounds__(256)
+conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int is_preimage, float m0, float m1,
+                   float m2, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out) {
+  __shared__ float sw[27 * 64];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long npix = static_cast<long long>(nimg) * H * W;
+  const long long pix = gid >> 1;
+  const int half = static_cast<int>(gid & 1);
+  if (pix >= npix) return;
+  const int x = static_cast<int>(pix % W);
+  const int y = static_cast<int>((pix / W) % H);
+  const long long img_base = (pix / (static_cast<long long>(W) * H)) * H * W;
+  const float mean[3] = {m0, m1, m2};
+
+  float patch[27];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int yy = y + r - 1, xx = x + s - 1;
+      const bool in = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+      const float* src = image + (img_base + static_cast<long long>(yy) * W + xx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = 0.0f;
+        if (in) {
+          v = __ldg(src + c);
+          if (is_preimage) v = sigmoidf_(v);
+          v = v * 255.0f - mean[c];
+        }
+        patch[(r * 3 + s) * 3 + c] = v;
+      }
+    }
+  }
+  float acc[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc[k] = sb[half * 32 + k];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const float4* w4 = reinterpret_cast<const float4*>(sw + t * 64 + half * 32);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 ww = w4[k];
+      acc[4 * k + 0] = fmaf(patch[t], ww.x, acc[4 * k + 0]);
+      acc[4 * k + 1] = fmaf(patch[t], ww.y, acc[4 * k + 1]);
+      acc[4 * k + 2] = fmaf(patch[t], ww.z, acc[4 * k + 2]);
+      acc[4 * k + 3] = fmaf(patch[t], ww.w, acc[4 * k + 3]);
+    }
+  }
+  uint4* o4 = reinterpret_cast<uint4*>(out + pix * 64 + half * 32);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    Pack8 pk;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      pk.h2[e] = __floats2bfloat162_rn(fmaxf(acc[8 * j + 2 * e], 0.0f), fmaxf(acc[8 * j + 2 * e + 1], 0.0f));
+    o4[j] = pk.u;
+  }
+}
+
+// conv1_1 input gradient. g is dL/d(pre-activation of conv1_1) [nimg,H,W,64] bf16. Four lanes per pixel, 16
+// channels each, reduced with shuffles. Chained with d(x*255 - mean)/dx = 255 and the optional sigmoid'.
+__global__ void __launch_bounds__(256)
+conv1_1_bwd_kernel(const bf16* __restrict__ g, const float* __restrict__ image, int nimg, int H, int W,
+                   int is_preimage, const float* __restrict__ w, float* __restrict__ grad_out) {
+  __shared__ float sw[27 * 64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long npix = static_cast<long long>(nimg) * H * W;
+  long long pix = gid >> 2;
+  const int part = static_cast<int>(gid & 3);
+  const bool live = pix < npix;
+  if (!live) pix = npix - 1;   // keep the whole warp in the shuffles
+  const int x = static_cast<int>(pix % W);
+  const int y = static_cast<int>((pix / W) % H);
+  const long long img_base = (pix / (static_cast<long long>(W) * H)) * H * W;
+
+  float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      // dx[y,x,c] = sum_{r,s,k} g[y - r + 1, x - s + 1, k] * w[r,s,c,k]
+      const int yy = y - r + 1, xx = x - s + 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const uint4* g4 = reinterpret_cast<const uint4*>(g + (img_base + static_cast<long long>(yy) * W + xx) * 64 + part * 16);
+      const float* w0 = sw + ((r * 3 + s) * 3 + 0) * 64 + part * 16;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        Pack8 pk;
+        pk.u = __ldg(g4 + j);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(pk.h2[e]);
+          const int k = 8 * j + 2 * e;
+          d0 = fmaf(f.x, w0[k], d0);
+          d0 = fmaf(f.y, w0[k + 1], d0);
+          d1 = fmaf(f.x, w0[64 + k], d1);
+          d1 = fmaf(f.y, w0[64 + k + 1], d1);
+          d2 = fmaf(f.x, w0[128 + k], d2);
+          d2 = fmaf(f.y, w0[128 + k + 1], d2);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  }
+  if (live && part < 3) {
+    float d = (part == 0) ? d0 : (part == 1 ? d1 : d2);
+    d *= 255.0f;
+    if (is_preimage) {
+      const float sg = sigmoidf_(image[pix * 3 + part]);
+      d *= sg * (1.0f - sg);
+    }
+    grad_out[pix * 3 + part] = d;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2x2 stride-2 average pooling, even H and W (vgg19.py:90-91; SAME == VALID for even sizes).
+__global__ void __launch_bounds__(256)
+avgpool2_fwd_kernel(const bf16* __restrict__ x, int nimg, int H, int W, int C, bf16* __restrict__ out) {
+  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
+  const long long total = static_cast<long long>(nimg) * Ho * Wo * C8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c8 = static_cast<int>(gid % C8);
+  const long long opix = gid / C8;
+  const int xo = static_cast<int>(opix % Wo);
+  const int yo = static_cast<int>((opix / Wo) % Ho);
+  const long long n = opix / (static_cast<long long>(Wo) * Ho);
+  const bf16* base = x + ((n * H + 2 * yo) * W + 2 * xo) * C + c8 * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      Pack8 pk;
+      pk.u = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(dy) * W + dx) * C));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(pk.h2[e]);
+        acc[2 * e] += f.x;
+        acc[2 * e + 1] += f.y;
+      }
+    }
+  }
+  Pack8 o;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o.h2[e] = __floats2bfloat162_rn(acc[2 * e] * 0.25f, acc[2 * e + 1] * 0.25f);
+  *reinterpret_cast<uint4*>(out + opix * C + c8 * 8) = o.u;
+}
+
+// AvgPoolGrad fused with the ReluGrad of the conv that feeds the pool.
+__global__ void __launch_bounds__(256)
+avgpool2_bwd_mask_kernel(const bf16* __restrict__ g_in, const bf16* __restrict__ act, int nimg, int H, int W, int C,
+                         bf16* __restrict__ out) {
+  const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
+  const long long total = static_cast<long long>(nimg) * H * W * C8;
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c8 = static_cast<int>(gid % C8);
+  const long long pix = gid / C8;
+  const int x = static_cast<int>(pix % W);
+  const int y = static_cast<int>((pix / W) % H);
+  const long long n = pix / (static_cast<long long>(W) * H);
+  Pack8 gi, a, o;
+  gi.u = __ldg(reinterpret_cast<const uint4*>(g_in + ((n * Ho + (y >> 1)) * Wo + (x >> 1)) * C + c8 * 8));
+  if (act) a.u = __ldg(reinterpret_cast<const uint4*>(act + pix * C + c8 * 8));
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 f = __bfloat1622float2(gi.h2[e]);
+    f.x *= 0.25f;
+    f.y *= 0.25f;
+    if (act) {
+      const float2 m = __bfloat1622float2(a.h2[e]);
+      if (!(m.x > 0.0f)) f.x = 0.0f;
+      if (!(m.y > 0.0f)) f.y = 0.0f;
+    }
+    o.h2[e] = __floats2bfloat162_rn(f.x, f.y);
+  }
+  *reinterpret_cast<uint4*>(out + pix * C + c8 * 8) = o.u;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, size_t n, bf16* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ x, size_t n, float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(x[i]);
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cin, int cout, bf16* __restrict__ wf,
+                                    bf16* __restrict__ wd) {
+  const long long total = 9LL * cin * cout;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // w is HWIO: i = ((tap * cin) + ci) * cout + co
+  const int co = static_cast<int>(i % cout);
+  const int ci = static_cast<int>((i / cout) % cin);
+  const int tap = static_cast<int>(i / (static_cast<long long>(cout) * cin));
+  const bf16 v = __float2bfloat16_rn(w[i]);
+  if (wf) wf[(static_cast<long long>(tap) * cout + co) * cin + ci] = v;
+  if (wd) wd[(static_cast<long long>(8 - tap) * cin + ci) * cout + co] = v;
+}
+
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const float* __restrict__ part, int count, int stride, float* __restrict__ out) {
+  const int img = blockIdx.x;
+  const float* p = part + static_cast<size_t>(img) * stride;
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < count; i += 256) s += p[i];
+  __shared__ float red[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    out[img] = t;
+  }
+}
+
+inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+}  // namespace
+
+int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3,
+                       const float* w, const float* b, bf16* out, cudaStream_t stream) {
+  STX_REQUIRE(image && w && b && out && mean3, "conv1_1 fwd: null operand");
+  const long long threads = 2LL * nimg * H * W;
+  conv1_1_fwd_kernel<<<blocks_for(threads, 256), 256, 0, stream>>>(image, nimg, H, W, is_preimage, mean3[0], mean3[1],
+                                                                  mean3[2], w, b, out);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+int conv1_1_bwd_launch(const bf16* g, const float* image, int nimg, int H, int W, int is_preimage, const float* w,
+                       float* grad_out, cudaStream_t stream) {
+  STX_REQUIRE(g && w && grad_out, "conv1_1 bwd: null operand");
+  STX_REQUIRE(!is_preimage || image, "conv1_1 bwd: pre-image mode needs the input");
+  const long long threads = 4LL * nimg * H * W;
+  conv1_1_bwd_kernel<<<blocks_for(threads, 256), 256, 0, stream>>>(g, image, nimg, H, W, is_preimage, w, grad_out);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+int avgpool2_fwd_launch(const bf16* x, int nimg, int H, int W, int C, bf16* out, cudaStream_t stream) {
+  STX_REQUIRE(x && out, "avgpool fwd: null operand");
+  STX_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "avgpool: H, W must be even and C a multiple of 8");
+  const long long total = static_cast<long long>(nimg) * (H / 2) * (W / 2) * (C / 8);
+  avgpool2_fwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(x, nimg, H, W, C, out);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+int avgpool2_bwd_mask_launch(const bf16* g_in, const bf16* act, int nimg, int H, int W, int C, bf16* out,
+                             cudaStream_t stream) {
+  STX_REQUIRE(g_in && out, "avgpool bwd: null operand");
+  STX_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "avgpool: H, W must be even and C a multiple of 8");
+  const long long total = static_cast<long long>(nimg) * H * W * (C / 8);
+  avgpool2_bwd_mask_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(g_in, act, nimg, H, W, C, out);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+int f32_to_bf16_launch(const float* x, size_t n, bf16* out, cudaStream_t stream) {
+  if (n == 0) return STX_OK;
+  f32_to_bf16_kernel<<<blocks_for(static_cast<long long>(n), 256), 256, 0, stream>>>(x, n, out);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+int bf16_to_f32_launch(const bf16* x, size_t n, float* out, cudaStream_t stream) {
+  if (n == 0) return STX_OK;
+  bf16_to_f32_kernel<<<blocks_for(static_cast<long long>(n), 256), 256, 0, stream>>>(x, n, out);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf16* w_dgrad, cudaStream_t stream) {
+  STX_REQUIRE(w_hwio, "pack_weights: null weights");
+  const long long total = 9LL * cin * cout;
+  pack_weights_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_hwio, cin, cout, w_fwd, w_dgrad);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+int sum_partials_launch(const float* part, int nimg, int count, int stride, float* out, cudaStream_t stream) {
+  sum_partials_kernel<<<nimg, 256, 0, stream>>>(part, count, stride, out);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+}  // namespace stx

@@ -1,0 +1,272 @@
+// Gram matrix G = F^T F / (HW + eps) of an NHWC bf16 feature map (reference: texture_utils/utils.py:8-21) as a
+// symmetric split-K tensor-core contraction, plus the fused style-loss / difference kernel (utils.py:44-49).
+//
+// F is [HW, C] with C contiguous, so both MMA operands are MN-major: a TMA box of 64 pixels x 64 channels lands
+// as 64 rows of 128 B (128-byte swizzle) and is consumed with MN-major shared-memory descriptors
+// (LBO = distance between 64-channel chunks, SBO = 8 pixel rows). Only the upper-triangle 128x128 tiles are
+// computed; diagonal tiles reuse the A stage as the B operand. Each CTA reduces one slab of pixels and writes
+// an fp32 partial tile; gram_finish_kernel sums the slabs in a fixed order (bit-reproducible, no atomics),
+// mirrors the triangle and produces the loss terms.
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace stx {
+
+int g_debug_gram_lbo = 0;   // 0 = default; set through stx_debug_set for descriptor bring-up
+int g_debug_gram_sbo = 0;
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kRowsPerStage = 64;                         // pixels (K) per pipeline stage
+constexpr int kChunkBytes = kRowsPerStage * 128;          // one 64-channel chunk: 8 KiB
+constexpr int kThreads = 192;
+constexpr int kSmemTotal = kStages * 4 * kChunkBytes + 128 + 1024;   // A: 2 chunks, B: up to 2 chunks
+
+struct GramKernelParams {
+  int C, splits, iters_per_split, total_iters, tiles_per_dim;
+  uint32_t lbo, sbo;
+  float* partial;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kStageBytes = 4 * kChunkBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* accum_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // Upper-triangle tile (ti <= tj).
+  int ti = 0, tj = 0;
+  {
+    int t = blockIdx.x;
+    int row_len = p.tiles_per_dim;
+    while (t >= row_len) {
+      t -= row_len;
+      ++ti;
+      --row_len;
+    }
+    tj = ti + t;
+  }
+  const int split = blockIdx.y;
+  const int img = blockIdx.z;
+  const int m0 = ti * 128, n0 = tj * 128;
+  const bool diag = (ti == tj);
+  const int a_chunks = (p.C >= 128) ? 2 : 1;
+  const int b_chunks = diag ? 0 : BN / 64;
+
+  int it_begin = split * p.iters_per_split;
+  int it_end = min(it_begin + p.iters_per_split, p.total_iters);
+  const int iters = max(it_end - it_begin, 0);
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmF);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
+        uint8_t* a_dst = smem + s * kStageBytes;
+        uint8_t* b_dst = a_dst + 2 * kChunkBytes;
+        const int row = (it_begin + it) * kRowsPerStage;
+        mbar_arrive_expect_tx(&full_bar[s], (a_chunks + b_chunks) * kChunkBytes);
+        for (int c = 0; c < a_chunks; ++c) tma_load_3d(a_dst + c * kChunkBytes, &tmF, &full_bar[s], m0 + 64 * c, row, img);
+        for (int c = 0; c < b_chunks; ++c) tma_load_3d(b_dst + c * kChunkBytes, &tmF, &full_bar[s], n0 + 64 * c, row, img);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_bar[s], ph, 200 + s);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+        const uint32_t b_addr = diag ? a_addr : a_addr + 2 * kChunkBytes;
+#pragma unroll
+        for (int k = 0; k < kRowsPerStage / 16; ++k) {
+          // 16 pixel rows per MMA: advance 16 * 128 B along K
+          const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 2048, p.lbo, p.sbo);
+          const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 2048, p.lbo, p.sbo);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (it | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int i = m0 + r;
+    float* dst = p.partial + ((static_cast<size_t>(img) * p.splits + split) * p.C + i) * p.C + n0;
+    if (iters > 0) {
+      mbar_wait(accum_bar, 0, 300);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      if (iters > 0) {
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+      }
+      if (i < p.C) {
+        float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BN);
+}
+
+constexpr int kFinishThreads = 256;
+
+__global__ void __launch_bounds__(kFinishThreads)
+gram_finish_kernel(const float* __restrict__ partial, int C, int splits, float norm, float* __restrict__ G_out,
+                   const float* __restrict__ target, long long target_stride, float dscale,
+                   bf16* __restrict__ dscaled, float loss_scale, float* __restrict__ loss_part, int part_stride) {
+  const int img = blockIdx.y;
+  const int e = blockIdx.x * kFinishThreads + threadIdx.x;
+  const int CC = C * C;
+  float sq = 0.0f;
+  if (e < CC) {
+    const int i = e / C, j = e % C;
+    // Only 128x128 tiles with tile(i) <= tile(j) were written; take the mirrored element otherwise.
+    const int si = ((i >> 7) <= (j >> 7)) ? i : j;
+    const int sj = ((i >> 7) <= (j >> 7)) ? j : i;
+    const float* src = partial + static_cast<size_t>(img) * splits * CC + static_cast<size_t>(si) * C + sj;
+    float s = 0.0f;
+    for (int k = 0; k < splits; ++k) s += src[static_cast<size_t>(k) * CC];
+    const float g = s / norm;
+    if (G_out) G_out[static_cast<size_t>(img) * CC + e] = g;
+    if (target) {
+      const float d = g - target[static_cast<size_t>(img) * target_stride + e];
+      if (dscaled) dscaled[static_cast<size_t>(img) * CC + e] = __float2bfloat16_rn(d * dscale);
+      sq = d * d * loss_scale;
+    }
+  }
+  if (loss_part) {
+    // fixed-shape block reduction (deterministic)
+    __shared__ float red[kFinishThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = (threadIdx.x < kFinishThreads / 32) ? red[threadIdx.x] : 0.0f;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) loss_part[static_cast<size_t>(img) * part_stride + blockIdx.x] = v;
+    }
+  }
+}
+
+}  // namespace
+
+static void gram_geometry(int nimg, int HW, int C, int* ntiles, int* splits, int* iters_per_split, int* total_iters) {
+  const int T = (C + 127) / 128;
+  *ntiles = T * (T + 1) / 2;
+  *total_iters = (HW + kRowsPerStage - 1) / kRowsPerStage;
+  // Aim for about two CTAs per SM overall, at least 2 pipeline iterations per CTA.
+  int want = (2 * 148 + (*ntiles) * nimg - 1) / ((*ntiles) * nimg);
+  int max_splits = (*total_iters + 1) / 2;
+  if (max_splits < 1) max_splits = 1;
+  int s = want < max_splits ? want : max_splits;
+  if (s < 1) s = 1;
+  *iters_per_split = (*total_iters + s - 1) / s;
+  *splits = (*total_iters + *iters_per_split - 1) / (*iters_per_split);
+}
+
+size_t gram_partial_bytes(int nimg, int HW, int C) {
+  int ntiles, splits, ips, total;
+  gram_geometry(nimg, HW, C, &ntiles, &splits, &ips, &total);
+  return static_cast<size_t>(nimg) * splits * C * C * sizeof(float);
+}
+
+int gram_prepare(GramOp* op, const bf16* feat, int nimg, int HW, int C, float* partial) {
+  STX_REQUIRE(feat && partial, "gram: null operand");
+  STX_REQUIRE(C == 64 || C % 128 == 0, "gram: C must be 64 or a multiple of 128");
+  STX_REQUIRE(nimg > 0 && HW > 0, "gram: empty feature map");
+  op->nimg = nimg;
+  op->HW = HW;
+  op->C = C;
+  op->bn = (C == 64) ? 64 : 128;
+  int total;
+  gram_geometry(nimg, HW, C, &op->ntiles, &op->splits, &op->iters_per_split, &total);
+  op->partial = partial;
+  const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(HW), static_cast<uint64_t>(nimg)};
+  const uint32_t box[3] = {64u, static_cast<uint32_t>(kRowsPerStage), 1u};
+  return encode_tmap_bf16(&op->tmF, feat, 3, dims, box);
+}
+
+int gram_launch(const GramOp& op, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    STX_CUDA(cudaFuncSetAttribute(gram_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    STX_CUDA(cudaFuncSetAttribute(gram_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    attr_set = true;
+  }
+  GramKernelParams p;
+  p.C = op.C;
+  p.splits = op.splits;
+  p.iters_per_split = op.iters_per_split;
+  p.total_iters = (op.HW + kRowsPerStage - 1) / kRowsPerStage;
+  p.tiles_per_dim = (op.C + 127) / 128;
+  p.lbo = g_debug_gram_lbo ? static_cast<uint32_t>(g_debug_gram_lbo) : static_cast<uint32_t>(kChunkBytes);
+  p.sbo = g_debug_gram_sbo ? static_cast<uint32_t>(g_debug_gram_sbo) : 1024u;
+  p.partial = op.partial;
+  dim3 grid(op.ntiles, op.splits, op.nimg);
+  if (op.bn == 64)
+    gram_kernel<64><<<grid, kThreads, kSmemTotal, stream>>>(op.tmF, p);
+  else
+    gram_kernel<128><<<grid, kThreads, kSmemTotal, stream>>>(op.tmF, p);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+int gram_finish_blocks(int C) { return (C * C + kFinishThreads - 1) / kFinishThreads; }
+
+int gram_finish_launch(const GramOp& op, float eps, float* G_out, const float* target, long long target_stride,
+                       float dscale, bf16* dscaled, float loss_scale, float* loss_part, int part_stride,
+                       cudaStream_t stream) {
+  // fp32 arithmetic as in the reference: normalizer = float32(HW) + float32(eps)  (utils.py:15, :20)
+  const float norm = static_cast<float>(op.HW) + eps;
+  dim3 grid(gram_finish_blocks(op.C), op.nimg);
+  gram_finish_kernel<<<grid, kFinishThreads, 0, stream>>>(op.partial, op.C, op.splits, norm, G_out, target,
+                                                          target_stride, dscale, dscaled, loss_scale, loss_part, part_stride);
+  STX_CUDA(cudaGetLastError());
+  return STX_OK;
+}
+
+}  // namespace stx

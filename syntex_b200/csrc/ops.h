@@ -1,0 +1,68 @@
+// Internal operator layer: one prepared-op struct + launcher per kernel family. The C-ABI (capi.cu) and the
+// f/g plan (plan.cu) are built from these. All pointers are device pointers; all launches are asynchronous on
+// the given stream and never synchronise.
+#pragma once
+#include "common.h"
+
+namespace stx {
+
+// ------------------------------------------------------------------ conv_igemm.cu
+struct ConvOp {
+  CUtensorMap tmA;   // activations [nimg,H,W,cin] bf16
+  CUtensorMap tmB;   // packed weights [taps|nimg][cout][cin] bf16
+  int nimg, H, W, cin, cout, taps, per_image_w;
+  int bw_log2, bh_log2, tiles_w, tiles_h, tiles_n, n_step, bn;
+  int relu;
+  const float* bias;
+  const bf16* addend;
+  const bf16* mask;
+  bf16* out;
+};
+int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
+                 int taps, int per_image_w, int force_bn);
+int conv_launch(const ConvOp& op, cudaStream_t stream);
+
+// ------------------------------------------------------------------ gram.cu
+struct GramOp {
+  CUtensorMap tmF;   // features viewed as [nimg][HW][C] bf16
+  int nimg, HW, C;
+  int bn;            // N tile (64 for C == 64, else 128)
+  int ntiles;        // upper-triangle 128x128 tiles
+  int splits;        // split-K factor over HW
+  int iters_per_split;
+  float* partial;    // [nimg][splits][C][C] fp32 (upper tiles written)
+};
+size_t gram_partial_bytes(int nimg, int HW, int C);
+int gram_prepare(GramOp* op, const bf16* feat, int nimg, int HW, int C, float* partial);
+int gram_launch(const GramOp& op, cudaStream_t stream);
+// Reduce the split-K partials into G = F^T F / (HW + eps) (mirrored to a full [nimg,C,C] matrix) and, when a
+// target is given, the scaled difference Dscaled = (G - T) * dscale (bf16, [nimg][C][C]) and per-block partial
+// sums of loss_scale * (G - T)^2 (one float per block; gram_finish_blocks() blocks per image).
+int gram_finish_blocks(int C);
+int gram_finish_launch(const GramOp& op, float eps, float* G_out /*nullable*/, const float* target /*nullable*/,
+                       long long target_stride /*elements between images, 0 = broadcast*/, float dscale,
+                       bf16* dscaled /*nullable*/, float loss_scale,
+                       float* loss_part /*nullable, [nimg][part_stride], blocks written per image*/, int part_stride,
+                       cudaStream_t stream);
+
+// ------------------------------------------------------------------ elementwise.cu
+// conv1_1: fp32 image in [0,1] (optionally a pre-image passed through a sigmoid) -> x*255 - mean ->
+// 3x3 SAME conv (3 -> 64) + bias + ReLU -> bf16 NHWC.   w: [27][64] fp32 ((r*3+s)*3+c major), b: [64]
+int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3,
+                       const float* w, const float* b, bf16* out, cudaStream_t stream);
+// dgrad of conv1_1 chained with the preprocessing derivative: g [nimg,H,W,64] bf16 (already ReLU-masked) ->
+// dL/d(input image or pre-image) fp32 [nimg,H,W,3].
+int conv1_1_bwd_launch(const bf16* g, const float* image, int nimg, int H, int W, int is_preimage, const float* w,
+                       float* grad_out, cudaStream_t stream);
+int avgpool2_fwd_launch(const bf16* x, int nimg, int H, int W, int C, bf16* out, cudaStream_t stream);
+// g_in [nimg,H/2,W/2,C] -> out[h,w,c] = 0.25 * g_in[h/2,w/2,c] * (act[h,w,c] > 0)   (act nullable: no mask)
+int avgpool2_bwd_mask_launch(const bf16* g_in, const bf16* act, int nimg, int H, int W, int C, bf16* out,
+                             cudaStream_t stream);
+int f32_to_bf16_launch(const float* x, size_t n, bf16* out, cudaStream_t stream);
+int bf16_to_f32_launch(const bf16* x, size_t n, float* out, cudaStream_t stream);
+// HWIO fp32 [3][3][cin][cout] -> forward pack [tap][cout][cin] and dgrad pack [tap'][cin][cout] (tap' = 8 - tap)
+int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf16* w_dgrad, cudaStream_t stream);
+// Sum loss partials: out[img] = sum_k part[img*stride + k], fixed order (deterministic).
+int sum_partials_launch(const float* part, int nimg, int count, int stride, float* out, cudaStream_t stream);
+
+}  // namespace stx

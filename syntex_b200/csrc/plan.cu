@@ -1,0 +1,375 @@
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace stx {
+
+static const LayerSpec kLayers[kNumLayers] = {
+    {true, 0, 3, 64},     {true, 1, 64, 64},    {false, -1, 64, 64},   {true, 2, 64, 128},
+    {true, 3, 128, 128},  {false, -1, 128, 128}, {true, 4, 128, 256},  {true, 5, 256, 256},
+    {true, 6, 256, 256},  {true, 7, 256, 256},  {false, -1, 256, 256}, {true, 8, 256, 512},
+    {true, 9, 512, 512},  {true, 10, 512, 512}, {true, 11, 512, 512},  {false, -1, 512, 512}};
+
+const LayerSpec& layer_spec(int layer) { return kLayers[layer]; }
+
+// ------------------------------------------------------------------------------------------------ weights
+Vgg::~Vgg() {
+  cudaFree(w0);
+  for (int i = 0; i < kNumConvs; ++i) {
+    cudaFree(bias[i]);
+    cudaFree(wf[i]);
+    cudaFree(wd[i]);
+  }
+}
+
+int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_convs, const float* mean3,
+               cudaStream_t stream) {
+  STX_REQUIRE(out && w && b && mean3, "vgg_create: null argument");
+  STX_REQUIRE(num_convs >= 1 && num_convs <= kNumConvs, "vgg_create: num_convs must be in [1,12]");
+  Vgg* v = new Vgg();
+  v->num_convs = num_convs;
+  for (int c = 0; c < 3; ++c) v->mean[c] = mean3[c];
+  int ci = 0;
+  int rc = STX_OK;
+  for (int l = 0; l < kNumLayers && ci < num_convs && rc == STX_OK; ++l) {
+    const LayerSpec& s = kLayers[l];
+    if (!s.is_conv) continue;
+    if (!w[ci] || !b[ci]) {
+      rc = fail(STX_ERR_INVALID, "vgg_create: null weight or bias pointer");
+      break;
+    }
+    const size_t wn = 9ull * s.cin * s.cout;
+    auto chk = [&](cudaError_t e, const char* what) {
+      if (e != cudaSuccess && rc == STX_OK) rc = cuda_fail(e, what);
+    };
+    chk(cudaMalloc(&v->bias[ci], s.cout * sizeof(float)), "cudaMalloc bias");
+    if (rc == STX_OK) chk(cudaMemcpyAsync(v->bias[ci], b[ci], s.cout * sizeof(float), cudaMemcpyHostToDevice, stream), "copy bias");
+    if (ci == 0) {
+      chk(cudaMalloc(&v->w0, wn * sizeof(float)), "cudaMalloc w0");
+      if (rc == STX_OK) chk(cudaMemcpyAsync(v->w0, w[ci], wn * sizeof(float), cudaMemcpyHostToDevice, stream), "copy w0");
+    } else {
+      float* tmp = nullptr;
+      chk(cudaMalloc(&tmp, wn * sizeof(float)), "cudaMalloc staging");
+      chk(cudaMalloc(&v->wf[ci], wn * sizeof(bf16)), "cudaMalloc wf");
+      chk(cudaMalloc(&v->wd[ci], wn * sizeof(bf16)), "cudaMalloc wd");
+      if (rc == STX_OK) chk(cudaMemcpyAsync(tmp, w[ci], wn * sizeof(float), cudaMemcpyHostToDevice, stream), "copy w");
+      if (rc == STX_OK) rc = pack_weights_launch(tmp, s.cin, s.cout, v->wf[ci], v->wd[ci], stream);
+      if (rc == STX_OK) chk(cudaStreamSynchronize(stream), "sync after pack");
+      cudaFree(tmp);
+    }
+    ++ci;
+  }
+  if (rc == STX_OK) {
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "vgg_create sync");
+  }
+  if (rc != STX_OK) {
+    delete v;
+    return rc;
+  }
+  *out = v;
+  return STX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+Plan::~Plan() {
+  cudaFree(arena);
+  if (pinned) cudaFreeHost(pinned);
+}
+
+namespace {
+
+// func[img] = sum_k coef_k/4 * L_k,  layer_loss[k][img] = L_k = sum of that layer's block partials (fixed order).
+__global__ void __launch_bounds__(128)
+loss_reduce_kernel(const float* __restrict__ part, int part_total, const int* __restrict__ offsets, int nloss,
+                   const float* __restrict__ coef4, int nimg, float* __restrict__ layer_loss, float* __restrict__ func) {
+  const int img = blockIdx.x;
+  const float* p = part + static_cast<size_t>(img) * part_total;
+  __shared__ float red[4];
+  float total = 0.0f;
+  for (int k = 0; k < nloss; ++k) {
+    float s = 0.0f;
+    for (int i = offsets[k] + threadIdx.x; i < offsets[k + 1]; i += 128) s += p[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    const float lk = (red[0] + red[1]) + (red[2] + red[3]);
+    __syncthreads();
+    if (threadIdx.x == 0 && layer_loss) layer_loss[k * nimg + img] = lk;
+    total += coef4[k] * lk;
+  }
+  if (threadIdx.x == 0 && func) func[img] = total;
+}
+
+struct Bump {
+  size_t off = 0;
+  char* base = nullptr;
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 1023) & ~size_t(1023);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+static int plan_layout(Plan* p, Bump& a) {
+  const int B = p->B;
+  for (int l = 0; l <= p->topmost; ++l) p->act[l] = a.take<bf16>(static_cast<size_t>(B) * p->lh[l] * p->lw[l] * p->lc[l]);
+  size_t gmax = 0;
+  for (int l = 0; l <= p->topmost; ++l) gmax = std::max(gmax, static_cast<size_t>(B) * p->lh[l] * p->lw[l] * p->lc[l]);
+  p->gbuf[0] = a.take<bf16>(gmax);
+  p->gbuf[1] = a.take<bf16>(gmax);
+  int part = 0;
+  for (LossLayer& ll : p->loss) {
+    const size_t cc = static_cast<size_t>(B) * ll.C * ll.C;
+    ll.G = a.take<float>(cc);
+    ll.target = a.take<float>(cc);
+    ll.dscaled = a.take<bf16>(cc);
+    float* partial = a.take<float>(gram_partial_bytes(B, ll.HW, ll.C) / sizeof(float));
+    ll.gram.partial = partial;
+    ll.part_offset = part;
+    ll.part_blocks = gram_finish_blocks(ll.C);
+    part += ll.part_blocks;
+  }
+  p->part_total = part;
+  p->loss_part = a.take<float>(static_cast<size_t>(B) * std::max(part, 1));
+  p->layer_loss = a.take<float>(static_cast<size_t>(B) * std::max<size_t>(p->loss.size(), 1));
+  p->d_coef = a.take<float>(std::max<size_t>(p->loss.size(), 1));
+  p->d_part_offsets = a.take<int>(p->loss.size() + 1);
+  p->x_dev = a.take<float>(p->image_elems());
+  p->grad_dev = a.take<float>(p->image_elems());
+  p->func_dev = a.take<float>(B);
+  return STX_OK;
+}
+
+int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, int nloss, const int* loss_layers,
+                const float* coefs) {
+  STX_REQUIRE(out && vgg, "plan_create: null argument");
+  STX_REQUIRE(B >= 1 && H >= 1 && W >= 1, "plan_create: batch/height/width must be positive");
+  STX_REQUIRE(topmost >= 0 && topmost < kNumLayers, "plan_create: topmost out of range");
+  STX_REQUIRE(nloss >= 0 && nloss <= kNumLayers, "plan_create: bad number of loss layers");
+  STX_REQUIRE(nloss == 0 || (loss_layers && coefs), "plan_create: loss layers without indices/coefs");
+  Plan* p = new Plan();
+  p->vgg = vgg;
+  p->B = B;
+  p->H = H;
+  p->W = W;
+  p->topmost = topmost;
+  int h = H, w = W, convs_needed = 0;
+  for (int l = 0; l <= topmost; ++l) {
+    const LayerSpec& s = kLayers[l];
+    if (!s.is_conv) {
+      if ((h & 1) || (w & 1)) {
+        delete p;
+        return fail(STX_ERR_UNSUPPORTED, "plan_create: odd feature-map size at a pooling layer (image side must be a multiple of 16 for pool4)");
+      }
+      h >>= 1;
+      w >>= 1;
+    } else {
+      convs_needed = s.conv_index + 1;
+    }
+    p->lh[l] = h;
+    p->lw[l] = w;
+    p->lc[l] = s.cout;
+  }
+  if (convs_needed > vgg->num_convs) {
+    delete p;
+    return fail(STX_ERR_INVALID, "plan_create: weights do not cover the requested topmost layer");
+  }
+  for (int k = 0; k < nloss; ++k) {
+    const int l = loss_layers[k];
+    if (l < 0 || l > topmost) {
+      delete p;
+      return fail(STX_ERR_INVALID, "plan_create: loss layer above topmost");
+    }
+    for (int j = 0; j < k; ++j)
+      if (loss_layers[j] == l) {
+        delete p;
+        return fail(STX_ERR_INVALID, "plan_create: duplicate loss layer");
+      }
+    LossLayer ll;
+    ll.layer = l;
+    ll.coef = coefs[k];
+    ll.C = p->lc[l];
+    ll.HW = p->lh[l] * p->lw[l];
+    p->loss.push_back(ll);
+  }
+
+  // Pass 1: size the arena; pass 2: carve it.
+  Bump sizing;
+  plan_layout(p, sizing);
+  p->arena_bytes = sizing.off + 4096;
+  cudaError_t e = cudaMalloc(&p->arena, p->arena_bytes);
+  if (e != cudaSuccess) {
+    delete p;
+    return cuda_fail(e, "cudaMalloc(plan arena)");
+  }
+  e = cudaMemset(p->arena, 0, p->arena_bytes);
+  if (e == cudaSuccess) e = cudaMallocHost(&p->pinned, (2 * p->image_elems() + B) * sizeof(float));
+  if (e != cudaSuccess) {
+    delete p;
+    return cuda_fail(e, "plan staging allocation");
+  }
+  Bump carve;
+  carve.base = static_cast<char*>(p->arena);
+  plan_layout(p, carve);
+
+  int rc = STX_OK;
+  // Forward ops.
+  for (int l = 1; l <= topmost && rc == STX_OK; ++l) {
+    const LayerSpec& s = kLayers[l];
+    if (!s.is_conv) continue;
+    ConvOp& op = p->fwd[l];
+    rc = conv_prepare(&op, p->act[l - 1], B, p->lh[l], p->lw[l], s.cin, vgg->wf[s.conv_index], s.cout, 9, 0, 0);
+    op.bias = vgg->bias[s.conv_index];
+    op.relu = 1;
+    op.out = p->act[l];
+  }
+  // Loss-layer ops.
+  std::vector<float> coef4;
+  std::vector<int> offs;
+  for (size_t k = 0; k < p->loss.size() && rc == STX_OK; ++k) {
+    LossLayer& ll = p->loss[k];
+    float* partial = ll.gram.partial;
+    rc = gram_prepare(&ll.gram, p->act[ll.layer], B, ll.HW, ll.C, partial);
+    coef4.push_back(ll.coef * 0.25f);
+    offs.push_back(ll.part_offset);
+  }
+  offs.push_back(p->part_total);
+  if (rc == STX_OK && !p->loss.empty()) {
+    e = cudaMemcpy(p->d_coef, coef4.data(), coef4.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_part_offsets, offs.data(), offs.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "plan constants upload");
+  }
+
+  // Backward program (reverse-mode over the forward chain; see DESIGN.md "backward program").
+  auto loss_index = [&](int layer) -> int {
+    for (size_t k = 0; k < p->loss.size(); ++k)
+      if (p->loss[k].layer == layer) return static_cast<int>(k);
+    return -1;
+  };
+  int top = -1;
+  for (const LossLayer& ll : p->loss) top = std::max(top, ll.layer);
+  bool have = false;
+  int cur = 0;
+  for (int l = top; l >= 0 && rc == STX_OK; --l) {
+    const LayerSpec& s = kLayers[l];
+    const int k = loss_index(l);
+    if (k >= 0) {
+      LossLayer& ll = p->loss[k];
+      BwdStep st;
+      st.kind = BwdStep::kGramGrad;
+      rc = conv_prepare(&st.conv, p->act[l], B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
+      st.conv.addend = have ? p->gbuf[cur] : nullptr;
+      st.conv.out = p->gbuf[cur];
+      st.conv.mask = s.is_conv ? p->act[l] : nullptr;
+      p->bwd.push_back(st);
+      have = true;
+      if (rc == STX_OK) {
+        rc = conv_prepare(&ll.layer_grad_op, p->act[l], B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
+        ll.layer_grad_op.out = p->gbuf[0];
+      }
+    }
+    if (!have || rc != STX_OK) continue;
+    if (l == 0) {
+      BwdStep st;
+      st.kind = BwdStep::kConv1Bwd;
+      st.in = p->gbuf[cur];
+      p->bwd.push_back(st);
+    } else if (s.is_conv) {
+      BwdStep st;
+      st.kind = BwdStep::kDgrad;
+      rc = conv_prepare(&st.conv, p->gbuf[cur], B, p->lh[l], p->lw[l], s.cout, vgg->wd[s.conv_index], s.cin, 9, 0, 0);
+      st.conv.out = p->gbuf[cur ^ 1];
+      st.conv.mask = (kLayers[l - 1].is_conv && loss_index(l - 1) < 0) ? p->act[l - 1] : nullptr;
+      p->bwd.push_back(st);
+      cur ^= 1;
+    } else {
+      BwdStep st;
+      st.kind = BwdStep::kPoolBwd;
+      st.in = p->gbuf[cur];
+      st.out = p->gbuf[cur ^ 1];
+      st.act = (loss_index(l - 1) < 0) ? p->act[l - 1] : nullptr;
+      st.H = p->lh[l - 1];
+      st.W = p->lw[l - 1];
+      st.C = p->lc[l - 1];
+      p->bwd.push_back(st);
+      cur ^= 1;
+    }
+  }
+  if (rc != STX_OK) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return STX_OK;
+}
+
+int Plan::forward(const float* image, int is_preimage, int with_grams, bool with_loss, cudaStream_t stream) {
+  STX_REQUIRE(image, "forward: null image");
+  STX_TRY(conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0], stream));
+  for (int l = 1; l <= topmost; ++l) {
+    if (kLayers[l].is_conv) {
+      STX_TRY(conv_launch(fwd[l], stream));
+    } else {
+      STX_TRY(avgpool2_fwd_launch(act[l - 1], B, lh[l - 1], lw[l - 1], lc[l - 1], act[l], stream));
+    }
+  }
+  if (with_grams || with_loss) {
+    for (LossLayer& ll : loss) {
+      STX_TRY(gram_launch(ll.gram, stream));
+      // dL/dF = F * (G - T) * coef / (C^2 * n):  loss_overall = sum coef/4 * mean((G-T)^2), G = F^T F / n
+      const float norm = static_cast<float>(ll.HW) + 1e-6f;
+      const float dscale = ll.coef / (static_cast<float>(ll.C) * static_cast<float>(ll.C) * norm);
+      const float lscale = 1.0f / (static_cast<float>(ll.C) * static_cast<float>(ll.C));
+      STX_TRY(gram_finish_launch(ll.gram, 1e-6f, ll.G, with_loss ? ll.target : nullptr, ll.target_stride, dscale,
+                                 with_loss ? ll.dscaled : nullptr, lscale,
+                                 with_loss ? loss_part + ll.part_offset : nullptr, part_total, stream));
+    }
+    have_grams = true;
+  }
+  return STX_OK;
+}
+
+int Plan::backward(const float* image, int is_preimage, float* grad, cudaStream_t stream) {
+  for (const BwdStep& st : bwd) {
+    switch (st.kind) {
+      case BwdStep::kGramGrad:
+      case BwdStep::kDgrad:
+        STX_TRY(conv_launch(st.conv, stream));
+        break;
+      case BwdStep::kPoolBwd:
+        STX_TRY(avgpool2_bwd_mask_launch(st.in, st.act, B, st.H, st.W, st.C, st.out, stream));
+        break;
+      case BwdStep::kConv1Bwd:
+        STX_TRY(conv1_1_bwd_launch(st.in, image, B, H, W, is_preimage, vgg->w0, grad, stream));
+        break;
+    }
+  }
+  return STX_OK;
+}
+
+int Plan::step(const float* x, int is_preimage, float* func, float* grad, float* layer_loss_out,
+               cudaStream_t stream) {
+  STX_REQUIRE(x && grad, "step: null x or grad");
+  if (loss.empty()) return fail(STX_ERR_STATE, "step: the plan has no loss layers");
+  if (!have_target) return fail(STX_ERR_STATE, "step: no target Grams set (call compute_gram(update=True) first)");
+  if (bwd.empty() || bwd.back().kind != BwdStep::kConv1Bwd)
+    return fail(STX_ERR_STATE, "step: backward program incomplete");
+  STX_TRY(forward(x, is_preimage, 1, true, stream));
+  loss_reduce_kernel<<<B, 128, 0, stream>>>(loss_part, part_total, d_part_offsets, static_cast<int>(loss.size()),
+                                            d_coef, B, layer_loss, func ? func : func_dev);
+  STX_CUDA(cudaGetLastError());
+  if (layer_loss_out)
+    STX_CUDA(cudaMemcpyAsync(layer_loss_out, layer_loss, loss.size() * B * sizeof(float), cudaMemcpyDeviceToDevice,
+                             stream));
+  STX_TRY(backward(x, is_preimage, grad, stream));
+  return STX_OK;
+}
+
+}  // namespace stx

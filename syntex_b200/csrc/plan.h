@@ -1,0 +1,88 @@
+// The f/g evaluation plan: every buffer, tensor map and launch of one Synthesizer.step
+// (reference: gatys/synthesizer.py:54-107 builds the same thing as a TF graph) prepared once for a fixed
+// (batch, height, width) and replayed without allocation or host synchronisation.
+#pragma once
+#include <vector>
+
+#include "ops.h"
+
+namespace stx {
+
+constexpr int kNumLayers = 16;
+constexpr int kNumConvs = 12;
+
+struct LayerSpec {
+  bool is_conv;
+  int conv_index;   // index among conv layers, -1 for pools
+  int cin, cout;
+};
+const LayerSpec& layer_spec(int layer);
+
+struct Vgg {
+  int num_convs = 0;
+  float mean[3] = {0, 0, 0};
+  float* w0 = nullptr;            // conv1_1 weights fp32 [27][64]
+  float* bias[kNumConvs] = {};    // fp32 [cout]
+  bf16* wf[kNumConvs] = {};       // forward pack [9][cout][cin] (conv index >= 1)
+  bf16* wd[kNumConvs] = {};       // dgrad pack   [9][cin][cout]
+  ~Vgg();
+};
+int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_convs, const float* mean3,
+               cudaStream_t stream);
+
+struct BwdStep {
+  enum Kind { kGramGrad, kPoolBwd, kDgrad, kConv1Bwd } kind;
+  ConvOp conv;             // kGramGrad, kDgrad
+  const bf16* in = nullptr;
+  const bf16* act = nullptr;
+  bf16* out = nullptr;
+  int H = 0, W = 0, C = 0;   // kPoolBwd: fine-resolution dims
+};
+
+struct LossLayer {
+  int layer;
+  float coef;
+  int C, HW;
+  GramOp gram;
+  float* G = nullptr;         // [B,C,C]
+  float* target = nullptr;    // [B,C,C]
+  long long target_stride = 0;
+  bf16* dscaled = nullptr;    // [B,C,C]
+  int part_offset = 0;        // into loss_part rows
+  int part_blocks = 0;
+  ConvOp layer_grad_op;       // calc_grad path (utils.py:50-55): F * D * 4/(C^2 n) into scratch
+};
+
+struct Plan {
+  const Vgg* vgg = nullptr;
+  int B = 0, H = 0, W = 0, topmost = 15;
+  int lh[kNumLayers], lw[kNumLayers], lc[kNumLayers];
+  bf16* act[kNumLayers] = {};
+  ConvOp fwd[kNumLayers];
+  std::vector<LossLayer> loss;
+  std::vector<BwdStep> bwd;
+  bf16* gbuf[2] = {nullptr, nullptr};
+  float* loss_part = nullptr;      // [B][part_total]
+  int part_total = 0;
+  float* layer_loss = nullptr;     // [nloss][B]
+  float* d_coef = nullptr;         // [nloss] coef/4
+  int* d_part_offsets = nullptr;   // [nloss+1]
+  bool have_target = false, have_grams = false;
+  // staging for the *_host entry points
+  float* x_dev = nullptr;
+  float* grad_dev = nullptr;
+  float* func_dev = nullptr;
+  float* pinned = nullptr;         // host pinned: x | grad | func
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  ~Plan();
+
+  int forward(const float* image, int is_preimage, int with_grams, bool with_loss, cudaStream_t stream);
+  int backward(const float* image, int is_preimage, float* grad, cudaStream_t stream);
+  int step(const float* x, int is_preimage, float* func, float* grad, float* layer_loss_out, cudaStream_t stream);
+  size_t image_elems() const { return static_cast<size_t>(B) * H * W * 3; }
+};
+int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, int nloss, const int* loss_layers,
+                const float* coefs);
+
+}  // namespace stx
