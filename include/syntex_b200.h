@@ -43,6 +43,8 @@ typedef struct stx_lbfgs stx_lbfgs; /* device-resident L-BFGS(-B) state bound to
 
 const char* stx_last_error(void);
 int stx_abi_version(void);
+/* Kernel launches issued by this library so far in this process (CUDA-graph replays count their kernel nodes). */
+long long stx_launch_count(void);
 /* Bring-up knobs (descriptor strides etc.); key/value meanings are internal. */
 int stx_debug_set(int key, int value);
 
@@ -57,9 +59,13 @@ void stx_vgg_destroy(stx_vgg* vgg);
 
 /* ---- plan: the graph that gatys/synthesizer.py:54-107 (Synthesizer.build) and po/model.py:51-69 construct ----
  * topmost: last layer index to compute (15 = pool4, the Vgg19Extractor default, vgg19_extractor.py:5-6).
- * loss_layers/coefs: the Gram layers and weights (Synthesizer.DEFAULT_COEFS, synthesizer.py:17-23). */
+ * loss_layers/coefs: the Gram layers and weights (Synthesizer.DEFAULT_COEFS, synthesizer.py:17-23).
+ * flags: 0 = accurate forward ("bf16x3": activations and weights carried as bf16 hi+lo pairs, three tensor-core
+ *        MMAs per K step, forward error ~1e-5, input gradient within BASELINE.json's 1e-2);
+ *        STX_PLAN_FAST_BF16 = single bf16 MMA forward (Grams within 5e-3, input gradient ~3e-2: ReLU sign flips). */
+#define STX_PLAN_FAST_BF16 1
 int stx_plan_create(stx_plan** out, const stx_vgg* vgg, int batch, int height, int width, int topmost,
-                    int num_loss_layers, const int* loss_layers, const float* coefs);
+                    int num_loss_layers, const int* loss_layers, const float* coefs, int flags);
 void stx_plan_destroy(stx_plan* plan);
 size_t stx_plan_device_bytes(const stx_plan* plan);
 
@@ -89,6 +95,12 @@ int stx_plan_step(stx_plan* plan, const float* x, int is_preimage, float* func, 
  * Synchronous. */
 int stx_plan_step_host(stx_plan* plan, const float* x_host, int is_preimage, float* func_host, float* grad_host,
                        void* stream);
+/* Instrumented step for the benchmark's roofline: CUDA events around every kernel launch of one f/g evaluation.
+ * ms[8]/count[8] (host) receive device milliseconds and launch counts per kernel class:
+ *   0 conv3x3 forward (tcgen05)  1 conv3x3 dgrad (tcgen05)  2 Gram dF 1x1 GEMM (tcgen05)  3 Gram (tcgen05)
+ *   4 Gram finish/loss  5 conv1_1 fwd+bwd  6 pooling fwd+bwd  7 other.   Synchronous. */
+int stx_plan_step_timed(stx_plan* plan, const float* x, int is_preimage, float* func, float* grad, float* ms,
+                        int* count, void* stream);
 /* Per-layer gradients of build_texture_loss(calc_grad=True) (utils.py:50-55): d loss_layer[k] / d feat[k],
  * fp32 [batch,h,w,c] device, for the features of the last forward and the current targets. */
 int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream);
@@ -114,6 +126,13 @@ int stx_lbfgs_minimize_host(stx_lbfgs* opt, const float* x0_host, int is_preimag
 /* HWIO fp32 (3,3,cin,cout) -> bf16 forward pack [9][cout][cin] and dgrad pack [9][cin][cout] (device pointers). */
 int stx_pack_conv_weights(const float* w_hwio, int cin, int cout, void* w_fwd_bf16, void* w_dgrad_bf16,
                           void* stream);
+/* Same plus the low halves bf16(w - bf16(w)) of the forward pack (for stx_conv_bf16x3). Any output may be NULL. */
+int stx_pack_conv_weights_split(const float* w_hwio, int cin, int cout, void* w_fwd_hi, void* w_fwd_lo,
+                                void* w_dgrad_bf16, void* stream);
+/* bf16x3 forward: relu(conv(x_hi + x_lo, w_hi + w_lo) + bias) -> out_hi, out_lo (3x3 only). */
+int stx_conv_bf16x3(const void* x_hi, const void* x_lo, int n, int H, int W, int cin, const void* w_hi,
+                    const void* w_lo, int cout, const float* bias, int relu, void* out_hi, void* out_lo,
+                    int force_bn, void* stream);
 /* out = epilogue(conv(x, w)) with x [n,H,W,cin] bf16, w packed [taps][cout][cin] bf16, taps in {9, 1}.
  * epilogue: (+ bias[cout] fp32) (+ addend bf16) (relu) (zero where mask <= 0); any of them may be NULL/0.
  * force_bn: 0 = automatic N tile, else 64 or 128. */
@@ -122,10 +141,11 @@ int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_pac
                   void* stream);
 /* conv1_1 (+preprocessing) forward and input-gradient. w27x64/b64 fp32 device. */
 int stx_conv1_1_fwd(const float* image, int n, int H, int W, int is_preimage, const float* mean3_host,
-                    const float* w27x64, const float* b64, void* out_bf16, void* stream);
+                    const float* w27x64, const float* b64, void* out_bf16, void* out_lo_bf16_or_null, void* stream);
 int stx_conv1_1_bwd(const void* g_bf16, const float* image, int n, int H, int W, int is_preimage,
                     const float* w27x64, float* grad_out, void* stream);
-int stx_avgpool2_fwd(const void* x_bf16, int n, int H, int W, int C, void* out_bf16, void* stream);
+int stx_avgpool2_fwd(const void* x_bf16, const void* x_lo_or_null, int n, int H, int W, int C, void* out_bf16,
+                     void* out_lo_or_null, void* stream);
 int stx_avgpool2_bwd(const void* g_bf16, const void* act_bf16_or_null, int n, int H, int W, int C, void* out_bf16,
                      void* stream);
 /* build_gram (utils.py:8-21) on a bf16 feature map [n,H*W,C]: G [n,C,C] fp32. workspace: stx_gram_workspace_bytes. */

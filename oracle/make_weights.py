@@ -15,7 +15,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import syntex_oracle as so  # noqa: E402
 
-SCALE_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "synth_scale.json")
+SCALE_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "syntex_b200", "synth_scale.json")
 
 
 def calibrate(seed=0, size=128):
@@ -36,13 +36,7 @@ def calibrate(seed=0, size=128):
     return scales
 
 
-def save_npz(path, weights):
-    arrs = {}
-    for k, (w, b) in weights.items():
-        o = np.empty(2, dtype=object)
-        o[0], o[1] = w, b
-        arrs[k] = o
-    np.savez(path, **arrs)
+from syntex_b200.synthetic import save_vgg_npz as save_npz  # noqa: E402
 
 
 if __name__ == "__main__":

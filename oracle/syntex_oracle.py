@@ -63,37 +63,12 @@ DEFAULT_COEFS = OrderedDict([  # synthesizer.py:17-23 == po/model.py:27-33
 
 
 # --------------------------------------------------------------------------------------------- weights
-# Per-layer rescaling that makes the mean post-ReLU activation of the synthetic network ~1 on a uniform-noise
-# image, mimicking "vgg19_normalised" (Gatys et al.). Computed once by oracle/make_weights.py --calibrate and
-# frozen here so that the weights are a pure function of the seed.
-def _default_scales(seed):
-    import json
-    import os
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "synth_scale.json")
-    d = json.load(open(path))
-    if d["seed"] != seed:
-        raise ValueError("oracle/synth_scale.json was calibrated for seed %d" % d["seed"])
-    return d["scales"]
-
-
-def synthetic_vgg_weights(seed: int = 0, scales="default") -> "OrderedDict[str, list]":
-    """Seeded He-normal weights N(0, 2/(9 Cin)), small biases, in the reference npz layout
-    {layer: [w (3,3,Cin,Cout) float32, b (Cout,) float32]} (texture_utils/caffe2npz.py:16-18).
-    These are the weights as stored on disk, i.e. BEFORE the RGB flip of vgg19.py:124-127."""
-    if isinstance(scales, str):
-        scales = _default_scales(seed)
-    rng = np.random.RandomState(seed)
-    out = OrderedDict()
-    for i, (name, shp) in enumerate((k, v) for k, v in PARAM_SHAPE.items() if v):
-        wshape, bshape = shp
-        cin = wshape[2]
-        w = rng.normal(0.0, np.sqrt(2.0 / (9 * cin)), size=wshape)
-        b = rng.normal(0.0, 0.05, size=bshape)
-        if scales is not None:
-            w = w * scales[i][0]
-            b = b * scales[i][1]
-        out[name] = [w.astype(np.float32), b.astype(np.float32)]
-    return out
+# Data generators (seeded synthetic weights / textures / initial images) are shared with the product package:
+# they are inputs, not arithmetic under test.
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from syntex_b200.synthetic import init_input, synthetic_texture, synthetic_vgg_weights  # noqa: E402,F401
 
 
 def load_vgg_weights(path_or_dict, is_rgb_input=True, topmost="pool4"):
@@ -286,30 +261,3 @@ def resize_crop(img, size):
     if ret.ndim == 2:
         ret = ret[:, :, np.newaxis]
     return ret[h_off:h_off + size, w_off:w_off + size, :]
-
-
-def init_input(shape, is_preimage, seed):
-    """synthesizer.py:179-182 with a fixed seed (the reference is unseeded)."""
-    rng = np.random.RandomState(seed)
-    if is_preimage:
-        return rng.uniform(-1.0, 1.0, size=shape)
-    return rng.uniform(1.0 / 255, 1.0 - 1.0 / 255, size=shape)
-
-
-def synthetic_texture(size, seed=0, channels=3):
-    """Seeded band-limited noise texture in [0,1] (stand-in exemplar where a JPEG may not be read)."""
-    rng = np.random.RandomState(seed)
-    acc = np.zeros((size, size, channels))
-    for octave, amp in ((4, 1.0), (8, 0.7), (16, 0.5), (32, 0.35), (64, 0.25)):
-        if octave > size:
-            break
-        coarse = rng.normal(size=(octave, octave, channels))
-        reps = size // octave
-        up = np.kron(coarse, np.ones((reps, reps, 1)))
-        # cheap separable blur
-        k = max(reps // 2, 1)
-        for ax in (0, 1):
-            up = sum(np.roll(up, s, axis=ax) for s in range(-k, k + 1)) / (2 * k + 1)
-        acc += amp * up
-    acc = (acc - acc.min()) / (acc.max() - acc.min() + 1e-12)
-    return acc

@@ -87,6 +87,29 @@ def stage_conv():
                 raise
 
 
+def split_case(n, H, W, cin, cout, bn=0, seed=0):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.randn((n, H, W, cin), device=dev, generator=g).relu()
+    xh = x.to(torch.bfloat16); xl = (x - xh.float()).to(torch.bfloat16)
+    w = (torch.randn((3, 3, cin, cout), device=dev, generator=g) / np.sqrt(9 * cin)).float()
+    b = torch.randn((cout,), device=dev, generator=g).float()
+    wh = torch.empty((9, cout, cin), dtype=torch.bfloat16, device=dev); wl = torch.empty_like(wh)
+    _lib.check(L.stx_pack_conv_weights_split(w.contiguous().data_ptr(), cin, cout, wh.data_ptr(), wl.data_ptr(), None, st()))
+    oh = torch.full((n, H, W, cout), float("nan"), dtype=torch.bfloat16, device=dev); ol = torch.full_like(oh, float("nan"))
+    _lib.check(L.stx_conv_bf16x3(xh.data_ptr(), xl.data_ptr(), n, H, W, cin, wh.data_ptr(), wl.data_ptr(), cout, b.data_ptr(), 1,
+                                 oh.data_ptr(), ol.data_ptr(), bn, st()))
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), b.double(), padding=1).relu().permute(0, 2, 3, 1)
+    return relerr(oh.float() + ol.float(), ref), relerr(oh.float(), ref)
+
+
+def stage_split():
+    for (n, H, W, ci, co, bn) in [(1, 16, 16, 64, 64, 0), (1, 32, 32, 128, 128, 128), (2, 8, 8, 128, 256, 64),
+                                  (1, 64, 64, 256, 256, 0), (1, 32, 32, 512, 512, 0), (1, 256, 256, 64, 64, 0)]:
+        e, eh = split_case(n, H, W, ci, co, bn)
+        print("split conv n%d %dx%d %d->%d bn%d: hi+lo rel %.2e max %.2e | hi only rel %.2e" % (n, H, W, ci, co, bn, e[0], e[1], eh[0]), flush=True)
+
+
 def gram_case(n, HW, C, seed=0):
     g = torch.Generator(device=dev).manual_seed(seed)
     f = torch.randn((n, HW, C), device=dev, generator=g).relu().to(torch.bfloat16)
@@ -114,12 +137,13 @@ def stage_elem():
     mean = (ctypes.c_float * 3)(123.68, 116.779, 103.939)
     for pre in (0, 1):
         out = torch.empty((n, H, W, 64), dtype=torch.bfloat16, device=dev)
-        _lib.check(L.stx_conv1_1_fwd(img.data_ptr(), n, H, W, pre, mean, w.data_ptr(), b.data_ptr(), out.data_ptr(), st()))
+        lo = torch.empty((n, H, W, 64), dtype=torch.bfloat16, device=dev)
+        _lib.check(L.stx_conv1_1_fwd(img.data_ptr(), n, H, W, pre, mean, w.data_ptr(), b.data_ptr(), out.data_ptr(), lo.data_ptr(), st()))
         xi = img.clone().requires_grad_(True)
         xx = torch.sigmoid(xi) if pre else xi
         xp = xx * 255.0 - torch.tensor([123.68, 116.779, 103.939], device=dev)
         ref = F.conv2d(xp.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=1).relu().permute(0, 2, 3, 1)
-        print("conv1_1 fwd pre=%d:" % pre, relerr(out.float(), ref.detach()), flush=True)
+        print("conv1_1 fwd pre=%d:" % pre, relerr(out.float(), ref.detach()), "hi+lo:", relerr(out.float() + lo.float(), ref.detach()), flush=True)
         gq = torch.randn((n, H, W, 64), device=dev, generator=g).to(torch.bfloat16)
         gm = (gq.float() * (ref.detach() > 0)).to(torch.bfloat16)
         gout = torch.empty((n, H, W, 3), dtype=torch.float32, device=dev)
@@ -128,7 +152,7 @@ def stage_elem():
         print("conv1_1 bwd pre=%d:" % pre, relerr(gout, gref), flush=True)
     x = torch.randn((n, H, W, 128), device=dev, generator=g).to(torch.bfloat16)
     o = torch.empty((n, H // 2, W // 2, 128), dtype=torch.bfloat16, device=dev)
-    _lib.check(L.stx_avgpool2_fwd(x.data_ptr(), n, H, W, 128, o.data_ptr(), st()))
+    _lib.check(L.stx_avgpool2_fwd(x.data_ptr(), None, n, H, W, 128, o.data_ptr(), None, st()))
     ref = F.avg_pool2d(x.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
     print("avgpool fwd:", relerr(o.float(), ref), flush=True)
     gi = torch.randn((n, H // 2, W // 2, 128), device=dev, generator=g).to(torch.bfloat16)
@@ -143,12 +167,13 @@ def stage_plan():
     from syntex_b200.gatys import Synthesizer
     raw = so.synthetic_vgg_weights(0)
     W = so.load_vgg_weights(raw)
-    for S in (64, 128, 256):
+    for S, prec in ((64, "bf16x3"), (128, "bf16x3"), (256, "bf16x3"), (256, "bf16"), (512, "bf16x3")):
         orc = so.SynthesizerOracle(W, S, dtype=torch.float64)
         tgt = so.synthetic_texture(S, seed=3)
         x0 = so.init_input((S, S, 3), False, 0)
-        syn = Synthesizer({"vgg19_npy_path": raw, "image_size": S, "maxiter": 10, "maxcor": 20})
+        syn = Synthesizer({"vgg19_npy_path": raw, "image_size": S, "maxiter": 10, "maxcor": 20, "precision": prec})
         syn.build()
+        print("---- S %d precision %s" % (S, prec), flush=True)
         t = time.time()
         go = orc.compute_gram(tgt, update=True)
         gg = syn.compute_gram(tgt, update=False)
@@ -175,10 +200,11 @@ def stage_lbfgs():
     import lbfgs_model as lm
     from syntex_b200.gatys import Synthesizer
     raw = so.synthetic_vgg_weights(0)
-    for S, IT in ((64, 50), (256, 100)):
+    for S, IT, prec in ((64, 50, "bf16x3"), (256, 100, "bf16x3"), (256, 100, "bf16")):
         tgt = so.synthetic_texture(S, seed=3)
         x0 = so.init_input((S, S, 3), False, 0)
-        syn = Synthesizer({"vgg19_npy_path": raw, "image_size": S, "maxiter": IT, "maxcor": 20})
+        print("---- S %d precision %s" % (S, prec), flush=True)
+        syn = Synthesizer({"vgg19_npy_path": raw, "image_size": S, "maxiter": IT, "maxcor": 20, "precision": prec})
         syn.build()
         syn.compute_gram(tgt, update=True)
         f0 = syn.step(x0)["func"].sum()
@@ -206,7 +232,7 @@ def stage_lbfgs():
 
 
 if __name__ == "__main__":
-    stages = sys.argv[1:] or ["elem", "conv", "gram", "plan", "lbfgs"]
+    stages = sys.argv[1:] or ["elem", "conv", "split", "gram", "plan", "lbfgs"]
     print(torch.cuda.get_device_name(0), flush=True)
     for s in stages:
         print("==== stage", s, flush=True)

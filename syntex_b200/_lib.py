@@ -19,12 +19,13 @@ def _declare(lib):
     sig = {
         "stx_last_error": (c_char_p, []),
         "stx_abi_version": (c_int, []),
+        "stx_launch_count": (ctypes.c_longlong, []),
         "stx_debug_set": (c_int, [c_int, c_int]),
         "stx_vgg_create": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int,
                                    POINTER(c_float), vp]),
         "stx_vgg_destroy": (None, [vp]),
         "stx_plan_create": (c_int, [POINTER(c_void_p), vp, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
-                                    POINTER(c_float)]),
+                                    POINTER(c_float), c_int]),
         "stx_plan_destroy": (None, [vp]),
         "stx_plan_device_bytes": (c_size_t, [vp]),
         "stx_plan_forward": (c_int, [vp, fp, c_int, c_int, vp]),
@@ -34,6 +35,7 @@ def _declare(lib):
         "stx_plan_update_target_from_forward": (c_int, [vp, vp]),
         "stx_plan_set_target_gram": (c_int, [vp, c_int, fp, c_int, vp]),
         "stx_plan_step": (c_int, [vp, fp, c_int, fp, fp, fp, vp]),
+        "stx_plan_step_timed": (c_int, [vp, fp, c_int, fp, fp, POINTER(c_float), POINTER(c_int), vp]),
         "stx_plan_step_host": (c_int, [vp, fp, c_int, fp, fp, vp]),
         "stx_plan_layer_grad": (c_int, [vp, c_int, fp, vp]),
         "stx_lbfgs_create": (c_int, [POINTER(c_void_p), vp, c_int, c_int, c_float, c_float]),
@@ -43,11 +45,13 @@ def _declare(lib):
         "stx_lbfgs_result": (c_int, [vp, fp, fp, ip, ip, vp]),
         "stx_lbfgs_minimize_host": (c_int, [vp, fp, c_int, c_int, fp, fp, ip, ip, vp]),
         "stx_pack_conv_weights": (c_int, [fp, c_int, c_int, vp, vp, vp]),
+        "stx_pack_conv_weights_split": (c_int, [fp, c_int, c_int, vp, vp, vp, vp]),
+        "stx_conv_bf16x3": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_int, fp, c_int, vp, vp, c_int, vp]),
         "stx_conv_bf16": (c_int, [vp, c_int, c_int, c_int, c_int, vp, c_int, c_int, fp, vp, vp, c_int, vp, c_int,
                                   vp]),
-        "stx_conv1_1_fwd": (c_int, [fp, c_int, c_int, c_int, c_int, POINTER(c_float), fp, fp, vp, vp]),
+        "stx_conv1_1_fwd": (c_int, [fp, c_int, c_int, c_int, c_int, POINTER(c_float), fp, fp, vp, vp, vp]),
         "stx_conv1_1_bwd": (c_int, [vp, fp, c_int, c_int, c_int, c_int, fp, fp, vp]),
-        "stx_avgpool2_fwd": (c_int, [vp, c_int, c_int, c_int, c_int, vp, vp]),
+        "stx_avgpool2_fwd": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, vp, vp]),
         "stx_avgpool2_bwd": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, vp]),
         "stx_gram_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
         "stx_gram_bf16": (c_int, [vp, c_int, c_int, c_int, c_float, fp, vp, vp]),

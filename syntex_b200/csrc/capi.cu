@@ -28,6 +28,7 @@ extern "C" {
 
 const char* stx_last_error(void) { return last_error().c_str(); }
 int stx_abi_version(void) { return 1; }
+long long stx_launch_count(void) { return launch_count(); }
 
 int stx_debug_set(int key, int value) {
   switch (key) {
@@ -54,10 +55,10 @@ void stx_vgg_destroy(stx_vgg* vgg) {
 
 // ------------------------------------------------------------------------------------------------ plan
 int stx_plan_create(stx_plan** out, const stx_vgg* vgg, int batch, int height, int width, int topmost,
-                    int num_loss_layers, const int* loss_layers, const float* coefs) {
+                    int num_loss_layers, const int* loss_layers, const float* coefs, int flags) {
   STX_REQUIRE(out && vgg, "stx_plan_create: null argument");
   Plan* p = nullptr;
-  STX_TRY(plan_create(&p, vgg->v, batch, height, width, topmost, num_loss_layers, loss_layers, coefs));
+  STX_TRY(plan_create(&p, vgg->v, batch, height, width, topmost, num_loss_layers, loss_layers, coefs, flags));
   *out = new stx_plan{p};
   return STX_OK;
 }
@@ -87,6 +88,7 @@ int stx_plan_copy_feature_f32(stx_plan* plan, int layer, float* out, void* strea
   Plan* p = plan->p;
   STX_REQUIRE(layer >= 0 && layer <= p->topmost, "layer index out of range for this plan");
   const size_t n = static_cast<size_t>(p->B) * p->lh[layer] * p->lw[layer] * p->lc[layer];
+  if (p->split) return bf16pair_to_f32_launch(p->act[layer], p->act_lo[layer], n, out, S(stream));
   return bf16_to_f32_launch(p->act[layer], n, out, S(stream));
 }
 
@@ -132,6 +134,12 @@ int stx_plan_step(stx_plan* plan, const float* x, int is_preimage, float* func, 
                   void* stream) {
   STX_REQUIRE(plan, "stx_plan_step: null plan");
   return plan->p->step(x, is_preimage, func, grad, layer_loss, S(stream));
+}
+
+int stx_plan_step_timed(stx_plan* plan, const float* x, int is_preimage, float* func, float* grad, float* ms,
+                        int* count, void* stream) {
+  STX_REQUIRE(plan, "stx_plan_step_timed: null plan");
+  return plan->p->step_timed(x, is_preimage, func, grad, ms, count, S(stream));
 }
 
 int stx_plan_step_host(stx_plan* plan, const float* x_host, int is_preimage, float* func_host, float* grad_host,
@@ -204,8 +212,28 @@ int stx_lbfgs_minimize_host(stx_lbfgs* opt, const float* x0_host, int is_preimag
 // ------------------------------------------------------------------------------------------------ stand-alone ops
 int stx_pack_conv_weights(const float* w_hwio, int cin, int cout, void* w_fwd_bf16, void* w_dgrad_bf16,
                           void* stream) {
-  return pack_weights_launch(w_hwio, cin, cout, static_cast<bf16*>(w_fwd_bf16), static_cast<bf16*>(w_dgrad_bf16),
-                             S(stream));
+  return pack_weights_launch(w_hwio, cin, cout, static_cast<bf16*>(w_fwd_bf16), nullptr,
+                             static_cast<bf16*>(w_dgrad_bf16), S(stream));
+}
+int stx_pack_conv_weights_split(const float* w_hwio, int cin, int cout, void* w_fwd_hi, void* w_fwd_lo,
+                                void* w_dgrad_bf16, void* stream) {
+  return pack_weights_launch(w_hwio, cin, cout, static_cast<bf16*>(w_fwd_hi), static_cast<bf16*>(w_fwd_lo),
+                             static_cast<bf16*>(w_dgrad_bf16), S(stream));
+}
+
+int stx_conv_bf16x3(const void* x_hi, const void* x_lo, int n, int H, int W, int cin, const void* w_hi,
+                    const void* w_lo, int cout, const float* bias, int relu, void* out_hi, void* out_lo,
+                    int force_bn, void* stream) {
+  STX_REQUIRE(out_hi && out_lo, "stx_conv_bf16x3: null output");
+  ConvOp op;
+  STX_TRY(conv_prepare(&op, static_cast<const bf16*>(x_hi), n, H, W, cin, static_cast<const bf16*>(w_hi), cout, 9, 0,
+                       force_bn));
+  STX_TRY(conv_prepare_split(&op, static_cast<const bf16*>(x_lo), static_cast<const bf16*>(w_lo)));
+  op.bias = bias;
+  op.relu = relu;
+  op.out = static_cast<bf16*>(out_hi);
+  op.out_lo = static_cast<bf16*>(out_lo);
+  return conv_launch(op, S(stream));
 }
 
 int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_packed, int cout, int taps,
@@ -224,17 +252,19 @@ int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_pac
 }
 
 int stx_conv1_1_fwd(const float* image, int n, int H, int W, int is_preimage, const float* mean3_host,
-                    const float* w27x64, const float* b64, void* out_bf16, void* stream) {
+                    const float* w27x64, const float* b64, void* out_bf16, void* out_lo, void* stream) {
   return conv1_1_fwd_launch(image, n, H, W, is_preimage, mean3_host, w27x64, b64, static_cast<bf16*>(out_bf16),
-                            S(stream));
+                            static_cast<bf16*>(out_lo), S(stream));
 }
 int stx_conv1_1_bwd(const void* g_bf16, const float* image, int n, int H, int W, int is_preimage,
                     const float* w27x64, float* grad_out, void* stream) {
   return conv1_1_bwd_launch(static_cast<const bf16*>(g_bf16), image, n, H, W, is_preimage, w27x64, grad_out,
                             S(stream));
 }
-int stx_avgpool2_fwd(const void* x_bf16, int n, int H, int W, int C, void* out_bf16, void* stream) {
-  return avgpool2_fwd_launch(static_cast<const bf16*>(x_bf16), n, H, W, C, static_cast<bf16*>(out_bf16), S(stream));
+int stx_avgpool2_fwd(const void* x_bf16, const void* x_lo, int n, int H, int W, int C, void* out_bf16,
+                     void* out_lo, void* stream) {
+  return avgpool2_fwd_launch(static_cast<const bf16*>(x_bf16), static_cast<const bf16*>(x_lo), n, H, W, C,
+                             static_cast<bf16*>(out_bf16), static_cast<bf16*>(out_lo), S(stream));
 }
 int stx_avgpool2_bwd(const void* g_bf16, const void* act, int n, int H, int W, int C, void* out_bf16, void* stream) {
   return avgpool2_bwd_mask_launch(static_cast<const bf16*>(g_bf16), static_cast<const bf16*>(act), n, H, W, C,

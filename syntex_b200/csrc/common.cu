@@ -2,11 +2,15 @@
 
 #include <cudaTypedefs.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace stx {
 
 static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+void count_launch(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 const std::string& last_error() { return g_last_error; }

@@ -19,6 +19,9 @@ void set_error(const std::string& msg);
 const std::string& last_error();
 int fail(int code, const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
+// Number of kernel launches issued by this library (graph replays count their kernel nodes). bench.py reports it.
+void count_launch(long long n = 1);
+long long launch_count();
 
 #define STX_CUDA(expr)                                   \
   do {                                                   \

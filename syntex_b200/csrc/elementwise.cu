@@ -21,7 +21,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 // Zero padding applies to the *preprocessed* image, as in the TF graph.
 __global__ void __launch_bounds__(256)
 conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int is_preimage, float m0, float m1,
-                   float m2, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out) {
+                   float m2, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
+                   bf16* __restrict__ out_lo) {
   __shared__ float sw[27 * 64];
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
@@ -73,13 +74,19 @@ conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int 
     }
   }
   uint4* o4 = reinterpret_cast<uint4*>(out + pix * 64 + half * 32);
+  uint4* l4 = out_lo ? reinterpret_cast<uint4*>(out_lo + pix * 64 + half * 32) : nullptr;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    Pack8 pk;
+    Pack8 pk, pl;
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      pk.h2[e] = __floats2bfloat162_rn(fmaxf(acc[8 * j + 2 * e], 0.0f), fmaxf(acc[8 * j + 2 * e + 1], 0.0f));
+    for (int e = 0; e < 4; ++e) {
+      const float a = fmaxf(acc[8 * j + 2 * e], 0.0f), bb = fmaxf(acc[8 * j + 2 * e + 1], 0.0f);
+      pk.h2[e] = __floats2bfloat162_rn(a, bb);
+      const float2 h = __bfloat1622float2(pk.h2[e]);
+      pl.h2[e] = __floats2bfloat162_rn(a - h.x, bb - h.y);
+    }
     o4[j] = pk.u;
+    if (l4) l4[j] = pl.u;
   }
 }
 
@@ -149,7 +156,8 @@ conv1_1_bwd_kernel(const bf16* __restrict__ g, const float* __restrict__ image, 
 // ---------------------------------------------------------------------------------------------------------
 // 2x2 stride-2 average pooling, even H and W (vgg19.py:90-91; SAME == VALID for even sizes).
 __global__ void __launch_bounds__(256)
-avgpool2_fwd_kernel(const bf16* __restrict__ x, int nimg, int H, int W, int C, bf16* __restrict__ out) {
+avgpool2_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ x_lo, int nimg, int H, int W, int C,
+                    bf16* __restrict__ out, bf16* __restrict__ out_lo) {
   const int Ho = H >> 1, Wo = W >> 1, C8 = C >> 3;
   const long long total = static_cast<long long>(nimg) * Ho * Wo * C8;
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -159,26 +167,42 @@ avgpool2_fwd_kernel(const bf16* __restrict__ x, int nimg, int H, int W, int C, b
   const int xo = static_cast<int>(opix % Wo);
   const int yo = static_cast<int>((opix / Wo) % Ho);
   const long long n = opix / (static_cast<long long>(Wo) * Ho);
-  const bf16* base = x + ((n * H + 2 * yo) * W + 2 * xo) * C + c8 * 8;
+  const long long base = ((n * H + 2 * yo) * W + 2 * xo) * C + c8 * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
     for (int dx = 0; dx < 2; ++dx) {
+      const long long o = base + (static_cast<long long>(dy) * W + dx) * C;
       Pack8 pk;
-      pk.u = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<long long>(dy) * W + dx) * C));
+      pk.u = __ldg(reinterpret_cast<const uint4*>(x + o));
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = __bfloat1622float2(pk.h2[e]);
         acc[2 * e] += f.x;
         acc[2 * e + 1] += f.y;
       }
+      if (x_lo) {
+        pk.u = __ldg(reinterpret_cast<const uint4*>(x_lo + o));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(pk.h2[e]);
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+      }
     }
   }
-  Pack8 o;
+  Pack8 o, ol;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) o.h2[e] = __floats2bfloat162_rn(acc[2 * e] * 0.25f, acc[2 * e + 1] * 0.25f);
+  for (int e = 0; e < 4; ++e) {
+    const float a = acc[2 * e] * 0.25f, b = acc[2 * e + 1] * 0.25f;
+    o.h2[e] = __floats2bfloat162_rn(a, b);
+    const float2 h = __bfloat1622float2(o.h2[e]);
+    ol.h2[e] = __floats2bfloat162_rn(a - h.x, b - h.y);
+  }
   *reinterpret_cast<uint4*>(out + opix * C + c8 * 8) = o.u;
+  if (out_lo) *reinterpret_cast<uint4*>(out_lo + opix * C + c8 * 8) = ol.u;
 }
 
 // AvgPoolGrad fused with the ReluGrad of the conv that feeds the pool.
@@ -221,8 +245,14 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ x, size_t n, float* 
   if (i < n) out[i] = __bfloat162float(x[i]);
 }
 
+__global__ void bf16pair_to_f32_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, size_t n,
+                                       float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(hi[i]) + __bfloat162float(lo[i]);
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ w, int cin, int cout, bf16* __restrict__ wf,
-                                    bf16* __restrict__ wd) {
+                                    bf16* __restrict__ wf_lo, bf16* __restrict__ wd) {
   const long long total = 9LL * cin * cout;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -232,6 +262,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cin, int co
   const int tap = static_cast<int>(i / (static_cast<long long>(cout) * cin));
   const bf16 v = __float2bfloat16_rn(w[i]);
   if (wf) wf[(static_cast<long long>(tap) * cout + co) * cin + ci] = v;
+  if (wf_lo) wf_lo[(static_cast<long long>(tap) * cout + co) * cin + ci] = __float2bfloat16_rn(w[i] - __bfloat162float(v));
   if (wd) wd[(static_cast<long long>(8 - tap) * cin + ci) * cout + co] = v;
 }
 
@@ -259,12 +290,13 @@ inline unsigned blocks_for(long long n, int threads) { return static_cast<unsign
 }  // namespace
 
 int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3,
-                       const float* w, const float* b, bf16* out, cudaStream_t stream) {
+                       const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream) {
   STX_REQUIRE(image && w && b && out && mean3, "conv1_1 fwd: null operand");
   const long long threads = 2LL * nimg * H * W;
   conv1_1_fwd_kernel<<<blocks_for(threads, 256), 256, 0, stream>>>(image, nimg, H, W, is_preimage, mean3[0], mean3[1],
-                                                                  mean3[2], w, b, out);
+                                                                  mean3[2], w, b, out, out_lo);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 
@@ -275,15 +307,18 @@ int conv1_1_bwd_launch(const bf16* g, const float* image, int nimg, int H, int W
   const long long threads = 4LL * nimg * H * W;
   conv1_1_bwd_kernel<<<blocks_for(threads, 256), 256, 0, stream>>>(g, image, nimg, H, W, is_preimage, w, grad_out);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 
-int avgpool2_fwd_launch(const bf16* x, int nimg, int H, int W, int C, bf16* out, cudaStream_t stream) {
+int avgpool2_fwd_launch(const bf16* x, const bf16* x_lo, int nimg, int H, int W, int C, bf16* out, bf16* out_lo,
+                        cudaStream_t stream) {
   STX_REQUIRE(x && out, "avgpool fwd: null operand");
   STX_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "avgpool: H, W must be even and C a multiple of 8");
   const long long total = static_cast<long long>(nimg) * (H / 2) * (W / 2) * (C / 8);
-  avgpool2_fwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(x, nimg, H, W, C, out);
+  avgpool2_fwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(x, x_lo, nimg, H, W, C, out, out_lo);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 
@@ -294,6 +329,7 @@ int avgpool2_bwd_mask_launch(const bf16* g_in, const bf16* act, int nimg, int H,
   const long long total = static_cast<long long>(nimg) * H * W * (C / 8);
   avgpool2_bwd_mask_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(g_in, act, nimg, H, W, C, out);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 
@@ -301,26 +337,39 @@ int f32_to_bf16_launch(const float* x, size_t n, bf16* out, cudaStream_t stream)
   if (n == 0) return STX_OK;
   f32_to_bf16_kernel<<<blocks_for(static_cast<long long>(n), 256), 256, 0, stream>>>(x, n, out);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 int bf16_to_f32_launch(const bf16* x, size_t n, float* out, cudaStream_t stream) {
   if (n == 0) return STX_OK;
   bf16_to_f32_kernel<<<blocks_for(static_cast<long long>(n), 256), 256, 0, stream>>>(x, n, out);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 
-int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf16* w_dgrad, cudaStream_t stream) {
+int bf16pair_to_f32_launch(const bf16* hi, const bf16* lo, size_t n, float* out, cudaStream_t stream) {
+  if (n == 0) return STX_OK;
+  bf16pair_to_f32_kernel<<<blocks_for(static_cast<long long>(n), 256), 256, 0, stream>>>(hi, lo, n, out);
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf16* w_fwd_lo, bf16* w_dgrad,
+                        cudaStream_t stream) {
   STX_REQUIRE(w_hwio, "pack_weights: null weights");
   const long long total = 9LL * cin * cout;
-  pack_weights_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_hwio, cin, cout, w_fwd, w_dgrad);
+  pack_weights_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_hwio, cin, cout, w_fwd, w_fwd_lo, w_dgrad);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 
 int sum_partials_launch(const float* part, int nimg, int count, int stride, float* out, cudaStream_t stream) {
   sum_partials_kernel<<<nimg, 256, 0, stream>>>(part, count, stride, out);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 

@@ -252,6 +252,7 @@ int gram_launch(const GramOp& op, cudaStream_t stream) {
   else
     gram_kernel<128><<<grid, kThreads, kSmemTotal, stream>>>(op.tmF, p);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 
@@ -266,6 +267,7 @@ int gram_finish_launch(const GramOp& op, float eps, float* G_out, const float* t
   gram_finish_kernel<<<grid, kFinishThreads, 0, stream>>>(op.partial, op.C, op.splits, norm, G_out, target,
                                                           target_stride, dscale, dscaled, loss_scale, loss_part, part_stride);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   return STX_OK;
 }
 

@@ -603,6 +603,7 @@ struct LbfgsImpl {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t graph = nullptr;
+  long long graph_nodes = 0;   // kernel launches per replay
   int graph_preimage = -1;
   bool started = false;
 };
@@ -689,6 +690,7 @@ static int launch_cycle(Lbfgs* o, cudaStream_t stream) {
   lbfgs_decide_kernel<<<im->B, 128, 0, stream>>>(v);
   lbfgs_update_kernel<<<grid, kThreads, 0, stream>>>(v);
   STX_CUDA(cudaGetLastError());
+  count_launch(3);
   return STX_OK;
 }
 
@@ -741,7 +743,10 @@ int Lbfgs::run(int maxiter, int max_evals, cudaStream_t caller) {
     max_evals -= 1;
     cudaGraph_t g = nullptr;
     STX_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    const long long before = launch_count();
     const int rc = launch_cycle(this, stream);
+    im->graph_nodes = launch_count() - before;
+    count_launch(-im->graph_nodes);   // captured, not launched
     const cudaError_t e = cudaStreamEndCapture(stream, &g);
     if (rc != STX_OK) {
       if (g) cudaGraphDestroy(g);
@@ -772,6 +777,7 @@ int Lbfgs::run(int maxiter, int max_evals, cudaStream_t caller) {
     int chunk = std::max(1, maxiter - min_nit);
     chunk = std::min(chunk, max_evals - evals);
     for (int i = 0; i < chunk; ++i) STX_CUDA(cudaGraphLaunch(im->graph, stream));
+    count_launch(im->graph_nodes * chunk);
     evals += chunk;
   }
   STX_TRY(fence_out(im, caller));

@@ -10,6 +10,10 @@ namespace stx {
 struct ConvOp {
   CUtensorMap tmA;   // activations [nimg,H,W,cin] bf16
   CUtensorMap tmB;   // packed weights [taps|nimg][cout][cin] bf16
+  CUtensorMap tmA2;  // split mode: low halves of the activations
+  CUtensorMap tmB2;  // split mode: low halves of the weights
+  int split;         // 1 = bf16x3 forward (hi/lo operands, hi/lo outputs)
+  bf16* out_lo;
   int nimg, H, W, cin, cout, taps, per_image_w;
   int bw_log2, bh_log2, tiles_w, tiles_h, tiles_n, n_step, bn;
   int relu;
@@ -20,6 +24,7 @@ struct ConvOp {
 };
 int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
                  int taps, int per_image_w, int force_bn);
+int conv_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
 int conv_launch(const ConvOp& op, cudaStream_t stream);
 
 // ------------------------------------------------------------------ gram.cu
@@ -48,20 +53,26 @@ int gram_finish_launch(const GramOp& op, float eps, float* G_out /*nullable*/, c
 // ------------------------------------------------------------------ elementwise.cu
 // conv1_1: fp32 image in [0,1] (optionally a pre-image passed through a sigmoid) -> x*255 - mean ->
 // 3x3 SAME conv (3 -> 64) + bias + ReLU -> bf16 NHWC.   w: [27][64] fp32 ((r*3+s)*3+c major), b: [64]
+// out_lo (nullable): low halves, out + out_lo carries the fp32 result to ~16 mantissa bits.
 int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3,
-                       const float* w, const float* b, bf16* out, cudaStream_t stream);
+                       const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream);
 // dgrad of conv1_1 chained with the preprocessing derivative: g [nimg,H,W,64] bf16 (already ReLU-masked) ->
 // dL/d(input image or pre-image) fp32 [nimg,H,W,3].
 int conv1_1_bwd_launch(const bf16* g, const float* image, int nimg, int H, int W, int is_preimage, const float* w,
                        float* grad_out, cudaStream_t stream);
-int avgpool2_fwd_launch(const bf16* x, int nimg, int H, int W, int C, bf16* out, cudaStream_t stream);
+// x_lo / out_lo nullable (split activations: pooled in fp32 from hi + lo, written back as hi / lo).
+int avgpool2_fwd_launch(const bf16* x, const bf16* x_lo, int nimg, int H, int W, int C, bf16* out, bf16* out_lo,
+                        cudaStream_t stream);
 // g_in [nimg,H/2,W/2,C] -> out[h,w,c] = 0.25 * g_in[h/2,w/2,c] * (act[h,w,c] > 0)   (act nullable: no mask)
 int avgpool2_bwd_mask_launch(const bf16* g_in, const bf16* act, int nimg, int H, int W, int C, bf16* out,
                              cudaStream_t stream);
 int f32_to_bf16_launch(const float* x, size_t n, bf16* out, cudaStream_t stream);
 int bf16_to_f32_launch(const bf16* x, size_t n, float* out, cudaStream_t stream);
+int bf16pair_to_f32_launch(const bf16* hi, const bf16* lo, size_t n, float* out, cudaStream_t stream);
 // HWIO fp32 [3][3][cin][cout] -> forward pack [tap][cout][cin] and dgrad pack [tap'][cin][cout] (tap' = 8 - tap)
-int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf16* w_dgrad, cudaStream_t stream);
+// w_fwd_lo (nullable): low halves bf16(w - bf16(w)) in the forward layout.
+int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf16* w_fwd_lo, bf16* w_dgrad,
+                        cudaStream_t stream);
 // Sum loss partials: out[img] = sum_k part[img*stride + k], fixed order (deterministic).
 int sum_partials_launch(const float* part, int nimg, int count, int stride, float* out, cudaStream_t stream);
 

@@ -19,6 +19,7 @@ Vgg::~Vgg() {
   for (int i = 0; i < kNumConvs; ++i) {
     cudaFree(bias[i]);
     cudaFree(wf[i]);
+    cudaFree(wf_lo[i]);
     cudaFree(wd[i]);
   }
 }
@@ -52,9 +53,10 @@ int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_
       float* tmp = nullptr;
       chk(cudaMalloc(&tmp, wn * sizeof(float)), "cudaMalloc staging");
       chk(cudaMalloc(&v->wf[ci], wn * sizeof(bf16)), "cudaMalloc wf");
+      chk(cudaMalloc(&v->wf_lo[ci], wn * sizeof(bf16)), "cudaMalloc wf_lo");
       chk(cudaMalloc(&v->wd[ci], wn * sizeof(bf16)), "cudaMalloc wd");
       if (rc == STX_OK) chk(cudaMemcpyAsync(tmp, w[ci], wn * sizeof(float), cudaMemcpyHostToDevice, stream), "copy w");
-      if (rc == STX_OK) rc = pack_weights_launch(tmp, s.cin, s.cout, v->wf[ci], v->wd[ci], stream);
+      if (rc == STX_OK) rc = pack_weights_launch(tmp, s.cin, s.cout, v->wf[ci], v->wf_lo[ci], v->wd[ci], stream);
       if (rc == STX_OK) chk(cudaStreamSynchronize(stream), "sync after pack");
       cudaFree(tmp);
     }
@@ -73,10 +75,36 @@ int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_
 }
 
 // ------------------------------------------------------------------------------------------------ plan
+cudaEvent_t Timeline::get() {
+  if (used == pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    pool.push_back(e);
+  }
+  return pool[used++];
+}
+Timeline::~Timeline() {
+  for (cudaEvent_t e : pool) cudaEventDestroy(e);
+}
+
 Plan::~Plan() {
   cudaFree(arena);
   if (pinned) cudaFreeHost(pinned);
 }
+
+// Launch `call`, bracketing it with events when a timeline is attached.
+#define STX_LAUNCH(cls, call)                               \
+  do {                                                      \
+    if (tl) {                                               \
+      Timeline::Rec _r{cls, tl->get(), tl->get()};          \
+      cudaEventRecord(_r.a, stream);                        \
+      STX_TRY(call);                                        \
+      cudaEventRecord(_r.b, stream);                        \
+      tl->recs.push_back(_r);                               \
+    } else {                                                \
+      STX_TRY(call);                                        \
+    }                                                       \
+  } while (0)
 
 namespace {
 
@@ -119,7 +147,11 @@ struct Bump {
 
 static int plan_layout(Plan* p, Bump& a) {
   const int B = p->B;
-  for (int l = 0; l <= p->topmost; ++l) p->act[l] = a.take<bf16>(static_cast<size_t>(B) * p->lh[l] * p->lw[l] * p->lc[l]);
+  for (int l = 0; l <= p->topmost; ++l) {
+    const size_t n = static_cast<size_t>(B) * p->lh[l] * p->lw[l] * p->lc[l];
+    p->act[l] = a.take<bf16>(n);
+    p->act_lo[l] = p->split ? a.take<bf16>(n) : nullptr;
+  }
   size_t gmax = 0;
   for (int l = 0; l <= p->topmost; ++l) gmax = std::max(gmax, static_cast<size_t>(B) * p->lh[l] * p->lw[l] * p->lc[l]);
   p->gbuf[0] = a.take<bf16>(gmax);
@@ -148,7 +180,7 @@ static int plan_layout(Plan* p, Bump& a) {
 }
 
 int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, int nloss, const int* loss_layers,
-                const float* coefs) {
+                const float* coefs, int flags) {
   STX_REQUIRE(out && vgg, "plan_create: null argument");
   STX_REQUIRE(B >= 1 && H >= 1 && W >= 1, "plan_create: batch/height/width must be positive");
   STX_REQUIRE(topmost >= 0 && topmost < kNumLayers, "plan_create: topmost out of range");
@@ -160,6 +192,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
   p->H = H;
   p->W = W;
   p->topmost = topmost;
+  p->split = (flags & STX_PLAN_FAST_BF16) ? 0 : 1;
   int h = H, w = W, convs_needed = 0;
   for (int l = 0; l <= topmost; ++l) {
     const LayerSpec& s = kLayers[l];
@@ -226,9 +259,11 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     if (!s.is_conv) continue;
     ConvOp& op = p->fwd[l];
     rc = conv_prepare(&op, p->act[l - 1], B, p->lh[l], p->lw[l], s.cin, vgg->wf[s.conv_index], s.cout, 9, 0, 0);
+    if (rc == STX_OK && p->split) rc = conv_prepare_split(&op, p->act_lo[l - 1], vgg->wf_lo[s.conv_index]);
     op.bias = vgg->bias[s.conv_index];
     op.relu = 1;
     op.out = p->act[l];
+    op.out_lo = p->act_lo[l];
   }
   // Loss-layer ops.
   std::vector<float> coef4;
@@ -312,24 +347,25 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
 
 int Plan::forward(const float* image, int is_preimage, int with_grams, bool with_loss, cudaStream_t stream) {
   STX_REQUIRE(image, "forward: null image");
-  STX_TRY(conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0], stream));
+  STX_LAUNCH(kClsConv1, conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0], act_lo[0], stream));
   for (int l = 1; l <= topmost; ++l) {
     if (kLayers[l].is_conv) {
-      STX_TRY(conv_launch(fwd[l], stream));
+      STX_LAUNCH(kClsConvFwd, conv_launch(fwd[l], stream));
     } else {
-      STX_TRY(avgpool2_fwd_launch(act[l - 1], B, lh[l - 1], lw[l - 1], lc[l - 1], act[l], stream));
+      STX_LAUNCH(kClsPool, avgpool2_fwd_launch(act[l - 1], act_lo[l - 1], B, lh[l - 1], lw[l - 1], lc[l - 1], act[l], act_lo[l], stream));
     }
   }
   if (with_grams || with_loss) {
     for (LossLayer& ll : loss) {
-      STX_TRY(gram_launch(ll.gram, stream));
+      STX_LAUNCH(kClsGram, gram_launch(ll.gram, stream));
       // dL/dF = F * (G - T) * coef / (C^2 * n):  loss_overall = sum coef/4 * mean((G-T)^2), G = F^T F / n
       const float norm = static_cast<float>(ll.HW) + 1e-6f;
       const float dscale = ll.coef / (static_cast<float>(ll.C) * static_cast<float>(ll.C) * norm);
       const float lscale = 1.0f / (static_cast<float>(ll.C) * static_cast<float>(ll.C));
-      STX_TRY(gram_finish_launch(ll.gram, 1e-6f, ll.G, with_loss ? ll.target : nullptr, ll.target_stride, dscale,
-                                 with_loss ? ll.dscaled : nullptr, lscale,
-                                 with_loss ? loss_part + ll.part_offset : nullptr, part_total, stream));
+      STX_LAUNCH(kClsGramFinish,
+                 gram_finish_launch(ll.gram, 1e-6f, ll.G, with_loss ? ll.target : nullptr, ll.target_stride, dscale,
+                                    with_loss ? ll.dscaled : nullptr, lscale,
+                                    with_loss ? loss_part + ll.part_offset : nullptr, part_total, stream));
     }
     have_grams = true;
   }
@@ -340,14 +376,16 @@ int Plan::backward(const float* image, int is_preimage, float* grad, cudaStream_
   for (const BwdStep& st : bwd) {
     switch (st.kind) {
       case BwdStep::kGramGrad:
+        STX_LAUNCH(kClsGramGrad, conv_launch(st.conv, stream));
+        break;
       case BwdStep::kDgrad:
-        STX_TRY(conv_launch(st.conv, stream));
+        STX_LAUNCH(kClsConvDgrad, conv_launch(st.conv, stream));
         break;
       case BwdStep::kPoolBwd:
-        STX_TRY(avgpool2_bwd_mask_launch(st.in, st.act, B, st.H, st.W, st.C, st.out, stream));
+        STX_LAUNCH(kClsPool, avgpool2_bwd_mask_launch(st.in, st.act, B, st.H, st.W, st.C, st.out, stream));
         break;
       case BwdStep::kConv1Bwd:
-        STX_TRY(conv1_1_bwd_launch(st.in, image, B, H, W, is_preimage, vgg->w0, grad, stream));
+        STX_LAUNCH(kClsConv1, conv1_1_bwd_launch(st.in, image, B, H, W, is_preimage, vgg->w0, grad, stream));
         break;
     }
   }
@@ -365,11 +403,36 @@ int Plan::step(const float* x, int is_preimage, float* func, float* grad, float*
   loss_reduce_kernel<<<B, 128, 0, stream>>>(loss_part, part_total, d_part_offsets, static_cast<int>(loss.size()),
                                             d_coef, B, layer_loss, func ? func : func_dev);
   STX_CUDA(cudaGetLastError());
+  count_launch();
   if (layer_loss_out)
     STX_CUDA(cudaMemcpyAsync(layer_loss_out, layer_loss, loss.size() * B * sizeof(float), cudaMemcpyDeviceToDevice,
                              stream));
   STX_TRY(backward(x, is_preimage, grad, stream));
   return STX_OK;
+}
+
+int Plan::step_timed(const float* x, int is_preimage, float* func, float* grad, float* ms, int* count,
+                     cudaStream_t stream) {
+  STX_REQUIRE(ms && count, "step_timed: null output");
+  Timeline local;
+  tl = &local;
+  int rc = step(x, is_preimage, func, grad, nullptr, stream);
+  tl = nullptr;   // ordinary steps stay event-free
+  const cudaError_t e = cudaStreamSynchronize(stream);
+  if (rc == STX_OK && e != cudaSuccess) rc = cuda_fail(e, "step_timed sync");
+  for (int c = 0; c < kNumClasses; ++c) {
+    ms[c] = 0.f;
+    count[c] = 0;
+  }
+  if (rc == STX_OK) {
+    for (const Timeline::Rec& r : local.recs) {
+      float v = 0.f;
+      cudaEventElapsedTime(&v, r.a, r.b);
+      ms[r.cls] += v;
+      count[r.cls] += 1;
+    }
+  }
+  return rc;
 }
 
 }  // namespace stx

@@ -23,7 +23,8 @@ struct Vgg {
   float mean[3] = {0, 0, 0};
   float* w0 = nullptr;            // conv1_1 weights fp32 [27][64]
   float* bias[kNumConvs] = {};    // fp32 [cout]
-  bf16* wf[kNumConvs] = {};       // forward pack [9][cout][cin] (conv index >= 1)
+  bf16* wf[kNumConvs] = {};       // forward pack [9][cout][cin] (conv index >= 1), high halves
+  bf16* wf_lo[kNumConvs] = {};    // low halves bf16(w - bf16(w)) for the bf16x3 forward
   bf16* wd[kNumConvs] = {};       // dgrad pack   [9][cin][cout]
   ~Vgg();
 };
@@ -53,11 +54,26 @@ struct LossLayer {
   ConvOp layer_grad_op;       // calc_grad path (utils.py:50-55): F * D * 4/(C^2 n) into scratch
 };
 
+// Optional per-launch timing (bench/roofline): CUDA events around every launch of a step, grouped by kernel class.
+enum KernelClass { kClsConvFwd = 0, kClsConvDgrad, kClsGramGrad, kClsGram, kClsGramFinish, kClsConv1, kClsPool, kClsOther, kNumClasses };
+struct Timeline {
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  cudaEvent_t get();
+  void reset() { recs.clear(); used = 0; }
+  ~Timeline();
+};
+
 struct Plan {
   const Vgg* vgg = nullptr;
+  Timeline* tl = nullptr;
   int B = 0, H = 0, W = 0, topmost = 15;
   int lh[kNumLayers], lw[kNumLayers], lc[kNumLayers];
-  bf16* act[kNumLayers] = {};
+  int split = 1;                   // 1 = bf16x3 forward (hi/lo activations), 0 = plain bf16 forward
+  bf16* act[kNumLayers] = {};      // recorded layers (high halves; the only halves in plain mode)
+  bf16* act_lo[kNumLayers] = {};   // low halves (split mode)
   ConvOp fwd[kNumLayers];
   std::vector<LossLayer> loss;
   std::vector<BwdStep> bwd;
@@ -80,9 +96,13 @@ struct Plan {
   int forward(const float* image, int is_preimage, int with_grams, bool with_loss, cudaStream_t stream);
   int backward(const float* image, int is_preimage, float* grad, cudaStream_t stream);
   int step(const float* x, int is_preimage, float* func, float* grad, float* layer_loss_out, cudaStream_t stream);
+  // One step with events around every launch; ms[kNumClasses] and count[kNumClasses] receive the device time and
+  // the number of launches per kernel class. Synchronous.
+  int step_timed(const float* x, int is_preimage, float* func, float* grad, float* ms, int* count,
+                 cudaStream_t stream);
   size_t image_elems() const { return static_cast<size_t>(B) * H * W * 3; }
 };
 int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, int nloss, const int* loss_layers,
-                const float* coefs);
+                const float* coefs, int flags);
 
 }  // namespace stx

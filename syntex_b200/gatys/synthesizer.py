@@ -52,6 +52,9 @@ class Synthesizer(object):
         if self.optimizer not in ("device", "scipy"):
             raise ValueError("optimizer must be 'device' or 'scipy'")
         self.batch = int(args.get("batch") or 1)
+        self.precision = args.get("precision") or "bf16x3"
+        if self.precision not in ("bf16x3", "bf16"):
+            raise ValueError("precision must be 'bf16x3' (accurate forward) or 'bf16' (fast forward)")
         self.sess = sess
         self._plan = None
         self._lbfgs = {}
@@ -73,6 +76,7 @@ class Synthesizer(object):
         # additions of this implementation
         ps.add("--optimizer", type=str, default="device", help="'device' (GPU L-BFGS) or 'scipy' (reference)")
         ps.add("--batch", type=int, default=1, help="independent jobs run side by side on one GPU")
+        ps.add("--precision", type=str, default="bf16x3", help="'bf16x3' (accurate forward) or 'bf16' (fast)")
         return ps
 
     def build(self):
@@ -80,7 +84,8 @@ class Synthesizer(object):
         self.vgg19 = Vgg19Extractor(self.vgg19_path)
         self.shape_input = [self.batch, self.image_size, self.image_size, 3]
         coefs = OrderedDict() if self.gram_only and False else Synthesizer.DEFAULT_COEFS
-        self._plan = self.vgg19.get_plan(self.batch, self.image_size, self.image_size, "pool4", coefs)
+        self._plan = self.vgg19.get_plan(self.batch, self.image_size, self.image_size, "pool4", coefs,
+                                         fast_bf16=(self.precision == "bf16"))
         self._have_target = False
 
     # ------------------------------------------------------------------ helpers

@@ -49,13 +49,15 @@ def get_default_vgg19_path():
 class _Plan(object):
     """Owner of one stx_plan handle."""
 
-    def __init__(self, vgg_handle, batch, height, width, topmost_idx, loss_layers, coefs):
+    FAST_BF16 = 1   # STX_PLAN_FAST_BF16
+
+    def __init__(self, vgg_handle, batch, height, width, topmost_idx, loss_layers, coefs, flags=0):
         self.handle = ctypes.c_void_p()
         n = len(loss_layers)
         ll = (ctypes.c_int * max(n, 1))(*loss_layers)
         cf = (ctypes.c_float * max(n, 1))(*coefs)
         _lib.check(_lib.lib().stx_plan_create(ctypes.byref(self.handle), vgg_handle, batch, height, width,
-                                              topmost_idx, n, ll, cf))
+                                              topmost_idx, n, ll, cf, int(flags)))
         self.batch, self.height, self.width = batch, height, width
         self.topmost_idx = topmost_idx
         self.loss_layers = list(loss_layers)
@@ -162,17 +164,19 @@ class Vgg19(object):
             self._vgg = h
         return self._vgg
 
-    def get_plan(self, batch, height, width, topmost=None, coefs=None):
-        """Cached stx_plan for this shape. coefs: OrderedDict layer name -> weight (Gram layers), or None."""
+    def get_plan(self, batch, height, width, topmost=None, coefs=None, fast_bf16=False):
+        """Cached stx_plan for this shape. coefs: OrderedDict layer name -> weight (Gram layers), or None.
+        fast_bf16: single-MMA bf16 forward instead of the accurate bf16x3 forward (see include/syntex_b200.h)."""
         topmost = self.topmost if topmost is None else topmost
         if LAYER_INDEX[topmost] > LAYER_INDEX[self.topmost]:
             raise ValueError("topmost %s is above the layers loaded (%s)" % (topmost, self.topmost))
         coefs = OrderedDict() if coefs is None else coefs
-        key = (batch, height, width, topmost, tuple((k, float(v)) for k, v in coefs.items()))
+        key = (batch, height, width, topmost, tuple((k, float(v)) for k, v in coefs.items()), bool(fast_bf16))
         plan = self._plans.get(key)
         if plan is None:
             plan = _Plan(self._vgg_handle(), batch, height, width, LAYER_INDEX[topmost],
-                         [LAYER_INDEX[k] for k in coefs], [float(v) for v in coefs.values()])
+                         [LAYER_INDEX[k] for k in coefs], [float(v) for v in coefs.values()],
+                         _Plan.FAST_BF16 if fast_bf16 else 0)
             plan.coef_names = list(coefs.keys())
             self._plans[key] = plan
         return plan
