@@ -1,0 +1,69 @@
+"""The texture_utils / po.model mirrors on the B200 against the oracle."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import syntex_oracle as so  # noqa: E402
+from gpu_util import relerr  # noqa: E402
+from syntex_b200.po import SynTexModelDesc  # noqa: E402
+from syntex_b200.texture_utils import Vgg19Extractor, build_gram, build_texture_loss  # noqa: E402
+
+
+def test_extractor_build_matches_oracle(raw_weights):
+    x = torch.rand((2, 64, 96, 3), generator=torch.Generator().manual_seed(0))
+    ext = Vgg19Extractor(raw_weights)
+    feats = ext.build(x.cuda())
+    ref = so.vgg_build(x.double(), so.TorchWeights(so.load_vgg_weights(raw_weights), torch.float64))
+    assert list(feats.keys()) == list(ref.keys()) and len(feats) == 16
+    for k in ref:
+        assert tuple(feats[k].shape) == tuple(ref[k].shape) and feats[k].dtype == torch.float32
+        assert relerr(feats[k], ref[k]) < 1e-4, k
+    part = ext.build(x.cuda(), topmost="pool2")
+    assert list(part.keys())[-1] == "pool2" and len(part) == 6
+    assert torch.equal(part["pool2"], feats["pool2"])
+
+
+def test_build_gram_and_texture_loss(raw_weights):
+    x = torch.rand((1, 64, 64, 3), generator=torch.Generator().manual_seed(1))
+    t = torch.rand((1, 64, 64, 3), generator=torch.Generator().manual_seed(2))
+    ext = Vgg19Extractor(raw_weights)
+    coefs = OrderedDict([("conv1_1", 1e5), ("pool2", 2e5), ("pool4", 5e4)])
+    fx, ft = ext.build(x.cuda()), ext.build(t.cuda())
+    gt = OrderedDict((k, build_gram(ft[k])) for k in coefs)
+    lo, ll, gl = build_texture_loss(fx, gt, coefs, calc_grad=True)
+    W = so.TorchWeights(so.load_vgg_weights(raw_weights), torch.float64)
+    rx = so.vgg_build(x.double(), W)
+    rx = OrderedDict((k, v.detach().requires_grad_(True)) for k, v in rx.items())
+    rt = so.vgg_build(t.double(), W)
+    rgt = OrderedDict((k, so.build_gram(rt[k])) for k in coefs)
+    rlo, rll, rgl = so.build_texture_loss(rx, rgt, coefs, calc_grad=True)
+    assert tuple(lo.shape) == (1,)
+    assert abs(float(lo[0]) - float(rlo[0])) / float(rlo[0]) < 5e-3
+    for k in coefs:
+        assert relerr(gt[k], rgt[k]) < 1e-3
+        assert abs(float(ll[k][0]) - float(rll[k][0])) / float(rll[k][0]) < 5e-3
+        assert tuple(gl[k].shape) == tuple(rgl[k].shape)
+        assert relerr(gl[k], rgl[k]) < 1e-2
+    lo2, _, none = build_texture_loss(fx, ft, coefs, is_gram_b=False)
+    assert none is None and torch.allclose(lo2, lo, rtol=1e-6)
+    with pytest.raises(NotImplementedError):
+        build_gram(fx["pool1"], mask=torch.ones((1, 32, 32)))
+
+
+def test_po_model_doors(raw_weights):
+    model = SynTexModelDesc({"vgg19_npy_path": raw_weights})
+    x = torch.rand((2, 64, 64, 3), generator=torch.Generator().manual_seed(3)).cuda()
+    feat, gram = model._build_extractor(x)
+    assert list(gram.keys()) == list(SynTexModelDesc.DEFAULT_COEFS.keys())
+    assert tuple(gram["pool4"].shape) == (2, 512, 512)
+    feat2, none = model._build_extractor(x, calc_gram=False)
+    assert none is None
+    lo, ll, g = model._build_loss(x, gram)
+    assert float(lo.abs().max()) == 0.0 and g is None          # loss of an image against its own Grams
+    y = torch.rand((2, 64, 64, 3), generator=torch.Generator().manual_seed(4)).cuda()
+    lo, ll, g = model._build_loss(y, gram, calc_grad=True)
+    assert (lo > 0).all() and set(g.keys()) == set(SynTexModelDesc.DEFAULT_COEFS.keys())
