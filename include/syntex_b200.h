@@ -47,6 +47,9 @@ int stx_abi_version(void);
 long long stx_launch_count(void);
 /* Bring-up knobs (descriptor strides etc.); key/value meanings are internal. */
 int stx_debug_set(int key, int value);
+/* Descriptor-addressing probe used while bringing up the halo-patch convolution (see csrc/probe.cu). */
+int stx_debug_patch_probe(const void* patch_bf16, int rows, const void* b_bf16, int start_row, int sbo_bytes,
+                          int base_mode, float* out, void* stream);
 
 /* ---- weights: texture_utils/vgg19.py:97-130 (Vgg19.__init__) and :192-206 (get_var, constants) ------------
  * weights_hwio[i] / biases[i]: host fp32 arrays for conv layer i in network order (conv1_1 .. conv4_4), laid out

@@ -17,7 +17,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 
 // ---------------------------------------------------------------------------------------------------------
 // conv1_1 forward. Reference: vgg19.py:142-146 (x*255 - mean) and :171-179 (conv + bias + relu), optional
-// sigmoid pre-image (gatys/synthesizer.py:59). Two threads per pixel, 32 output channels each.
+// sigmoid pre-image (gatys/synthesizer.py:59). Each thread computes 32 output channels of TWO horizontally adjacent
+// pixels, so every shared-memory weight vector (broadcast LDS.128) feeds 8 FMAs and the 3x4 input patch is shared.
 // Zero padding applies to the *preprocessed* image, as in the TF graph.
 __global__ void __launch_bounds__(256)
 conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int is_preimage, float m0, float m1,
@@ -28,21 +29,22 @@ conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int 
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
   __syncthreads();
+  const int Wp = (W + 1) >> 1;                                   // pixel pairs per row
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long npix = static_cast<long long>(nimg) * H * W;
-  const long long pix = gid >> 1;
+  const long long npairs = static_cast<long long>(nimg) * H * Wp;
+  const long long pair = gid >> 1;
   const int half = static_cast<int>(gid & 1);
-  if (pix >= npix) return;
-  const int x = static_cast<int>(pix % W);
-  const int y = static_cast<int>((pix / W) % H);
-  const long long img_base = (pix / (static_cast<long long>(W) * H)) * H * W;
+  if (pair >= npairs) return;
+  const int x = static_cast<int>(pair % Wp) * 2;
+  const int y = static_cast<int>((pair / Wp) % H);
+  const long long img_base = (pair / (static_cast<long long>(Wp) * H)) * H * W;
   const float mean[3] = {m0, m1, m2};
 
-  float patch[27];
+  float patch[3][4][3];                                          // rows y-1..y+1, columns x-1..x+2
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < 4; ++s) {
       const int yy = y + r - 1, xx = x + s - 1;
       const bool in = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
       const float* src = image + (img_base + static_cast<long long>(yy) * W + xx) * 3;
@@ -54,39 +56,56 @@ conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int 
           if (is_preimage) v = sigmoidf_(v);
           v = v * 255.0f - mean[c];
         }
-        patch[(r * 3 + s) * 3 + c] = v;
+        patch[r][s][c] = v;
       }
     }
   }
-  float acc[32];
+  float acc0[32], acc1[32];
 #pragma unroll
-  for (int k = 0; k < 32; ++k) acc[k] = sb[half * 32 + k];
+  for (int k = 0; k < 32; ++k) acc0[k] = acc1[k] = sb[half * 32 + k];
 #pragma unroll
-  for (int t = 0; t < 27; ++t) {
-    const float4* w4 = reinterpret_cast<const float4*>(sw + t * 64 + half * 32);
+  for (int r = 0; r < 3; ++r) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 ww = w4[k];
-      acc[4 * k + 0] = fmaf(patch[t], ww.x, acc[4 * k + 0]);
-      acc[4 * k + 1] = fmaf(patch[t], ww.y, acc[4 * k + 1]);
-      acc[4 * k + 2] = fmaf(patch[t], ww.z, acc[4 * k + 2]);
-      acc[4 * k + 3] = fmaf(patch[t], ww.w, acc[4 * k + 3]);
+    for (int s = 0; s < 3; ++s) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4* w4 = reinterpret_cast<const float4*>(sw + ((r * 3 + s) * 3 + c) * 64 + half * 32);
+        const float p0 = patch[r][s][c], p1 = patch[r][s + 1][c];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 ww = w4[k];
+          acc0[4 * k + 0] = fmaf(p0, ww.x, acc0[4 * k + 0]);
+          acc0[4 * k + 1] = fmaf(p0, ww.y, acc0[4 * k + 1]);
+          acc0[4 * k + 2] = fmaf(p0, ww.z, acc0[4 * k + 2]);
+          acc0[4 * k + 3] = fmaf(p0, ww.w, acc0[4 * k + 3]);
+          acc1[4 * k + 0] = fmaf(p1, ww.x, acc1[4 * k + 0]);
+          acc1[4 * k + 1] = fmaf(p1, ww.y, acc1[4 * k + 1]);
+          acc1[4 * k + 2] = fmaf(p1, ww.z, acc1[4 * k + 2]);
+          acc1[4 * k + 3] = fmaf(p1, ww.w, acc1[4 * k + 3]);
+        }
+      }
     }
   }
-  uint4* o4 = reinterpret_cast<uint4*>(out + pix * 64 + half * 32);
-  uint4* l4 = out_lo ? reinterpret_cast<uint4*>(out_lo + pix * 64 + half * 32) : nullptr;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    Pack8 pk, pl;
+  for (int px = 0; px < 2; ++px) {
+    if (x + px >= W) break;
+    const float* acc = px ? acc1 : acc0;
+    const long long pix = img_base + static_cast<long long>(y) * W + x + px;
+    uint4* o4 = reinterpret_cast<uint4*>(out + pix * 64 + half * 32);
+    uint4* l4 = out_lo ? reinterpret_cast<uint4*>(out_lo + pix * 64 + half * 32) : nullptr;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a = fmaxf(acc[8 * j + 2 * e], 0.0f), bb = fmaxf(acc[8 * j + 2 * e + 1], 0.0f);
-      pk.h2[e] = __floats2bfloat162_rn(a, bb);
-      const float2 h = __bfloat1622float2(pk.h2[e]);
-      pl.h2[e] = __floats2bfloat162_rn(a - h.x, bb - h.y);
+    for (int j = 0; j < 4; ++j) {
+      Pack8 pk, pl;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = fmaxf(acc[8 * j + 2 * e], 0.0f), bb = fmaxf(acc[8 * j + 2 * e + 1], 0.0f);
+        pk.h2[e] = __floats2bfloat162_rn(a, bb);
+        const float2 h = __bfloat1622float2(pk.h2[e]);
+        pl.h2[e] = __floats2bfloat162_rn(a - h.x, bb - h.y);
+      }
+      o4[j] = pk.u;
+      if (l4) l4[j] = pl.u;
     }
-    o4[j] = pk.u;
-    if (l4) l4[j] = pl.u;
   }
 }
 
@@ -292,7 +311,7 @@ inline unsigned blocks_for(long long n, int threads) { return static_cast<unsign
 int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3,
                        const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream) {
   STX_REQUIRE(image && w && b && out && mean3, "conv1_1 fwd: null operand");
-  const long long threads = 2LL * nimg * H * W;
+  const long long threads = 2LL * nimg * H * ((W + 1) / 2);
   conv1_1_fwd_kernel<<<blocks_for(threads, 256), 256, 0, stream>>>(image, nimg, H, W, is_preimage, mean3[0], mean3[1],
                                                                   mean3[2], w, b, out, out_lo);
   STX_CUDA(cudaGetLastError());

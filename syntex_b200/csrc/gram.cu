@@ -151,23 +151,35 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
 }
 
 constexpr int kFinishThreads = 256;
+constexpr int kFinishLanes = 8;                                   // threads cooperating on one Gram element
+constexpr int kFinishElems = kFinishThreads / kFinishLanes;       // elements per block
 
+// One Gram element per group of 8 consecutive lanes: lane q sums slabs q, q+8, ... (coalesced across elements is
+// traded for 8x shorter serial chains; the slab count reaches ~300 for the conv1_1 level at batch 1), then a fixed
+// xor-shuffle tree combines the 8 partial sums. Deterministic.
 __global__ void __launch_bounds__(kFinishThreads)
 gram_finish_kernel(const float* __restrict__ partial, int C, int splits, float norm, float* __restrict__ G_out,
                    const float* __restrict__ target, long long target_stride, float dscale,
                    bf16* __restrict__ dscaled, float loss_scale, float* __restrict__ loss_part, int part_stride) {
   const int img = blockIdx.y;
-  const int e = blockIdx.x * kFinishThreads + threadIdx.x;
+  const int q = threadIdx.x & (kFinishLanes - 1);
+  const int e = blockIdx.x * kFinishElems + (threadIdx.x >> 3);
   const int CC = C * C;
   float sq = 0.0f;
+  float s = 0.0f;
+  int i = 0, j = 0;
   if (e < CC) {
-    const int i = e / C, j = e % C;
+    i = e / C;
+    j = e % C;
     // Only 128x128 tiles with tile(i) <= tile(j) were written; take the mirrored element otherwise.
     const int si = ((i >> 7) <= (j >> 7)) ? i : j;
     const int sj = ((i >> 7) <= (j >> 7)) ? j : i;
     const float* src = partial + static_cast<size_t>(img) * splits * CC + static_cast<size_t>(si) * C + sj;
-    float s = 0.0f;
-    for (int k = 0; k < splits; ++k) s += src[static_cast<size_t>(k) * CC];
+    for (int k = q; k < splits; k += kFinishLanes) s += src[static_cast<size_t>(k) * CC];
+  }
+#pragma unroll
+  for (int o = 1; o < kFinishLanes; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (e < CC && q == 0) {
     const float g = s / norm;
     if (G_out) G_out[static_cast<size_t>(img) * CC + e] = g;
     if (target) {
@@ -256,7 +268,7 @@ int gram_launch(const GramOp& op, cudaStream_t stream) {
   return STX_OK;
 }
 
-int gram_finish_blocks(int C) { return (C * C + kFinishThreads - 1) / kFinishThreads; }
+int gram_finish_blocks(int C) { return (C * C + kFinishElems - 1) / kFinishElems; }
 
 int gram_finish_launch(const GramOp& op, float eps, float* G_out, const float* target, long long target_stride,
                        float dscale, bf16* dscaled, float loss_scale, float* loss_part, int part_stride,
