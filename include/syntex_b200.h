@@ -138,7 +138,9 @@ int stx_conv_bf16x3(const void* x_hi, const void* x_lo, int n, int H, int W, int
                     int force_bn, void* stream);
 /* out = epilogue(conv(x, w)) with x [n,H,W,cin] bf16, w packed [taps][cout][cin] bf16, taps in {9, 1}.
  * epilogue: (+ bias[cout] fp32) (+ addend bf16) (relu) (zero where mask <= 0); any of them may be NULL/0.
- * force_bn: 0 = automatic N tile, else 64 or 128. */
+ * force_bn ("variant"): 0 = automatic kernel and tile choice; otherwise bn + 1000 * mt + 100000 * per_tap, with
+ *   bn in {0, 64, 128, 256} the N tile, mt in {0, 1, 2} the stacked 16x8 output tiles of the halo-patch kernel and
+ *   per_tap = 1 forcing the general per-tap kernel (conv_igemm.cu) instead of the halo-patch one (conv_patch.cu). */
 int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_packed, int cout, int taps,
                   const float* bias, const void* addend, const void* mask, int relu, void* out, int force_bn,
                   void* stream);

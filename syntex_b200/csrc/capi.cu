@@ -225,10 +225,10 @@ int stx_conv_bf16x3(const void* x_hi, const void* x_lo, int n, int H, int W, int
                     const void* w_lo, int cout, const float* bias, int relu, void* out_hi, void* out_lo,
                     int force_bn, void* stream) {
   STX_REQUIRE(out_hi && out_lo, "stx_conv_bf16x3: null output");
+  STX_REQUIRE(x_lo && w_lo, "stx_conv_bf16x3: null low-half operand");
   ConvOp op;
-  STX_TRY(conv_prepare(&op, static_cast<const bf16*>(x_hi), n, H, W, cin, static_cast<const bf16*>(w_hi), cout, 9, 0,
-                       force_bn));
-  STX_TRY(conv_prepare_split(&op, static_cast<const bf16*>(x_lo), static_cast<const bf16*>(w_lo)));
+  STX_TRY(conv3x3_prepare(&op, static_cast<const bf16*>(x_hi), static_cast<const bf16*>(x_lo), n, H, W, cin,
+                          static_cast<const bf16*>(w_hi), static_cast<const bf16*>(w_lo), cout, force_bn));
   op.bias = bias;
   op.relu = relu;
   op.out = static_cast<bf16*>(out_hi);
@@ -241,8 +241,13 @@ int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_pac
                   void* stream) {
   STX_REQUIRE(out, "stx_conv_bf16: null output");
   ConvOp op;
-  STX_TRY(conv_prepare(&op, static_cast<const bf16*>(x), n, H, W, cin, static_cast<const bf16*>(w_packed), cout, taps,
-                       0, force_bn));
+  if (taps == 9) {
+    STX_TRY(conv3x3_prepare(&op, static_cast<const bf16*>(x), nullptr, n, H, W, cin,
+                            static_cast<const bf16*>(w_packed), nullptr, cout, force_bn));
+  } else {
+    STX_TRY(conv_prepare(&op, static_cast<const bf16*>(x), n, H, W, cin, static_cast<const bf16*>(w_packed), cout,
+                         taps, 0, force_bn % 1000));
+  }
   op.bias = bias;
   op.addend = static_cast<const bf16*>(addend);
   op.mask = static_cast<const bf16*>(mask);

@@ -23,9 +23,8 @@
 //   dgrad        (conv(dy, rot180(W)^T) [+ addend]) * [a > 0]   (Conv2DBackpropInput + ReluGrad of tf.gradients,
 //                                                               gatys/synthesizer.py:79)
 //   Gram dF      F * Dscaled as a 1x1 convolution with per-image weights (utils.py:54), accumulated in place.
-#include "common.h"
+#include "conv_common.cuh"
 #include "ops.h"
-#include "ptx.cuh"
 
 namespace stx {
 
@@ -44,28 +43,6 @@ struct SmemLayout {
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * kOperandBytes;  // SPLIT: [A_hi | W_hi | A_lo | W_lo]
   static constexpr int kBarrierOffset = kStages * kStageBytes;
   static constexpr int kTotal = kBarrierOffset + 128 /*barriers + tmem slot*/ + 1024 /*alignment slack*/;
-};
-
-struct ConvKernelParams {
-  int H, W, nimg;
-  int cout;            // total output channels (row pitch of out/addend/mask)
-  int cchunks;         // C_in / 64
-  int taps;            // 9 or 1
-  int bw_log2, bh_log2;
-  int tiles_w, tiles_h;
-  int n_step;          // images advanced per tile along the batch axis
-  int per_image_w;     // weight "tap" index = image index (Gram dF mode); only rows of the first image are stored
-  int relu;
-  const float* bias;   // [cout] or null
-  const bf16* addend;  // [nimg,H,W,cout] or null (may alias out)
-  const bf16* mask;    // [nimg,H,W,cout] or null: result is zeroed where mask <= 0
-  bf16* out;           // [nimg,H,W,cout]
-  bf16* out_lo;        // SPLIT: low halves of the output (out holds the high halves)
-};
-
-union Pack8 {
-  uint4 u;
-  __nv_bfloat162 h2[4];
 };
 
 template <int BN, bool SPLIT>
@@ -197,68 +174,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
       tmem_ld_wait();
-      if (valid) {
-        if (p.bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nblk * BN + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j + 0] += b.x;
-            v[4 * j + 1] += b.y;
-            v[4 * j + 2] += b.z;
-            v[4 * j + 3] += b.w;
-          }
-        }
-        if (p.addend) {
-          const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + row_off + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            Pack8 pk;
-            pk.u = a4[j];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(pk.h2[e]);
-              v[8 * j + 2 * e] += f.x;
-              v[8 * j + 2 * e + 1] += f.y;
-            }
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        if (p.mask) {
-          const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + row_off + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            Pack8 pk;
-            pk.u = __ldg(m4 + j);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(pk.h2[e]);
-              if (!(f.x > 0.0f)) v[8 * j + 2 * e] = 0.0f;
-              if (!(f.y > 0.0f)) v[8 * j + 2 * e + 1] = 0.0f;
-            }
-          }
-        }
-        uint4* o4 = reinterpret_cast<uint4*>(p.out + row_off + c0);
-        uint4* l4 = SPLIT ? reinterpret_cast<uint4*>(p.out_lo + row_off + c0) : nullptr;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          Pack8 pk, pl;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-            pk.h2[e] = __floats2bfloat162_rn(a, b);
-            if (SPLIT) {
-              const float2 h = __bfloat1622float2(pk.h2[e]);
-              pl.h2[e] = __floats2bfloat162_rn(a - h.x, b - h.y);
-            }
-          }
-          o4[j] = pk.u;
-          if (SPLIT) l4[j] = pl.u;
-        }
-      }
+      if (valid) conv_epilogue_store<SPLIT>(p, v, row_off + c0, nblk * BN + c0);
     }
   }
 
@@ -335,6 +251,8 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->cout = cout;
   op->taps = taps;
   op->per_image_w = per_image_w;
+  op->patch = 0;
+  op->mt = 1;
   // Tile geometry: BW x BH x BNI pixels = 128 accumulator rows.
   int bw = 16;
   while (bw > 1 && (bw >> 1) >= W) bw >>= 1;       // smallest power of two >= W, capped at 16
@@ -372,8 +290,24 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   return STX_OK;
 }
 
+int conv3x3_prepare(ConvOp* op, const bf16* x, const bf16* x_lo, int nimg, int H, int W, int cin, const bf16* w,
+                    const bf16* w_lo, int cout, int variant) {
+  const int force_igemm = variant / 100000;
+  const int force_mt = (variant / 1000) % 100;
+  const int force_bn = variant % 1000;
+  const int split = (x_lo != nullptr) ? 1 : 0;
+  if (!force_igemm) {
+    const int rc = conv_patch_prepare(op, x, nimg, H, W, cin, w, cout, split, force_bn, force_mt);
+    if (rc == STX_OK) return split ? conv_patch_prepare_split(op, x_lo, w_lo) : STX_OK;
+    if (rc != STX_ERR_UNSUPPORTED) return rc;
+  }
+  STX_TRY(conv_prepare(op, x, nimg, H, W, cin, w, cout, 9, 0, force_bn == 256 ? 128 : force_bn));
+  return split ? conv_prepare_split(op, x_lo, w_lo) : STX_OK;
+}
+
 int conv_launch(const ConvOp& op, cudaStream_t stream) {
   STX_REQUIRE(op.out != nullptr, "conv: output not set");
+  if (op.patch) return conv_patch_launch(op, stream);
   if (op.split) {
     STX_REQUIRE(op.out_lo != nullptr, "conv split: low-half output not set");
     if (op.bn == 128) return launch_bn<128, true>(op, stream);

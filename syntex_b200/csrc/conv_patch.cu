@@ -1,0 +1,310 @@
+// 3x3 SAME convolution, halo-patch variant of the tcgen05 implicit GEMM (the throughput path; conv_igemm.cu is
+// the general one).
+//
+// conv_igemm.cu fetches one 128-pixel x 64-channel A tile per filter tap, i.e. it pulls every activation through
+// L2 -> SMEM nine times; with 128x128 tiles that is 64 FLOP per L2 byte and the measured kernels sit on the L2
+// bandwidth roof (~10 TB/s), not on the tensor pipe (profiles/r01_launches_fg_eval_b8_256.md). Here each
+// 64-channel chunk of the (16*MT + 2) x 10 pixel halo patch around a (16*MT) x 8 output tile is loaded ONCE (one
+// 4-D TMA box, zero-filled outside the image = SAME padding) and all nine taps read it in place: tcgen05
+// shared-memory descriptors address any 128-byte row of a 128B-swizzled buffer (the swizzle is a function of the
+// absolute shared-memory address - verified on the B200 by csrc/probe.cu, profiles/r01_descriptor_probe_*), so
+// tap (r, s) is just "start address + (r*10 + s) * 128 B, stride between 8-row groups = 10 * 128 B".
+// MT = 2 stacks two 16x8 output tiles (two TMEM accumulators) on one weight stream, halving the weight traffic per
+// FLOP as well: 195-220 FLOP per L2 byte.
+//
+// Pipelines: patch ring (2 stages, one fill per channel chunk) and weight ring (one [BN x 64] tile per tap),
+// both TMA -> mbarrier -> tcgen05.mma -> tcgen05.commit. Warp roles as in conv_igemm.cu.
+#include "conv_common.cuh"
+#include "ops.h"
+
+namespace stx {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kPatchW = 10;                       // 8 output columns + 2 halo
+constexpr int kPatchStages = 2;
+
+template <int BN, int MT, bool SPLIT>
+struct PatchSmem {
+  static constexpr int kPatchRows = (16 * MT + 2) * kPatchW;
+  static constexpr int kPatchBytes = kPatchRows * 128;                        // TMA transaction bytes
+  static constexpr int kPatchStride = (kPatchBytes + 1023) & ~1023;           // keep every buffer 1024-aligned
+  static constexpr int kPatchStageBytes = (SPLIT ? 2 : 1) * kPatchStride;     // [hi | lo]
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBStageBytes = (SPLIT ? 2 : 1) * kBBytes;              // [hi | lo]
+  static constexpr int kBStages = SPLIT ? 3 : (BN * MT >= 256 ? 4 : 3);
+  static constexpr int kBOffset = kPatchStages * kPatchStageBytes;
+  static constexpr int kBarrierOffset = kBOffset + kBStages * kBStageBytes;
+  static constexpr int kTotal = kBarrierOffset + 256 + 1024;
+  static constexpr int kTmemCols = BN * MT;
+};
+
+template <int BN, int MT, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                  const ConvKernelParams p) {
+  using L = PatchSmem<BN, MT, SPLIT>;
+  constexpr int kBStages = L::kBStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
+  uint64_t* pempty = pfull + kPatchStages;
+  uint64_t* bfull = pempty + kPatchStages;
+  uint64_t* bempty = bfull + kBStages;
+  uint64_t* accum_bar = bempty + kBStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w;
+  const int th = (tile / p.tiles_w) % p.tiles_h;
+  const int n = tile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * 8;
+  const int h0 = th * (16 * MT);
+  const int nblk = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (SPLIT) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kPatchStages; ++s) {
+      mbar_init(&pfull[s], 1);
+      mbar_init(&pempty[s], 1);
+    }
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, L::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int chunks = p.cchunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int bit = 0;   // weight-tile counter
+      for (int c = 0; c < chunks; ++c) {
+        const int ps = c % kPatchStages;
+        mbar_wait(&pempty[ps], ((c / kPatchStages) & 1) ^ 1, 100 + ps);
+        uint8_t* pdst = smem + ps * L::kPatchStageBytes;
+        mbar_arrive_expect_tx(&pfull[ps], (SPLIT ? 2 : 1) * L::kPatchBytes);
+        tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
+        if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
+        for (int tap = 0; tap < 9; ++tap, ++bit) {
+          const int bs = bit % kBStages;
+          mbar_wait(&bempty[bs], ((bit / kBStages) & 1) ^ 1, 110 + bs);
+          uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
+          mbar_arrive_expect_tx(&bfull[bs], L::kBStageBytes);
+          tma_load_3d(bdst, &tmB, &bfull[bs], c * 64, nblk * BN, tap);
+          if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t kGroupStride = kPatchW * 128;     // bytes between consecutive 8-pixel row groups
+      int bit = 0;
+      for (int c = 0; c < chunks; ++c) {
+        const int ps = c % kPatchStages;
+        mbar_wait(&pfull[ps], (c / kPatchStages) & 1, 200 + ps);
+        const uint32_t patch = smem_u32(smem + ps * L::kPatchStageBytes);
+        for (int tap = 0; tap < 9; ++tap, ++bit) {
+          const int bs = bit % kBStages;
+          mbar_wait(&bfull[bs], (bit / kBStages) & 1, 210 + bs);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(smem + L::kBOffset + bs * L::kBStageBytes);
+          const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
+          const uint64_t bdesc_lo = make_smem_desc_sw128(b_addr + L::kBBytes, 16, 1024);
+          const uint32_t tap_off = ((tap / 3) * kPatchW + (tap % 3)) * 128;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t a_addr = patch + tap_off + mt * 16 * kGroupStride;
+            const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, kGroupStride);
+            const uint64_t adesc_lo = make_smem_desc_sw128(a_addr + L::kPatchStride, 16, kGroupStride);
+            const uint32_t d = tmem_base + mt * BN;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t first = (c | tap | k) != 0;
+              if (SPLIT) {
+                umma_bf16(d, adesc_lo + 2 * k, bdesc + 2 * k, idesc, first);   // A_lo * W_hi
+                umma_bf16(d, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1);       // A_hi * W_lo
+                umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);          // A_hi * W_hi
+              } else {
+                umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, first);
+              }
+            }
+          }
+          umma_commit(&bempty[bs]);
+        }
+        umma_commit(&pempty[ps]);
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ww = r & 7;
+    const int w = w0 + ww;
+    mbar_wait(accum_bar, 0, 300);
+    tc_fence_after();
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int h = h0 + mt * 16 + (r >> 3);
+      const bool valid = (h < p.H) && (w < p.W);
+      const size_t row_off = ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.cout + nblk * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BN + c0, v);
+        tmem_ld_wait();
+        if (valid) conv_epilogue_store<SPLIT>(p, v, row_off + c0, nblk * BN + c0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, L::kTmemCols);
+}
+
+template <int BN, int MT, bool SPLIT>
+int launch_patch(const ConvOp& op, cudaStream_t stream) {
+  using L = PatchSmem<BN, MT, SPLIT>;
+  static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
+  static bool attr_set = false;
+  if (!attr_set) {
+    STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  L::kTotal));
+    attr_set = true;
+  }
+  ConvKernelParams p;
+  p.H = op.H;
+  p.W = op.W;
+  p.nimg = op.nimg;
+  p.cout = op.cout;
+  p.cchunks = op.cin / 64;
+  p.taps = 9;
+  p.bw_log2 = 3;
+  p.bh_log2 = 4;
+  p.tiles_w = op.tiles_w;
+  p.tiles_h = op.tiles_h;
+  p.n_step = 1;
+  p.per_image_w = 0;
+  p.relu = op.relu;
+  p.bias = op.bias;
+  p.addend = op.addend;
+  p.mask = op.mask;
+  p.out = op.out;
+  p.out_lo = op.out_lo;
+  dim3 grid(op.tiles_w * op.tiles_h * op.nimg, op.cout / BN, 1);
+  conv_patch_kernel<BN, MT, SPLIT><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
+                                                                           SPLIT ? op.tmB2 : op.tmB, p);
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+}  // namespace
+
+// Geometry + tensor maps of the patch variant. Returns STX_ERR_UNSUPPORTED (without touching op) when the shape
+// does not qualify (needs W >= 8: an 8-pixel row group must be contiguous in the patch).
+int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
+                       int split, int force_bn, int force_mt) {
+  STX_REQUIRE(x && wpacked, "conv: null operand");
+  STX_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv: channels must be multiples of 64");
+  if (W < 8) return STX_ERR_UNSUPPORTED;
+  op->nimg = nimg;
+  op->H = H;
+  op->W = W;
+  op->cin = cin;
+  op->cout = cout;
+  op->taps = 9;
+  op->per_image_w = 0;
+  op->patch = 1;
+  // N tile and the number of stacked M tiles: prefer the configuration with the most reuse that still yields at
+  // least one CTA per SM (148); the split forward keeps MT = 1 (its hi/lo patches already fill shared memory).
+  const int tiles_w = (W + 7) / 8;
+  auto ctas = [&](int bn, int mt) { return tiles_w * ((H + 16 * mt - 1) / (16 * mt)) * nimg * (cout / bn); };
+  int bn = 64, mt = 1;
+  if (cout % 128 == 0 && ctas(128, 1) >= 148) bn = 128;
+  if (!split) {
+    if (ctas(bn, 2) >= 148) mt = 2;
+    if (cout % 256 == 0 && mt == 2 && ctas(256, 2) >= 148) bn = 256;
+  }
+  if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0) || (force_bn == 256 && cout % 256 == 0 && !split))
+    bn = force_bn;
+  if (force_mt == 1 || (force_mt == 2 && !split)) mt = force_mt;
+  if (bn == 256 && mt == 1) mt = 2;     // only the <256, 2> instance exists
+  op->bn = bn;
+  op->mt = mt;
+  op->tiles_w = tiles_w;
+  op->tiles_h = (H + 16 * mt - 1) / (16 * mt);
+  op->tiles_n = nimg;
+  op->n_step = 1;
+  op->bw_log2 = 3;
+  op->bh_log2 = 4;
+  const uint64_t adims[4] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                             static_cast<uint64_t>(nimg)};
+  const uint32_t abox[4] = {64u, static_cast<uint32_t>(kPatchW), static_cast<uint32_t>(16 * mt + 2), 1u};
+  STX_TRY(encode_tmap_bf16(&op->tmA, x, 4, adims, abox));
+  const uint64_t bdims[3] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(cout), 9u};
+  const uint32_t bbox[3] = {64u, static_cast<uint32_t>(bn), 1u};
+  STX_TRY(encode_tmap_bf16(&op->tmB, wpacked, 3, bdims, bbox));
+  op->bias = nullptr;
+  op->addend = nullptr;
+  op->mask = nullptr;
+  op->out = nullptr;
+  op->out_lo = nullptr;
+  op->split = 0;
+  op->relu = 0;
+  return STX_OK;
+}
+
+int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo) {
+  STX_REQUIRE(x_lo && w_lo, "conv split: null low-half operand");
+  STX_REQUIRE(op->patch && op->mt == 1, "conv split: patch geometry must be prepared with split = 1");
+  const uint64_t adims[4] = {static_cast<uint64_t>(op->cin), static_cast<uint64_t>(op->W),
+                             static_cast<uint64_t>(op->H), static_cast<uint64_t>(op->nimg)};
+  const uint32_t abox[4] = {64u, static_cast<uint32_t>(kPatchW), 18u, 1u};
+  STX_TRY(encode_tmap_bf16(&op->tmA2, x_lo, 4, adims, abox));
+  const uint64_t bdims[3] = {static_cast<uint64_t>(op->cin), static_cast<uint64_t>(op->cout), 9u};
+  const uint32_t bbox[3] = {64u, static_cast<uint32_t>(op->bn), 1u};
+  STX_TRY(encode_tmap_bf16(&op->tmB2, w_lo, 3, bdims, bbox));
+  op->split = 1;
+  return STX_OK;
+}
+
+int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
+  STX_REQUIRE(op.out != nullptr, "conv: output not set");
+  if (op.split) {
+    STX_REQUIRE(op.out_lo != nullptr, "conv split: low-half output not set");
+    if (op.bn == 128) return launch_patch<128, 1, true>(op, stream);
+    return launch_patch<64, 1, true>(op, stream);
+  }
+  if (op.bn == 256) return launch_patch<256, 2, false>(op, stream);
+  if (op.bn == 128) return op.mt == 2 ? launch_patch<128, 2, false>(op, stream) : launch_patch<128, 1, false>(op, stream);
+  return op.mt == 2 ? launch_patch<64, 2, false>(op, stream) : launch_patch<64, 1, false>(op, stream);
+}
+
+}  // namespace stx

@@ -13,6 +13,8 @@ struct ConvOp {
   CUtensorMap tmA2;  // split mode: low halves of the activations
   CUtensorMap tmB2;  // split mode: low halves of the weights
   int split;         // 1 = bf16x3 forward (hi/lo operands, hi/lo outputs)
+  int patch;         // 1 = halo-patch kernel (conv_patch.cu), 0 = per-tap kernel (conv_igemm.cu)
+  int mt;            // patch kernel: 16x8 output tiles stacked per CTA (1 or 2)
   bf16* out_lo;
   int nimg, H, W, cin, cout, taps, per_image_w;
   int bw_log2, bh_log2, tiles_w, tiles_h, tiles_n, n_step, bn;
@@ -25,6 +27,15 @@ struct ConvOp {
 int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
                  int taps, int per_image_w, int force_bn);
 int conv_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
+// Halo-patch variant (3x3 only, W >= 8); returns STX_ERR_UNSUPPORTED for shapes it does not cover.
+int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
+                       int split, int force_bn, int force_mt);
+int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
+int conv_patch_launch(const ConvOp& op, cudaStream_t stream);
+// Picks the halo-patch kernel when the shape qualifies, else the per-tap kernel. x_lo / w_lo non-null = bf16x3.
+// variant: 0 = automatic; otherwise bn + 1000 * mt + 100000 * (force the per-tap kernel).
+int conv3x3_prepare(ConvOp* op, const bf16* x, const bf16* x_lo, int nimg, int H, int W, int cin, const bf16* w,
+                    const bf16* w_lo, int cout, int variant);
 int conv_launch(const ConvOp& op, cudaStream_t stream);
 
 // ------------------------------------------------------------------ gram.cu

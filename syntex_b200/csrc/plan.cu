@@ -258,8 +258,8 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     const LayerSpec& s = kLayers[l];
     if (!s.is_conv) continue;
     ConvOp& op = p->fwd[l];
-    rc = conv_prepare(&op, p->act[l - 1], B, p->lh[l], p->lw[l], s.cin, vgg->wf[s.conv_index], s.cout, 9, 0, 0);
-    if (rc == STX_OK && p->split) rc = conv_prepare_split(&op, p->act_lo[l - 1], vgg->wf_lo[s.conv_index]);
+    rc = conv3x3_prepare(&op, p->act[l - 1], p->split ? p->act_lo[l - 1] : nullptr, B, p->lh[l], p->lw[l], s.cin,
+                         vgg->wf[s.conv_index], p->split ? vgg->wf_lo[s.conv_index] : nullptr, s.cout, 0);
     op.bias = vgg->bias[s.conv_index];
     op.relu = 1;
     op.out = p->act[l];
@@ -319,7 +319,8 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     } else if (s.is_conv) {
       BwdStep st;
       st.kind = BwdStep::kDgrad;
-      rc = conv_prepare(&st.conv, p->gbuf[cur], B, p->lh[l], p->lw[l], s.cout, vgg->wd[s.conv_index], s.cin, 9, 0, 0);
+      rc = conv3x3_prepare(&st.conv, p->gbuf[cur], nullptr, B, p->lh[l], p->lw[l], s.cout, vgg->wd[s.conv_index],
+                           nullptr, s.cin, 0);
       st.conv.out = p->gbuf[cur ^ 1];
       st.conv.mask = (kLayers[l - 1].is_conv && loss_index(l - 1) < 0) ? p->act[l - 1] : nullptr;
       p->bwd.push_back(st);

@@ -54,6 +54,27 @@ def test_conv_forward_and_dgrad(n, H, W, cin, cout, bn):
     assert relerr(dx.float(), refd) < BF16_OUT
 
 
+VARIANTS = [0, 64, 128, 256, 1064, 2064, 1128, 2128, 2256, 100064, 100128]   # bn + 1000*mt + 100000*per_tap
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("n,H,W,cin,cout", [(2, 40, 24, 64, 256), (1, 16, 8, 128, 256), (3, 9, 17, 64, 256)])
+def test_conv_kernel_variants_agree_with_reference(n, H, W, cin, cout, variant):
+    """Every tile configuration of both kernels (halo-patch / per-tap) on ragged and multi-image shapes."""
+    g = gen(10)
+    x = torch.randn((n, H, W, cin), device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn((3, 3, cin, cout), device="cuda", generator=g) / np.sqrt(9 * cin)).float()
+    b = torch.randn((cout,), device="cuda", generator=g).float()
+    msk = torch.randn((n, H, W, cout), device="cuda", generator=g).to(torch.bfloat16)
+    wf, _, _ = pack(w)
+    out = torch.full((n, H, W, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L().stx_conv_bf16(x.data_ptr(), n, H, W, cin, wf.data_ptr(), cout, 9, b.data_ptr(), None,
+                                 msk.data_ptr(), 0, out.data_ptr(), variant, st()))
+    ref = (conv_ref(x.float(), w.to(torch.bfloat16).float(), b)) * (msk.float() > 0)
+    assert torch.isfinite(out.float()).all()
+    assert relerr(out.float(), ref) < BF16_OUT
+
+
 def test_conv_epilogue_addend_mask_inplace():
     n, H, W, cin, cout = 2, 24, 16, 128, 64
     g = gen(1)
@@ -84,7 +105,8 @@ def test_conv_1x1_is_a_plain_gemm():
 
 @pytest.mark.parametrize("n,H,W,cin,cout,bn", [(1, 16, 16, 64, 64, 0), (1, 32, 32, 128, 128, 128),
                                                (2, 8, 8, 128, 256, 64), (1, 64, 64, 256, 256, 0),
-                                               (1, 32, 32, 512, 512, 0), (1, 20, 12, 64, 128, 0)])
+                                               (1, 32, 32, 512, 512, 0), (1, 20, 12, 64, 128, 0),
+                                               (1, 32, 32, 128, 128, 100128), (2, 4, 4, 128, 128, 0)])
 def test_conv_bf16x3_forward(n, H, W, cin, cout, bn):
     g = gen(3)
     x = torch.randn((n, H, W, cin), device="cuda", generator=g).relu()
