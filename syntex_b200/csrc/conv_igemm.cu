@@ -165,8 +165,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int nn = r >> (p.bw_log2 + p.bh_log2);
     const int n = n0 + nn, h = h0 + hh, w = w0 + ww;
     const bool valid = (n < p.nimg) && (h < p.H) && (w < p.W) && (!p.per_image_w || nn == 0);
-    const size_t row_off = ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.cout + nblk * BN;
-
     mbar_wait(accum_bar, 0, 300);
     tc_fence_after();
 #pragma unroll 1
@@ -174,7 +172,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
       tmem_ld_wait();
-      if (valid) conv_epilogue_store<SPLIT>(p, v, row_off + c0, nblk * BN + c0);
+      conv_epilogue_store<SPLIT>(p, v, valid, n, h, w, nblk * BN + c0);
     }
   }
 
@@ -211,6 +209,13 @@ int launch_bn(const ConvOp& op, cudaStream_t stream) {
   p.mask = op.mask;
   p.out = op.out;
   p.out_lo = op.out_lo;
+  p.rgb_out = nullptr;
+  p.rgb_image = nullptr;
+  p.rgb_preimage = 0;
+  p.pool_out = nullptr;      // the per-tap kernel's row mapping does not match the fused pooling
+  p.pool_out_lo = nullptr;
+  p.up_out = op.up_out;
+  p.up_mask = op.up_mask;
   dim3 grid(op.tiles_w * op.tiles_h * op.tiles_n, op.cout / BN, 1);
   conv_igemm_kernel<BN, SPLIT><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
                                                                         SPLIT ? op.tmB2 : op.tmB, p);
@@ -267,8 +272,8 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->tiles_n = (nimg + op->n_step - 1) / op->n_step;
   // N tile: 128 when that still fills the machine, otherwise 64 (more CTAs for the small deep layers).
   const int tiles_m = op->tiles_w * op->tiles_h * op->tiles_n;
-  int bn = 64;
-  if (cout % 128 == 0 && tiles_m * (cout / 128) >= 148) bn = 128;
+  int bn = (cout % 128 == 0) ? 128 : 64;
+  (void)tiles_m;
   if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0)) bn = force_bn;
   op->bn = bn;
 
@@ -285,6 +290,13 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->mask = nullptr;
   op->out = nullptr;
   op->out_lo = nullptr;
+  op->rgb_out = nullptr;
+  op->rgb_image = nullptr;
+  op->rgb_preimage = 0;
+  op->pool_out = nullptr;
+  op->pool_out_lo = nullptr;
+  op->up_out = nullptr;
+  op->up_mask = nullptr;
   op->split = 0;
   op->relu = 0;
   return STX_OK;
@@ -306,8 +318,9 @@ int conv3x3_prepare(ConvOp* op, const bf16* x, const bf16* x_lo, int nimg, int H
 }
 
 int conv_launch(const ConvOp& op, cudaStream_t stream) {
-  STX_REQUIRE(op.out != nullptr, "conv: output not set");
   if (op.patch) return conv_patch_launch(op, stream);
+  STX_REQUIRE(op.out != nullptr || op.up_out != nullptr, "conv: output not set");
+  STX_REQUIRE(op.pool_out == nullptr, "conv: fused pooling needs the halo-patch kernel");
   if (op.split) {
     STX_REQUIRE(op.out_lo != nullptr, "conv split: low-half output not set");
     if (op.bn == 128) return launch_bn<128, true>(op, stream);

@@ -31,13 +31,13 @@ struct PatchSmem {
   static constexpr int kPatchBytes = kPatchRows * 128;                        // TMA transaction bytes
   static constexpr int kPatchStride = (kPatchBytes + 1023) & ~1023;           // keep every buffer 1024-aligned
   static constexpr int kPatchStageBytes = (SPLIT ? 2 : 1) * kPatchStride;     // [hi | lo]
-  static constexpr int kBBytes = BN * 128;
+  static constexpr int kBBytes = (BN * 128 + 1023) & ~1023;
   static constexpr int kBStageBytes = (SPLIT ? 2 : 1) * kBBytes;              // [hi | lo]
   static constexpr int kBStages = SPLIT ? 3 : (BN * MT >= 256 ? 4 : 3);
   static constexpr int kBOffset = kPatchStages * kPatchStageBytes;
   static constexpr int kBarrierOffset = kBOffset + kBStages * kBStageBytes;
   static constexpr int kTotal = kBarrierOffset + 256 + 1024;
-  static constexpr int kTmemCols = BN * MT;
+  static constexpr int kTmemCols = BN * MT < 32 ? 32 : BN * MT;
 };
 
 template <int BN, int MT, bool SPLIT>
@@ -110,7 +110,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int bs = bit % kBStages;
           mbar_wait(&bempty[bs], ((bit / kBStages) & 1) ^ 1, 110 + bs);
           uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
-          mbar_arrive_expect_tx(&bfull[bs], L::kBStageBytes);
+          mbar_arrive_expect_tx(&bfull[bs], (SPLIT ? 2 : 1) * BN * 128);
           tma_load_3d(bdst, &tmB, &bfull[bs], c * 64, nblk * BN, tap);
           if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
         }
@@ -168,17 +168,38 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int w = w0 + ww;
     mbar_wait(accum_bar, 0, 300);
     tc_fence_after();
+    if (BN == 16) {
+      // conv1_1 input gradient: both stacked tiles sit in one 32-column TMEM slab (16 columns each, 3 real).
+      float v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int h = h0 + mt * 16 + (r >> 3);
+        if (h < p.H && w < p.W) {
+          const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float d = v[mt * 16 + c] * 255.0f;
+            if (p.rgb_preimage) {
+              const float sg = 1.0f / (1.0f + __expf(-p.rgb_image[pix * 3 + c]));
+              d *= sg * (1.0f - sg);
+            }
+            p.rgb_out[pix * 3 + c] = d;
+          }
+        }
+      }
+    } else
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       const int h = h0 + mt * 16 + (r >> 3);
       const bool valid = (h < p.H) && (w < p.W);
-      const size_t row_off = ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.cout + nblk * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BN + c0, v);
         tmem_ld_wait();
-        if (valid) conv_epilogue_store<SPLIT>(p, v, row_off + c0, nblk * BN + c0);
+        conv_epilogue_store<SPLIT>(p, v, valid, n, h, w, nblk * BN + c0);
       }
     }
   }
@@ -217,6 +238,13 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.mask = op.mask;
   p.out = op.out;
   p.out_lo = op.out_lo;
+  p.rgb_out = op.rgb_out;
+  p.rgb_image = op.rgb_image;
+  p.rgb_preimage = op.rgb_preimage;
+  p.pool_out = op.pool_out;
+  p.pool_out_lo = op.pool_out_lo;
+  p.up_out = op.up_out;
+  p.up_mask = op.up_mask;
   dim3 grid(op.tiles_w * op.tiles_h * op.nimg, op.cout / BN, 1);
   conv_patch_kernel<BN, MT, SPLIT><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
                                                                            SPLIT ? op.tmB2 : op.tmB, p);
@@ -232,7 +260,7 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
 int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
                        int split, int force_bn, int force_mt) {
   STX_REQUIRE(x && wpacked, "conv: null operand");
-  STX_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "conv: channels must be multiples of 64");
+  STX_REQUIRE(cin % 64 == 0 && (cout % 64 == 0 || cout == 16), "conv: channels must be multiples of 64");
   if (W < 8) return STX_ERR_UNSUPPORTED;
   op->nimg = nimg;
   op->H = H;
@@ -242,20 +270,31 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->taps = 9;
   op->per_image_w = 0;
   op->patch = 1;
-  // N tile and the number of stacked M tiles: prefer the configuration with the most reuse that still yields at
-  // least one CTA per SM (148); the split forward keeps MT = 1 (its hi/lo patches already fill shared memory).
+  // N tile and number of stacked 16x8 tiles, from the measured variant table (profiles/r01_conv_variants_*.log):
+  // 128-wide N tiles with one tile per CTA (two CTAs per SM) by default; 256 x (2 tiles) when even that coarse grid
+  // fills ~the machine (best reuse); 64-wide tiles only for 64-channel layers. The split forward keeps MT = 1
+  // (its hi/lo patches already fill shared memory) and is tensor-bound in every configuration.
   const int tiles_w = (W + 7) / 8;
   auto ctas = [&](int bn, int mt) { return tiles_w * ((H + 16 * mt - 1) / (16 * mt)) * nimg * (cout / bn); };
   int bn = 64, mt = 1;
-  if (cout % 128 == 0 && ctas(128, 1) >= 148) bn = 128;
-  if (!split) {
-    if (ctas(bn, 2) >= 148) mt = 2;
-    if (cout % 256 == 0 && mt == 2 && ctas(256, 2) >= 148) bn = 256;
+  if (cout == 16) {
+    bn = 16;
+    mt = 2;
+  } else {
+    if (cout % 128 == 0) bn = 128;      // never slower than 64 in the measured table, even on tiny grids
+    if (!split) {
+      if (cout % 256 == 0 && ctas(256, 2) >= 120) {
+        bn = 256;
+        mt = 2;
+      } else if (bn == 64 && ctas(64, 2) >= 296) {
+        mt = 2;
+      }
+    }
+    if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0) || (force_bn == 256 && cout % 256 == 0 && !split))
+      bn = force_bn;
+    if (force_mt == 1 || (force_mt == 2 && !split)) mt = force_mt;
+    if (bn == 256) mt = 2;              // only the <256, 2> instance exists
   }
-  if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0) || (force_bn == 256 && cout % 256 == 0 && !split))
-    bn = force_bn;
-  if (force_mt == 1 || (force_mt == 2 && !split)) mt = force_mt;
-  if (bn == 256 && mt == 1) mt = 2;     // only the <256, 2> instance exists
   op->bn = bn;
   op->mt = mt;
   op->tiles_w = tiles_w;
@@ -276,6 +315,13 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->mask = nullptr;
   op->out = nullptr;
   op->out_lo = nullptr;
+  op->rgb_out = nullptr;
+  op->rgb_image = nullptr;
+  op->rgb_preimage = 0;
+  op->pool_out = nullptr;
+  op->pool_out_lo = nullptr;
+  op->up_out = nullptr;
+  op->up_mask = nullptr;
   op->split = 0;
   op->relu = 0;
   return STX_OK;
@@ -296,7 +342,12 @@ int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo) {
 }
 
 int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
-  STX_REQUIRE(op.out != nullptr, "conv: output not set");
+  if (op.bn == 16) {
+    STX_REQUIRE(op.rgb_out != nullptr && op.mt == 2 && !op.split, "conv1_1 dgrad: bad configuration");
+    return launch_patch<16, 2, false>(op, stream);
+  }
+  STX_REQUIRE(op.out != nullptr || op.up_out != nullptr, "conv: output not set");
+  STX_REQUIRE(op.pool_out == nullptr || (op.H % 2 == 0 && op.W % 2 == 0), "conv: fused pooling needs even H and W");
   if (op.split) {
     STX_REQUIRE(op.out_lo != nullptr, "conv split: low-half output not set");
     if (op.bn == 128) return launch_patch<128, 1, true>(op, stream);

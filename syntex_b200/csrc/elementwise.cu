@@ -285,6 +285,15 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cin, int co
   if (wd) wd[(static_cast<long long>(8 - tap) * cin + ci) * cout + co] = v;
 }
 
+__global__ void pack_conv1_1_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [9][16][64]
+  if (i >= 9 * 16 * 64) return;
+  const int k = i & 63, c = (i >> 6) & 15, tap = i >> 10;
+  float v = 0.0f;
+  if (c < 3) v = w[((8 - tap) * 3 + c) * 64 + k];
+  out[i] = __float2bfloat16_rn(v);
+}
+
 __global__ void __launch_bounds__(256)
 sum_partials_kernel(const float* __restrict__ part, int count, int stride, float* __restrict__ out) {
   const int img = blockIdx.x;
@@ -380,6 +389,14 @@ int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf1
   STX_REQUIRE(w_hwio, "pack_weights: null weights");
   const long long total = 9LL * cin * cout;
   pack_weights_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_hwio, cin, cout, w_fwd, w_fwd_lo, w_dgrad);
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+int pack_conv1_1_dgrad_launch(const float* w27x64, bf16* out, cudaStream_t stream) {
+  STX_REQUIRE(w27x64 && out, "pack conv1_1 dgrad: null argument");
+  pack_conv1_1_dgrad_kernel<<<(9 * 16 * 64 + 255) / 256, 256, 0, stream>>>(w27x64, out);
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;

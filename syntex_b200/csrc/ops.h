@@ -16,6 +16,13 @@ struct ConvOp {
   int patch;         // 1 = halo-patch kernel (conv_patch.cu), 0 = per-tap kernel (conv_igemm.cu)
   int mt;            // patch kernel: 16x8 output tiles stacked per CTA (1 or 2)
   bf16* out_lo;
+  bf16* pool_out;            // fused 2x2 average pool outputs (patch kernel only)
+  bf16* pool_out_lo;
+  bf16* up_out;              // fused AvgPoolGrad + ReluGrad scatter (replaces `out`)
+  const bf16* up_mask;
+  float* rgb_out;            // conv1_1 input-gradient mode of the patch kernel (bn == 16)
+  const float* rgb_image;
+  int rgb_preimage;
   int nimg, H, W, cin, cout, taps, per_image_w;
   int bw_log2, bh_log2, tiles_w, tiles_h, tiles_n, n_step, bn;
   int relu;
@@ -85,6 +92,9 @@ int bf16pair_to_f32_launch(const bf16* hi, const bf16* lo, size_t n, float* out,
 int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf16* w_fwd_lo, bf16* w_dgrad,
                         cudaStream_t stream);
 // Sum loss partials: out[img] = sum_k part[img*stride + k], fixed order (deterministic).
+// conv1_1 weights fp32 [27][64] -> dgrad pack for the tensor-core path: [9][16][64] bf16, rows 0..2 = colours
+// (taps rotated 180 degrees), rows 3..15 zero.
+int pack_conv1_1_dgrad_launch(const float* w27x64, bf16* out, cudaStream_t stream);
 int sum_partials_launch(const float* part, int nimg, int count, int stride, float* out, cudaStream_t stream);
 
 }  // namespace stx

@@ -16,6 +16,7 @@ const LayerSpec& layer_spec(int layer) { return kLayers[layer]; }
 // ------------------------------------------------------------------------------------------------ weights
 Vgg::~Vgg() {
   cudaFree(w0);
+  cudaFree(wd0);
   for (int i = 0; i < kNumConvs; ++i) {
     cudaFree(bias[i]);
     cudaFree(wf[i]);
@@ -49,6 +50,8 @@ int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_
     if (ci == 0) {
       chk(cudaMalloc(&v->w0, wn * sizeof(float)), "cudaMalloc w0");
       if (rc == STX_OK) chk(cudaMemcpyAsync(v->w0, w[ci], wn * sizeof(float), cudaMemcpyHostToDevice, stream), "copy w0");
+      chk(cudaMalloc(&v->wd0, 9 * 16 * 64 * sizeof(bf16)), "cudaMalloc wd0");
+      if (rc == STX_OK) rc = pack_conv1_1_dgrad_launch(v->w0, v->wd0, stream);
     } else {
       float* tmp = nullptr;
       chk(cudaMalloc(&tmp, wn * sizeof(float)), "cudaMalloc staging");
@@ -264,6 +267,11 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     op.relu = 1;
     op.out = p->act[l];
     op.out_lo = p->act_lo[l];
+    if (rc == STX_OK && op.patch && l + 1 <= topmost && !kLayers[l + 1].is_conv) {
+      op.pool_out = p->act[l + 1];            // 2x2 average pool fused into this convolution's epilogue
+      op.pool_out_lo = p->act_lo[l + 1];
+      p->pool_fused[l + 1] = true;
+    }
   }
   // Loss-layer ops.
   std::vector<float> coef4;
@@ -315,6 +323,10 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       BwdStep st;
       st.kind = BwdStep::kConv1Bwd;
       st.in = p->gbuf[cur];
+      // tensor-core input gradient (N tile 16) when the halo-patch kernel covers the shape, CUDA cores otherwise
+      const int prc = conv_patch_prepare(&st.conv, p->gbuf[cur], B, H, W, 64, vgg->wd0, 16, 0, 0, 0);
+      if (prc == STX_OK) st.kind = BwdStep::kConv1BwdTensor;
+      else if (prc != STX_ERR_UNSUPPORTED) rc = prc;
       p->bwd.push_back(st);
     } else if (s.is_conv) {
       BwdStep st;
@@ -324,6 +336,14 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       st.conv.out = p->gbuf[cur ^ 1];
       st.conv.mask = (kLayers[l - 1].is_conv && loss_index(l - 1) < 0) ? p->act[l - 1] : nullptr;
       p->bwd.push_back(st);
+      cur ^= 1;
+    } else if (loss_index(l - 1) < 0 && !p->bwd.empty() &&
+               (p->bwd.back().kind == BwdStep::kGramGrad || p->bwd.back().kind == BwdStep::kDgrad)) {
+      // AvgPoolGrad + ReluGrad fused into the epilogue of the launch that completes dL/d(pool output): it scatters
+      // 0.25 * g to the four fine pixels, masked by the activations of the convolution that fed the pool.
+      ConvOp& prod = p->bwd.back().conv;
+      prod.up_out = p->gbuf[cur ^ 1];
+      prod.up_mask = p->act[l - 1];
       cur ^= 1;
     } else {
       BwdStep st;
@@ -352,7 +372,7 @@ int Plan::forward(const float* image, int is_preimage, int with_grams, bool with
   for (int l = 1; l <= topmost; ++l) {
     if (kLayers[l].is_conv) {
       STX_LAUNCH(kClsConvFwd, conv_launch(fwd[l], stream));
-    } else {
+    } else if (!pool_fused[l]) {
       STX_LAUNCH(kClsPool, avgpool2_fwd_launch(act[l - 1], act_lo[l - 1], B, lh[l - 1], lw[l - 1], lc[l - 1], act[l], act_lo[l], stream));
     }
   }
@@ -388,6 +408,14 @@ int Plan::backward(const float* image, int is_preimage, float* grad, cudaStream_
       case BwdStep::kConv1Bwd:
         STX_LAUNCH(kClsConv1, conv1_1_bwd_launch(st.in, image, B, H, W, is_preimage, vgg->w0, grad, stream));
         break;
+      case BwdStep::kConv1BwdTensor: {
+        ConvOp op = st.conv;
+        op.rgb_out = grad;
+        op.rgb_image = image;
+        op.rgb_preimage = is_preimage;
+        STX_LAUNCH(kClsConv1, conv_launch(op, stream));
+        break;
+      }
     }
   }
   return STX_OK;
@@ -398,7 +426,7 @@ int Plan::step(const float* x, int is_preimage, float* func, float* grad, float*
   STX_REQUIRE(x && grad, "step: null x or grad");
   if (loss.empty()) return fail(STX_ERR_STATE, "step: the plan has no loss layers");
   if (!have_target) return fail(STX_ERR_STATE, "step: no target Grams set (call compute_gram(update=True) first)");
-  if (bwd.empty() || bwd.back().kind != BwdStep::kConv1Bwd)
+  if (bwd.empty() || (bwd.back().kind != BwdStep::kConv1Bwd && bwd.back().kind != BwdStep::kConv1BwdTensor))
     return fail(STX_ERR_STATE, "step: backward program incomplete");
   STX_TRY(forward(x, is_preimage, 1, true, stream));
   loss_reduce_kernel<<<B, 128, 0, stream>>>(loss_part, part_total, d_part_offsets, static_cast<int>(loss.size()),

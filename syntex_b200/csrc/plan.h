@@ -22,6 +22,7 @@ struct Vgg {
   int num_convs = 0;
   float mean[3] = {0, 0, 0};
   float* w0 = nullptr;            // conv1_1 weights fp32 [27][64]
+  bf16* wd0 = nullptr;            // conv1_1 dgrad pack [9][16][64] (tensor-core input-gradient path)
   float* bias[kNumConvs] = {};    // fp32 [cout]
   bf16* wf[kNumConvs] = {};       // forward pack [9][cout][cin] (conv index >= 1), high halves
   bf16* wf_lo[kNumConvs] = {};    // low halves bf16(w - bf16(w)) for the bf16x3 forward
@@ -32,7 +33,7 @@ int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_
                cudaStream_t stream);
 
 struct BwdStep {
-  enum Kind { kGramGrad, kPoolBwd, kDgrad, kConv1Bwd } kind;
+  enum Kind { kGramGrad, kPoolBwd, kDgrad, kConv1Bwd, kConv1BwdTensor } kind;
   ConvOp conv;             // kGramGrad, kDgrad
   const bf16* in = nullptr;
   const bf16* act = nullptr;
@@ -75,6 +76,7 @@ struct Plan {
   bf16* act[kNumLayers] = {};      // recorded layers (high halves; the only halves in plain mode)
   bf16* act_lo[kNumLayers] = {};   // low halves (split mode)
   ConvOp fwd[kNumLayers];
+  bool pool_fused[kNumLayers] = {};   // pooling layer computed in the epilogue of the convolution that feeds it
   std::vector<LossLayer> loss;
   std::vector<BwdStep> bwd;
   bf16* gbuf[2] = {nullptr, nullptr};
