@@ -151,36 +151,39 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
 }
 
 constexpr int kFinishThreads = 256;
-constexpr int kFinishLanes = 8;                                   // threads cooperating on one Gram element
-constexpr int kFinishElems = kFinishThreads / kFinishLanes;       // elements per block
+constexpr int kFinishElems = 32;                                  // Gram elements per block (one per lane)
+constexpr int kFinishWarps = kFinishThreads / 32;                 // slab subsets summed in parallel
 
-// One Gram element per group of 8 consecutive lanes: lane q sums slabs q, q+8, ... (coalesced across elements is
-// traded for 8x shorter serial chains; the slab count reaches ~300 for the conv1_1 level at batch 1), then a fixed
-// xor-shuffle tree combines the 8 partial sums. Deterministic.
+// 32 consecutive Gram elements per block. Warp w sums slabs w, w+8, ... for those elements (each slab read is one
+// coalesced 128-byte line), then the 8 partial sums are combined through shared memory in a fixed order. The slab
+// count reaches ~300 for the conv1_1 level at batch 1, so the serial chain per thread is <= 37. Deterministic.
 __global__ void __launch_bounds__(kFinishThreads)
 gram_finish_kernel(const float* __restrict__ partial, int C, int splits, float norm, float* __restrict__ G_out,
                    const float* __restrict__ target, long long target_stride, float dscale,
                    bf16* __restrict__ dscaled, float loss_scale, float* __restrict__ loss_part, int part_stride) {
+  __shared__ float red[kFinishWarps][32];
   const int img = blockIdx.y;
-  const int q = threadIdx.x & (kFinishLanes - 1);
-  const int e = blockIdx.x * kFinishElems + (threadIdx.x >> 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * kFinishElems + lane;
   const int CC = C * C;
-  float sq = 0.0f;
   float s = 0.0f;
-  int i = 0, j = 0;
   if (e < CC) {
-    i = e / C;
-    j = e % C;
+    const int i = e / C, j = e % C;
     // Only 128x128 tiles with tile(i) <= tile(j) were written; take the mirrored element otherwise.
     const int si = ((i >> 7) <= (j >> 7)) ? i : j;
     const int sj = ((i >> 7) <= (j >> 7)) ? j : i;
     const float* src = partial + static_cast<size_t>(img) * splits * CC + static_cast<size_t>(si) * C + sj;
-    for (int k = q; k < splits; k += kFinishLanes) s += src[static_cast<size_t>(k) * CC];
+    for (int k = warp; k < splits; k += kFinishWarps) s += src[static_cast<size_t>(k) * CC];
   }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp != 0) return;
+  float sq = 0.0f;
+  if (e < CC) {
+    float t = 0.0f;
 #pragma unroll
-  for (int o = 1; o < kFinishLanes; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (e < CC && q == 0) {
-    const float g = s / norm;
+    for (int w = 0; w < kFinishWarps; ++w) t += red[w][lane];
+    const float g = t / norm;
     if (G_out) G_out[static_cast<size_t>(img) * CC + e] = g;
     if (target) {
       const float d = g - target[static_cast<size_t>(img) * target_stride + e];
@@ -189,18 +192,9 @@ gram_finish_kernel(const float* __restrict__ partial, int C, int splits, float n
     }
   }
   if (loss_part) {
-    // fixed-shape block reduction (deterministic)
-    __shared__ float red[kFinishThreads / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float v = (threadIdx.x < kFinishThreads / 32) ? red[threadIdx.x] : 0.0f;
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (threadIdx.x == 0) loss_part[static_cast<size_t>(img) * part_stride + blockIdx.x] = v;
-    }
+    if (lane == 0) loss_part[static_cast<size_t>(img) * part_stride + blockIdx.x] = sq;
   }
 }
 
