@@ -151,50 +151,62 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
 }
 
 constexpr int kFinishThreads = 256;
-constexpr int kFinishElems = 32;                                  // Gram elements per block (one per lane)
-constexpr int kFinishWarps = kFinishThreads / 32;                 // slab subsets summed in parallel
+constexpr int kFinishElems = 256;                                 // Gram elements per block
+constexpr int kFinishWarps = kFinishThreads / 32;
 
-// 32 consecutive Gram elements per block. Warp w sums slabs w, w+8, ... for those elements (each slab read is one
-// coalesced 128-byte line), then the 8 partial sums are combined through shared memory in a fixed order. The slab
-// count reaches ~300 for the conv1_1 level at batch 1, so the serial chain per thread is <= 37. Deterministic.
+// 256 consecutive Gram elements per block, 32 per pass: `kw` warps (1, 2, 4 or 8, chosen from the slab count) share
+// the slabs of one 32-element group (warp w takes slabs w, w+kw, ...: every read is one coalesced 128-byte line) and
+// the 8/kw groups of a pass run side by side; partial sums meet in shared memory in a fixed order. The slab count
+// ranges from 4 (pool4, batch 8) to ~300 (conv1_1, batch 1). Deterministic.
 __global__ void __launch_bounds__(kFinishThreads)
-gram_finish_kernel(const float* __restrict__ partial, int C, int splits, float norm, float* __restrict__ G_out,
-                   const float* __restrict__ target, long long target_stride, float dscale,
+gram_finish_kernel(const float* __restrict__ partial, int C, int splits, int kw, float norm,
+                   float* __restrict__ G_out, const float* __restrict__ target, long long target_stride, float dscale,
                    bf16* __restrict__ dscaled, float loss_scale, float* __restrict__ loss_part, int part_stride) {
   __shared__ float red[kFinishWarps][32];
+  __shared__ float sq_warp[kFinishWarps];
   const int img = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * kFinishElems + lane;
+  const int groups = kFinishWarps / kw;        // 32-element groups handled per pass
+  const int grp = warp / kw, sub = warp % kw;  // this warp's group and slab subset
   const int CC = C * C;
-  float s = 0.0f;
-  if (e < CC) {
-    const int i = e / C, j = e % C;
-    // Only 128x128 tiles with tile(i) <= tile(j) were written; take the mirrored element otherwise.
-    const int si = ((i >> 7) <= (j >> 7)) ? i : j;
-    const int sj = ((i >> 7) <= (j >> 7)) ? j : i;
-    const float* src = partial + static_cast<size_t>(img) * splits * CC + static_cast<size_t>(si) * C + sj;
-    for (int k = warp; k < splits; k += kFinishWarps) s += src[static_cast<size_t>(k) * CC];
-  }
-  red[warp][lane] = s;
-  __syncthreads();
-  if (warp != 0) return;
   float sq = 0.0f;
-  if (e < CC) {
-    float t = 0.0f;
-#pragma unroll
-    for (int w = 0; w < kFinishWarps; ++w) t += red[w][lane];
-    const float g = t / norm;
-    if (G_out) G_out[static_cast<size_t>(img) * CC + e] = g;
-    if (target) {
-      const float d = g - target[static_cast<size_t>(img) * target_stride + e];
-      if (dscaled) dscaled[static_cast<size_t>(img) * CC + e] = __float2bfloat16_rn(d * dscale);
-      sq = d * d * loss_scale;
+  for (int pass = 0; pass < kFinishElems / 32; pass += groups) {
+    const int e = blockIdx.x * kFinishElems + (pass + grp) * 32 + lane;
+    float s = 0.0f;
+    if (e < CC) {
+      const int i = e / C, j = e % C;
+      // Only 128x128 tiles with tile(i) <= tile(j) were written; take the mirrored element otherwise.
+      const int si = ((i >> 7) <= (j >> 7)) ? i : j;
+      const int sj = ((i >> 7) <= (j >> 7)) ? j : i;
+      const float* src = partial + static_cast<size_t>(img) * splits * CC + static_cast<size_t>(si) * C + sj;
+      for (int k = sub; k < splits; k += kw) s += src[static_cast<size_t>(k) * CC];
     }
+    red[warp][lane] = s;
+    __syncthreads();
+    if (sub == 0 && e < CC) {
+      float t = 0.0f;
+      for (int w = 0; w < kw; ++w) t += red[warp + w][lane];
+      const float g = t / norm;
+      if (G_out) G_out[static_cast<size_t>(img) * CC + e] = g;
+      if (target) {
+        const float d = g - target[static_cast<size_t>(img) * target_stride + e];
+        if (dscaled) dscaled[static_cast<size_t>(img) * CC + e] = __float2bfloat16_rn(d * dscale);
+        sq += d * d * loss_scale;
+      }
+    }
+    __syncthreads();
   }
   if (loss_part) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if (lane == 0) loss_part[static_cast<size_t>(img) * part_stride + blockIdx.x] = sq;
+    if (lane == 0) sq_warp[warp] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kFinishWarps; ++w) t += sq_warp[w];
+      loss_part[static_cast<size_t>(img) * part_stride + blockIdx.x] = t;
+    }
   }
 }
 
@@ -270,7 +282,9 @@ int gram_finish_launch(const GramOp& op, float eps, float* G_out, const float* t
   // fp32 arithmetic as in the reference: normalizer = float32(HW) + float32(eps)  (utils.py:15, :20)
   const float norm = static_cast<float>(op.HW) + eps;
   dim3 grid(gram_finish_blocks(op.C), op.nimg);
-  gram_finish_kernel<<<grid, kFinishThreads, 0, stream>>>(op.partial, op.C, op.splits, norm, G_out, target,
+  int kw = 1;
+  while (kw < kFinishWarps && op.splits > 8 * kw) kw *= 2;      // keep the serial chain per thread <= ~8..37 slabs
+  gram_finish_kernel<<<grid, kFinishThreads, 0, stream>>>(op.partial, op.C, op.splits, kw, norm, G_out, target,
                                                           target_stride, dscale, dscaled, loss_scale, loss_part, part_stride);
   STX_CUDA(cudaGetLastError());
   count_launch();

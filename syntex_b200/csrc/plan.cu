@@ -93,6 +93,10 @@ Timeline::~Timeline() {
 Plan::~Plan() {
   cudaFree(arena);
   if (pinned) cudaFreeHost(pinned);
+  if (side) cudaStreamDestroy(side);
+  for (cudaEvent_t e : ev_fork)
+    if (e) cudaEventDestroy(e);
+  if (ev_join) cudaEventDestroy(ev_join);
 }
 
 // Launch `call`, bracketing it with events when a timeline is attached.
@@ -246,6 +250,9 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     return cuda_fail(e, "cudaMalloc(plan arena)");
   }
   e = cudaMemset(p->arena, 0, p->arena_bytes);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+  for (int l = 0; l < kNumLayers && e == cudaSuccess; ++l) e = cudaEventCreateWithFlags(&p->ev_fork[l], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMallocHost(&p->pinned, (2 * p->image_elems() + B) * sizeof(float));
   if (e != cudaSuccess) {
     delete p;
@@ -368,28 +375,47 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
 
 int Plan::forward(const float* image, int is_preimage, int with_grams, bool with_loss, cudaStream_t stream) {
   STX_REQUIRE(image, "forward: null image");
+  const bool grams = with_grams || with_loss;
+  bool forked = false;
+  // Gram + finish of loss layer `l`, on the side stream, as soon as act[l] exists.
+  auto launch_gram = [&](int l) -> int {
+    for (LossLayer& ll : loss) {
+      if (ll.layer != l) continue;
+      STX_CUDA(cudaEventRecord(ev_fork[l], stream));
+      STX_CUDA(cudaStreamWaitEvent(side, ev_fork[l], 0));
+      forked = true;
+      cudaStream_t main_stream = stream;
+      {
+        cudaStream_t stream = side;   // STX_LAUNCH records/launches on `stream`
+        (void)main_stream;
+        STX_LAUNCH(kClsGram, gram_launch(ll.gram, stream));
+        // dL/dF = F * (G - T) * coef / (C^2 * n):  loss_overall = sum coef/4 * mean((G-T)^2), G = F^T F / n
+        const float norm = static_cast<float>(ll.HW) + 1e-6f;
+        const float dscale = ll.coef / (static_cast<float>(ll.C) * static_cast<float>(ll.C) * norm);
+        const float lscale = 1.0f / (static_cast<float>(ll.C) * static_cast<float>(ll.C));
+        STX_LAUNCH(kClsGramFinish,
+                   gram_finish_launch(ll.gram, 1e-6f, ll.G, with_loss ? ll.target : nullptr, ll.target_stride, dscale,
+                                      with_loss ? ll.dscaled : nullptr, lscale,
+                                      with_loss ? loss_part + ll.part_offset : nullptr, part_total, stream));
+      }
+    }
+    return STX_OK;
+  };
   STX_LAUNCH(kClsConv1, conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0], act_lo[0], stream));
+  if (grams) STX_TRY(launch_gram(0));
   for (int l = 1; l <= topmost; ++l) {
     if (kLayers[l].is_conv) {
       STX_LAUNCH(kClsConvFwd, conv_launch(fwd[l], stream));
     } else if (!pool_fused[l]) {
       STX_LAUNCH(kClsPool, avgpool2_fwd_launch(act[l - 1], act_lo[l - 1], B, lh[l - 1], lw[l - 1], lc[l - 1], act[l], act_lo[l], stream));
     }
+    if (grams) STX_TRY(launch_gram(l));
   }
-  if (with_grams || with_loss) {
-    for (LossLayer& ll : loss) {
-      STX_LAUNCH(kClsGram, gram_launch(ll.gram, stream));
-      // dL/dF = F * (G - T) * coef / (C^2 * n):  loss_overall = sum coef/4 * mean((G-T)^2), G = F^T F / n
-      const float norm = static_cast<float>(ll.HW) + 1e-6f;
-      const float dscale = ll.coef / (static_cast<float>(ll.C) * static_cast<float>(ll.C) * norm);
-      const float lscale = 1.0f / (static_cast<float>(ll.C) * static_cast<float>(ll.C));
-      STX_LAUNCH(kClsGramFinish,
-                 gram_finish_launch(ll.gram, 1e-6f, ll.G, with_loss ? ll.target : nullptr, ll.target_stride, dscale,
-                                    with_loss ? ll.dscaled : nullptr, lscale,
-                                    with_loss ? loss_part + ll.part_offset : nullptr, part_total, stream));
-    }
-    have_grams = true;
+  if (forked) {
+    STX_CUDA(cudaEventRecord(ev_join, side));
+    STX_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
   }
+  if (grams) have_grams = true;
   return STX_OK;
 }
 

@@ -86,6 +86,11 @@ struct Plan {
   float* d_coef = nullptr;         // [nloss] coef/4
   int* d_part_offsets = nullptr;   // [nloss+1]
   bool have_target = false, have_grams = false;
+  // Gram + finish launches run on a side stream, forked right after their layer is produced and joined before the
+  // loss reduction: they are bandwidth-bound and hide under the tensor-bound convolutions of the deeper layers.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork[kNumLayers] = {};
+  cudaEvent_t ev_join = nullptr;
   // staging for the *_host entry points
   float* x_dev = nullptr;
   float* grad_dev = nullptr;
