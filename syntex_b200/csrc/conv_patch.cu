@@ -9,11 +9,17 @@
 // shared-memory descriptors address any 128-byte row of a 128B-swizzled buffer (the swizzle is a function of the
 // absolute shared-memory address - verified on the B200 by csrc/probe.cu, profiles/r01_descriptor_probe_*), so
 // tap (r, s) is just "start address + (r*10 + s) * 128 B, stride between 8-row groups = 10 * 128 B".
-// MT = 2 stacks two 16x8 output tiles (two TMEM accumulators) on one weight stream, halving the weight traffic per
-// FLOP as well: 195-220 FLOP per L2 byte.
+// MT = 2 stacks two 16x8 output tiles (two TMEM accumulators) on one weight stream.
 //
-// Pipelines: patch ring (2 stages, one fill per channel chunk) and weight ring (one [BN x 64] tile per tap),
-// both TMA -> mbarrier -> tcgen05.mma -> tcgen05.commit. Warp roles as in conv_igemm.cu.
+// The kernel is PERSISTENT: one CTA per SM walks a static round-robin list of (tile, N-block) work items, so the
+// prologue (barrier init, TMEM allocation, descriptor prefetch) is paid once and the whole shared memory is one deep
+// TMA ring. The TMEM accumulator is double-buffered (when 2 * BN * MT <= 512 columns): eight epilogue warps drain
+// tile i (tcgen05.ld -> bias / ReLU / mask / pooling -> bf16 hi/lo stores) while the MMA warp already accumulates
+// tile i+1. This matters most for the 64-channel layers, whose 2.6 us of MMA work per tile used to sit between
+// ~4 us of per-CTA fixed cost (profiles/r01_ncu_full_conv_patch_b8.md).
+//
+// Rings (all TMA -> mbarrier -> tcgen05.mma -> tcgen05.commit): halo patches (one fill per 64-channel chunk),
+// weight tiles (one [BN x 64] tile per tap), accumulators (MMA -> epilogue -> MMA).
 #include "conv_common.cuh"
 #include "ops.h"
 
@@ -21,9 +27,16 @@ namespace stx {
 
 namespace {
 
-constexpr int kThreads = 192;
-constexpr int kPatchW = 10;                       // 8 output columns + 2 halo
-constexpr int kPatchStages = 2;
+constexpr int kEpilogueWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpilogueWarps;   // warp 0: TMA, warp 1: MMA (+TMEM alloc), warps 2..9: epilogue
+constexpr int kPatchW = 10;                          // 8 output columns + 2 halo
+constexpr int kSmemBudget = 224 * 1024;              // of the 227 KB a CTA may use
+
+constexpr int pow2_at_least(int v) {
+  int p = 32;
+  while (p < v) p *= 2;
+  return p;
+}
 
 template <int BN, int MT, bool SPLIT>
 struct PatchSmem {
@@ -31,41 +44,45 @@ struct PatchSmem {
   static constexpr int kPatchBytes = kPatchRows * 128;                        // TMA transaction bytes
   static constexpr int kPatchStride = (kPatchBytes + 1023) & ~1023;           // keep every buffer 1024-aligned
   static constexpr int kPatchStageBytes = (SPLIT ? 2 : 1) * kPatchStride;     // [hi | lo]
+  static constexpr int kPatchStages = (SPLIT || MT == 2) ? 2 : 3;
   static constexpr int kBBytes = (BN * 128 + 1023) & ~1023;
   static constexpr int kBStageBytes = (SPLIT ? 2 : 1) * kBBytes;              // [hi | lo]
-  static constexpr int kBStages = SPLIT ? 3 : (BN * MT >= 256 ? 4 : 3);
+  static constexpr int kBRoom = (kSmemBudget - 2048 - kPatchStages * kPatchStageBytes) / kBStageBytes;
+  static constexpr int kBStages = kBRoom > 10 ? 10 : kBRoom;
   static constexpr int kBOffset = kPatchStages * kPatchStageBytes;
   static constexpr int kBarrierOffset = kBOffset + kBStages * kBStageBytes;
-  static constexpr int kTotal = kBarrierOffset + 256 + 1024;
-  static constexpr int kTmemCols = BN * MT < 32 ? 32 : BN * MT;
+  static constexpr int kTotal = kBarrierOffset + 512 + 1024;
+  static constexpr int kAccStages = (2 * BN * MT <= 512) ? 2 : 1;             // TMEM accumulator buffers
+  static constexpr int kAccCols = BN * MT;
+  static constexpr int kTmemCols = pow2_at_least(kAccStages * kAccCols);
+  static_assert(kBStages >= 3, "weight ring too shallow");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget exceeded");
+};
+
+struct PatchSched {
+  int total_items;   // tiles * N-blocks
+  int nblocks;       // cout / BN
 };
 
 template <int BN, int MT, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                  const ConvKernelParams p) {
+                  const ConvKernelParams p, const PatchSched sched) {
   using L = PatchSmem<BN, MT, SPLIT>;
-  constexpr int kBStages = L::kBStages;
+  constexpr int kPS = L::kPatchStages, kBS = L::kBStages, kAS = L::kAccStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
-  uint64_t* pempty = pfull + kPatchStages;
-  uint64_t* bfull = pempty + kPatchStages;
-  uint64_t* bempty = bfull + kBStages;
-  uint64_t* accum_bar = bempty + kBStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* pempty = pfull + kPS;
+  uint64_t* bfull = pempty + kPS;
+  uint64_t* bempty = bfull + kBS;
+  uint64_t* afull = bempty + kBS;
+  uint64_t* aempty = afull + kAS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + kAS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int tile = blockIdx.x;
-  const int tw = tile % p.tiles_w;
-  const int th = (tile / p.tiles_w) % p.tiles_h;
-  const int n = tile / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * 8;
-  const int h0 = th * (16 * MT);
-  const int nblk = blockIdx.y;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -74,45 +91,54 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tma_prefetch_desc(&tmA2);
       tma_prefetch_desc(&tmB2);
     }
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kPatchStages; ++s) {
+    for (int s = 0; s < kPS; ++s) {
       mbar_init(&pfull[s], 1);
       mbar_init(&pempty[s], 1);
     }
-    for (int s = 0; s < kBStages; ++s) {
+    for (int s = 0; s < kBS; ++s) {
       mbar_init(&bfull[s], 1);
       mbar_init(&bempty[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < kAS; ++s) {
+      mbar_init(&afull[s], 1);
+      mbar_init(&aempty[s], kEpilogueWarps);
+    }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, L::kTmemCols);
+  if (warp == 1) tmem_alloc(tmem_slot, L::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int chunks = p.cchunks;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int bit = 0;   // weight-tile counter
-      for (int c = 0; c < chunks; ++c) {
-        const int ps = c % kPatchStages;
-        mbar_wait(&pempty[ps], ((c / kPatchStages) & 1) ^ 1, 100 + ps);
-        uint8_t* pdst = smem + ps * L::kPatchStageBytes;
-        mbar_arrive_expect_tx(&pfull[ps], (SPLIT ? 2 : 1) * L::kPatchBytes);
-        tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
-        if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
-        for (int tap = 0; tap < 9; ++tap, ++bit) {
-          const int bs = bit % kBStages;
-          mbar_wait(&bempty[bs], ((bit / kBStages) & 1) ^ 1, 110 + bs);
-          uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
-          mbar_arrive_expect_tx(&bfull[bs], (SPLIT ? 2 : 1) * BN * 128);
-          tma_load_3d(bdst, &tmB, &bfull[bs], c * 64, nblk * BN, tap);
-          if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
+      int pit = 0, bit = 0;   // ring counters, running across work items
+      for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x) {
+        const int nblk = item % sched.nblocks;
+        const int tm = item / sched.nblocks;
+        const int w0 = (tm % p.tiles_w) * 8;
+        const int h0 = ((tm / p.tiles_w) % p.tiles_h) * (16 * MT);
+        const int n = tm / tiles_per_img;
+        for (int c = 0; c < chunks; ++c, ++pit) {
+          const int ps = pit % kPS;
+          mbar_wait(&pempty[ps], ((pit / kPS) & 1) ^ 1, 100 + ps);
+          uint8_t* pdst = smem + ps * L::kPatchStageBytes;
+          mbar_arrive_expect_tx(&pfull[ps], (SPLIT ? 2 : 1) * L::kPatchBytes);
+          tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
+          if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
+          for (int tap = 0; tap < 9; ++tap, ++bit) {
+            const int bs = bit % kBS;
+            mbar_wait(&bempty[bs], ((bit / kBS) & 1) ^ 1, 120 + bs);
+            uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
+            mbar_arrive_expect_tx(&bfull[bs], (SPLIT ? 2 : 1) * BN * 128);
+            tma_load_3d(bdst, &tmB, &bfull[bs], c * 64, nblk * BN, tap);
+            if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
+          }
         }
       }
     }
@@ -122,97 +148,136 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t kGroupStride = kPatchW * 128;     // bytes between consecutive 8-pixel row groups
-      int bit = 0;
-      for (int c = 0; c < chunks; ++c) {
-        const int ps = c % kPatchStages;
-        mbar_wait(&pfull[ps], (c / kPatchStages) & 1, 200 + ps);
-        const uint32_t patch = smem_u32(smem + ps * L::kPatchStageBytes);
-        for (int tap = 0; tap < 9; ++tap, ++bit) {
-          const int bs = bit % kBStages;
-          mbar_wait(&bfull[bs], (bit / kBStages) & 1, 210 + bs);
-          tc_fence_after();
-          const uint32_t b_addr = smem_u32(smem + L::kBOffset + bs * L::kBStageBytes);
-          const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
-          const uint64_t bdesc_lo = make_smem_desc_sw128(b_addr + L::kBBytes, 16, 1024);
-          const uint32_t tap_off = ((tap / 3) * kPatchW + (tap % 3)) * 128;
+      int pit = 0, bit = 0, ait = 0;
+      for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x, ++ait) {
+        const int as = ait % kAS;
+        mbar_wait(&aempty[as], ((ait / kAS) & 1) ^ 1, 300 + as);    // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + as * L::kAccCols;
+        for (int c = 0; c < chunks; ++c, ++pit) {
+          const int ps = pit % kPS;
+          mbar_wait(&pfull[ps], (pit / kPS) & 1, 200 + ps);
+          const uint32_t patch = smem_u32(smem + ps * L::kPatchStageBytes);
+          for (int tap = 0; tap < 9; ++tap, ++bit) {
+            const int bs = bit % kBS;
+            mbar_wait(&bfull[bs], (bit / kBS) & 1, 220 + bs);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(smem + L::kBOffset + bs * L::kBStageBytes);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
+            const uint64_t bdesc_lo = make_smem_desc_sw128(b_addr + L::kBBytes, 16, 1024);
+            const uint32_t tap_off = ((tap / 3) * kPatchW + (tap % 3)) * 128;
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t a_addr = patch + tap_off + mt * 16 * kGroupStride;
-            const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, kGroupStride);
-            const uint64_t adesc_lo = make_smem_desc_sw128(a_addr + L::kPatchStride, 16, kGroupStride);
-            const uint32_t d = tmem_base + mt * BN;
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t a_addr = patch + tap_off + mt * 16 * kGroupStride;
+              const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, kGroupStride);
+              const uint64_t adesc_lo = make_smem_desc_sw128(a_addr + L::kPatchStride, 16, kGroupStride);
+              const uint32_t d = acc + mt * BN;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t first = (c | tap | k) != 0;
-              if (SPLIT) {
-                umma_bf16(d, adesc_lo + 2 * k, bdesc + 2 * k, idesc, first);   // A_lo * W_hi
-                umma_bf16(d, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1);       // A_hi * W_lo
-                umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);          // A_hi * W_hi
-              } else {
-                umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, first);
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t accumulate = (c | tap | k) != 0;
+                if (SPLIT) {
+                  umma_bf16(d, adesc_lo + 2 * k, bdesc + 2 * k, idesc, accumulate);   // A_lo * W_hi
+                  umma_bf16(d, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1);            // A_hi * W_lo
+                  umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);               // A_hi * W_hi
+                } else {
+                  umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                }
               }
             }
+            umma_commit(&bempty[bs]);
           }
-          umma_commit(&bempty[bs]);
+          umma_commit(&pempty[ps]);
         }
-        umma_commit(&pempty[ps]);
+        umma_commit(&afull[as]);
       }
-      umma_commit(accum_bar);
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;         // which half of the 32-column chunks this warp drains
     const int r = q * 32 + lane;
     const int ww = r & 7;
-    const int w = w0 + ww;
-    mbar_wait(accum_bar, 0, 300);
-    tc_fence_after();
-    if (BN == 16) {
-      // conv1_1 input gradient: both stacked tiles sit in one 32-column TMEM slab (16 columns each, 3 real).
-      float v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), v);
-      tmem_ld_wait();
+    int ait = 0;
+    for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x, ++ait) {
+      const int nblk = item % sched.nblocks;
+      const int tm = item / sched.nblocks;
+      const int w = (tm % p.tiles_w) * 8 + ww;
+      const int h0 = ((tm / p.tiles_w) % p.tiles_h) * (16 * MT);
+      const int n = tm / tiles_per_img;
+      const int as = ait % kAS;
+      const uint32_t acc = tmem_base + as * L::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+      mbar_wait(&afull[as], (ait / kAS) & 1, 400 + as);
+      tc_fence_after();
+      if (BN == 16) {
+        // conv1_1 input gradient: both stacked tiles sit in one 32-column slab (16 columns each, 3 real).
+        float v[32];
+        if (half == 0) {
+          tmem_ld_32x32(acc, v);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aempty[as]);
+        if (half == 0) {
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        const int h = h0 + mt * 16 + (r >> 3);
-        if (h < p.H && w < p.W) {
-          const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+          for (int mt = 0; mt < MT; ++mt) {
+            const int h = h0 + mt * 16 + (r >> 3);
+            if (h < p.H && w < p.W) {
+              const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float d = v[mt * 16 + c] * 255.0f;
-            if (p.rgb_preimage) {
-              const float sg = 1.0f / (1.0f + __expf(-p.rgb_image[pix * 3 + c]));
-              d *= sg * (1.0f - sg);
+              for (int c = 0; c < 3; ++c) {
+                float d = v[mt * 16 + c] * 255.0f;
+                if (p.rgb_preimage) {
+                  const float sg = 1.0f / (1.0f + __expf(-p.rgb_image[pix * 3 + c]));
+                  d *= sg * (1.0f - sg);
+                }
+                p.rgb_out[pix * 3 + c] = d;
+              }
             }
-            p.rgb_out[pix * 3 + c] = d;
           }
         }
-      }
-    } else
+      } else {
+        constexpr int kChunksPerTile = BN / 32;
+        constexpr int kChunks = MT * kChunksPerTile;
+        constexpr int kStep = kChunks >= 2 ? 2 : 1;
+        const int first = kChunks >= 2 ? half : 0;
+        const int last = first + ((kChunks - 1 - first) / kStep) * kStep;   // last chunk this warp handles
+        bool released = false;
+        if (kChunks < 2 && half == 1) {       // nothing to drain for this warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&aempty[as]);
+          released = true;
+        }
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      const int h = h0 + mt * 16 + (r >> 3);
-      const bool valid = (h < p.H) && (w < p.W);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BN + c0, v);
-        tmem_ld_wait();
-        conv_epilogue_store<SPLIT>(p, v, valid, n, h, w, nblk * BN + c0);
+        for (int j = first; j < kChunks && !released; j += kStep) {
+          const int mt = j / kChunksPerTile;
+          const int c0 = (j % kChunksPerTile) * 32;
+          const int h = h0 + mt * 16 + (r >> 3);
+          const bool valid = (h < p.H) && (w < p.W);
+          float v[32];
+          tmem_ld_32x32(acc + mt * BN + c0, v);
+          tmem_ld_wait();
+          if (j == last) {                    // accumulator fully read by this warp: hand it back before storing
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&aempty[as]);
+          }
+          conv_epilogue_store<SPLIT>(p, v, valid, n, h, w, nblk * BN + c0);
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, L::kTmemCols);
+  if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
 }
 
 template <int BN, int MT, bool SPLIT>
 int launch_patch(const ConvOp& op, cudaStream_t stream) {
   using L = PatchSmem<BN, MT, SPLIT>;
-  static_assert(L::kTotal <= 227 * 1024, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
     STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -245,9 +310,18 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.pool_out_lo = op.pool_out_lo;
   p.up_out = op.up_out;
   p.up_mask = op.up_mask;
-  dim3 grid(op.tiles_w * op.tiles_h * op.nimg, op.cout / BN, 1);
+  PatchSched sched;
+  sched.nblocks = op.cout / BN;
+  sched.total_items = op.tiles_w * op.tiles_h * op.nimg * sched.nblocks;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    STX_CUDA(cudaGetDevice(&dev));
+    STX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = sched.total_items < num_sms ? sched.total_items : num_sms;   // persistent: one CTA per SM
   conv_patch_kernel<BN, MT, SPLIT><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
-                                                                           SPLIT ? op.tmB2 : op.tmB, p);
+                                                                           SPLIT ? op.tmB2 : op.tmB, p, sched);
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;
