@@ -38,25 +38,26 @@ constexpr int pow2_at_least(int v) {
   return p;
 }
 
-template <int BN, int MT, bool SPLIT>
+template <int BN, int MT, bool SPLIT, int OCC>
 struct PatchSmem {
   static constexpr int kPatchRows = (16 * MT + 2) * kPatchW;
   static constexpr int kPatchBytes = kPatchRows * 128;                        // TMA transaction bytes
   static constexpr int kPatchStride = (kPatchBytes + 1023) & ~1023;           // keep every buffer 1024-aligned
   static constexpr int kPatchStageBytes = (SPLIT ? 2 : 1) * kPatchStride;     // [hi | lo]
-  static constexpr int kPatchStages = (SPLIT || MT == 2) ? 2 : 3;
+  static constexpr int kPatchStages = (SPLIT || MT == 2 || OCC == 2) ? 2 : 3;
   static constexpr int kBBytes = (BN * 128 + 1023) & ~1023;
   static constexpr int kBStageBytes = (SPLIT ? 2 : 1) * kBBytes;              // [hi | lo]
-  static constexpr int kBRoom = (kSmemBudget - 2048 - kPatchStages * kPatchStageBytes) / kBStageBytes;
+  static constexpr int kBRoom = (kSmemBudget / OCC - 2048 - kPatchStages * kPatchStageBytes) / kBStageBytes;
   static constexpr int kBStages = kBRoom > 10 ? 10 : kBRoom;
   static constexpr int kBOffset = kPatchStages * kPatchStageBytes;
   static constexpr int kBarrierOffset = kBOffset + kBStages * kBStageBytes;
   static constexpr int kTotal = kBarrierOffset + 512 + 1024;
-  static constexpr int kAccStages = (2 * BN * MT <= 512) ? 2 : 1;             // TMEM accumulator buffers
+  static constexpr int kAccStages = (2 * BN * MT * OCC <= 512) ? 2 : 1;       // TMEM accumulator buffers
   static constexpr int kAccCols = BN * MT;
   static constexpr int kTmemCols = pow2_at_least(kAccStages * kAccCols);
   static_assert(kBStages >= 3, "weight ring too shallow");
-  static_assert(kTotal <= 227 * 1024, "shared memory budget exceeded");
+  static_assert(kTotal * OCC <= 227 * 1024, "shared memory budget exceeded");
+  static_assert(OCC * pow2_at_least(kAccStages * BN * MT) <= 512, "TMEM budget exceeded");
 };
 
 struct PatchSched {
@@ -64,12 +65,12 @@ struct PatchSched {
   int nblocks;       // cout / BN
 };
 
-template <int BN, int MT, bool SPLIT>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int MT, bool SPLIT, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                   const ConvKernelParams p, const PatchSched sched) {
-  using L = PatchSmem<BN, MT, SPLIT>;
+  using L = PatchSmem<BN, MT, SPLIT, OCC>;
   constexpr int kPS = L::kPatchStages, kBS = L::kBStages, kAS = L::kAccStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -275,12 +276,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
 }
 
-template <int BN, int MT, bool SPLIT>
+template <int BN, int MT, bool SPLIT, int OCC>
 int launch_patch(const ConvOp& op, cudaStream_t stream) {
-  using L = PatchSmem<BN, MT, SPLIT>;
+  using L = PatchSmem<BN, MT, SPLIT, OCC>;
   static bool attr_set = false;
   if (!attr_set) {
-    STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   L::kTotal));
     attr_set = true;
   }
@@ -319,8 +320,9 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
     STX_CUDA(cudaGetDevice(&dev));
     STX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = sched.total_items < num_sms ? sched.total_items : num_sms;   // persistent: one CTA per SM
-  conv_patch_kernel<BN, MT, SPLIT><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
+  const int slots = num_sms * OCC;                                              // persistent: OCC CTAs per SM
+  const int grid = sched.total_items < slots ? sched.total_items : slots;
+  conv_patch_kernel<BN, MT, SPLIT, OCC><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
                                                                            SPLIT ? op.tmB2 : op.tmB, p, sched);
   STX_CUDA(cudaGetLastError());
   count_launch();
@@ -332,7 +334,7 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
 // Geometry + tensor maps of the patch variant. Returns STX_ERR_UNSUPPORTED (without touching op) when the shape
 // does not qualify (needs W >= 8: an 8-pixel row group must be contiguous in the patch).
 int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
-                       int split, int force_bn, int force_mt) {
+                       int split, int force_bn, int force_mt, int force_occ) {
   STX_REQUIRE(x && wpacked, "conv: null operand");
   STX_REQUIRE(cin % 64 == 0 && (cout % 64 == 0 || cout == 16), "conv: channels must be multiples of 64");
   if (W < 8) return STX_ERR_UNSUPPORTED;
@@ -371,6 +373,7 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   }
   op->bn = bn;
   op->mt = mt;
+  op->occ = force_occ == 2 ? 2 : 1;
   op->tiles_w = tiles_w;
   op->tiles_h = (H + 16 * mt - 1) / (16 * mt);
   op->tiles_n = nimg;
@@ -418,18 +421,23 @@ int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo) {
 int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
   if (op.bn == 16) {
     STX_REQUIRE(op.rgb_out != nullptr && op.mt == 2 && !op.split, "conv1_1 dgrad: bad configuration");
-    return launch_patch<16, 2, false>(op, stream);
+    return launch_patch<16, 2, false, 1>(op, stream);
   }
   STX_REQUIRE(op.out != nullptr || op.up_out != nullptr, "conv: output not set");
   STX_REQUIRE(op.pool_out == nullptr || (op.H % 2 == 0 && op.W % 2 == 0), "conv: fused pooling needs even H and W");
   if (op.split) {
     STX_REQUIRE(op.out_lo != nullptr, "conv split: low-half output not set");
-    if (op.bn == 128) return launch_patch<128, 1, true>(op, stream);
-    return launch_patch<64, 1, true>(op, stream);
+    if (op.bn == 128) return launch_patch<128, 1, true, 1>(op, stream);
+    return launch_patch<64, 1, true, 1>(op, stream);
   }
-  if (op.bn == 256) return launch_patch<256, 2, false>(op, stream);
-  if (op.bn == 128) return op.mt == 2 ? launch_patch<128, 2, false>(op, stream) : launch_patch<128, 1, false>(op, stream);
-  return op.mt == 2 ? launch_patch<64, 2, false>(op, stream) : launch_patch<64, 1, false>(op, stream);
+  const bool two = op.occ == 2;
+  if (op.bn == 256) return launch_patch<256, 2, false, 1>(op, stream);
+  if (op.bn == 128) {
+    if (op.mt == 2) return launch_patch<128, 2, false, 1>(op, stream);
+    return two ? launch_patch<128, 1, false, 2>(op, stream) : launch_patch<128, 1, false, 1>(op, stream);
+  }
+  if (op.mt == 2) return launch_patch<64, 2, false, 1>(op, stream);
+  return two ? launch_patch<64, 1, false, 2>(op, stream) : launch_patch<64, 1, false, 1>(op, stream);
 }
 
 }  // namespace stx

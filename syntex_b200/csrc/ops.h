@@ -15,6 +15,7 @@ struct ConvOp {
   int split;         // 1 = bf16x3 forward (hi/lo operands, hi/lo outputs)
   int patch;         // 1 = halo-patch kernel (conv_patch.cu), 0 = per-tap kernel (conv_igemm.cu)
   int mt;            // patch kernel: 16x8 output tiles stacked per CTA (1 or 2)
+  int occ;           // patch kernel: persistent CTAs per SM (1 or 2)
   bf16* out_lo;
   bf16* pool_out;            // fused 2x2 average pool outputs (patch kernel only)
   bf16* pool_out_lo;
@@ -36,11 +37,11 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
 int conv_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
 // Halo-patch variant (3x3 only, W >= 8); returns STX_ERR_UNSUPPORTED for shapes it does not cover.
 int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
-                       int split, int force_bn, int force_mt);
+                       int split, int force_bn, int force_mt, int force_occ);
 int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
 int conv_patch_launch(const ConvOp& op, cudaStream_t stream);
 // Picks the halo-patch kernel when the shape qualifies, else the per-tap kernel. x_lo / w_lo non-null = bf16x3.
-// variant: 0 = automatic; otherwise bn + 1000 * mt + 100000 * (force the per-tap kernel).
+// variant: 0 = automatic; otherwise bn + 1000 * mt + 10000 * occ + 100000 * (force the per-tap kernel).
 int conv3x3_prepare(ConvOp* op, const bf16* x, const bf16* x_lo, int nimg, int H, int W, int cin, const bf16* w,
                     const bf16* w_lo, int cout, int variant);
 int conv_launch(const ConvOp& op, cudaStream_t stream);

@@ -331,7 +331,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       st.kind = BwdStep::kConv1Bwd;
       st.in = p->gbuf[cur];
       // tensor-core input gradient (N tile 16) when the halo-patch kernel covers the shape, CUDA cores otherwise
-      const int prc = conv_patch_prepare(&st.conv, p->gbuf[cur], B, H, W, 64, vgg->wd0, 16, 0, 0, 0);
+      const int prc = conv_patch_prepare(&st.conv, p->gbuf[cur], B, H, W, 64, vgg->wd0, 16, 0, 0, 0, 0);
       if (prc == STX_OK) st.kind = BwdStep::kConv1BwdTensor;
       else if (prc != STX_ERR_UNSUPPORTED) rc = prc;
       p->bwd.push_back(st);
