@@ -283,8 +283,6 @@ def run_ours(args, rank, world, local_rank):
         peaks = measured_peaks()
         achieved = flops / (conv_ms * 1e-3) / 1e12
         # the accurate forward issues three bf16 MMAs per algorithmic MAC (bf16x3): tensor-pipe work actually executed
-        executed = (3.0 * conv_flops_one_direction(size) * batch / (float(acc[0]) * 1e-3)
-                    + conv_flops_one_direction(size) * batch / (float(acc[1]) * 1e-3)) / 2 / 1e12 if acc[0] > 0 and acc[1] > 0 else None
         exec_total = (3.0 + 1.0) * conv_flops_one_direction(size) * batch / (conv_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "conv_patch_kernel (persistent tcgen05 3x3 implicit GEMM, fwd+dgrad, %d launches per f/g evaluation)" % conv_launches,
                     "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

@@ -208,7 +208,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n = tm / tiles_per_img;
       const int as = ait % kAS;
       const uint32_t acc = tmem_base + as * L::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
-      mbar_wait(&afull[as], (ait / kAS) & 1, 400 + as);
+      mbar_wait_relaxed(&afull[as], (ait / kAS) & 1, 400 + as);
       tc_fence_after();
       if (BN == 16) {
         // conv1_1 input gradient: both stacked tiles sit in one 32-column slab (16 columns each, 3 real).
@@ -346,34 +346,31 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->taps = 9;
   op->per_image_w = 0;
   op->patch = 1;
-  // N tile and number of stacked 16x8 tiles, from the measured variant table (profiles/r01_conv_variants_*.log):
-  // 128-wide N tiles with one tile per CTA (two CTAs per SM) by default; 256 x (2 tiles) when even that coarse grid
-  // fills ~the machine (best reuse); 64-wide tiles only for 64-channel layers. The split forward keeps MT = 1
-  // (its hi/lo patches already fill shared memory) and is tensor-bound in every configuration.
-  const int tiles_w = (W + 7) / 8;
-  auto ctas = [&](int bn, int mt) { return tiles_w * ((H + 16 * mt - 1) / (16 * mt)) * nimg * (cout / bn); };
-  int bn = 64, mt = 1;
+  // Tile configuration from the measured variant tables (profiles/r01_conv_variants_*_persistent.log):
+  //  * N tile 128 whenever the channel count allows it (never slower than 64, even on tiny grids);
+  //  * single-MMA kernels (dgrad, fast forward): one 16x8 tile per work item and TWO persistent CTAs per SM - one
+  //    issuing thread cannot keep the tensor pipe fed at 4 MMAs per weight tile, two can (1025 vs 666 TFLOP/s on
+  //    conv4_2 dgrad);
+  //  * bf16x3 forward: one CTA per SM (12 MMAs per weight tile keep a single issuer busy; its hi/lo rings need the
+  //    whole shared memory).
+  int bn = 64, mt = 1, occ = split ? 1 : 2;
   if (cout == 16) {
     bn = 16;
     mt = 2;
+    occ = 1;
   } else {
-    if (cout % 128 == 0) bn = 128;      // never slower than 64 in the measured table, even on tiny grids
-    if (!split) {
-      if (cout % 256 == 0 && ctas(256, 2) >= 120) {
-        bn = 256;
-        mt = 2;
-      } else if (bn == 64 && ctas(64, 2) >= 296) {
-        mt = 2;
-      }
-    }
+    if (cout % 128 == 0) bn = 128;
     if (force_bn == 64 || (force_bn == 128 && cout % 128 == 0) || (force_bn == 256 && cout % 256 == 0 && !split))
       bn = force_bn;
     if (force_mt == 1 || (force_mt == 2 && !split)) mt = force_mt;
     if (bn == 256) mt = 2;              // only the <256, 2> instance exists
+    if (force_occ == 1 || force_occ == 2) occ = force_occ;
+    if (split || mt == 2) occ = 1;      // only MT = 1 single-MMA instances exist with two CTAs per SM
   }
+  const int tiles_w = (W + 7) / 8;
   op->bn = bn;
   op->mt = mt;
-  op->occ = force_occ == 2 ? 2 : 1;
+  op->occ = occ;
   op->tiles_w = tiles_w;
   op->tiles_h = (H + 16 * mt - 1) / (16 * mt);
   op->tiles_n = nimg;

@@ -67,6 +67,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// Same, for waits that are expected to be long (an epilogue warp waiting for a whole tile of MMAs): back off between
+// probes so that the spinning warps do not take issue slots from the TMA / MMA issuing warps on the same SM.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(200);
+    if (clock64() - t0 > 8000000000LL) {
+      printf("[syntex_b200] mbarrier watchdog: block (%d,%d,%d) thread %d tag %d parity %u\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, tag, parity);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
