@@ -67,6 +67,9 @@ void stx_vgg_destroy(stx_vgg* vgg);
  *        MMAs per K step, forward error ~1e-5, input gradient within BASELINE.json's 1e-2);
  *        STX_PLAN_FAST_BF16 = single bf16 MMA forward (Grams within 5e-3, input gradient ~3e-2: ReLU sign flips). */
 #define STX_PLAN_FAST_BF16 1
+/* keep, for every loss layer k, the total gradient d sum(loss_overall) / d feat[k] of each step (what the PO models'
+ * stage preparation takes with tf.gradients(loss, [feat[k]...]), po/improved_model.py:227-231) */
+#define STX_PLAN_EXPORT_LAYER_GRADS 2
 int stx_plan_create(stx_plan** out, const stx_vgg* vgg, int batch, int height, int width, int topmost,
                     int num_loss_layers, const int* loss_layers, const float* coefs, int flags);
 void stx_plan_destroy(stx_plan* plan);
@@ -104,6 +107,9 @@ int stx_plan_step_host(stx_plan* plan, const float* x_host, int is_preimage, flo
  *   4 Gram finish/loss  5 conv1_1 fwd+bwd  6 pooling fwd+bwd  7 other.   Synchronous. */
 int stx_plan_step_timed(stx_plan* plan, const float* x, int is_preimage, float* func, float* grad, float* ms,
                         int* count, void* stream);
+/* After a step on a plan created with STX_PLAN_EXPORT_LAYER_GRADS: d sum(loss_overall) / d feat[loss layer k],
+ * back-propagated from every loss layer above and including k, fp32 [batch,h,w,c] (device). */
+int stx_plan_copy_layer_total_grad(stx_plan* plan, int k, float* out, void* stream);
 /* Per-layer gradients of build_texture_loss(calc_grad=True) (utils.py:50-55): d loss_layer[k] / d feat[k],
  * fp32 [batch,h,w,c] device, for the features of the last forward and the current targets. */
 int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream);

@@ -39,6 +39,7 @@ def _declare(lib):
         "stx_plan_step_timed": (c_int, [vp, fp, c_int, fp, fp, POINTER(c_float), POINTER(c_int), vp]),
         "stx_plan_step_host": (c_int, [vp, fp, c_int, fp, fp, vp]),
         "stx_plan_layer_grad": (c_int, [vp, c_int, fp, vp]),
+        "stx_plan_copy_layer_total_grad": (c_int, [vp, c_int, fp, vp]),
         "stx_lbfgs_create": (c_int, [POINTER(c_void_p), vp, c_int, c_int, c_float, c_float]),
         "stx_lbfgs_destroy": (None, [vp]),
         "stx_lbfgs_reset": (c_int, [vp, fp, c_int, vp]),

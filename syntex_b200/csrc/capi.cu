@@ -161,6 +161,15 @@ int stx_plan_step_host(stx_plan* plan, const float* x_host, int is_preimage, flo
   return STX_OK;
 }
 
+int stx_plan_copy_layer_total_grad(stx_plan* plan, int k, float* out, void* stream) {
+  STX_REQUIRE(plan && out, "stx_plan_copy_layer_total_grad: null argument");
+  Plan* p = plan->p;
+  STX_REQUIRE(k >= 0 && k < static_cast<int>(p->loss.size()), "loss-layer index out of range");
+  if (!p->export_grads) return fail(STX_ERR_STATE, "plan was not created with STX_PLAN_EXPORT_LAYER_GRADS");
+  const LossLayer& ll = p->loss[k];
+  return bf16_to_f32_launch(ll.dfeat, static_cast<size_t>(p->B) * ll.HW * ll.C, out, S(stream));
+}
+
 int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream) {
   STX_REQUIRE(plan && out, "stx_plan_layer_grad: null argument");
   Plan* p = plan->p;

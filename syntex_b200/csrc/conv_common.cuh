@@ -21,6 +21,9 @@ struct ConvKernelParams {
   const bf16* mask;    // [nimg,H,W,cout] or null: result is zeroed where mask <= 0
   bf16* out;           // [nimg,H,W,cout]
   bf16* out_lo;        // SPLIT: low halves of the output (out holds the high halves)
+  // Optional copy of v right after the addend (before ReLU / mask / scatter): the total gradient dL/dF_k that the
+  // PO models consume (tf.gradients(loss, feat[k]), po/improved_model.py:227-231)
+  bf16* export_out;
   // Fused 2x2 average pooling of the result (patch kernel only; vgg19.py:90-91): pooled hi/lo planes [n,H/2,W/2,cout]
   bf16* pool_out;
   bf16* pool_out_lo;
@@ -74,6 +77,16 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
           v[8 * j + 2 * e] += f.x;
           v[8 * j + 2 * e + 1] += f.y;
         }
+      }
+    }
+    if (p.export_out) {
+      uint4* e4 = reinterpret_cast<uint4*>(p.export_out + off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        Pack8 pk;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pk.h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+        e4[j] = pk.u;
       }
     }
     if (p.relu) {

@@ -216,6 +216,7 @@ int launch_bn(const ConvOp& op, cudaStream_t stream) {
   p.pool_out_lo = nullptr;
   p.up_out = op.up_out;
   p.up_mask = op.up_mask;
+  p.export_out = op.export_out;
   dim3 grid(op.tiles_w * op.tiles_h * op.tiles_n, op.cout / BN, 1);
   conv_igemm_kernel<BN, SPLIT><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
                                                                         SPLIT ? op.tmB2 : op.tmB, p);
@@ -259,6 +260,7 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->patch = 0;
   op->mt = 1;
   op->occ = 1;
+  op->gram_chunks = 0;
   // Tile geometry: BW x BH x BNI pixels = 128 accumulator rows.
   int bw = 16;
   while (bw > 1 && (bw >> 1) >= W) bw >>= 1;       // smallest power of two >= W, capped at 16
@@ -298,6 +300,7 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->pool_out_lo = nullptr;
   op->up_out = nullptr;
   op->up_mask = nullptr;
+  op->export_out = nullptr;
   op->split = 0;
   op->relu = 0;
   return STX_OK;

@@ -63,12 +63,14 @@ struct PatchSmem {
 struct PatchSched {
   int total_items;   // tiles * N-blocks
   int nblocks;       // cout / BN
+  int gram_chunks;   // fused Gram gradient: extra 1x1 K chunks (C / 64) accumulating F * Dscaled, 0 = none
 };
 
 template <int BN, int MT, bool SPLIT, int OCC>
 __global__ void __launch_bounds__(kThreads, OCC)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                  const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmD,
                   const ConvKernelParams p, const PatchSched sched) {
   using L = PatchSmem<BN, MT, SPLIT, OCC>;
   constexpr int kPS = L::kPatchStages, kBS = L::kBStages, kAS = L::kAccStages;
@@ -141,6 +143,20 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
           }
         }
+        // Fused Gram gradient (utils.py:54): the features of this tile (dense 128-row K-major tiles, staged in a patch
+        // buffer) times the per-image scaled Gram difference, accumulated into the same TMEM tile.
+        for (int cf = 0; cf < sched.gram_chunks; ++cf, ++pit, ++bit) {
+          const int ps = pit % kPS;
+          mbar_wait(&pempty[ps], ((pit / kPS) & 1) ^ 1, 140 + ps);
+          uint8_t* pdst = smem + ps * L::kPatchStageBytes;
+          mbar_arrive_expect_tx(&pfull[ps], MT * 16384);
+          for (int mt = 0; mt < MT; ++mt) tma_load_4d(pdst + mt * 16384, &tmF, &pfull[ps], cf * 64, w0, h0 + 16 * mt, n);
+          const int bs = bit % kBS;
+          mbar_wait(&bempty[bs], ((bit / kBS) & 1) ^ 1, 160 + bs);
+          uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
+          mbar_arrive_expect_tx(&bfull[bs], BN * 128);
+          tma_load_3d(bdst, &tmD, &bfull[bs], cf * 64, nblk * BN, n);
+        }
       }
     }
     __syncwarp();
@@ -187,6 +203,23 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             umma_commit(&bempty[bs]);
           }
+          umma_commit(&pempty[ps]);
+        }
+        for (int cf = 0; cf < sched.gram_chunks; ++cf, ++pit, ++bit) {
+          const int ps = pit % kPS;
+          const int bs = bit % kBS;
+          mbar_wait(&pfull[ps], (pit / kPS) & 1, 240 + ps);
+          mbar_wait(&bfull[bs], (bit / kBS) & 1, 260 + bs);
+          tc_fence_after();
+          const uint32_t f_addr = smem_u32(smem + ps * L::kPatchStageBytes);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + L::kBOffset + bs * L::kBStageBytes), 16, 1024);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = make_smem_desc_sw128(f_addr + mt * 16384, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(acc + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+          }
+          umma_commit(&bempty[bs]);
           umma_commit(&pempty[ps]);
         }
         umma_commit(&afull[as]);
@@ -311,9 +344,11 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.pool_out_lo = op.pool_out_lo;
   p.up_out = op.up_out;
   p.up_mask = op.up_mask;
+  p.export_out = op.export_out;
   PatchSched sched;
   sched.nblocks = op.cout / BN;
   sched.total_items = op.tiles_w * op.tiles_h * op.nimg * sched.nblocks;
+  sched.gram_chunks = (!SPLIT && op.gram_chunks > 0) ? op.gram_chunks : 0;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -323,7 +358,9 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   const int slots = num_sms * OCC;                                              // persistent: OCC CTAs per SM
   const int grid = sched.total_items < slots ? sched.total_items : slots;
   conv_patch_kernel<BN, MT, SPLIT, OCC><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
-                                                                           SPLIT ? op.tmB2 : op.tmB, p, sched);
+                                                                           SPLIT ? op.tmB2 : op.tmB,
+                                                                           sched.gram_chunks ? op.tmF : op.tmA,
+                                                                           sched.gram_chunks ? op.tmD : op.tmB, p, sched);
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;
@@ -392,12 +429,31 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->rgb_out = nullptr;
   op->rgb_image = nullptr;
   op->rgb_preimage = 0;
+  op->gram_chunks = 0;
   op->pool_out = nullptr;
   op->pool_out_lo = nullptr;
   op->up_out = nullptr;
   op->up_mask = nullptr;
+  op->export_out = nullptr;
   op->split = 0;
   op->relu = 0;
+  return STX_OK;
+}
+
+// Attach the fused Gram gradient to a prepared single-MMA patch op whose output lives on the layer of `feat`:
+// out += feat [nimg,H,W,cout] x dscaled [nimg][cout][cout] (per image), accumulated in TMEM before the epilogue.
+int conv_patch_attach_gram(ConvOp* op, const bf16* feat, const bf16* dscaled) {
+  STX_REQUIRE(op->patch && !op->split && op->bn != 16, "fused Gram gradient: needs a single-MMA halo-patch op");
+  STX_REQUIRE(feat && dscaled, "fused Gram gradient: null operand");
+  const uint64_t fdims[4] = {static_cast<uint64_t>(op->cout), static_cast<uint64_t>(op->W),
+                             static_cast<uint64_t>(op->H), static_cast<uint64_t>(op->nimg)};
+  const uint32_t fbox[4] = {64u, 8u, 16u, 1u};
+  STX_TRY(encode_tmap_bf16(&op->tmF, feat, 4, fdims, fbox));
+  const uint64_t ddims[3] = {static_cast<uint64_t>(op->cout), static_cast<uint64_t>(op->cout),
+                             static_cast<uint64_t>(op->nimg)};
+  const uint32_t dbox[3] = {64u, static_cast<uint32_t>(op->bn), 1u};
+  STX_TRY(encode_tmap_bf16(&op->tmD, dscaled, 3, ddims, dbox));
+  op->gram_chunks = op->cout / 64;
   return STX_OK;
 }
 

@@ -12,6 +12,9 @@ struct ConvOp {
   CUtensorMap tmB;   // packed weights [taps|nimg][cout][cin] bf16
   CUtensorMap tmA2;  // split mode: low halves of the activations
   CUtensorMap tmB2;  // split mode: low halves of the weights
+  CUtensorMap tmF;   // fused Gram gradient: features of the output layer [nimg,H,W,cout]
+  CUtensorMap tmD;   // fused Gram gradient: scaled Gram difference [nimg][cout][cout]
+  int gram_chunks;   // cout / 64 when the Gram gradient is fused, else 0
   int split;         // 1 = bf16x3 forward (hi/lo operands, hi/lo outputs)
   int patch;         // 1 = halo-patch kernel (conv_patch.cu), 0 = per-tap kernel (conv_igemm.cu)
   int mt;            // patch kernel: 16x8 output tiles stacked per CTA (1 or 2)
@@ -21,6 +24,7 @@ struct ConvOp {
   bf16* pool_out_lo;
   bf16* up_out;              // fused AvgPoolGrad + ReluGrad scatter (replaces `out`)
   const bf16* up_mask;
+  bf16* export_out;          // copy of the value after the addend (total gradient w.r.t. this layer's features)
   float* rgb_out;            // conv1_1 input-gradient mode of the patch kernel (bn == 16)
   const float* rgb_image;
   int rgb_preimage;
@@ -39,6 +43,7 @@ int conv_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
 int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
                        int split, int force_bn, int force_mt, int force_occ);
 int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
+int conv_patch_attach_gram(ConvOp* op, const bf16* feat, const bf16* dscaled);
 int conv_patch_launch(const ConvOp& op, cudaStream_t stream);
 // Picks the halo-patch kernel when the shape qualifies, else the per-tap kernel. x_lo / w_lo non-null = bf16x3.
 // variant: 0 = automatic; otherwise bn + 1000 * mt + 10000 * occ + 100000 * (force the per-tap kernel).

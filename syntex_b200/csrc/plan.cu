@@ -169,6 +169,7 @@ static int plan_layout(Plan* p, Bump& a) {
     ll.G = a.take<float>(cc);
     ll.target = a.take<float>(cc);
     ll.dscaled = a.take<bf16>(cc);
+    ll.dfeat = p->export_grads ? a.take<bf16>(static_cast<size_t>(B) * ll.HW * ll.C) : nullptr;
     float* partial = a.take<float>(gram_partial_bytes(B, ll.HW, ll.C) / sizeof(float));
     ll.gram.partial = partial;
     ll.part_offset = part;
@@ -200,6 +201,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
   p->W = W;
   p->topmost = topmost;
   p->split = (flags & STX_PLAN_FAST_BF16) ? 0 : 1;
+  p->export_grads = (flags & STX_PLAN_EXPORT_LAYER_GRADS) ? 1 : 0;
   int h = H, w = W, convs_needed = 0;
   for (int l = 0; l <= topmost; ++l) {
     const LayerSpec& s = kLayers[l];
@@ -310,7 +312,20 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
   for (int l = top; l >= 0 && rc == STX_OK; --l) {
     const LayerSpec& s = kLayers[l];
     const int k = loss_index(l);
-    if (k >= 0) {
+    if (k >= 0 && have && !p->bwd.empty() && p->bwd.back().kind == BwdStep::kDgrad && p->bwd.back().conv.patch &&
+        !p->bwd.back().conv.split) {
+      // Gram gradient of this layer fused into the dgrad launch that produces dL/d(act[l]): F * Dscaled is
+      // accumulated into the same TMEM tile, then the epilogue masks (conv layers) / exports as configured.
+      LossLayer& ll = p->loss[k];
+      ConvOp& prod = p->bwd.back().conv;
+      rc = conv_patch_attach_gram(&prod, p->act[l], ll.dscaled);
+      prod.mask = s.is_conv ? p->act[l] : nullptr;
+      prod.export_out = ll.dfeat;
+      if (rc == STX_OK) {
+        rc = conv_prepare(&ll.layer_grad_op, p->act[l], B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
+        ll.layer_grad_op.out = p->gbuf[0];
+      }
+    } else if (k >= 0) {
       LossLayer& ll = p->loss[k];
       BwdStep st;
       st.kind = BwdStep::kGramGrad;
@@ -318,6 +333,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       st.conv.addend = have ? p->gbuf[cur] : nullptr;
       st.conv.out = p->gbuf[cur];
       st.conv.mask = s.is_conv ? p->act[l] : nullptr;
+      st.conv.export_out = ll.dfeat;
       p->bwd.push_back(st);
       have = true;
       if (rc == STX_OK) {
@@ -381,13 +397,16 @@ int Plan::forward(const float* image, int is_preimage, int with_grams, bool with
   auto launch_gram = [&](int l) -> int {
     for (LossLayer& ll : loss) {
       if (ll.layer != l) continue;
-      STX_CUDA(cudaEventRecord(ev_fork[l], stream));
-      STX_CUDA(cudaStreamWaitEvent(side, ev_fork[l], 0));
-      forked = true;
+      // (the instrumented step keeps everything on one stream so that per-class times are not polluted by waiting)
+      const bool use_side = (tl == nullptr);
+      if (use_side) {
+        STX_CUDA(cudaEventRecord(ev_fork[l], stream));
+        STX_CUDA(cudaStreamWaitEvent(side, ev_fork[l], 0));
+        forked = true;
+      }
       cudaStream_t main_stream = stream;
       {
-        cudaStream_t stream = side;   // STX_LAUNCH records/launches on `stream`
-        (void)main_stream;
+        cudaStream_t stream = use_side ? side : main_stream;   // STX_LAUNCH records/launches on `stream`
         STX_LAUNCH(kClsGram, gram_launch(ll.gram, stream));
         // dL/dF = F * (G - T) * coef / (C^2 * n):  loss_overall = sum coef/4 * mean((G-T)^2), G = F^T F / n
         const float norm = static_cast<float>(ll.HW) + 1e-6f;

@@ -50,6 +50,7 @@ struct LossLayer {
   float* target = nullptr;    // [B,C,C]
   long long target_stride = 0;
   bf16* dscaled = nullptr;    // [B,C,C]
+  bf16* dfeat = nullptr;      // [B,h,w,C] total gradient dL/dF_k (only with STX_PLAN_EXPORT_LAYER_GRADS)
   int part_offset = 0;        // into loss_part rows
   int part_blocks = 0;
   ConvOp layer_grad_op;       // calc_grad path (utils.py:50-55): F * D * 4/(C^2 n) into scratch
@@ -72,6 +73,7 @@ struct Plan {
   Timeline* tl = nullptr;
   int B = 0, H = 0, W = 0, topmost = 15;
   int lh[kNumLayers], lw[kNumLayers], lc[kNumLayers];
+  int export_grads = 0;            // keep dL/dF_k of every loss layer (PO stage preparation)
   int split = 1;                   // 1 = bf16x3 forward (hi/lo activations), 0 = plain bf16 forward
   bf16* act[kNumLayers] = {};      // recorded layers (high halves; the only halves in plain mode)
   bf16* act_lo[kNumLayers] = {};   // low halves (split mode)

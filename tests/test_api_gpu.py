@@ -68,3 +68,29 @@ def test_po_model_doors(raw_weights):
     y = torch.rand((2, 64, 64, 3), generator=torch.Generator().manual_seed(4)).cuda()
     lo, ll, g = model._build_loss(y, gram, calc_grad=True)
     assert (lo > 0).all() and set(g.keys()) == set(SynTexModelDesc.DEFAULT_COEFS.keys())
+
+
+def test_stage_preparation_gradients_match_autograd(raw_weights):
+    """po/improved_model.py:209-232: features to the stage's top layer + full VGG back-propagation of the loss to
+    every Gram layer's activations."""
+    from syntex_b200.po import build_stage_preparation
+    x = torch.rand((2, 64, 64, 3), generator=torch.Generator().manual_seed(5))
+    t = torch.as_tensor(np.stack([so.synthetic_texture(64, seed=7), so.synthetic_texture(64, seed=8)])).float()
+    coefs = OrderedDict([("conv1_1", 1e5), ("pool1", 1e5), ("pool2", 1e5)])     # stage 3 of 5
+    ext = Vgg19Extractor(raw_weights)
+    W = so.TorchWeights(so.load_vgg_weights(raw_weights), torch.float64)
+    rt = so.vgg_build(t.double(), W, topmost="pool2")
+    rgt = OrderedDict((k, so.build_gram(rt[k])) for k in coefs)
+    feat, loss_input, loss_layer, grads = build_stage_preparation(
+        ext, x.cuda(), OrderedDict((k, v.float()) for k, v in rgt.items()), coefs)
+    assert list(feat.keys())[-1] == "pool2" and len(feat) == 6
+    xr = x.double().requires_grad_(True)
+    rf = so.vgg_build(xr, W, topmost="pool2")
+    lo, ll, _ = so.build_texture_loss(rf, rgt, coefs)
+    ref = torch.autograd.grad(lo.sum(), [rf[k] for k in coefs])
+    for (k, g), r in zip(grads.items(), ref):
+        assert tuple(g.shape) == tuple(r.shape)
+        assert relerr(g, r) < 1e-2, k
+        assert abs(float(loss_layer[k][0]) - float(ll[k][0])) / float(ll[k][0]) < 5e-3
+    want = sum(coefs[k] / 4 * ll[k] for k in list(coefs)[:-1]).detach()
+    assert relerr(loss_input, want) < 5e-3
