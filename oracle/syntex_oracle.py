@@ -133,7 +133,11 @@ def vgg_build(image_nhwc: torch.Tensor, weights, topmost="pool4", is_rgb_input=T
                 x = F.avg_pool2d(x, 2, 2, ceil_mode=True, count_include_pad=False)
             else:
                 x = F.max_pool2d(x, 2, 2, ceil_mode=True)
-        layers[layer] = x.permute(0, 2, 3, 1)
+        # the recorded NHWC tensor is the one that feeds the next layer, so gradients taken w.r.t. a recorded layer
+        # (tf.gradients(loss, feat[k]), po/improved_model.py:227-231) include every path through the layers above
+        feat = x.permute(0, 2, 3, 1)
+        layers[layer] = feat
+        x = feat.permute(0, 3, 1, 2)
         if layer == topmost:
             break
     return layers

@@ -216,8 +216,9 @@ static void gram_geometry(int nimg, int HW, int C, int* ntiles, int* splits, int
   const int T = (C + 127) / 128;
   *ntiles = T * (T + 1) / 2;
   *total_iters = (HW + kRowsPerStage - 1) / kRowsPerStage;
-  // Aim for about two CTAs per SM overall, at least 2 pipeline iterations per CTA.
-  int want = (2 * 148 + (*ntiles) * nimg - 1) / ((*ntiles) * nimg);
+  // Aim for about one CTA per SM overall (more slabs only make the fixed-order reduction longer), at least 2
+  // pipeline iterations per CTA.
+  int want = (148 + (*ntiles) * nimg - 1) / ((*ntiles) * nimg);
   int max_splits = (*total_iters + 1) / 2;
   if (max_splits < 1) max_splits = 1;
   int s = want < max_splits ? want : max_splits;
