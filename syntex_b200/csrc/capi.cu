@@ -10,6 +10,9 @@ using namespace stx;
 namespace stx {
 extern int g_debug_gram_lbo;
 extern int g_debug_gram_sbo;
+extern int g_debug_dgrad_variant;
+extern int g_debug_no_gram_fusion;
+extern int g_debug_no_poolbwd_fusion;
 }  // namespace stx
 
 struct stx_vgg {
@@ -34,6 +37,9 @@ int stx_debug_set(int key, int value) {
   switch (key) {
     case 1: g_debug_gram_lbo = value; return STX_OK;
     case 2: g_debug_gram_sbo = value; return STX_OK;
+    case 3: g_debug_dgrad_variant = value; return STX_OK;
+    case 4: g_debug_no_gram_fusion = value; return STX_OK;
+    case 5: g_debug_no_poolbwd_fusion = value; return STX_OK;
     default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
   }
 }

@@ -5,6 +5,11 @@
 
 namespace stx {
 
+// bring-up switches (stx_debug_set keys 3..5)
+int g_debug_dgrad_variant = 0;      // variant code for the dgrad convolutions (0 = automatic)
+int g_debug_no_gram_fusion = 0;     // 1 = stand-alone Gram-gradient launches
+int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
+
 static const LayerSpec kLayers[kNumLayers] = {
     {true, 0, 3, 64},     {true, 1, 64, 64},    {false, -1, 64, 64},   {true, 2, 64, 128},
     {true, 3, 128, 128},  {false, -1, 128, 128}, {true, 4, 128, 256},  {true, 5, 256, 256},
@@ -312,7 +317,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
   for (int l = top; l >= 0 && rc == STX_OK; --l) {
     const LayerSpec& s = kLayers[l];
     const int k = loss_index(l);
-    if (k >= 0 && have && !p->bwd.empty() && p->bwd.back().kind == BwdStep::kDgrad && p->bwd.back().conv.patch &&
+    if (k >= 0 && have && !g_debug_no_gram_fusion && !p->bwd.empty() && p->bwd.back().kind == BwdStep::kDgrad && p->bwd.back().conv.patch &&
         !p->bwd.back().conv.split) {
       // Gram gradient of this layer fused into the dgrad launch that produces dL/d(act[l]): F * Dscaled is
       // accumulated into the same TMEM tile, then the epilogue masks (conv layers) / exports as configured.
@@ -355,19 +360,26 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       BwdStep st;
       st.kind = BwdStep::kDgrad;
       rc = conv3x3_prepare(&st.conv, p->gbuf[cur], nullptr, B, p->lh[l], p->lw[l], s.cout, vgg->wd[s.conv_index],
-                           nullptr, s.cin, 0);
+                           nullptr, s.cin, g_debug_dgrad_variant);
       st.conv.out = p->gbuf[cur ^ 1];
       st.conv.mask = (kLayers[l - 1].is_conv && loss_index(l - 1) < 0) ? p->act[l - 1] : nullptr;
       p->bwd.push_back(st);
       cur ^= 1;
-    } else if (loss_index(l - 1) < 0 && !p->bwd.empty() &&
+    } else if (loss_index(l - 1) < 0 && !g_debug_no_poolbwd_fusion && !p->bwd.empty() &&
                (p->bwd.back().kind == BwdStep::kGramGrad || p->bwd.back().kind == BwdStep::kDgrad)) {
       // AvgPoolGrad + ReluGrad fused into the epilogue of the launch that completes dL/d(pool output): it scatters
       // 0.25 * g to the four fine pixels, masked by the activations of the convolution that fed the pool.
+      // Buffer choice: a dgrad launch reads its input patches (with halos, across tiles) from gbuf[cur ^ 1], so its
+      // scatter must go to gbuf[cur] - the buffer its plain output would have used (unused in scatter mode). The
+      // stand-alone Gram gradient reads its addend from gbuf[cur], so its scatter goes to the other buffer.
       ConvOp& prod = p->bwd.back().conv;
-      prod.up_out = p->gbuf[cur ^ 1];
+      if (p->bwd.back().kind == BwdStep::kDgrad) {
+        prod.up_out = p->gbuf[cur];
+      } else {
+        prod.up_out = p->gbuf[cur ^ 1];
+        cur ^= 1;
+      }
       prod.up_mask = p->act[l - 1];
-      cur ^= 1;
     } else {
       BwdStep st;
       st.kind = BwdStep::kPoolBwd;

@@ -121,6 +121,27 @@ def test_batched_jobs_equal_single_jobs_bitwise(raw_weights):
         np.testing.assert_array_equal(r1["grad"][0], rb["grad"][j])
 
 
+def test_large_batch_backward_has_no_cross_tile_race(raw_weights):
+    """Regression: with many work items per persistent CTA, a scatter aliasing the dgrad input showed up as wrong
+    gradients for the later images of a batch of 16 at 256^2 (never at batch <= 3)."""
+    S, B = 256, 16
+    tg = np.stack([so.synthetic_texture(S, seed=100 + j) for j in range(B)])
+    x0 = np.stack([so.init_input((S, S, 3), False, j) for j in range(B)])
+    synb = make_syn(raw_weights, S, batch=B)
+    synb.compute_gram(tg, update=True)
+    rb = synb.step(x0)
+    rb2 = synb.step(x0)
+    np.testing.assert_array_equal(rb["grad"], rb2["grad"])
+    syn1 = make_syn(raw_weights, S, batch=1)
+    for j in (0, 5, 11, 15):
+        syn1.compute_gram(tg[j], update=True)
+        r1 = syn1.step(x0[j])
+        # not bitwise: the Gram split-K geometry depends on the batch size (summation order), which perturbs the
+        # bf16-rounded Gram difference; anything beyond that is a bug
+        assert relerr(rb["grad"][j], r1["grad"][0]) < 5e-3
+        assert abs(rb["func"][j] - r1["func"][0]) < 1e-4 * r1["func"][0]
+
+
 def test_step_is_deterministic(raw_weights):
     S = 128
     syn = make_syn(raw_weights, S)
