@@ -45,6 +45,7 @@ struct PatchSmem {
   static constexpr int kPatchStride = (kPatchBytes + 1023) & ~1023;           // keep every buffer 1024-aligned
   static constexpr int kPatchStageBytes = (SPLIT ? 2 : 1) * kPatchStride;     // [hi | lo]
   static constexpr int kPatchStages = (SPLIT || MT == 2 || OCC == 2) ? 2 : 3;
+  static_assert(OCC == 1 || (OCC == 2 && (MT == 1 || BN == 16)), "two CTAs per SM: single-tile or N = 16 instances only");
   static constexpr int kBBytes = (BN * 128 + 1023) & ~1023;
   static constexpr int kBStageBytes = (SPLIT ? 2 : 1) * kBBytes;              // [hi | lo]
   static constexpr int kBRoom = (kSmemBudget / OCC - 2048 - kPatchStages * kPatchStageBytes) / kBStageBytes;
@@ -474,7 +475,7 @@ int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo) {
 int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
   if (op.bn == 16) {
     STX_REQUIRE(op.rgb_out != nullptr && op.mt == 2 && !op.split, "conv1_1 dgrad: bad configuration");
-    return launch_patch<16, 2, false, 1>(op, stream);
+    return launch_patch<16, 2, false, 2>(op, stream);   // two CTAs per SM: the single MMA issuer is the limit
   }
   STX_REQUIRE(op.out != nullptr || op.up_out != nullptr, "conv: output not set");
   STX_REQUIRE(op.pool_out == nullptr || (op.H % 2 == 0 && op.W % 2 == 0), "conv: fused pooling needs even H and W");

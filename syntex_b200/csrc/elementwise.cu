@@ -20,7 +20,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 // sigmoid pre-image (gatys/synthesizer.py:59). Each thread computes 32 output channels of TWO horizontally adjacent
 // pixels, so every shared-memory weight vector (broadcast LDS.128) feeds 8 FMAs and the 3x4 input patch is shared.
 // Zero padding applies to the *preprocessed* image, as in the TF graph.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 4)
 conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int is_preimage, float m0, float m1,
                    float m2, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
                    bf16* __restrict__ out_lo) {
@@ -321,7 +321,7 @@ int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preima
                        const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream) {
   STX_REQUIRE(image && w && b && out && mean3, "conv1_1 fwd: null operand");
   const long long threads = 2LL * nimg * H * ((W + 1) / 2);
-  conv1_1_fwd_kernel<<<blocks_for(threads, 256), 256, 0, stream>>>(image, nimg, H, W, is_preimage, mean3[0], mean3[1],
+  conv1_1_fwd_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(image, nimg, H, W, is_preimage, mean3[0], mean3[1],
                                                                   mean3[2], w, b, out, out_lo);
   STX_CUDA(cudaGetLastError());
   count_launch();
