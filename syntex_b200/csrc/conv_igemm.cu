@@ -261,6 +261,9 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->mt = 1;
   op->occ = 1;
   op->gram_chunks = 0;
+  op->ksplit = 1;
+  op->splitk_ws = nullptr;
+  op->splitk_counters = nullptr;
   // Tile geometry: BW x BH x BNI pixels = 128 accumulator rows.
   int bw = 16;
   while (bw > 1 && (bw >> 1) >= W) bw >>= 1;       // smallest power of two >= W, capped at 16

@@ -65,6 +65,9 @@ struct PatchSched {
   int total_items;   // tiles * N-blocks
   int nblocks;       // cout / BN
   int gram_chunks;   // fused Gram gradient: extra 1x1 K chunks (C / 64) accumulating F * Dscaled, 0 = none
+  int ksplit;        // split-K factor (small grids): work item = (tile, N-block, K slice)
+  float* ws;         // split-K partial tiles [tile*nblocks][ksplit][MT*128][BN] fp32
+  int* counters;     // split-K arrival counters [tile*nblocks], zero between launches
 };
 
 template <int BN, int MT, bool SPLIT, int OCC>
@@ -84,6 +87,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* afull = bempty + kBS;
   uint64_t* aempty = afull + kAS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + kAS);
+  volatile int* splitk_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -123,12 +127,16 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int pit = 0, bit = 0;   // ring counters, running across work items
       for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x) {
-        const int nblk = item % sched.nblocks;
-        const int tm = item / sched.nblocks;
+        const int ks = item % sched.ksplit;
+        const int rest = item / sched.ksplit;
+        const int nblk = rest % sched.nblocks;
+        const int tm = rest / sched.nblocks;
         const int w0 = (tm % p.tiles_w) * 8;
         const int h0 = ((tm / p.tiles_w) % p.tiles_h) * (16 * MT);
         const int n = tm / tiles_per_img;
-        for (int c = 0; c < chunks; ++c, ++pit) {
+        const int c_begin = ks * chunks / sched.ksplit, c_end = (ks + 1) * chunks / sched.ksplit;
+        const int gram_chunks = (ks == sched.ksplit - 1) ? sched.gram_chunks : 0;
+        for (int c = c_begin; c < c_end; ++c, ++pit) {
           const int ps = pit % kPS;
           mbar_wait(&pempty[ps], ((pit / kPS) & 1) ^ 1, 100 + ps);
           uint8_t* pdst = smem + ps * L::kPatchStageBytes;
@@ -146,7 +154,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         // Fused Gram gradient (utils.py:54): the features of this tile (dense 128-row K-major tiles, staged in a patch
         // buffer) times the per-image scaled Gram difference, accumulated into the same TMEM tile.
-        for (int cf = 0; cf < sched.gram_chunks; ++cf, ++pit, ++bit) {
+        for (int cf = 0; cf < gram_chunks; ++cf, ++pit, ++bit) {
           const int ps = pit % kPS;
           mbar_wait(&pempty[ps], ((pit / kPS) & 1) ^ 1, 140 + ps);
           uint8_t* pdst = smem + ps * L::kPatchStageBytes;
@@ -172,7 +180,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&aempty[as], ((ait / kAS) & 1) ^ 1, 300 + as);    // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + as * L::kAccCols;
-        for (int c = 0; c < chunks; ++c, ++pit) {
+        const int ks = item % sched.ksplit;
+        const int c_begin = ks * chunks / sched.ksplit, c_end = (ks + 1) * chunks / sched.ksplit;
+        const int gram_chunks = (ks == sched.ksplit - 1) ? sched.gram_chunks : 0;
+        for (int c = c_begin; c < c_end; ++c, ++pit) {
           const int ps = pit % kPS;
           mbar_wait(&pfull[ps], (pit / kPS) & 1, 200 + ps);
           const uint32_t patch = smem_u32(smem + ps * L::kPatchStageBytes);
@@ -192,7 +203,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const uint32_t d = acc + mt * BN;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint32_t accumulate = (c | tap | k) != 0;
+                const uint32_t accumulate = ((c - c_begin) | tap | k) != 0;
                 if (SPLIT) {
                   umma_bf16(d, adesc_lo + 2 * k, bdesc + 2 * k, idesc, accumulate);   // A_lo * W_hi
                   umma_bf16(d, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1);            // A_hi * W_lo
@@ -206,7 +217,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           umma_commit(&pempty[ps]);
         }
-        for (int cf = 0; cf < sched.gram_chunks; ++cf, ++pit, ++bit) {
+        for (int cf = 0; cf < gram_chunks; ++cf, ++pit, ++bit) {
           const int ps = pit % kPS;
           const int bs = bit % kBS;
           mbar_wait(&pfull[ps], (pit / kPS) & 1, 240 + ps);
@@ -235,8 +246,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ww = r & 7;
     int ait = 0;
     for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x, ++ait) {
-      const int nblk = item % sched.nblocks;
-      const int tm = item / sched.nblocks;
+      const int ks = item % sched.ksplit;
+      const int rest = item / sched.ksplit;
+      const int nblk = rest % sched.nblocks;
+      const int tm = rest / sched.nblocks;
       const int w = (tm % p.tiles_w) * 8 + ww;
       const int h0 = ((tm / p.tiles_w) % p.tiles_h) * (16 * MT);
       const int n = tm / tiles_per_img;
@@ -278,6 +291,63 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         constexpr int kStep = kChunks >= 2 ? 2 : 1;
         const int first = kChunks >= 2 ? half : 0;
         const int last = first + ((kChunks - 1 - first) / kStep) * kStep;   // last chunk this warp handles
+        if (sched.ksplit > 1) {
+          // Split-K: park the fp32 partial tile in the workspace; the last slice to arrive sums all slices in a
+          // fixed order (bit-reproducible whichever CTA is last) and runs the real epilogue.
+          float* wsme = sched.ws + (static_cast<size_t>(rest) * sched.ksplit + ks) * (MT * 128 * BN);
+#pragma unroll 1
+          for (int j = first; j < kChunks; j += kStep) {
+            const int mt = j / kChunksPerTile;
+            const int c0 = (j % kChunksPerTile) * 32;
+            float v[32];
+            tmem_ld_32x32(acc + mt * BN + c0, v);
+            tmem_ld_wait();
+            float4* d4 = reinterpret_cast<float4*>(wsme + (static_cast<size_t>(mt) * 128 + r) * BN + c0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&aempty[as]);
+          __threadfence();
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
+          if (threadIdx.x == 64) {
+            const int old = atomicAdd(&sched.counters[rest], 1);
+            const int is_last = (old == sched.ksplit - 1);
+            if (is_last) sched.counters[rest] = 0;
+            *splitk_flag = is_last;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
+          if (*splitk_flag) {
+            __threadfence();
+            const float* wsall = sched.ws + static_cast<size_t>(rest) * sched.ksplit * (MT * 128 * BN);
+#pragma unroll 1
+            for (int j = first; j < kChunks; j += kStep) {
+              const int mt = j / kChunksPerTile;
+              const int c0 = (j % kChunksPerTile) * 32;
+              const int h = h0 + mt * 16 + (r >> 3);
+              const bool valid = (h < p.H) && (w < p.W);
+              float v[32];
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = 0.0f;
+              for (int sl = 0; sl < sched.ksplit; ++sl) {
+                const float4* s4 = reinterpret_cast<const float4*>(
+                    wsall + (static_cast<size_t>(sl) * MT * 128 + static_cast<size_t>(mt) * 128 + r) * BN + c0);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float4 t = __ldcg(s4 + e);
+                  v[4 * e] += t.x;
+                  v[4 * e + 1] += t.y;
+                  v[4 * e + 2] += t.z;
+                  v[4 * e + 3] += t.w;
+                }
+              }
+              conv_epilogue_store<SPLIT>(p, v, valid, n, h, w, nblk * BN + c0);
+            }
+          }
+          // the flag is re-written only after every warp has passed the second barrier of the NEXT item
+          continue;
+        }
         bool released = false;
         if (kChunks < 2 && half == 1) {       // nothing to drain for this warp
           tc_fence_before();
@@ -348,7 +418,10 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.export_out = op.export_out;
   PatchSched sched;
   sched.nblocks = op.cout / BN;
-  sched.total_items = op.tiles_w * op.tiles_h * op.nimg * sched.nblocks;
+  sched.ksplit = (op.ksplit > 1 && op.splitk_ws && op.splitk_counters && BN != 16) ? op.ksplit : 1;
+  sched.ws = op.splitk_ws;
+  sched.counters = op.splitk_counters;
+  sched.total_items = op.tiles_w * op.tiles_h * op.nimg * sched.nblocks * sched.ksplit;
   sched.gram_chunks = (!SPLIT && op.gram_chunks > 0) ? op.gram_chunks : 0;
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -431,6 +504,9 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->rgb_image = nullptr;
   op->rgb_preimage = 0;
   op->gram_chunks = 0;
+  op->ksplit = 1;
+  op->splitk_ws = nullptr;
+  op->splitk_counters = nullptr;
   op->pool_out = nullptr;
   op->pool_out_lo = nullptr;
   op->up_out = nullptr;
@@ -439,6 +515,24 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->split = 0;
   op->relu = 0;
   return STX_OK;
+}
+
+// Split-K for grids that leave most SMs idle (deep layers at batch 1): returns the factor that fills the machine
+// (<= number of 64-channel chunks), and the workspace this op then needs.
+int conv_patch_plan_splitk(const ConvOp& op, size_t* ws_floats, size_t* counters) {
+  *ws_floats = 0;
+  *counters = 0;
+  if (!op.patch || op.bn == 16) return 1;
+  const int items = op.tiles_w * op.tiles_h * op.nimg * (op.cout / op.bn);
+  const int slots = 148 * op.occ;
+  const int chunks = op.cin / 64;
+  int ks = 1;
+  if (items * 2 <= slots) ks = slots / items;
+  if (ks > chunks) ks = chunks;
+  if (ks < 2) return 1;
+  *ws_floats = static_cast<size_t>(items) * ks * op.mt * 128 * op.bn;
+  *counters = static_cast<size_t>(items);
+  return ks;
 }
 
 // Attach the fused Gram gradient to a prepared single-MMA patch op whose output lives on the layer of `feat`:

@@ -15,6 +15,9 @@ struct ConvOp {
   CUtensorMap tmF;   // fused Gram gradient: features of the output layer [nimg,H,W,cout]
   CUtensorMap tmD;   // fused Gram gradient: scaled Gram difference [nimg][cout][cout]
   int gram_chunks;   // cout / 64 when the Gram gradient is fused, else 0
+  int ksplit;        // split-K factor of the patch kernel (1 = off)
+  float* splitk_ws;  // fp32 partial tiles (shared by all ops of a plan; launches are stream-ordered)
+  int* splitk_counters;
   int split;         // 1 = bf16x3 forward (hi/lo operands, hi/lo outputs)
   int patch;         // 1 = halo-patch kernel (conv_patch.cu), 0 = per-tap kernel (conv_igemm.cu)
   int mt;            // patch kernel: 16x8 output tiles stacked per CTA (1 or 2)
@@ -44,6 +47,7 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
                        int split, int force_bn, int force_mt, int force_occ);
 int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
 int conv_patch_attach_gram(ConvOp* op, const bf16* feat, const bf16* dscaled);
+int conv_patch_plan_splitk(const ConvOp& op, size_t* ws_floats, size_t* counters);
 int conv_patch_launch(const ConvOp& op, cudaStream_t stream);
 // Picks the halo-patch kernel when the shape qualifies, else the per-tap kernel. x_lo / w_lo non-null = bf16x3.
 // variant: 0 = automatic; otherwise bn + 1000 * mt + 10000 * occ + 100000 * (force the per-tap kernel).

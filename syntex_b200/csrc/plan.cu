@@ -9,6 +9,7 @@ namespace stx {
 int g_debug_dgrad_variant = 0;      // variant code for the dgrad convolutions (0 = automatic)
 int g_debug_no_gram_fusion = 0;     // 1 = stand-alone Gram-gradient launches
 int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
+int g_debug_no_splitk = 0;          // 1 = no split-K
 
 static const LayerSpec kLayers[kNumLayers] = {
     {true, 0, 3, 64},     {true, 1, 64, 64},    {false, -1, 64, 64},   {true, 2, 64, 128},
@@ -97,6 +98,8 @@ Timeline::~Timeline() {
 
 Plan::~Plan() {
   cudaFree(arena);
+  cudaFree(splitk_ws);
+  cudaFree(splitk_counters);
   if (pinned) cudaFreeHost(pinned);
   if (side) cudaStreamDestroy(side);
   for (cudaEvent_t e : ev_fork)
@@ -391,6 +394,31 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       st.C = p->lc[l - 1];
       p->bwd.push_back(st);
       cur ^= 1;
+    }
+  }
+  // Split-K for the convolutions whose grid would leave most SMs idle (deep layers at small batch).
+  if (rc == STX_OK && !g_debug_no_splitk) {
+    std::vector<ConvOp*> ops;
+    for (int l = 1; l <= topmost; ++l)
+      if (kLayers[l].is_conv) ops.push_back(&p->fwd[l]);
+    for (BwdStep& st : p->bwd)
+      if (st.kind == BwdStep::kDgrad) ops.push_back(&st.conv);
+    size_t ws_max = 0, cnt_max = 0;
+    for (ConvOp* op : ops) {
+      size_t ws = 0, cnt = 0;
+      op->ksplit = conv_patch_plan_splitk(*op, &ws, &cnt);
+      ws_max = std::max(ws_max, ws);
+      cnt_max = std::max(cnt_max, cnt);
+    }
+    if (ws_max > 0) {
+      e = cudaMalloc(&p->splitk_ws, ws_max * sizeof(float));
+      if (e == cudaSuccess) e = cudaMalloc(&p->splitk_counters, cnt_max * sizeof(int));
+      if (e == cudaSuccess) e = cudaMemset(p->splitk_counters, 0, cnt_max * sizeof(int));
+      if (e != cudaSuccess) rc = cuda_fail(e, "split-K workspace allocation");
+      for (ConvOp* op : ops) {
+        op->splitk_ws = p->splitk_ws;
+        op->splitk_counters = p->splitk_counters;
+      }
     }
   }
   if (rc != STX_OK) {

@@ -100,6 +100,8 @@ struct Plan {
   float* pinned = nullptr;         // host pinned: x | grad | func
   void* arena = nullptr;
   size_t arena_bytes = 0;
+  float* splitk_ws = nullptr;      // split-K workspace shared by the convolutions of this plan (small grids only)
+  int* splitk_counters = nullptr;
   ~Plan();
 
   int forward(const float* image, int is_preimage, int with_grams, bool with_loss, cudaStream_t stream);
