@@ -81,6 +81,10 @@ def lib():
         l = ctypes.CDLL(LIB_PATH)
         EXPORTED = _declare(l)
         _lib = l
+        # bring-up switches: STX_DEBUG="key=value,key=value" (see stx_debug_set)
+        for kv in filter(None, os.environ.get("STX_DEBUG", "").split(",")):
+            k, v = kv.split("=")
+            l.stx_debug_set(int(k), int(v))
     return _lib
 
 

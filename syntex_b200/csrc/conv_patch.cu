@@ -327,19 +327,48 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int c0 = (j % kChunksPerTile) * 32;
               const int h = h0 + mt * 16 + (r >> 3);
               const bool valid = (h < p.H) && (w < p.W);
+              // slices summed in a fixed order; two slices (16 independent 16-byte loads) in flight at a time
               float v[32];
+              const float4* s4 = reinterpret_cast<const float4*>(wsall + (static_cast<size_t>(mt) * 128 + r) * BN + c0);
+              const size_t slice_stride4 = static_cast<size_t>(MT) * 128 * BN / 4;
+              {
+                float4 t[8];
 #pragma unroll
-              for (int e = 0; e < 32; ++e) v[e] = 0.0f;
-              for (int sl = 0; sl < sched.ksplit; ++sl) {
-                const float4* s4 = reinterpret_cast<const float4*>(
-                    wsall + (static_cast<size_t>(sl) * MT * 128 + static_cast<size_t>(mt) * 128 + r) * BN + c0);
+                for (int e = 0; e < 8; ++e) t[e] = __ldcg(s4 + e);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  const float4 t = __ldcg(s4 + e);
-                  v[4 * e] += t.x;
-                  v[4 * e + 1] += t.y;
-                  v[4 * e + 2] += t.z;
-                  v[4 * e + 3] += t.w;
+                  v[4 * e] = t[e].x;
+                  v[4 * e + 1] = t[e].y;
+                  v[4 * e + 2] = t[e].z;
+                  v[4 * e + 3] = t[e].w;
+                }
+              }
+              int sl = 1;
+              for (; sl + 1 < sched.ksplit; sl += 2) {
+                float4 ta[8], tb[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  ta[e] = __ldcg(s4 + sl * slice_stride4 + e);
+                  tb[e] = __ldcg(s4 + (sl + 1) * slice_stride4 + e);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  v[4 * e] = (v[4 * e] + ta[e].x) + tb[e].x;
+                  v[4 * e + 1] = (v[4 * e + 1] + ta[e].y) + tb[e].y;
+                  v[4 * e + 2] = (v[4 * e + 2] + ta[e].z) + tb[e].z;
+                  v[4 * e + 3] = (v[4 * e + 3] + ta[e].w) + tb[e].w;
+                }
+              }
+              if (sl < sched.ksplit) {
+                float4 ta[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) ta[e] = __ldcg(s4 + sl * slice_stride4 + e);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  v[4 * e] += ta[e].x;
+                  v[4 * e + 1] += ta[e].y;
+                  v[4 * e + 2] += ta[e].z;
+                  v[4 * e + 3] += ta[e].w;
                 }
               }
               conv_epilogue_store<SPLIT>(p, v, valid, n, h, w, nblk * BN + c0);
@@ -528,6 +557,7 @@ int conv_patch_plan_splitk(const ConvOp& op, size_t* ws_floats, size_t* counters
   const int chunks = op.cin / 64;
   int ks = 1;
   if (items * 2 <= slots) ks = slots / items;
+  if (ks > 4) ks = 4;                 // the fix-up of the last slice is serial per tile: keep it short
   if (ks > chunks) ks = chunks;
   if (ks < 2) return 1;
   *ws_floats = static_cast<size_t>(items) * ks * op.mt * 128 * op.bn;
