@@ -504,6 +504,10 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
       bn = force_bn;
     if (force_mt == 1 || (force_mt == 2 && !split)) mt = force_mt;
     if (bn == 256) mt = 2;              // only the <256, 2> instance exists
+    // Two CTAs per SM only pay when there are work items for them: with a grid of <= one item per SM (deep layers
+    // at batch 1) the one-CTA layout wins because its 9-stage weight ring covers the L2 latency on its own.
+    const int items = ((W + 7) / 8) * ((H + 16 * mt - 1) / (16 * mt)) * nimg * (cout / bn);
+    if (items <= 148) occ = 1;
     if (force_occ == 1 || force_occ == 2) occ = force_occ;
     if (split || mt == 2) occ = 1;      // only MT = 1 single-MMA instances exist with two CTAs per SM
   }

@@ -9,7 +9,7 @@ namespace stx {
 int g_debug_dgrad_variant = 0;      // variant code for the dgrad convolutions (0 = automatic)
 int g_debug_no_gram_fusion = 0;     // 1 = stand-alone Gram-gradient launches
 int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
-int g_debug_no_splitk = 0;          // 1 = no split-K
+int g_debug_splitk = 0;             // 1 = split-K work items for small grids (measured slower at 256^2: off)
 
 static const LayerSpec kLayers[kNumLayers] = {
     {true, 0, 3, 64},     {true, 1, 64, 64},    {false, -1, 64, 64},   {true, 2, 64, 128},
@@ -396,8 +396,10 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       cur ^= 1;
     }
   }
-  // Split-K for the convolutions whose grid would leave most SMs idle (deep layers at small batch).
-  if (rc == STX_OK && !g_debug_no_splitk) {
+  // Split-K for the convolutions whose grid would leave most SMs idle (deep layers at small batch). Implemented and
+  // parity-tested, but off by default: at 256^2, batch 1, the per-item fixed cost (pipeline fill, partial-tile
+  // round trip through L2, serial fix-up) outweighs the extra parallelism (profiles/r01_splitk_b1.md).
+  if (rc == STX_OK && g_debug_splitk) {
     std::vector<ConvOp*> ops;
     for (int l = 1; l <= topmost; ++l)
       if (kLayers[l].is_conv) ops.push_back(&p->fwd[l]);
