@@ -261,6 +261,8 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->mt = 1;
   op->occ = 1;
   op->gram_chunks = 0;
+  op->w_tiled = nullptr;
+  op->w_tiled_lo = nullptr;
   op->ksplit = 1;
   op->splitk_ws = nullptr;
   op->splitk_counters = nullptr;

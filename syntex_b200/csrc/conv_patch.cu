@@ -68,6 +68,9 @@ struct PatchSched {
   int ksplit;        // split-K factor (small grids): work item = (tile, N-block, K slice)
   float* ws;         // split-K partial tiles [tile*nblocks][ksplit][MT*128][BN] fp32
   int* counters;     // split-K arrival counters [tile*nblocks], zero between launches
+  const bf16* wt;    // tiled pre-swizzled weights [tap][K/64][N/64][64][64] (null: fetch through tmB / tmB2)
+  const bf16* wt_lo;
+  int nblocks64;     // N / 64
 };
 
 template <int BN, int MT, bool SPLIT, int OCC>
@@ -148,8 +151,15 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_wait(&bempty[bs], ((bit / kBS) & 1) ^ 1, 120 + bs);
             uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
             mbar_arrive_expect_tx(&bfull[bs], (SPLIT ? 2 : 1) * BN * 128);
-            tma_load_3d(bdst, &tmB, &bfull[bs], c * 64, nblk * BN, tap);
-            if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
+            if (sched.wt != nullptr && BN >= 64) {
+              // one contiguous, pre-swizzled BN*128-byte run per weight tile
+              const size_t woff = ((static_cast<size_t>(tap) * chunks + c) * sched.nblocks64 + nblk * (BN / 64)) * 4096;
+              bulk_load_1d(bdst, sched.wt + woff, BN * 128, &bfull[bs]);
+              if (SPLIT) bulk_load_1d(bdst + L::kBBytes, sched.wt_lo + woff, BN * 128, &bfull[bs]);
+            } else {
+              tma_load_3d(bdst, &tmB, &bfull[bs], c * 64, nblk * BN, tap);
+              if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
+            }
           }
         }
         // Fused Gram gradient (utils.py:54): the features of this tile (dense 128-row K-major tiles, staged in a patch
@@ -448,6 +458,10 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   PatchSched sched;
   sched.nblocks = op.cout / BN;
   sched.ksplit = (op.ksplit > 1 && op.splitk_ws && op.splitk_counters && BN != 16) ? op.ksplit : 1;
+  sched.wt = op.w_tiled;
+  sched.wt_lo = SPLIT ? op.w_tiled_lo : nullptr;
+  if (SPLIT && !op.w_tiled_lo) sched.wt = nullptr;
+  sched.nblocks64 = op.cout / 64;
   sched.ws = op.splitk_ws;
   sched.counters = op.splitk_counters;
   sched.total_items = op.tiles_w * op.tiles_h * op.nimg * sched.nblocks * sched.ksplit;
@@ -537,6 +551,8 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->rgb_image = nullptr;
   op->rgb_preimage = 0;
   op->gram_chunks = 0;
+  op->w_tiled = nullptr;
+  op->w_tiled_lo = nullptr;
   op->ksplit = 1;
   op->splitk_ws = nullptr;
   op->splitk_counters = nullptr;

@@ -285,6 +285,30 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cin, int co
   if (wd) wd[(static_cast<long long>(8 - tap) * cin + ci) * cout + co] = v;
 }
 
+// Tiled, pre-swizzled packs for the halo-patch kernel: [tap][K/64][N/64] blocks of 64 rows x 128 bytes laid out
+// exactly as a 128B-swizzled shared-memory tile (16-byte chunk j of row r stored at chunk j ^ (r & 7)), so that a
+// [BN x 64] weight tile is ONE contiguous BN*128-byte run and lands with a single 1-D bulk copy instead of BN
+// strided 128-byte TMA rows. forward: N = cout, K = cin; dgrad: N = cin, K = cout, taps rotated by 180 degrees.
+__global__ void pack_weights_tiled_kernel(const float* __restrict__ w, int cin, int cout, bf16* __restrict__ f_hi,
+                                          bf16* __restrict__ f_lo, bf16* __restrict__ d_hi) {
+  const long long total = 9LL * cin * cout;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % cout);
+  const int ci = static_cast<int>((i / cout) % cin);
+  const int tap = static_cast<int>(i / (static_cast<long long>(cout) * cin));
+  const float x = w[i];
+  const bf16 hi = __float2bfloat16_rn(x);
+  auto offset = [](int tap_, int n, int k, int N, int K) -> long long {
+    const int r = n & 63, kk = k & 63;
+    const long long block = (static_cast<long long>(tap_) * (K / 64) + (k >> 6)) * (N / 64) + (n >> 6);
+    return block * 4096 + r * 64 + (((kk >> 3) ^ (r & 7)) << 3) + (kk & 7);     // in bf16 elements
+  };
+  if (f_hi) f_hi[offset(tap, co, ci, cout, cin)] = hi;
+  if (f_lo) f_lo[offset(tap, co, ci, cout, cin)] = __float2bfloat16_rn(x - __bfloat162float(hi));
+  if (d_hi) d_hi[offset(8 - tap, ci, co, cin, cout)] = hi;
+}
+
 __global__ void pack_conv1_1_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [9][16][64]
   if (i >= 9 * 16 * 64) return;
@@ -389,6 +413,17 @@ int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf1
   STX_REQUIRE(w_hwio, "pack_weights: null weights");
   const long long total = 9LL * cin * cout;
   pack_weights_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_hwio, cin, cout, w_fwd, w_fwd_lo, w_dgrad);
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+int pack_weights_tiled_launch(const float* w_hwio, int cin, int cout, bf16* f_hi, bf16* f_lo, bf16* d_hi,
+                              cudaStream_t stream) {
+  STX_REQUIRE(w_hwio, "pack_weights_tiled: null weights");
+  STX_REQUIRE(cin % 64 == 0 && cout % 64 == 0, "pack_weights_tiled: channels must be multiples of 64");
+  const long long total = 9LL * cin * cout;
+  pack_weights_tiled_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_hwio, cin, cout, f_hi, f_lo, d_hi);
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;

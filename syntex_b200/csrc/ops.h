@@ -15,6 +15,8 @@ struct ConvOp {
   CUtensorMap tmF;   // fused Gram gradient: features of the output layer [nimg,H,W,cout]
   CUtensorMap tmD;   // fused Gram gradient: scaled Gram difference [nimg][cout][cout]
   int gram_chunks;   // cout / 64 when the Gram gradient is fused, else 0
+  const bf16* w_tiled;     // patch kernel: tiled pre-swizzled weights (1-D bulk copies); null = use tmB
+  const bf16* w_tiled_lo;  // split mode low halves
   int ksplit;        // split-K factor of the patch kernel (1 = off)
   float* splitk_ws;  // fp32 partial tiles (shared by all ops of a plan; launches are stream-ordered)
   int* splitk_counters;
@@ -104,6 +106,9 @@ int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf1
 // Sum loss partials: out[img] = sum_k part[img*stride + k], fixed order (deterministic).
 // conv1_1 weights fp32 [27][64] -> dgrad pack for the tensor-core path: [9][16][64] bf16, rows 0..2 = colours
 // (taps rotated 180 degrees), rows 3..15 zero.
+// Tiled + pre-swizzled packs (see elementwise.cu): forward hi / lo and dgrad, any of them nullable.
+int pack_weights_tiled_launch(const float* w_hwio, int cin, int cout, bf16* f_hi, bf16* f_lo, bf16* d_hi,
+                              cudaStream_t stream);
 int pack_conv1_1_dgrad_launch(const float* w27x64, bf16* out, cudaStream_t stream);
 int sum_partials_launch(const float* part, int nimg, int count, int stride, float* out, cudaStream_t stream);
 

@@ -27,6 +27,9 @@ struct Vgg {
   bf16* wf[kNumConvs] = {};       // forward pack [9][cout][cin] (conv index >= 1), high halves
   bf16* wf_lo[kNumConvs] = {};    // low halves bf16(w - bf16(w)) for the bf16x3 forward
   bf16* wd[kNumConvs] = {};       // dgrad pack   [9][cin][cout]
+  bf16* wft[kNumConvs] = {};      // tiled pre-swizzled forward pack (hi), see pack_weights_tiled_kernel
+  bf16* wft_lo[kNumConvs] = {};
+  bf16* wdt[kNumConvs] = {};      // tiled pre-swizzled dgrad pack
   ~Vgg();
 };
 int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_convs, const float* mean3,
