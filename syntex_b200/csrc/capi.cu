@@ -14,7 +14,7 @@ extern int g_debug_dgrad_variant;
 extern int g_debug_no_gram_fusion;
 extern int g_debug_no_poolbwd_fusion;
 extern int g_debug_splitk;
-extern int g_debug_no_tiled_weights;
+extern int g_debug_tiled_weights;
 }  // namespace stx
 
 struct stx_vgg {
@@ -43,7 +43,7 @@ int stx_debug_set(int key, int value) {
     case 4: g_debug_no_gram_fusion = value; return STX_OK;
     case 5: g_debug_no_poolbwd_fusion = value; return STX_OK;
     case 6: g_debug_splitk = value; return STX_OK;
-    case 7: g_debug_no_tiled_weights = value; return STX_OK;
+    case 7: g_debug_tiled_weights = value; return STX_OK;
     default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
   }
 }

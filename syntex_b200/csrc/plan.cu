@@ -9,7 +9,8 @@ namespace stx {
 int g_debug_dgrad_variant = 0;      // variant code for the dgrad convolutions (0 = automatic)
 int g_debug_no_gram_fusion = 0;     // 1 = stand-alone Gram-gradient launches
 int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
-int g_debug_no_tiled_weights = 0;   // 1 = fetch weight tiles through tensor maps instead of 1-D bulk copies
+int g_debug_tiled_weights = 0;      // 1 = fetch weight tiles with 1-D bulk copies from tiled pre-swizzled packs
+                                    // (measured: no gain over tensor-map fetches, costs a second weight copy: off)
 int g_debug_splitk = 0;             // 1 = split-K work items for small grids (measured slower at 256^2: off)
 
 static const LayerSpec kLayers[kNumLayers] = {
@@ -69,11 +70,14 @@ int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_
       chk(cudaMalloc(&v->wf_lo[ci], wn * sizeof(bf16)), "cudaMalloc wf_lo");
       chk(cudaMalloc(&v->wd[ci], wn * sizeof(bf16)), "cudaMalloc wd");
       if (rc == STX_OK) chk(cudaMemcpyAsync(tmp, w[ci], wn * sizeof(float), cudaMemcpyHostToDevice, stream), "copy w");
-      chk(cudaMalloc(&v->wft[ci], wn * sizeof(bf16)), "cudaMalloc wft");
-      chk(cudaMalloc(&v->wft_lo[ci], wn * sizeof(bf16)), "cudaMalloc wft_lo");
-      chk(cudaMalloc(&v->wdt[ci], wn * sizeof(bf16)), "cudaMalloc wdt");
       if (rc == STX_OK) rc = pack_weights_launch(tmp, s.cin, s.cout, v->wf[ci], v->wf_lo[ci], v->wd[ci], stream);
-      if (rc == STX_OK) rc = pack_weights_tiled_launch(tmp, s.cin, s.cout, v->wft[ci], v->wft_lo[ci], v->wdt[ci], stream);
+      if (g_debug_tiled_weights) {
+        chk(cudaMalloc(&v->wft[ci], wn * sizeof(bf16)), "cudaMalloc wft");
+        chk(cudaMalloc(&v->wft_lo[ci], wn * sizeof(bf16)), "cudaMalloc wft_lo");
+        chk(cudaMalloc(&v->wdt[ci], wn * sizeof(bf16)), "cudaMalloc wdt");
+        if (rc == STX_OK)
+          rc = pack_weights_tiled_launch(tmp, s.cin, s.cout, v->wft[ci], v->wft_lo[ci], v->wdt[ci], stream);
+      }
       if (rc == STX_OK) chk(cudaStreamSynchronize(stream), "sync after pack");
       cudaFree(tmp);
     }
@@ -288,8 +292,8 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     ConvOp& op = p->fwd[l];
     rc = conv3x3_prepare(&op, p->act[l - 1], p->split ? p->act_lo[l - 1] : nullptr, B, p->lh[l], p->lw[l], s.cin,
                          vgg->wf[s.conv_index], p->split ? vgg->wf_lo[s.conv_index] : nullptr, s.cout, 0);
-    op.w_tiled = g_debug_no_tiled_weights ? nullptr : vgg->wft[s.conv_index];
-    op.w_tiled_lo = g_debug_no_tiled_weights ? nullptr : vgg->wft_lo[s.conv_index];
+    op.w_tiled = g_debug_tiled_weights ? vgg->wft[s.conv_index] : nullptr;
+    op.w_tiled_lo = g_debug_tiled_weights ? vgg->wft_lo[s.conv_index] : nullptr;
     op.bias = vgg->bias[s.conv_index];
     op.relu = 1;
     op.out = p->act[l];
@@ -374,7 +378,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       st.kind = BwdStep::kDgrad;
       rc = conv3x3_prepare(&st.conv, p->gbuf[cur], nullptr, B, p->lh[l], p->lw[l], s.cout, vgg->wd[s.conv_index],
                            nullptr, s.cin, g_debug_dgrad_variant);
-      st.conv.w_tiled = g_debug_no_tiled_weights ? nullptr : vgg->wdt[s.conv_index];
+      st.conv.w_tiled = g_debug_tiled_weights ? vgg->wdt[s.conv_index] : nullptr;
       st.conv.out = p->gbuf[cur ^ 1];
       st.conv.mask = (kLayers[l - 1].is_conv && loss_index(l - 1) < 0) ? p->act[l - 1] : nullptr;
       p->bwd.push_back(st);
