@@ -98,20 +98,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
-        const int tap = it / p.cchunks;
-        const int cc = it - tap * p.cchunks;
-        int dy = 0, dx = 0;
-        if (p.taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
-        }
-        uint8_t* a_dst = smem + s * L::kStageBytes;
-        uint8_t* b_dst = a_dst + kABytes;
+    // Whole warp in the loop, one elected lane issuing: keeps every operand provably warp-uniform (no
+    // ELECT / BRA.U.ANY serialisation loops around the uniform-datapath instructions).
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
+      const int tap = it / p.cchunks;
+      const int cc = it - tap * p.cchunks;
+      int dy = 0, dx = 0;
+      if (p.taps == 9) {
+        dy = tap / 3 - 1;
+        dx = tap % 3 - 1;
+      }
+      uint8_t* a_dst = smem + s * L::kStageBytes;
+      uint8_t* b_dst = a_dst + kABytes;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[s], L::kStageBytes);
         tma_load_4d(a_dst, &tmA, &full_bar[s], cc * kChunkK, w0 + dx, h0 + dy, n0);
         tma_load_3d(b_dst, &tmB, &full_bar[s], cc * kChunkK, nblk * BN, p.per_image_w ? n0 : tap);
@@ -120,11 +122,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tma_load_3d(b_dst + L::kOperandBytes, &tmB2, &full_bar[s], cc * kChunkK, nblk * BN, tap);
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
       for (int it = 0; it < iters; ++it) {
         const int s = it % kStages;
@@ -135,27 +137,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t b_addr = a_addr + kABytes;
         const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
         const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
-        if (SPLIT) {
-          const uint64_t adesc_lo = make_smem_desc_sw128(a_addr + L::kOperandBytes, 16, 1024);
-          const uint64_t bdesc_lo = make_smem_desc_sw128(b_addr + L::kOperandBytes, 16, 1024);
+        if (elect_one()) {
+          if (SPLIT) {
+            const uint64_t adesc_lo = make_smem_desc_sw128(a_addr + L::kOperandBytes, 16, 1024);
+            const uint64_t bdesc_lo = make_smem_desc_sw128(b_addr + L::kOperandBytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) {
-            umma_bf16(tmem_base, adesc_lo + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);   // A_lo * W_hi
-            umma_bf16(tmem_base, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1);               // A_hi * W_lo
-            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1);                  // A_hi * W_hi
-          }
-        } else {
+            for (int k = 0; k < kChunkK / 16; ++k) {
+              umma_bf16(tmem_base, adesc_lo + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);   // A_lo * W_hi
+              umma_bf16(tmem_base, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1);               // A_hi * W_lo
+              umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1);                  // A_hi * W_hi
+            }
+          } else {
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            for (int k = 0; k < kChunkK / 16; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+              umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            }
           }
+          umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+          if (it == iters - 1) umma_commit(accum_bar);   // accumulator complete
         }
-        umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs have read it
+        __syncwarp();
       }
-      umma_commit(accum_bar);         // accumulator complete
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;           // TMEM lane quarter this warp may access

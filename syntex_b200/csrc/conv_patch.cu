@@ -127,7 +127,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // Whole warp in the loops, one elected lane issuing (see the MMA warp for why).
+    {
       int pit = 0, bit = 0;   // ring counters, running across work items
       for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x) {
         const int ks = item % sched.ksplit;
@@ -143,23 +144,30 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int ps = pit % kPS;
           mbar_wait(&pempty[ps], ((pit / kPS) & 1) ^ 1, 100 + ps);
           uint8_t* pdst = smem + ps * L::kPatchStageBytes;
-          mbar_arrive_expect_tx(&pfull[ps], (SPLIT ? 2 : 1) * L::kPatchBytes);
-          tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
-          if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&pfull[ps], (SPLIT ? 2 : 1) * L::kPatchBytes);
+            tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
+            if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
+          }
+          __syncwarp();
           for (int tap = 0; tap < 9; ++tap, ++bit) {
             const int bs = bit % kBS;
             mbar_wait(&bempty[bs], ((bit / kBS) & 1) ^ 1, 120 + bs);
             uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
-            mbar_arrive_expect_tx(&bfull[bs], (SPLIT ? 2 : 1) * BN * 128);
-            if (sched.wt != nullptr && BN >= 64) {
-              // one contiguous, pre-swizzled BN*128-byte run per weight tile
-              const size_t woff = ((static_cast<size_t>(tap) * chunks + c) * sched.nblocks64 + nblk * (BN / 64)) * 4096;
-              bulk_load_1d(bdst, sched.wt + woff, BN * 128, &bfull[bs]);
-              if (SPLIT) bulk_load_1d(bdst + L::kBBytes, sched.wt_lo + woff, BN * 128, &bfull[bs]);
-            } else {
-              tma_load_3d(bdst, &tmB, &bfull[bs], c * 64, nblk * BN, tap);
-              if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bfull[bs], (SPLIT ? 2 : 1) * BN * 128);
+              if (sched.wt != nullptr && BN >= 64) {
+                // one contiguous, pre-swizzled BN*128-byte run per weight tile
+                const size_t woff =
+                    ((static_cast<size_t>(tap) * chunks + c) * sched.nblocks64 + nblk * (BN / 64)) * 4096;
+                bulk_load_1d(bdst, sched.wt + woff, BN * 128, &bfull[bs]);
+                if (SPLIT) bulk_load_1d(bdst + L::kBBytes, sched.wt_lo + woff, BN * 128, &bfull[bs]);
+              } else {
+                tma_load_3d(bdst, &tmB, &bfull[bs], c * 64, nblk * BN, tap);
+                if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
+              }
             }
+            __syncwarp();
           }
         }
         // Fused Gram gradient (utils.py:54): the features of this tile (dense 128-row K-major tiles, staged in a patch
@@ -167,21 +175,28 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int cf = 0; cf < gram_chunks; ++cf, ++pit, ++bit) {
           const int ps = pit % kPS;
           mbar_wait(&pempty[ps], ((pit / kPS) & 1) ^ 1, 140 + ps);
-          uint8_t* pdst = smem + ps * L::kPatchStageBytes;
-          mbar_arrive_expect_tx(&pfull[ps], MT * 16384);
-          for (int mt = 0; mt < MT; ++mt) tma_load_4d(pdst + mt * 16384, &tmF, &pfull[ps], cf * 64, w0, h0 + 16 * mt, n);
           const int bs = bit % kBS;
           mbar_wait(&bempty[bs], ((bit / kBS) & 1) ^ 1, 160 + bs);
+          uint8_t* pdst = smem + ps * L::kPatchStageBytes;
           uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
-          mbar_arrive_expect_tx(&bfull[bs], BN * 128);
-          tma_load_3d(bdst, &tmD, &bfull[bs], cf * 64, nblk * BN, n);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&pfull[ps], MT * 16384);
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_4d(pdst + mt * 16384, &tmF, &pfull[ps], cf * 64, w0, h0 + 16 * mt, n);
+            mbar_arrive_expect_tx(&bfull[bs], BN * 128);
+            tma_load_3d(bdst, &tmD, &bfull[bs], cf * 64, nblk * BN, n);
+          }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loops (so every value below is provably warp-uniform and lives in uniform
+    // registers); one elected lane issues the tcgen05 instructions. With `if (lane == 0)` around the loops the
+    // compiler wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY serialisation loop, which costs more
+    // issue time than a 32-cycle N = 64 MMA takes to execute.
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t kGroupStride = kPatchW * 128;     // bytes between consecutive 8-pixel row groups
       int pit = 0, bit = 0, ait = 0;
@@ -205,27 +220,30 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
             const uint64_t bdesc_lo = make_smem_desc_sw128(b_addr + L::kBBytes, 16, 1024);
             const uint32_t tap_off = ((tap / 3) * kPatchW + (tap % 3)) * 128;
+            if (elect_one()) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint32_t a_addr = patch + tap_off + mt * 16 * kGroupStride;
-              const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, kGroupStride);
-              const uint64_t adesc_lo = make_smem_desc_sw128(a_addr + L::kPatchStride, 16, kGroupStride);
-              const uint32_t d = acc + mt * BN;
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t a_addr = patch + tap_off + mt * 16 * kGroupStride;
+                const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, kGroupStride);
+                const uint64_t adesc_lo = make_smem_desc_sw128(a_addr + L::kPatchStride, 16, kGroupStride);
+                const uint32_t d = acc + mt * BN;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t accumulate = ((c - c_begin) | tap | k) != 0;
-                if (SPLIT) {
-                  umma_bf16(d, adesc_lo + 2 * k, bdesc + 2 * k, idesc, accumulate);   // A_lo * W_hi
-                  umma_bf16(d, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1);            // A_hi * W_lo
-                  umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);               // A_hi * W_hi
-                } else {
-                  umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t accumulate = ((c - c_begin) | tap | k) != 0;
+                  if (SPLIT) {
+                    umma_bf16(d, adesc_lo + 2 * k, bdesc + 2 * k, idesc, accumulate);   // A_lo * W_hi
+                    umma_bf16(d, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1);            // A_hi * W_lo
+                    umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);               // A_hi * W_hi
+                  } else {
+                    umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                  }
                 }
               }
+              umma_commit(&bempty[bs]);
+              if (tap == 8) umma_commit(&pempty[ps]);
             }
-            umma_commit(&bempty[bs]);
+            __syncwarp();
           }
-          umma_commit(&pempty[ps]);
         }
         for (int cf = 0; cf < gram_chunks; ++cf, ++pit, ++bit) {
           const int ps = pit % kPS;
@@ -235,19 +253,22 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint32_t f_addr = smem_u32(smem + ps * L::kPatchStageBytes);
           const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + L::kBOffset + bs * L::kBStageBytes), 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t adesc = make_smem_desc_sw128(f_addr + mt * 16384, 16, 1024);
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t adesc = make_smem_desc_sw128(f_addr + mt * 16384, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(acc + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+              for (int k = 0; k < 4; ++k) umma_bf16(acc + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+            }
+            umma_commit(&bempty[bs]);
+            umma_commit(&pempty[ps]);
           }
-          umma_commit(&bempty[bs]);
-          umma_commit(&pempty[ps]);
+          __syncwarp();
         }
-        umma_commit(&afull[as]);
+        if (elect_one()) umma_commit(&afull[as]);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;                   // TMEM lane quarter this warp may access

@@ -82,30 +82,31 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
-        uint8_t* a_dst = smem + s * kStageBytes;
-        uint8_t* b_dst = a_dst + 2 * kChunkBytes;
-        const int row = (it_begin + it) * kRowsPerStage;
+    // whole warp in the loop, one elected lane issuing (keeps the operands provably warp-uniform)
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
+      uint8_t* a_dst = smem + s * kStageBytes;
+      uint8_t* b_dst = a_dst + 2 * kChunkBytes;
+      const int row = (it_begin + it) * kRowsPerStage;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[s], (a_chunks + b_chunks) * kChunkBytes);
         for (int c = 0; c < a_chunks; ++c) tma_load_3d(a_dst + c * kChunkBytes, &tmF, &full_bar[s], m0 + 64 * c, row, img);
         for (int c = 0; c < b_chunks; ++c) tma_load_3d(b_dst + c * kChunkBytes, &tmF, &full_bar[s], n0 + 64 * c, row, img);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full_bar[s], ph, 200 + s);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-        const uint32_t b_addr = diag ? a_addr : a_addr + 2 * kChunkBytes;
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(&full_bar[s], ph, 200 + s);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+      const uint32_t b_addr = diag ? a_addr : a_addr + 2 * kChunkBytes;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kRowsPerStage / 16; ++k) {
           // 16 pixel rows per MMA: advance 16 * 128 B along K
@@ -114,10 +115,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
           umma_bf16(tmem_base, adesc, bdesc, idesc, (it | k) != 0);
         }
         umma_commit(&empty_bar[s]);
+        if (it == iters - 1) umma_commit(accum_bar);
       }
-      umma_commit(accum_bar);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
