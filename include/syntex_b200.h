@@ -114,6 +114,22 @@ int stx_plan_copy_layer_total_grad(stx_plan* plan, int k, float* out, void* stre
  * fp32 [batch,h,w,c] device, for the features of the last forward and the current targets. */
 int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream);
 
+/* Zero-copy view of a recorded layer of the last forward: device pointers to the bf16 planes [batch,h,w,c] the
+ * plan owns (hi = bf16(value); lo = bf16(value - hi) in the accurate mode, NULL in STX_PLAN_FAST_BF16 mode; `lo` may
+ * be NULL when not wanted). Valid until the next forward on this plan. */
+int stx_plan_feature_bf16(stx_plan* plan, int layer, const void** hi, const void** lo);
+
+/* Backward of the last stx_plan_forward with caller-supplied per-layer matrices (the generalisation the PO models
+ * need): for every loss layer k the gradient injected at feat[k] is
+ *     dL/dfeat[k] = feat[k] * M[k] + E[k]
+ * M[k]: fp32 [batch,C,C] device (rounded to bf16), E[k]: bf16 [batch,h,w,C] device or NULL (E itself may be NULL);
+ * the sum is back-propagated through VGG19 (ReluGrad / AvgPoolGrad / Conv2DBackpropInput, as tf.gradients does in
+ * po/progressive_model.py's training graph) to grad [batch,H,W,3] fp32. With M[k] = upstream_k * 4/(C^2 n) *
+ * (G_k - T_k) this is the first-order style gradient (utils.py:46-54); the second-order term of differentiating
+ * through grad_layer[k] = alpha F (G - T) adds alpha/n * (F^T U + U^T F) to M[k] and alpha * U (G - T) to E[k]. */
+int stx_plan_backward_custom(stx_plan* plan, const float* image, int is_preimage, const float* const* M,
+                             const void* const* E, float* grad, void* stream);
+
 /* ---- device-resident L-BFGS with box bounds: the optimiser loop of synthesizer.py:127-151 ----------------
  * Replaces scipy.optimize.minimize(method="L-BFGS-B", jac=True, bounds=[0,1]^n, options={maxiter, maxcor,
  * ftol=0, gtol=0}) with a projected L-BFGS whose state (x, history, line search) never leaves the GPU.
@@ -163,6 +179,11 @@ int stx_avgpool2_bwd(const void* g_bf16, const void* act_bf16_or_null, int n, in
 size_t stx_gram_workspace_bytes(int n, int HW, int C);
 int stx_gram_bf16(const void* feat_bf16, int n, int HW, int C, float eps, float* G_out, void* workspace,
                   void* stream);
+/* A^T B / (HW + eps) for two bf16 feature maps [n,HW,C] (the F^T U contraction of the double backward through
+ * build_texture_loss(calc_grad=True), utils.py:50-55): out [n,C,C] fp32, not symmetric. */
+size_t stx_gram_cross_workspace_bytes(int n, int HW, int C);
+int stx_gram_cross_bf16(const void* a_bf16, const void* b_bf16, int n, int HW, int C, float eps, float* out,
+                        void* workspace, void* stream);
 int stx_f32_to_bf16(const float* x, size_t count, void* out_bf16, void* stream);
 int stx_bf16_to_f32(const void* x_bf16, size_t count, float* out, void* stream);
 

@@ -161,8 +161,9 @@ def build_gram(feat: torch.Tensor, mask=None, eps=1e-6):
     return torch.matmul(fr.transpose(1, 2), fr) / normalizer
 
 
-def build_texture_loss(a, b, coefs, is_gram_a=False, is_gram_b=True, calc_grad=False):
-    """utils.py:23-57. Returns (loss_overall [B], loss_layer {k: [B]}, grad_layer {k: like a[k]} or None)."""
+def build_texture_loss(a, b, coefs, is_gram_a=False, is_gram_b=True, calc_grad=False, create_graph=False):
+    """utils.py:23-57. Returns (loss_overall [B], loss_layer {k: [B]}, grad_layer {k: like a[k]} or None).
+    create_graph=True keeps grad_layer differentiable (what TF does when a PO model trains through it)."""
     gram_a = a if is_gram_a else OrderedDict((k, build_gram(a[k])) for k in coefs)
     gram_b = b if is_gram_b else OrderedDict((k, build_gram(b[k])) for k in coefs)
     loss_layer = OrderedDict()
@@ -174,9 +175,38 @@ def build_texture_loss(a, b, coefs, is_gram_a=False, is_gram_b=True, calc_grad=F
         grad_layer = OrderedDict()
         for k in coefs:
             # tf.gradients(loss_layer[k], a[k]) = gradient of the batch sum
-            grad_layer[k] = torch.autograd.grad(loss_layer[k].sum(), a[k], retain_graph=True)[0]
+            grad_layer[k] = torch.autograd.grad(loss_layer[k].sum(), a[k], retain_graph=True,
+                                                create_graph=create_graph)[0]
         return loss_overall, loss_layer, grad_layer
     return loss_overall, loss_layer, None
+
+
+class OracleTexture:
+    """CPU restatement of the PO models' door into the hot path (po/progressive_model.py:157-160 +
+    po/model.py:51-69): same protocol as syntex_b200.po.texture_op.CudaTexture, plain torch autograd with
+    create_graph=True, so that back-propagating a training loss through grad_layer exercises the second-order
+    term exactly as tf.gradients does in the reference graph. Test infrastructure only."""
+
+    def __init__(self, weights, default_layers, dtype=torch.float64):
+        self.weights = weights if isinstance(weights, TorchWeights) else TorchWeights(weights, dtype)
+        self.dtype = dtype
+        self.default_layers = list(default_layers)
+
+    def grams(self, image, layers=None):
+        layers = self.default_layers if layers is None else list(layers)
+        feat = vgg_build(image.detach().to("cpu", self.dtype), self.weights, topmost=layers[-1])
+        return OrderedDict((k, build_gram(feat[k]).detach()) for k in layers)
+
+    def __call__(self, image, layers, gram_target, slot, calc_grad):
+        layers = list(layers)
+        image = image.to("cpu", self.dtype)
+        if not image.requires_grad:      # first stage: the input is data; autograd.grad still needs a graph
+            image = image.detach().requires_grad_(True)
+        feat = vgg_build(image, self.weights, topmost=layers[-1])
+        coefs = OrderedDict((k, 1.0) for k in layers)
+        target = OrderedDict((k, gram_target[k].to("cpu", self.dtype)) for k in layers)
+        _, loss_layer, grad_layer = build_texture_loss(feat, target, coefs, calc_grad=calc_grad, create_graph=True)
+        return loss_layer, grad_layer
 
 
 class SynthesizerOracle:

@@ -40,6 +40,8 @@ def _declare(lib):
         "stx_plan_step_host": (c_int, [vp, fp, c_int, fp, fp, vp]),
         "stx_plan_layer_grad": (c_int, [vp, c_int, fp, vp]),
         "stx_plan_copy_layer_total_grad": (c_int, [vp, c_int, fp, vp]),
+        "stx_plan_feature_bf16": (c_int, [vp, c_int, POINTER(c_void_p), POINTER(c_void_p)]),
+        "stx_plan_backward_custom": (c_int, [vp, fp, c_int, POINTER(c_void_p), POINTER(c_void_p), fp, vp]),
         "stx_lbfgs_create": (c_int, [POINTER(c_void_p), vp, c_int, c_int, c_float, c_float]),
         "stx_lbfgs_destroy": (None, [vp]),
         "stx_lbfgs_reset": (c_int, [vp, fp, c_int, vp]),
@@ -57,6 +59,8 @@ def _declare(lib):
         "stx_avgpool2_bwd": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, vp]),
         "stx_gram_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
         "stx_gram_bf16": (c_int, [vp, c_int, c_int, c_int, c_float, fp, vp, vp]),
+        "stx_gram_cross_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+        "stx_gram_cross_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_float, fp, vp, vp]),
         "stx_f32_to_bf16": (c_int, [fp, c_size_t, vp, vp]),
         "stx_bf16_to_f32": (c_int, [vp, c_size_t, fp, vp]),
     }

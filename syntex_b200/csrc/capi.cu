@@ -197,6 +197,21 @@ int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream) {
   return bf16_to_f32_launch(p->gbuf[0], n, out, S(stream));
 }
 
+int stx_plan_feature_bf16(stx_plan* plan, int layer, const void** hi, const void** lo) {
+  STX_REQUIRE(plan && hi, "stx_plan_feature_bf16: null argument");
+  Plan* p = plan->p;
+  STX_REQUIRE(layer >= 0 && layer <= p->topmost, "stx_plan_feature_bf16: layer out of range");
+  *hi = p->act[layer];
+  if (lo) *lo = p->act_lo[layer];
+  return STX_OK;
+}
+
+int stx_plan_backward_custom(stx_plan* plan, const float* image, int is_preimage, const float* const* M,
+                             const void* const* E, float* grad, void* stream) {
+  STX_REQUIRE(plan, "stx_plan_backward_custom: null plan");
+  return plan->p->backward_custom(image, is_preimage, M, reinterpret_cast<const bf16* const*>(E), grad, S(stream));
+}
+
 // ------------------------------------------------------------------------------------------------ L-BFGS
 int stx_lbfgs_create(stx_lbfgs** out, stx_plan* plan, int maxcor, int bounded, float lower, float upper) {
   STX_REQUIRE(out && plan, "stx_lbfgs_create: null argument");
@@ -299,6 +314,20 @@ size_t stx_gram_workspace_bytes(int n, int HW, int C) {
   if (n <= 0 || HW <= 0 || C <= 0) return 0;
   return gram_partial_bytes(n, HW, C);
 }
+size_t stx_gram_cross_workspace_bytes(int n, int HW, int C) {
+  if (n <= 0 || HW <= 0 || C <= 0) return 0;
+  return gram_cross_partial_bytes(n, HW, C);
+}
+int stx_gram_cross_bf16(const void* a_bf16, const void* b_bf16, int n, int HW, int C, float eps, float* out,
+                        void* workspace, void* stream) {
+  STX_REQUIRE(out, "stx_gram_cross_bf16: null output");
+  GramOp op;
+  STX_TRY(gram_cross_prepare(&op, static_cast<const bf16*>(a_bf16), static_cast<const bf16*>(b_bf16), n, HW, C,
+                             static_cast<float*>(workspace)));
+  STX_TRY(gram_launch(op, S(stream)));
+  return gram_finish_launch(op, eps, out, nullptr, 0, 0.0f, nullptr, 0.0f, nullptr, 0, S(stream));
+}
+
 int stx_gram_bf16(const void* feat_bf16, int n, int HW, int C, float eps, float* G_out, void* workspace,
                   void* stream) {
   STX_REQUIRE(G_out, "stx_gram_bf16: null output");

@@ -25,13 +25,14 @@ constexpr int kSmemTotal = kStages * 4 * kChunkBytes + 128 + 1024;   // A: 2 chu
 
 struct GramKernelParams {
   int C, splits, iters_per_split, total_iters, tiles_per_dim;
+  int cross;   // 1 = A^T B of two different maps (all T x T tiles, B operand from tmU); 0 = symmetric F^T F
   uint32_t lbo, sbo;
   float* partial;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
+gram_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmU, const GramKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kStageBytes = 4 * kChunkBytes;
@@ -45,7 +46,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
 
   // Upper-triangle tile (ti <= tj).
   int ti = 0, tj = 0;
-  {
+  if (p.cross) {
+    ti = blockIdx.x / p.tiles_per_dim;
+    tj = blockIdx.x % p.tiles_per_dim;
+  } else {
     int t = blockIdx.x;
     int row_len = p.tiles_per_dim;
     while (t >= row_len) {
@@ -58,7 +62,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
   const int split = blockIdx.y;
   const int img = blockIdx.z;
   const int m0 = ti * 128, n0 = tj * 128;
-  const bool diag = (ti == tj);
+  const bool diag = (ti == tj) && !p.cross;
   const int a_chunks = (p.C >= 128) ? 2 : 1;
   const int b_chunks = diag ? 0 : BN / 64;
 
@@ -66,7 +70,10 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
   int it_end = min(it_begin + p.iters_per_split, p.total_iters);
   const int iters = max(it_end - it_begin, 0);
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmF);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmF);
+    if (p.cross) tma_prefetch_desc(&tmU);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -93,7 +100,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const GramKernelParams p) {
       if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[s], (a_chunks + b_chunks) * kChunkBytes);
         for (int c = 0; c < a_chunks; ++c) tma_load_3d(a_dst + c * kChunkBytes, &tmF, &full_bar[s], m0 + 64 * c, row, img);
-        for (int c = 0; c < b_chunks; ++c) tma_load_3d(b_dst + c * kChunkBytes, &tmF, &full_bar[s], n0 + 64 * c, row, img);
+        for (int c = 0; c < b_chunks; ++c)
+          tma_load_3d(b_dst + c * kChunkBytes, p.cross ? &tmU : &tmF, &full_bar[s], n0 + 64 * c, row, img);
       }
       __syncwarp();
     }
@@ -160,7 +168,7 @@ constexpr int kFinishWarps = kFinishThreads / 32;
 // the 8/kw groups of a pass run side by side; partial sums meet in shared memory in a fixed order. The slab count
 // ranges from 4 (pool4, batch 8) to ~300 (conv1_1, batch 1). Deterministic.
 __global__ void __launch_bounds__(kFinishThreads)
-gram_finish_kernel(const float* __restrict__ partial, int C, int splits, int kw, float norm,
+gram_finish_kernel(const float* __restrict__ partial, int C, int splits, int kw, int cross, float norm,
                    float* __restrict__ G_out, const float* __restrict__ target, long long target_stride, float dscale,
                    bf16* __restrict__ dscaled, float loss_scale, float* __restrict__ loss_part, int part_stride) {
   __shared__ float red[kFinishWarps][32];
@@ -177,8 +185,9 @@ gram_finish_kernel(const float* __restrict__ partial, int C, int splits, int kw,
     if (e < CC) {
       const int i = e / C, j = e % C;
       // Only 128x128 tiles with tile(i) <= tile(j) were written; take the mirrored element otherwise.
-      const int si = ((i >> 7) <= (j >> 7)) ? i : j;
-      const int sj = ((i >> 7) <= (j >> 7)) ? j : i;
+      const bool upper = cross || ((i >> 7) <= (j >> 7));
+      const int si = upper ? i : j;
+      const int sj = upper ? j : i;
       const float* src = partial + static_cast<size_t>(img) * splits * CC + static_cast<size_t>(si) * C + sj;
       for (int k = sub; k < splits; k += kw) s += src[static_cast<size_t>(k) * CC];
     }
@@ -213,9 +222,10 @@ gram_finish_kernel(const float* __restrict__ partial, int C, int splits, int kw,
 
 }  // namespace
 
-static void gram_geometry(int nimg, int HW, int C, int* ntiles, int* splits, int* iters_per_split, int* total_iters) {
+static void gram_geometry(int nimg, int HW, int C, int* ntiles, int* splits, int* iters_per_split, int* total_iters,
+                          int cross = 0) {
   const int T = (C + 127) / 128;
-  *ntiles = T * (T + 1) / 2;
+  *ntiles = cross ? T * T : T * (T + 1) / 2;
   *total_iters = (HW + kRowsPerStage - 1) / kRowsPerStage;
   // Aim for about one CTA per SM overall (more slabs only make the fixed-order reduction longer), at least 2
   // pipeline iterations per CTA.
@@ -242,12 +252,39 @@ int gram_prepare(GramOp* op, const bf16* feat, int nimg, int HW, int C, float* p
   op->HW = HW;
   op->C = C;
   op->bn = (C == 64) ? 64 : 128;
+  op->cross = 0;
   int total;
   gram_geometry(nimg, HW, C, &op->ntiles, &op->splits, &op->iters_per_split, &total);
   op->partial = partial;
   const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(HW), static_cast<uint64_t>(nimg)};
   const uint32_t box[3] = {64u, static_cast<uint32_t>(kRowsPerStage), 1u};
   return encode_tmap_bf16(&op->tmF, feat, 3, dims, box);
+}
+
+// A^T B / (HW + eps) of two feature maps of the same shape (the F^T U contraction of the second-order term of the
+// per-layer style gradient). Every 128x128 tile is computed (no symmetry).
+size_t gram_cross_partial_bytes(int nimg, int HW, int C) {
+  int ntiles, splits, ips, total;
+  gram_geometry(nimg, HW, C, &ntiles, &splits, &ips, &total, 1);
+  return static_cast<size_t>(nimg) * splits * C * C * sizeof(float);
+}
+
+int gram_cross_prepare(GramOp* op, const bf16* a, const bf16* b, int nimg, int HW, int C, float* partial) {
+  STX_REQUIRE(a && b && partial, "gram_cross: null operand");
+  STX_REQUIRE(C == 64 || C % 128 == 0, "gram_cross: C must be 64 or a multiple of 128");
+  STX_REQUIRE(nimg > 0 && HW > 0, "gram_cross: empty feature map");
+  op->nimg = nimg;
+  op->HW = HW;
+  op->C = C;
+  op->bn = (C == 64) ? 64 : 128;
+  op->cross = 1;
+  int total;
+  gram_geometry(nimg, HW, C, &op->ntiles, &op->splits, &op->iters_per_split, &total, 1);
+  op->partial = partial;
+  const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(HW), static_cast<uint64_t>(nimg)};
+  const uint32_t box[3] = {64u, static_cast<uint32_t>(kRowsPerStage), 1u};
+  STX_TRY(encode_tmap_bf16(&op->tmF, a, 3, dims, box));
+  return encode_tmap_bf16(&op->tmU, b, 3, dims, box);
 }
 
 int gram_launch(const GramOp& op, cudaStream_t stream) {
@@ -266,11 +303,12 @@ int gram_launch(const GramOp& op, cudaStream_t stream) {
   p.lbo = g_debug_gram_lbo ? static_cast<uint32_t>(g_debug_gram_lbo) : static_cast<uint32_t>(kChunkBytes);
   p.sbo = g_debug_gram_sbo ? static_cast<uint32_t>(g_debug_gram_sbo) : 1024u;
   p.partial = op.partial;
+  p.cross = op.cross;
   dim3 grid(op.ntiles, op.splits, op.nimg);
   if (op.bn == 64)
-    gram_kernel<64><<<grid, kThreads, kSmemTotal, stream>>>(op.tmF, p);
+    gram_kernel<64><<<grid, kThreads, kSmemTotal, stream>>>(op.tmF, op.cross ? op.tmU : op.tmF, p);
   else
-    gram_kernel<128><<<grid, kThreads, kSmemTotal, stream>>>(op.tmF, p);
+    gram_kernel<128><<<grid, kThreads, kSmemTotal, stream>>>(op.tmF, op.cross ? op.tmU : op.tmF, p);
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;
@@ -286,7 +324,7 @@ int gram_finish_launch(const GramOp& op, float eps, float* G_out, const float* t
   dim3 grid(gram_finish_blocks(op.C), op.nimg);
   int kw = 1;
   while (kw < kFinishWarps && op.splits > 8 * kw) kw *= 2;      // keep the serial chain per thread <= ~8..37 slabs
-  gram_finish_kernel<<<grid, kFinishThreads, 0, stream>>>(op.partial, op.C, op.splits, kw, norm, G_out, target,
+  gram_finish_kernel<<<grid, kFinishThreads, 0, stream>>>(op.partial, op.C, op.splits, kw, op.cross, norm, G_out, target,
                                                           target_stride, dscale, dscaled, loss_scale, loss_part, part_stride);
   STX_CUDA(cudaGetLastError());
   count_launch();

@@ -60,6 +60,8 @@ int conv_launch(const ConvOp& op, cudaStream_t stream);
 // ------------------------------------------------------------------ gram.cu
 struct GramOp {
   CUtensorMap tmF;   // features viewed as [nimg][HW][C] bf16
+  CUtensorMap tmU;   // cross mode: the second map (B operand)
+  int cross = 0;     // 1 = A^T B of two maps, every tile computed
   int nimg, HW, C;
   int bn;            // N tile (64 for C == 64, else 128)
   int ntiles;        // upper-triangle 128x128 tiles
@@ -69,6 +71,8 @@ struct GramOp {
 };
 size_t gram_partial_bytes(int nimg, int HW, int C);
 int gram_prepare(GramOp* op, const bf16* feat, int nimg, int HW, int C, float* partial);
+size_t gram_cross_partial_bytes(int nimg, int HW, int C);
+int gram_cross_prepare(GramOp* op, const bf16* a, const bf16* b, int nimg, int HW, int C, float* partial);
 int gram_launch(const GramOp& op, cudaStream_t stream);
 // Reduce the split-K partials into G = F^T F / (HW + eps) (mirrored to a full [nimg,C,C] matrix) and, when a
 // target is given, the scaled difference Dscaled = (G - T) * dscale (bf16, [nimg][C][C]) and per-block partial

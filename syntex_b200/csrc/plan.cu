@@ -343,6 +343,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       rc = conv_patch_attach_gram(&prod, p->act[l], ll.dscaled);
       prod.mask = s.is_conv ? p->act[l] : nullptr;
       prod.export_out = ll.dfeat;
+      p->bwd.back().inject_k = k;
       if (rc == STX_OK) {
         rc = conv_prepare(&ll.layer_grad_op, p->act[l], B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
         ll.layer_grad_op.out = p->gbuf[0];
@@ -356,6 +357,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       st.conv.out = p->gbuf[cur];
       st.conv.mask = s.is_conv ? p->act[l] : nullptr;
       st.conv.export_out = ll.dfeat;
+      st.inject_k = have ? -1 : k;   // the addend slot is free only for the topmost loss layer
       p->bwd.push_back(st);
       have = true;
       if (rc == STX_OK) {
@@ -495,14 +497,36 @@ int Plan::forward(const float* image, int is_preimage, int with_grams, bool with
   return STX_OK;
 }
 
-int Plan::backward(const float* image, int is_preimage, float* grad, cudaStream_t stream) {
+int Plan::backward(const float* image, int is_preimage, float* grad, cudaStream_t stream,
+                   const bf16* const* inject) {
+  if (inject) {
+    for (size_t k = 0; k < loss.size(); ++k) {
+      if (!inject[k]) continue;
+      bool found = false;
+      for (const BwdStep& st : bwd) found = found || st.inject_k == static_cast<int>(k);
+      if (!found) return fail(STX_ERR_UNSUPPORTED, "backward: no launch can take the external gradient of this loss layer");
+    }
+  }
   for (const BwdStep& st : bwd) {
+    const bf16* extra = (inject && st.inject_k >= 0) ? inject[st.inject_k] : nullptr;
     switch (st.kind) {
       case BwdStep::kGramGrad:
-        STX_LAUNCH(kClsGramGrad, conv_launch(st.conv, stream));
+        if (extra) {
+          ConvOp op = st.conv;
+          op.addend = extra;
+          STX_LAUNCH(kClsGramGrad, conv_launch(op, stream));
+        } else {
+          STX_LAUNCH(kClsGramGrad, conv_launch(st.conv, stream));
+        }
         break;
       case BwdStep::kDgrad:
-        STX_LAUNCH(kClsConvDgrad, conv_launch(st.conv, stream));
+        if (extra) {
+          ConvOp op = st.conv;
+          op.addend = extra;
+          STX_LAUNCH(kClsConvDgrad, conv_launch(op, stream));
+        } else {
+          STX_LAUNCH(kClsConvDgrad, conv_launch(st.conv, stream));
+        }
         break;
       case BwdStep::kPoolBwd:
         STX_LAUNCH(kClsPool, avgpool2_bwd_mask_launch(st.in, st.act, B, st.H, st.W, st.C, st.out, stream));
@@ -521,6 +545,20 @@ int Plan::backward(const float* image, int is_preimage, float* grad, cudaStream_
     }
   }
   return STX_OK;
+}
+
+int Plan::backward_custom(const float* image, int is_preimage, const float* const* M, const bf16* const* E,
+                          float* grad, cudaStream_t stream) {
+  STX_REQUIRE(image && M && grad, "backward_custom: null argument");
+  if (loss.empty()) return fail(STX_ERR_STATE, "backward_custom: the plan has no loss layers");
+  if (bwd.empty() || (bwd.back().kind != BwdStep::kConv1Bwd && bwd.back().kind != BwdStep::kConv1BwdTensor))
+    return fail(STX_ERR_STATE, "backward_custom: backward program incomplete");
+  for (size_t k = 0; k < loss.size(); ++k) {
+    LossLayer& ll = loss[k];
+    STX_REQUIRE(M[k], "backward_custom: null matrix");
+    STX_TRY(f32_to_bf16_launch(M[k], static_cast<size_t>(B) * ll.C * ll.C, ll.dscaled, stream));
+  }
+  return backward(image, is_preimage, grad, stream, E);
 }
 
 int Plan::step(const float* x, int is_preimage, float* func, float* grad, float* layer_loss_out,

@@ -42,6 +42,7 @@ struct BwdStep {
   const bf16* act = nullptr;
   bf16* out = nullptr;
   int H = 0, W = 0, C = 0;   // kPoolBwd: fine-resolution dims
+  int inject_k = -1;         // loss layer whose external gradient (Plan::backward `inject`) this launch can add
 };
 
 struct LossLayer {
@@ -108,7 +109,14 @@ struct Plan {
   ~Plan();
 
   int forward(const float* image, int is_preimage, int with_grams, bool with_loss, cudaStream_t stream);
-  int backward(const float* image, int is_preimage, float* grad, cudaStream_t stream);
+  // inject (nullable): per loss layer k, an external gradient [B,h,w,C] bf16 (or null) added to dL/dF_k before it is
+  // back-propagated - the part of a caller's upstream gradient that is not of the form F_k * M (po/ double backward).
+  int backward(const float* image, int is_preimage, float* grad, cudaStream_t stream,
+               const bf16* const* inject = nullptr);
+  // Backward of the last forward with caller-supplied matrices: dL/dF_k = F_k * M_k + E_k, M_k fp32 [B,C,C]
+  // (device), E_k bf16 [B,h,w,C] or null; back-propagated through VGG to the image.
+  int backward_custom(const float* image, int is_preimage, const float* const* M, const bf16* const* E, float* grad,
+                      cudaStream_t stream);
   int step(const float* x, int is_preimage, float* func, float* grad, float* layer_loss_out, cudaStream_t stream);
   // One step with events around every launch; ms[kNumClasses] and count[kNumClasses] receive the device time and
   // the number of launches per kernel class. Synchronous.

@@ -1,0 +1,152 @@
+"""SynTexTrainer (po/model.py:77-136): synchronous data-parallel training of a PO model.
+
+Reference semantics: N replicated towers, loss = mean of the tower losses, one Adam step on shared variables, learning
+rate pre-multiplied by n_gpu (po/progressive_model.py:36-37), per-GPU batch BATCH. Here: one process per GPU
+(torch.distributed, NCCL over NVLink), identical replicas, and a gradient MEAN all-reduce - the only exchange step of
+the path (SURVEY.md section 8 row e). Parameters and gradients of the generator live in two flat buffers, one
+contiguous slice per stage; the all-reduce of a stage's slice is launched from a hook as soon as the last gradient
+of that stage has been accumulated, so it overlaps the back-propagation of the earlier stages (backward visits the
+stages last to first).
+"""
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _FlatBuckets(object):
+    """Re-homes the parameters of `groups` (list of lists of nn.Parameter) into one flat buffer, gradients into
+    another, group by group; all-reduces a group's gradient slice asynchronously once all its gradients are in."""
+
+    def __init__(self, groups, world_size):
+        self.world_size = world_size
+        params = [p for g in groups for p in g]
+        dev, dtype = params[0].device, params[0].dtype
+        total = sum(p.numel() for p in params)
+        self.flat_param = torch.empty(total, device=dev, dtype=dtype)
+        self.flat_grad = torch.zeros(total, device=dev, dtype=dtype)
+        self.slices, self.pending, self.handles = [], [], []
+        off = 0
+        for gi, g in enumerate(groups):
+            start = off
+            for p in g:
+                n = p.numel()
+                self.flat_param[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat_param[off:off + n].view_as(p.data)
+                p.grad = self.flat_grad[off:off + n].view_as(p.data)
+                off += n
+                if world_size > 1:
+                    p.register_post_accumulate_grad_hook(self._make_hook(gi))
+            self.slices.append((start, off))
+            self.pending.append(len(g))
+        self.group_sizes = [len(g) for g in groups]
+        self.allreduce_bytes = total * self.flat_grad.element_size()
+
+    def _make_hook(self, gi):
+        def hook(_param):
+            self.pending[gi] -= 1
+            if self.pending[gi] == 0:
+                a, b = self.slices[gi]
+                self.handles.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, async_op=True))
+        return hook
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        self.pending = list(self.group_sizes)
+        self.handles = []
+
+    def finish(self):
+        """Wait for the in-flight all-reduces and turn the sums into means (mean of tower losses, po/model.py:132)."""
+        if self.world_size > 1:
+            for gi, left in enumerate(self.pending):      # groups whose hooks did not all fire (unused parameters)
+                if left != 0:
+                    a, b = self.slices[gi]
+                    self.handles.append(dist.all_reduce(self.flat_grad[a:b], op=dist.ReduceOp.SUM, async_op=True))
+            for h in self.handles:
+                h.wait()
+            self.flat_grad.mul_(1.0 / self.world_size)
+
+
+class SynTexTrainer(object):
+    def __init__(self, input, model, num_gpu=1):
+        """input: iterable of (pre_image_input, image_target) batches for THIS rank; model: a PO model
+        (nn.Module with build_graph / optimizer / vars); num_gpu: world size (one process per GPU)."""
+        self.input = input
+        self.model = model
+        self.num_gpu = max(int(num_gpu), 1)
+        if self.num_gpu > 1:
+            if not dist.is_initialized():
+                raise RuntimeError("SynTexTrainer(num_gpu=%d): torch.distributed is not initialised (launch with "
+                                   "torch.distributed.run, one process per GPU)" % self.num_gpu)
+            if dist.get_world_size() != self.num_gpu:
+                raise ValueError("num_gpu=%d but world size is %d" % (self.num_gpu, dist.get_world_size()))
+            for p in model.vars:                      # identical replicas: rank 0's initial values everywhere
+                dist.broadcast(p.data, src=0)
+        groups = [list(stage.parameters()) for stage in model.syn] if hasattr(model, "syn") else [list(model.vars)]
+        self.buckets = _FlatBuckets(groups, self.num_gpu)
+        self.opt = model.optimizer()
+        self.base_lr = self.opt.param_groups[0]["lr"]
+        self.global_step = 0
+        self.allreduce_wait_s = 0.0
+
+    def set_learning_rate(self, lr):
+        for g in self.opt.param_groups:
+            g["lr"] = lr
+
+    def run_step(self, batch=None):
+        """One synchronous training step; returns the (local) loss as a 0-d tensor."""
+        if batch is None:
+            batch = next(self._iter())
+        pre_image_input, image_target = batch
+        self.buckets.zero_grad()
+        loss = self.model.build_graph(pre_image_input, image_target)
+        loss.backward()
+        self.buckets.finish()
+        self.opt.step()
+        self.global_step += 1
+        return loss.detach()
+
+    def _iter(self):
+        if not hasattr(self, "_it"):
+            self._it = iter(self.input)
+        return self._it
+
+    def train_with_defaults(self, callbacks=None, max_epoch=1, steps_per_epoch=1, session_init=None,
+                            start_dec_epoch=None, log_every=0):
+        """Epoch loop with the reference's schedule (progressive_model.py:344-367): constant learning rate until
+        start_dec_epoch (default max_epoch // 2), then linear decay to 0 at max_epoch. callbacks: callables
+        (trainer, epoch) run after every epoch."""
+        steps_per_epoch = max(int(steps_per_epoch), 1)
+        if start_dec_epoch is None:
+            start_dec_epoch = max_epoch // 2
+        for epoch in range(1, int(max_epoch) + 1):
+            if epoch > start_dec_epoch and max_epoch > start_dec_epoch:
+                frac = (max_epoch - epoch) / float(max_epoch - start_dec_epoch)
+                self.set_learning_rate(self.base_lr * max(frac, 0.0))
+            t0 = time.time()
+            last = None
+            for _ in range(steps_per_epoch):
+                last = self.run_step()
+            if log_every and (epoch % log_every == 0) and (self.num_gpu == 1 or dist.get_rank() == 0):
+                print("epoch %d: loss %.6g  (%.2f s)" % (epoch, float(last), time.time() - t0))
+            for cb in (callbacks or []):
+                cb(self, epoch)
+        return self
+
+
+class SyntheticPOData(object):
+    """Endless (pre_image_input ~ U(-1,1), image_target in [0,255]) batches of synthetic textures: the bench/test
+    stand-in for get_data (progressive_model.py:274-296), which joins RandomZData([size,size,3], -1, 1) with
+    augmented exemplar crops."""
+
+    def __init__(self, batch, size, seed=0, device="cuda"):
+        self.batch, self.size, self.device = batch, size, device
+        self.rng = np.random.RandomState(seed)
+
+    def __iter__(self):
+        from ..synthetic import synthetic_texture
+        while True:
+            z = self.rng.uniform(-1, 1, size=(self.batch, self.size, self.size, 3)).astype(np.float32)
+            t = np.stack([synthetic_texture(self.size, seed=int(self.rng.randint(1 << 30))) for _ in range(self.batch)])
+            yield (torch.as_tensor(z).to(self.device), torch.as_tensor(t * 255.0, dtype=torch.float32).to(self.device))

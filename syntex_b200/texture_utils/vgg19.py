@@ -165,15 +165,18 @@ class Vgg19(object):
             self._vgg = h
         return self._vgg
 
-    def get_plan(self, batch, height, width, topmost=None, coefs=None, fast_bf16=False, export_layer_grads=False):
+    def get_plan(self, batch, height, width, topmost=None, coefs=None, fast_bf16=False, export_layer_grads=False,
+                 slot=0):
         """Cached stx_plan for this shape. coefs: OrderedDict layer name -> weight (Gram layers), or None.
-        fast_bf16: single-MMA bf16 forward instead of the accurate bf16x3 forward (see include/syntex_b200.h)."""
+        fast_bf16: single-MMA bf16 forward instead of the accurate bf16x3 forward (see include/syntex_b200.h).
+        slot: distinct slots give distinct plans of the same shape (each keeps the activations of its own last
+        forward - the PO training graph evaluates VGG once per stage and back-propagates through all of them)."""
         topmost = self.topmost if topmost is None else topmost
         if LAYER_INDEX[topmost] > LAYER_INDEX[self.topmost]:
             raise ValueError("topmost %s is above the layers loaded (%s)" % (topmost, self.topmost))
         coefs = OrderedDict() if coefs is None else coefs
         key = (batch, height, width, topmost, tuple((k, float(v)) for k, v in coefs.items()), bool(fast_bf16),
-               bool(export_layer_grads))
+               bool(export_layer_grads), int(slot))
         plan = self._plans.get(key)
         if plan is None:
             plan = _Plan(self._vgg_handle(), batch, height, width, LAYER_INDEX[topmost],
