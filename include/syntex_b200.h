@@ -70,6 +70,10 @@ void stx_vgg_destroy(stx_vgg* vgg);
 /* keep, for every loss layer k, the total gradient d sum(loss_overall) / d feat[k] of each step (what the PO models'
  * stage preparation takes with tf.gradients(loss, [feat[k]...]), po/improved_model.py:227-231) */
 #define STX_PLAN_EXPORT_LAYER_GRADS 2
+/* keep the low half of EVERY recorded layer. Without it the accurate forward skips the low-half store of the
+ * convolutions that only feed a pooling layer (conv1_2, conv2_2, conv3_4, conv4_4): nothing on the f/g path reads it,
+ * and stx_plan_copy_feature_f32 then returns those four layers rounded to bf16. Vgg19.build sets this flag. */
+#define STX_PLAN_FULL_FEATURES 4
 int stx_plan_create(stx_plan** out, const stx_vgg* vgg, int batch, int height, int width, int topmost,
                     int num_loss_layers, const int* loss_layers, const float* coefs, int flags);
 void stx_plan_destroy(stx_plan* plan);

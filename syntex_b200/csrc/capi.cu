@@ -15,6 +15,7 @@ extern int g_debug_no_gram_fusion;
 extern int g_debug_no_poolbwd_fusion;
 extern int g_debug_splitk;
 extern int g_debug_tiled_weights;
+extern int g_debug_resident;
 }  // namespace stx
 
 struct stx_vgg {
@@ -44,6 +45,7 @@ int stx_debug_set(int key, int value) {
     case 5: g_debug_no_poolbwd_fusion = value; return STX_OK;
     case 6: g_debug_splitk = value; return STX_OK;
     case 7: g_debug_tiled_weights = value; return STX_OK;
+    case 8: g_debug_resident = value; return STX_OK;
     default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
   }
 }
@@ -98,7 +100,7 @@ int stx_plan_copy_feature_f32(stx_plan* plan, int layer, float* out, void* strea
   Plan* p = plan->p;
   STX_REQUIRE(layer >= 0 && layer <= p->topmost, "layer index out of range for this plan");
   const size_t n = static_cast<size_t>(p->B) * p->lh[layer] * p->lw[layer] * p->lc[layer];
-  if (p->split) return bf16pair_to_f32_launch(p->act[layer], p->act_lo[layer], n, out, S(stream));
+  if (p->split && p->lo_valid[layer]) return bf16pair_to_f32_launch(p->act[layer], p->act_lo[layer], n, out, S(stream));
   return bf16_to_f32_launch(p->act[layer], n, out, S(stream));
 }
 
@@ -202,7 +204,7 @@ int stx_plan_feature_bf16(stx_plan* plan, int layer, const void** hi, const void
   Plan* p = plan->p;
   STX_REQUIRE(layer >= 0 && layer <= p->topmost, "stx_plan_feature_bf16: layer out of range");
   *hi = p->act[layer];
-  if (lo) *lo = p->act_lo[layer];
+  if (lo) *lo = p->lo_valid[layer] ? p->act_lo[layer] : nullptr;
   return STX_OK;
 }
 

@@ -132,7 +132,9 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
       }
     } else {
       uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
-      uint4* l4 = SPLIT ? reinterpret_cast<uint4*>(p.out_lo + off) : nullptr;
+      // the low halves are optional even in split mode: a layer that only feeds a fused pool (whose hi/lo outputs
+      // carry the precision forward) and the backward mask needs its high plane only
+      uint4* l4 = (SPLIT && p.out_lo) ? reinterpret_cast<uint4*>(p.out_lo + off) : nullptr;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         Pack8 pk, pl;
@@ -146,7 +148,7 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
           }
         }
         o4[j] = pk.u;
-        if (SPLIT) l4[j] = pl.u;
+        if (SPLIT && l4) l4[j] = pl.u;
       }
     }
   }

@@ -262,6 +262,7 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->taps = taps;
   op->per_image_w = per_image_w;
   op->patch = 0;
+  op->res = 0;
   op->mt = 1;
   op->occ = 1;
   op->gram_chunks = 0;

@@ -25,6 +25,10 @@
 
 namespace stx {
 
+int g_debug_resident = 0;      // 1 = resident-weight instances for the 64-channel layers (stx_debug_set key 8).
+                               // Measured after the issue-loop fixes: no gain over the ring (conv1_2 forward 116 us
+                               // resident with one patch stage vs 109 us ring with two; dgrad 66 us either way), so off.
+
 namespace {
 
 constexpr int kEpilogueWarps = 8;
@@ -38,27 +42,46 @@ constexpr int pow2_at_least(int v) {
   return p;
 }
 
-template <int BN, int MT, bool SPLIT, int OCC>
+// RES > 0: the weights of the whole layer (9 taps x RES 64-channel chunks, N = BN = C_out) stay RESIDENT in shared
+// memory for the life of the persistent CTA instead of streaming through a ring once per work item. For the
+// 64-channel layers a work item is only ~1-2 us of MMA time but used to pull 72-144 KB of weights from L2 every time
+// (4x the bytes of its activation patch): 148 SMs fetching the same tiles in lock step made those layers
+// L2-delivery-bound (conv1_2 forward: 5.2 us per tile against 1.8 us of tensor work).
+template <int BN, int MT, bool SPLIT, int OCC, int RES>
 struct PatchSmem {
   static constexpr int kPatchRows = (16 * MT + 2) * kPatchW;
   static constexpr int kPatchBytes = kPatchRows * 128;                        // TMA transaction bytes
   static constexpr int kPatchStride = (kPatchBytes + 1023) & ~1023;           // keep every buffer 1024-aligned
   static constexpr int kPatchStageBytes = (SPLIT ? 2 : 1) * kPatchStride;     // [hi | lo]
-  static constexpr int kPatchStages = (SPLIT || MT == 2 || OCC == 2) ? 2 : 3;
   static_assert(OCC == 1 || (OCC == 2 && (MT == 1 || BN == 16)), "two CTAs per SM: single-tile or N = 16 instances only");
   static constexpr int kBBytes = (BN * 128 + 1023) & ~1023;
   static constexpr int kBStageBytes = (SPLIT ? 2 : 1) * kBBytes;              // [hi | lo]
-  static constexpr int kBRoom = (kSmemBudget / OCC - 2048 - kPatchStages * kPatchStageBytes) / kBStageBytes;
-  static constexpr int kBStages = kBRoom > 10 ? 10 : kBRoom;
+  static constexpr int kBudget = kSmemBudget / OCC - 2048;
+  // resident mode: a small ring for the per-image Gram-difference tiles of the fused Gram gradient
+  static constexpr int kDStages = (RES > 0 && !SPLIT) ? (OCC == 2 ? 1 : 2) : 0;
+  static constexpr int kResRoom = (kBudget - 9 * RES * kBStageBytes - kDStages * kBBytes) / kPatchStageBytes;
+  static constexpr int kPatchStages = RES > 0 ? (kResRoom > 4 ? 4 : kResRoom)
+                                              : ((SPLIT || MT == 2 || OCC == 2) ? 2 : 3);
+  static constexpr int kBRoom = (kBudget - kPatchStages * kPatchStageBytes) / kBStageBytes;
+  static constexpr int kBStages = RES > 0 ? 9 * RES : (kBRoom > 10 ? 10 : kBRoom);
+  static constexpr int kBBarriers = RES > 0 ? 1 : kBStages;
   static constexpr int kBOffset = kPatchStages * kPatchStageBytes;
-  static constexpr int kBarrierOffset = kBOffset + kBStages * kBStageBytes;
+  static constexpr int kDOffset = kBOffset + kBStages * kBStageBytes;
+  static constexpr int kBarrierOffset = kDOffset + kDStages * kBBytes;
   static constexpr int kTotal = kBarrierOffset + 512 + 1024;
-  static constexpr int kAccStages = (2 * BN * MT * OCC <= 512) ? 2 : 1;       // TMEM accumulator buffers
-  static constexpr int kAccCols = BN * MT;
+  // MERGE (bf16x3 with N = 64): A_hi * [W_hi ; W_lo] is issued as ONE N = 128 MMA into two column ranges that the
+  // epilogue adds. An M = 128, K = 16 MMA costs ~64 cycles however small N is (measured: ~70 cycles per N = 64 MMA,
+  // ~72 per N = 128 MMA - the A operand streams out of shared memory at 64 B/clk), so two N = 64 MMAs on the same
+  // A tile cost twice what one N = 128 MMA does.
+  static constexpr bool kMerge = SPLIT && BN == 64;
+  static constexpr int kAccCols = (kMerge ? 2 : 1) * BN * MT;
+  static constexpr int kAccStages = (2 * kAccCols * OCC <= 512) ? 2 : 1;      // TMEM accumulator buffers
   static constexpr int kTmemCols = pow2_at_least(kAccStages * kAccCols);
+  static_assert(kPatchStages >= 1, "no room for a patch stage");
   static_assert(kBStages >= 3, "weight ring too shallow");
+  static_assert(2 * (kPatchStages + kBBarriers + kDStages + kAccStages) * 8 + 16 <= 512, "barrier block overflow");
   static_assert(kTotal * OCC <= 227 * 1024, "shared memory budget exceeded");
-  static_assert(OCC * pow2_at_least(kAccStages * BN * MT) <= 512, "TMEM budget exceeded");
+  static_assert(OCC * pow2_at_least(kAccStages * kAccCols) <= 512, "TMEM budget exceeded");
 };
 
 struct PatchSched {
@@ -73,21 +96,24 @@ struct PatchSched {
   int nblocks64;     // N / 64
 };
 
-template <int BN, int MT, bool SPLIT, int OCC>
+template <int BN, int MT, bool SPLIT, int OCC, int RES>
 __global__ void __launch_bounds__(kThreads, OCC)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                   const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmD,
                   const ConvKernelParams p, const PatchSched sched) {
-  using L = PatchSmem<BN, MT, SPLIT, OCC>;
+  using L = PatchSmem<BN, MT, SPLIT, OCC, RES>;
   constexpr int kPS = L::kPatchStages, kBS = L::kBStages, kAS = L::kAccStages;
+  constexpr int kBB = L::kBBarriers, kDS = L::kDStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + L::kBarrierOffset);
   uint64_t* pempty = pfull + kPS;
   uint64_t* bfull = pempty + kPS;
-  uint64_t* bempty = bfull + kBS;
-  uint64_t* afull = bempty + kBS;
+  uint64_t* bempty = bfull + kBB;
+  uint64_t* dfull = bempty + kBB;      // resident mode: ring of Gram-difference tiles
+  uint64_t* dempty = dfull + kDS;
+  uint64_t* afull = dempty + kDS;
   uint64_t* aempty = afull + kAS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + kAS);
   volatile int* splitk_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
@@ -106,9 +132,13 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&pfull[s], 1);
       mbar_init(&pempty[s], 1);
     }
-    for (int s = 0; s < kBS; ++s) {
+    for (int s = 0; s < kBB; ++s) {
       mbar_init(&bfull[s], 1);
       mbar_init(&bempty[s], 1);
+    }
+    for (int s = 0; s < kDS; ++s) {
+      mbar_init(&dfull[s], 1);
+      mbar_init(&dempty[s], 1);
     }
     for (int s = 0; s < kAS; ++s) {
       mbar_init(&afull[s], 1);
@@ -130,6 +160,18 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // Whole warp in the loops, one elected lane issuing (see the MMA warp for why).
     {
       int pit = 0, bit = 0;   // ring counters, running across work items
+      if (RES > 0) {
+        // the whole layer's weights, once: tile (chunk c, tap) -> slot c * 9 + tap
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bfull[0], kBS * (SPLIT ? 2 : 1) * BN * 128);
+          for (int t = 0; t < kBS; ++t) {
+            uint8_t* bdst = smem + L::kBOffset + t * L::kBStageBytes;
+            tma_load_3d(bdst, &tmB, &bfull[0], (t / 9) * 64, 0, t % 9);
+            if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[0], (t / 9) * 64, 0, t % 9);
+          }
+        }
+        __syncwarp();
+      }
       for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x) {
         const int ks = item % sched.ksplit;
         const int rest = item / sched.ksplit;
@@ -150,7 +192,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
           }
           __syncwarp();
-          for (int tap = 0; tap < 9; ++tap, ++bit) {
+          for (int tap = 0; RES == 0 && tap < 9; ++tap, ++bit) {
             const int bs = bit % kBS;
             mbar_wait(&bempty[bs], ((bit / kBS) & 1) ^ 1, 120 + bs);
             uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
@@ -175,16 +217,19 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int cf = 0; cf < gram_chunks; ++cf, ++pit, ++bit) {
           const int ps = pit % kPS;
           mbar_wait(&pempty[ps], ((pit / kPS) & 1) ^ 1, 140 + ps);
-          const int bs = bit % kBS;
-          mbar_wait(&bempty[bs], ((bit / kBS) & 1) ^ 1, 160 + bs);
+          constexpr int kRing = RES > 0 ? (kDS > 0 ? kDS : 1) : kBS;
+          const int bs = bit % kRing;
+          uint64_t* ring_empty = RES > 0 ? dempty : bempty;
+          uint64_t* ring_full = RES > 0 ? dfull : bfull;
+          mbar_wait(&ring_empty[bs], ((bit / kRing) & 1) ^ 1, 160 + bs);
           uint8_t* pdst = smem + ps * L::kPatchStageBytes;
-          uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
+          uint8_t* bdst = RES > 0 ? smem + L::kDOffset + bs * L::kBBytes : smem + L::kBOffset + bs * L::kBStageBytes;
           if (elect_one()) {
             mbar_arrive_expect_tx(&pfull[ps], MT * 16384);
             for (int mt = 0; mt < MT; ++mt)
               tma_load_4d(pdst + mt * 16384, &tmF, &pfull[ps], cf * 64, w0, h0 + 16 * mt, n);
-            mbar_arrive_expect_tx(&bfull[bs], BN * 128);
-            tma_load_3d(bdst, &tmD, &bfull[bs], cf * 64, nblk * BN, n);
+            mbar_arrive_expect_tx(&ring_full[bs], BN * 128);
+            tma_load_3d(bdst, &tmD, &ring_full[bs], cf * 64, nblk * BN, n);
           }
           __syncwarp();
         }
@@ -199,7 +244,13 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t kGroupStride = kPatchW * 128;     // bytes between consecutive 8-pixel row groups
+      constexpr uint32_t kDescHiA = desc_hi_sw128(kGroupStride);   // activations: 8-row groups kGroupStride apart
+      constexpr uint32_t kDescHiB = desc_hi_sw128(1024);           // weights: dense 128-byte rows
       int pit = 0, bit = 0, ait = 0;
+      if (RES > 0) {
+        mbar_wait(&bfull[0], 0, 219);     // resident weights have landed
+        tc_fence_after();
+      }
       for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x, ++ait) {
         const int as = ait % kAS;
         mbar_wait(&aempty[as], ((ait / kAS) & 1) ^ 1, 300 + as);    // epilogue has drained this accumulator
@@ -211,48 +262,79 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int c = c_begin; c < c_end; ++c, ++pit) {
           const int ps = pit % kPS;
           mbar_wait(&pfull[ps], (pit / kPS) & 1, 200 + ps);
+          // Descriptors differ between MMAs only in their 14-bit start-address field (bits 0..13, address >> 4;
+          // shared memory ends below 2^18 bytes, so adding offsets never carries out of the field): keep the upper
+          // word constant and do 32-bit adds on the lower one. The issuing lane then spends one or two uniform-ALU
+          // instructions per MMA instead of rebuilding 64-bit descriptors - at N = 64 an MMA executes in 32 cycles
+          // and the issue stream, not the tensor pipe, was the limit (43 % pipe utilisation on conv1_2).
           const uint32_t patch = smem_u32(smem + ps * L::kPatchStageBytes);
-          for (int tap = 0; tap < 9; ++tap, ++bit) {
-            const int bs = bit % kBS;
-            mbar_wait(&bfull[bs], (bit / kBS) & 1, 220 + bs);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(smem + L::kBOffset + bs * L::kBStageBytes);
-            const uint64_t bdesc = make_smem_desc_sw128(b_addr, 16, 1024);
-            const uint64_t bdesc_lo = make_smem_desc_sw128(b_addr + L::kBBytes, 16, 1024);
-            const uint32_t tap_off = ((tap / 3) * kPatchW + (tap % 3)) * 128;
-            if (elect_one()) {
+          const uint32_t a_lo0 = (patch >> 4) & 0x3FFF;
+          auto issue_tap = [&](int tap, uint32_t b_lo0, bool first_chunk) {
+            const uint32_t tap_off16 = (((tap / 3) * kPatchW + (tap % 3)) * 128) >> 4;
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t a_addr = patch + tap_off + mt * 16 * kGroupStride;
-                const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, kGroupStride);
-                const uint64_t adesc_lo = make_smem_desc_sw128(a_addr + L::kPatchStride, 16, kGroupStride);
-                const uint32_t d = acc + mt * BN;
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t a_lo = a_lo0 + tap_off16 + ((mt * 16 * kGroupStride) >> 4);
+              const uint32_t d = acc + mt * (L::kMerge ? 2 : 1) * BN;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t accumulate = ((c - c_begin) | tap | k) != 0;
-                  if (SPLIT) {
-                    umma_bf16(d, adesc_lo + 2 * k, bdesc + 2 * k, idesc, accumulate);   // A_lo * W_hi
-                    umma_bf16(d, adesc + 2 * k, bdesc_lo + 2 * k, idesc, 1);            // A_hi * W_lo
-                    umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, 1);               // A_hi * W_hi
-                  } else {
-                    umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-                  }
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t accumulate = (first_chunk && tap == 0 && k == 0) ? 0u : 1u;
+                const uint64_t ad = desc_pack(a_lo + 2 * k, kDescHiA);
+                const uint64_t bd = desc_pack(b_lo0 + 2 * k, kDescHiB);
+                if (L::kMerge) {
+                  const uint64_t ad_lo = desc_pack(a_lo + (L::kPatchStride >> 4) + 2 * k, kDescHiA);
+                  // [W_hi ; W_lo] are adjacent 64-row tiles of one stage: a single N = 128 operand
+                  umma_bf16(d, ad, bd, make_idesc_bf16(128, 2 * BN, 0, 0), accumulate);   // A_hi * [W_hi ; W_lo]
+                  umma_bf16(d, ad_lo, bd, idesc, 1);                                      // A_lo * W_hi
+                } else if (SPLIT) {
+                  const uint64_t ad_lo = desc_pack(a_lo + (L::kPatchStride >> 4) + 2 * k, kDescHiA);
+                  const uint64_t bd_lo = desc_pack(b_lo0 + (L::kBBytes >> 4) + 2 * k, kDescHiB);
+                  umma_bf16(d, ad_lo, bd, idesc, accumulate);   // A_lo * W_hi
+                  umma_bf16(d, ad, bd_lo, idesc, 1);            // A_hi * W_lo
+                  umma_bf16(d, ad, bd, idesc, 1);               // A_hi * W_hi
+                } else {
+                  umma_bf16(d, ad, bd, idesc, accumulate);
                 }
               }
-              umma_commit(&bempty[bs]);
-              if (tap == 8) umma_commit(&pempty[ps]);
+            }
+          };
+          if (RES > 0) {
+            // resident weights: no barrier inside the chunk, nine taps issued as one straight-line block
+            tc_fence_after();
+            const uint32_t b_base = ((smem_u32(smem + L::kBOffset) >> 4) & 0x3FFF) + c * 9 * (L::kBStageBytes >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) issue_tap(tap, b_base + tap * (L::kBStageBytes >> 4), c == c_begin);
+              umma_commit(&pempty[ps]);
             }
             __syncwarp();
+          } else {
+            const uint32_t b_ring = (smem_u32(smem + L::kBOffset) >> 4) & 0x3FFF;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap, ++bit) {
+              const int bs = bit % kBS;
+              mbar_wait(&bfull[bs], (bit / kBS) & 1, 220 + bs);
+              tc_fence_after();
+              if (elect_one()) {
+                issue_tap(tap, b_ring + bs * (L::kBStageBytes >> 4), c == c_begin);
+                umma_commit(&bempty[bs]);
+                if (tap == 8) umma_commit(&pempty[ps]);
+              }
+              __syncwarp();
+            }
           }
         }
         for (int cf = 0; cf < gram_chunks; ++cf, ++pit, ++bit) {
+          constexpr int kRing = RES > 0 ? (kDS > 0 ? kDS : 1) : kBS;
+          uint64_t* ring_empty = RES > 0 ? dempty : bempty;
+          uint64_t* ring_full = RES > 0 ? dfull : bfull;
           const int ps = pit % kPS;
-          const int bs = bit % kBS;
+          const int bs = bit % kRing;
           mbar_wait(&pfull[ps], (pit / kPS) & 1, 240 + ps);
-          mbar_wait(&bfull[bs], (bit / kBS) & 1, 260 + bs);
+          mbar_wait(&ring_full[bs], (bit / kRing) & 1, 260 + bs);
           tc_fence_after();
           const uint32_t f_addr = smem_u32(smem + ps * L::kPatchStageBytes);
-          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem + L::kBOffset + bs * L::kBStageBytes), 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(
+              smem_u32(RES > 0 ? smem + L::kDOffset + bs * L::kBBytes : smem + L::kBOffset + bs * L::kBStageBytes), 16, 1024);
           if (elect_one()) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -260,7 +342,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int k = 0; k < 4; ++k) umma_bf16(acc + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
             }
-            umma_commit(&bempty[bs]);
+            umma_commit(&ring_empty[bs]);
             umma_commit(&pempty[ps]);
           }
           __syncwarp();
@@ -286,6 +368,26 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int n = tm / tiles_per_img;
       const int as = ait % kAS;
       const uint32_t acc = tmem_base + as * L::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+      if (BN != 16 && (p.mask || p.up_mask || p.addend)) {
+        // While the tile is still accumulating: pull the epilogue's global operands (ReLU masks, addend) into L1, so
+        // that the loads issued after the TMEM read hit instead of paying a DRAM/L2 round trip per chunk on the
+        // critical path of the 64-channel layers (whose tiles are only ~1 us of tensor work).
+        constexpr int kCPT = BN / 32, kC = MT * kCPT;
+        for (int j = (kC >= 2 ? half : 0); j < kC; j += (kC >= 2 ? 2 : 1)) {
+          const int h = h0 + (j / kCPT) * 16 + (r >> 3);
+          if (h < p.H && w < p.W) {
+            const int ch0 = nblk * BN + (j % kCPT) * 32;
+            const size_t off = ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.cout + ch0;
+            if (p.mask) prefetch_l1(p.mask + off);
+            if (p.addend) prefetch_l1(p.addend + off);
+            if (p.up_mask) {
+#pragma unroll
+              for (int d = 0; d < 4; ++d)
+                prefetch_l1(p.up_mask + ((static_cast<size_t>(n) * 2 * p.H + 2 * h + (d >> 1)) * 2 * p.W + 2 * w + (d & 1)) * p.cout + ch0);
+            }
+          }
+        }
+      }
       mbar_wait_relaxed(&afull[as], (ait / kAS) & 1, 400 + as);
       tc_fence_after();
       if (BN == 16) {
@@ -422,8 +524,17 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int h = h0 + mt * 16 + (r >> 3);
           const bool valid = (h < p.H) && (w < p.W);
           float v[32];
-          tmem_ld_32x32(acc + mt * BN + c0, v);
-          tmem_ld_wait();
+          if (L::kMerge) {
+            float u[32];
+            tmem_ld_32x32(acc + mt * 2 * BN + c0, v);
+            tmem_ld_32x32(acc + mt * 2 * BN + BN + c0, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] += u[e];
+          } else {
+            tmem_ld_32x32(acc + mt * BN + c0, v);
+            tmem_ld_wait();
+          }
           if (j == last) {                    // accumulator fully read by this warp: hand it back before storing
             tc_fence_before();
             __syncwarp();
@@ -440,12 +551,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
 }
 
-template <int BN, int MT, bool SPLIT, int OCC>
+template <int BN, int MT, bool SPLIT, int OCC, int RES = 0>
 int launch_patch(const ConvOp& op, cudaStream_t stream) {
-  using L = PatchSmem<BN, MT, SPLIT, OCC>;
+  using L = PatchSmem<BN, MT, SPLIT, OCC, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT, OCC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   L::kTotal));
     attr_set = true;
   }
@@ -478,7 +589,7 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.export_out = op.export_out;
   PatchSched sched;
   sched.nblocks = op.cout / BN;
-  sched.ksplit = (op.ksplit > 1 && op.splitk_ws && op.splitk_counters && BN != 16) ? op.ksplit : 1;
+  sched.ksplit = (op.ksplit > 1 && op.splitk_ws && op.splitk_counters && BN != 16 && !L::kMerge) ? op.ksplit : 1;
   sched.wt = op.w_tiled;
   sched.wt_lo = SPLIT ? op.w_tiled_lo : nullptr;
   if (SPLIT && !op.w_tiled_lo) sched.wt = nullptr;
@@ -495,7 +606,12 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   }
   const int slots = num_sms * OCC;                                              // persistent: OCC CTAs per SM
   const int grid = sched.total_items < slots ? sched.total_items : slots;
-  conv_patch_kernel<BN, MT, SPLIT, OCC><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
+  if (RES > 0) {
+    sched.wt = nullptr;
+    STX_REQUIRE(sched.nblocks == 1 && sched.ksplit == 1 && op.cin == 64 * RES,
+                "conv: resident-weight instance on a shape it does not cover");
+  }
+  conv_patch_kernel<BN, MT, SPLIT, OCC, RES><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
                                                                            SPLIT ? op.tmB2 : op.tmB,
                                                                            sched.gram_chunks ? op.tmF : op.tmA,
                                                                            sched.gram_chunks ? op.tmD : op.tmB, p, sched);
@@ -546,10 +662,23 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
     if (force_occ == 1 || force_occ == 2) occ = force_occ;
     if (split || mt == 2) occ = 1;      // only MT = 1 single-MMA instances exist with two CTAs per SM
   }
+  // Resident weights (see PatchSmem): 64-channel outputs, one N block, at most two input chunks, enough work items
+  // per CTA to amortise loading the whole layer once.
+  int res = 0;
+  if (g_debug_resident != 0 && bn == 64 && cout == 64 && mt == 1 && force_bn == 0 && force_mt == 0 && force_occ == 0) {
+    const int items = ((W + 7) / 8) * ((H + 15) / 16) * nimg;
+    if (items >= 2 * 148) {
+      if (cin == 64) res = 1;
+      else if (cin == 128 && !split) res = 2;
+    }
+    if (res == 1) occ = split ? 1 : 2;
+    if (res == 2) occ = 1;
+  }
   const int tiles_w = (W + 7) / 8;
   op->bn = bn;
   op->mt = mt;
   op->occ = occ;
+  op->res = res;
   op->tiles_w = tiles_w;
   op->tiles_h = (H + 16 * mt - 1) / (16 * mt);
   op->tiles_n = nimg;
@@ -645,10 +774,13 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
   STX_REQUIRE(op.out != nullptr || op.up_out != nullptr, "conv: output not set");
   STX_REQUIRE(op.pool_out == nullptr || (op.H % 2 == 0 && op.W % 2 == 0), "conv: fused pooling needs even H and W");
   if (op.split) {
-    STX_REQUIRE(op.out_lo != nullptr, "conv split: low-half output not set");
+    STX_REQUIRE(op.out_lo != nullptr || op.pool_out_lo != nullptr, "conv split: low-half output not set");
     if (op.bn == 128) return launch_patch<128, 1, true, 1>(op, stream);
+    if (op.res == 1) return launch_patch<64, 1, true, 1, 1>(op, stream);
     return launch_patch<64, 1, true, 1>(op, stream);
   }
+  if (op.res == 1) return launch_patch<64, 1, false, 2, 1>(op, stream);
+  if (op.res == 2) return launch_patch<64, 1, false, 1, 2>(op, stream);
   const bool two = op.occ == 2;
   if (op.bn == 256) return launch_patch<256, 2, false, 1>(op, stream);
   if (op.bn == 128) {

@@ -292,7 +292,7 @@ __device__ void solve_direction(Ctrl& c, const double* p1, const double* yp) {
   }
 }
 
-__global__ void __launch_bounds__(128) lbfgs_decide_kernel(Vecs v) {
+__global__ void __launch_bounds__(512) lbfgs_decide_kernel(Vecs v) {
   const int b = blockIdx.x;
   Ctrl& c = v.ctrl[b];
   if (c.mode == kDone) {
@@ -302,17 +302,24 @@ __global__ void __launch_bounds__(128) lbfgs_decide_kernel(Vecs v) {
   __shared__ double sums[kNP + 1];
   const int nh = c.nh;
   const int np = 6 + 4 * nh;
-  // Sum the block partials in a fixed order; one thread per quantity.
-  for (int k = threadIdx.x; k <= np; k += blockDim.x) {
-    double t = 0.0;
-    if (k < np) {
-      const float* src = v.part + static_cast<size_t>(b) * v.nblk * kNP + k;
-      for (int j = 0; j < v.nblk; ++j) t += static_cast<double>(src[static_cast<size_t>(j) * kNP]);
-    } else {
-      const float* src = v.part2 + static_cast<size_t>(b) * v.nblk;
-      for (int j = 0; j < v.nblk; ++j) t += static_cast<double>(src[j]);
+  // Sum the block partials in a fixed order: one warp per quantity, lane l takes blocks l, l+32, ... (a serial chain
+  // of nblk dependent L2 round trips per quantity used to make this kernel the longest of the optimiser, ~57 us),
+  // then a butterfly over the lanes. Deterministic: the summation tree depends only on nblk.
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int k = warp; k <= np; k += nwarps) {
+      double t = 0.0;
+      if (k < np) {
+        const float* src = v.part + static_cast<size_t>(b) * v.nblk * kNP + k;
+        for (int j = lane; j < v.nblk; j += 32) t += static_cast<double>(src[static_cast<size_t>(j) * kNP]);
+      } else {
+        const float* src = v.part2 + static_cast<size_t>(b) * v.nblk;
+        for (int j = lane; j < v.nblk; j += 32) t += static_cast<double>(src[j]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) sums[k < np ? k : kNP] = t;
     }
-    sums[k < np ? k : kNP] = t;
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -687,7 +694,7 @@ static int launch_cycle(Lbfgs* o, cudaStream_t stream) {
   STX_TRY(o->plan->step(v.xt, o->is_preimage, v.ft, v.gt, nullptr, stream));
   dim3 grid(v.nblk, im->B);
   lbfgs_dots_kernel<<<grid, kThreads, 0, stream>>>(v);
-  lbfgs_decide_kernel<<<im->B, 128, 0, stream>>>(v);
+  lbfgs_decide_kernel<<<im->B, 512, 0, stream>>>(v);
   lbfgs_update_kernel<<<grid, kThreads, 0, stream>>>(v);
   STX_CUDA(cudaGetLastError());
   count_launch(3);

@@ -24,6 +24,7 @@ struct ConvOp {
   int patch;         // 1 = halo-patch kernel (conv_patch.cu), 0 = per-tap kernel (conv_igemm.cu)
   int mt;            // patch kernel: 16x8 output tiles stacked per CTA (1 or 2)
   int occ;           // patch kernel: persistent CTAs per SM (1 or 2)
+  int res;           // patch kernel: 64-channel input chunks whose weights stay resident in shared memory (0 = ring)
   bf16* out_lo;
   bf16* pool_out;            // fused 2x2 average pool outputs (patch kernel only)
   bf16* pool_out_lo;

@@ -222,6 +222,8 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
   p->topmost = topmost;
   p->split = (flags & STX_PLAN_FAST_BF16) ? 0 : 1;
   p->export_grads = (flags & STX_PLAN_EXPORT_LAYER_GRADS) ? 1 : 0;
+  p->full_features = (flags & STX_PLAN_FULL_FEATURES) ? 1 : 0;
+  for (int l = 0; l < kNumLayers; ++l) p->lo_valid[l] = p->split != 0;
   int h = H, w = W, convs_needed = 0;
   for (int l = 0; l <= topmost; ++l) {
     const LayerSpec& s = kLayers[l];
@@ -302,6 +304,12 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       op.pool_out = p->act[l + 1];            // 2x2 average pool fused into this convolution's epilogue
       op.pool_out_lo = p->act_lo[l + 1];
       p->pool_fused[l + 1] = true;
+      if (!p->full_features) {
+        // nothing on the path reads the low half of a convolution that only feeds a fused pool: the pool's own
+        // hi/lo outputs carry the precision forward, the backward mask and the Gram use the high plane
+        op.out_lo = nullptr;
+        p->lo_valid[l] = false;
+      }
     }
   }
   // Loss-layer ops.

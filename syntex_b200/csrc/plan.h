@@ -79,6 +79,8 @@ struct Plan {
   int lh[kNumLayers], lw[kNumLayers], lc[kNumLayers];
   int export_grads = 0;            // keep dL/dF_k of every loss layer (PO stage preparation)
   int split = 1;                   // 1 = bf16x3 forward (hi/lo activations), 0 = plain bf16 forward
+  int full_features = 0;           // keep the low half of every recorded layer (feature export), not only those the path reads
+  bool lo_valid[kNumLayers] = {};  // act_lo[l] is written by the forward
   bf16* act[kNumLayers] = {};      // recorded layers (high halves; the only halves in plain mode)
   bf16* act_lo[kNumLayers] = {};   // low halves (split mode)
   ConvOp fwd[kNumLayers];

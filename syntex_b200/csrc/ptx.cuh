@@ -25,6 +25,10 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -182,6 +186,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+
+// The same descriptor as two 32-bit words: the low word is (start address >> 4) | (LBO >> 4) << 16 with LBO = 16,
+// the high word carries SBO, version and layout and is a compile-time constant of the operand kind.
+__host__ __device__ constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t desc_pack(uint32_t start_field, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | static_cast<uint64_t>(start_field | (1u << 16));
 }
 
 // Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.

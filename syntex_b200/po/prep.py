@@ -31,7 +31,7 @@ def build_stage_preparation(vgg19, image_input, gram_target, coefs, stop_grad=Tr
     layers = list(coefs.keys())
     x = image_input.to(device="cuda", dtype=torch.float32).contiguous()
     B, H, W, _ = x.shape
-    plan = vgg19.get_plan(B, H, W, topmost=layers[-1], coefs=coefs, export_layer_grads=True)
+    plan = vgg19.get_plan(B, H, W, topmost=layers[-1], coefs=coefs, export_layer_grads=True, full_features=True)
     L = _lib.lib()
     st = _lib.stream_ptr()
     for k, name_k in enumerate(layers):

@@ -75,6 +75,50 @@ def test_conv_kernel_variants_agree_with_reference(n, H, W, cin, cout, variant):
     assert relerr(out.float(), ref) < BF16_OUT
 
 
+@pytest.mark.parametrize("n,H,W,cin,cout", [(1, 256, 256, 64, 64), (3, 104, 120, 64, 64), (2, 128, 128, 128, 64),
+                                            (1, 250, 199, 128, 64)])
+def test_conv_resident_weights_match_the_ring_bitwise(n, H, W, cin, cout):
+    """Resident-weight instances (conv_patch.cu, RES; opt-in through stx_debug_set(8, 1) since they measured no
+    faster than the ring) against the streaming ring: same MMA order, so identical bits."""
+    g = gen(21)
+    x = torch.randn((n, H, W, cin), device="cuda", generator=g)
+    xh = x.to(torch.bfloat16)
+    xl = (x - xh.float()).to(torch.bfloat16)
+    w = (torch.randn((3, 3, cin, cout), device="cuda", generator=g) / np.sqrt(9 * cin)).float()
+    b = torch.randn((cout,), device="cuda", generator=g).float()
+    msk = torch.randn((n, H, W, cout), device="cuda", generator=g).to(torch.bfloat16)
+    wf, wl, _ = pack(w, split=True)
+    outs = []
+    for variant in (0, 1064):
+        o = torch.full((n, H, W, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+        L().stx_debug_set(8, 1 if variant == 0 else 0)
+        try:
+            _lib.check(L().stx_conv_bf16(xh.data_ptr(), n, H, W, cin, wf.data_ptr(), cout, 9, b.data_ptr(), None,
+                                         msk.data_ptr(), 0, o.data_ptr(), variant, st()))
+        finally:
+            L().stx_debug_set(8, 0)
+        outs.append(o)
+    assert torch.equal(outs[0], outs[1])
+    ref = (conv_ref(xh.float(), w.to(torch.bfloat16).float(), b)) * (msk.float() > 0)
+    assert relerr(outs[0].float(), ref) < BF16_OUT
+    if cin == 64:       # the bf16x3 forward has a resident instance for 64 -> 64 only
+        res = []
+        for variant in (0, 64):
+            oh = torch.full((n, H, W, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            ol = torch.full_like(oh, float("nan"))
+            L().stx_debug_set(8, 1 if variant == 0 else 0)
+            try:
+                _lib.check(L().stx_conv_bf16x3(xh.data_ptr(), xl.data_ptr(), n, H, W, cin, wf.data_ptr(),
+                                               wl.data_ptr(), cout, b.data_ptr(), 1, oh.data_ptr(), ol.data_ptr(),
+                                               variant, st()))
+            finally:
+                L().stx_debug_set(8, 0)
+            res.append((oh, ol))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        ref3 = conv_ref(x.double(), w.double(), b.double()).relu()
+        assert relerr(res[0][0].double() + res[0][1].double(), ref3) < 1e-4
+
+
 def test_conv_epilogue_addend_mask_inplace():
     n, H, W, cin, cout = 2, 24, 16, 128, 64
     g = gen(1)
