@@ -35,9 +35,14 @@ def timed(fn, warmup, steps):
     return a.elapsed_time(b) / steps
 
 
+GEN_BF16 = os.environ.get("STX_PO_GENERATOR_BF16", "0") == "1"
+
+
 def infer(batch, size):
     torch.manual_seed(0)
-    model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size}).cuda().eval()
+    torch.backends.cudnn.benchmark = True
+    model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size,
+                               "generator_bf16": GEN_BF16}).cuda().eval().to(memory_format=torch.channels_last)
     z, t = next(iter(SyntheticPOData(batch, size, seed=0)))
     l0 = _lib.lib().stx_launch_count()
 
@@ -49,7 +54,7 @@ def infer(batch, size):
     # one of the target, plus the per-layer F*D products
     print(json.dumps({"workload": "po_progressive_inference", "batch": batch, "size": size, "images_per_s": batch / ms * 1e3,
                       "ms_per_batch": ms, "hot_path_launches_per_batch": (_lib.lib().stx_launch_count() - l0) // 7,
-                      "losses": [float(l) for l in model.losses],
+                      "losses": [float(l) for l in model.losses], "generator": "bf16 autocast" if GEN_BF16 else "fp32 (TF32 convs)",
                       "note": "config 3 measured on ProgressiveSynTex (single_model.py is stale against the current "
                               "extractor, SURVEY section 2 #8); random generator weights: throughput only"}))
 
@@ -63,7 +68,9 @@ def train(size, steps):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.manual_seed(0)
-    model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size, "n_gpu": world}).cuda()
+    torch.backends.cudnn.benchmark = True
+    model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size, "n_gpu": world,
+                               "generator_bf16": GEN_BF16}).cuda().to(memory_format=torch.channels_last)
     data = SyntheticPOData(1, size, seed=rank)
     batch = next(iter(data))
     trainer = SynTexTrainer(data, model, world)
@@ -97,6 +104,7 @@ def train(size, steps):
                           "allreduce_bytes": trainer.buckets.allreduce_bytes, "allreduce_alone_ms": ar_ms,
                           "allreduce_share_if_exposed": ar_ms / float(ms),
                           "generator_params": int(trainer.buckets.flat_param.numel()),
+                          "generator": "bf16 autocast" if GEN_BF16 else "fp32 (TF32 convs)",
                           "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
                           "lr": trainer.opt.param_groups[0]["lr"]}))
     if world > 1:

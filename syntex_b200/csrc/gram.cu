@@ -17,11 +17,14 @@ int g_debug_gram_sbo = 0;
 
 namespace {
 
-constexpr int kStages = 4;
-constexpr int kRowsPerStage = 64;                         // pixels (K) per pipeline stage
-constexpr int kChunkBytes = kRowsPerStage * 128;          // one 64-channel chunk: 8 KiB
+// Pipeline: 6 stages of 32 KiB. C >= 128: a stage is 64 pixels x (2 A chunks + 2 B chunks) of 64 channels; C == 64:
+// 128 pixels x (1 A chunk [+ 1 B chunk in cross mode]). The conv1_1 / pool1 Grams are pure streaming (8 MB in, 16 KB
+// out per image): with 4 stages of 8 KiB in flight per SM they ran at 1.6 TB/s, a quarter of HBM speed.
+constexpr int kStages = 6;
+constexpr int kSlotBytes = 32 * 1024;
+__host__ __device__ constexpr int rows_per_stage(int C) { return C == 64 ? 128 : 64; }
 constexpr int kThreads = 192;
-constexpr int kSmemTotal = kStages * 4 * kChunkBytes + 128 + 1024;   // A: 2 chunks, B: up to 2 chunks
+constexpr int kSmemTotal = kStages * kSlotBytes + 128 + 1024;
 
 struct GramKernelParams {
   int C, splits, iters_per_split, total_iters, tiles_per_dim;
@@ -35,7 +38,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 gram_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmU, const GramKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kStageBytes = 4 * kChunkBytes;
+  constexpr int kStageBytes = kSlotBytes;
+  constexpr int kRowsPerStage = rows_per_stage(BN == 64 ? 64 : 128);   // pixels (K) per pipeline stage
+  constexpr int kChunkBytes = kRowsPerStage * 128;                     // one 64-channel chunk
+  constexpr int kBOffset = (BN == 64 ? 1 : 2) * kChunkBytes;           // B chunks follow the A chunks
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* accum_bar = empty_bar + kStages;
@@ -95,7 +101,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUt
       const uint32_t ph = (it / kStages) & 1;
       mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
       uint8_t* a_dst = smem + s * kStageBytes;
-      uint8_t* b_dst = a_dst + 2 * kChunkBytes;
+      uint8_t* b_dst = a_dst + kBOffset;
       const int row = (it_begin + it) * kRowsPerStage;
       if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[s], (a_chunks + b_chunks) * kChunkBytes);
@@ -113,7 +119,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUt
       mbar_wait(&full_bar[s], ph, 200 + s);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-      const uint32_t b_addr = diag ? a_addr : a_addr + 2 * kChunkBytes;
+      const uint32_t b_addr = diag ? a_addr : a_addr + kBOffset;
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < kRowsPerStage / 16; ++k) {
@@ -167,10 +173,11 @@ constexpr int kFinishWarps = kFinishThreads / 32;
 // the slabs of one 32-element group (warp w takes slabs w, w+kw, ...: every read is one coalesced 128-byte line) and
 // the 8/kw groups of a pass run side by side; partial sums meet in shared memory in a fixed order. The slab count
 // ranges from 4 (pool4, batch 8) to ~300 (conv1_1, batch 1). Deterministic.
-__global__ void __launch_bounds__(kFinishThreads)
-gram_finish_kernel(const float* __restrict__ partial, int C, int splits, int kw, int cross, float norm,
-                   float* __restrict__ G_out, const float* __restrict__ target, long long target_stride, float dscale,
-                   bf16* __restrict__ dscaled, float loss_scale, float* __restrict__ loss_part, int part_stride) {
+__device__ __forceinline__ void gram_finish_block(int block, const float* __restrict__ partial, int C, int splits,
+                                                  int kw, int cross, float norm, float* __restrict__ G_out,
+                                                  const float* __restrict__ target, long long target_stride,
+                                                  float dscale, bf16* __restrict__ dscaled, float loss_scale,
+                                                  float* __restrict__ loss_part, int part_stride) {
   __shared__ float red[kFinishWarps][32];
   __shared__ float sq_warp[kFinishWarps];
   const int img = blockIdx.y;
@@ -180,7 +187,7 @@ gram_finish_kernel(const float* __restrict__ partial, int C, int splits, int kw,
   const int CC = C * C;
   float sq = 0.0f;
   for (int pass = 0; pass < kFinishElems / 32; pass += groups) {
-    const int e = blockIdx.x * kFinishElems + (pass + grp) * 32 + lane;
+    const int e = block * kFinishElems + (pass + grp) * 32 + lane;
     float s = 0.0f;
     if (e < CC) {
       const int i = e / C, j = e % C;
@@ -215,9 +222,27 @@ gram_finish_kernel(const float* __restrict__ partial, int C, int splits, int kw,
       float t = 0.0f;
 #pragma unroll
       for (int w = 0; w < kFinishWarps; ++w) t += sq_warp[w];
-      loss_part[static_cast<size_t>(img) * part_stride + blockIdx.x] = t;
+      loss_part[static_cast<size_t>(img) * part_stride + block] = t;
     }
   }
+}
+
+
+__global__ void __launch_bounds__(kFinishThreads)
+gram_finish_kernel(const float* __restrict__ partial, int C, int splits, int kw, int cross, float norm,
+                   float* __restrict__ G_out, const float* __restrict__ target, long long target_stride, float dscale,
+                   bf16* __restrict__ dscaled, float loss_scale, float* __restrict__ loss_part, int part_stride) {
+  gram_finish_block(blockIdx.x, partial, C, splits, kw, cross, norm, G_out, target, target_stride, dscale, dscaled,
+                    loss_scale, loss_part, part_stride);
+}
+
+// All loss layers of a plan in ONE launch: blockIdx.x runs over the concatenated block ranges of the layers.
+__global__ void __launch_bounds__(kFinishThreads) gram_finish_multi_kernel(const GramFinishBatch fb) {
+  int k = 0;
+  while (k + 1 < fb.n && static_cast<int>(blockIdx.x) >= fb.l[k + 1].block_begin) ++k;
+  const GramFinishLayer& f = fb.l[k];
+  gram_finish_block(blockIdx.x - f.block_begin, f.partial, f.C, f.splits, f.kw, 0, f.norm, f.G_out, f.target,
+                    f.target_stride, f.dscale, f.dscaled, f.loss_scale, f.loss_part, fb.part_stride);
 }
 
 }  // namespace
@@ -226,7 +251,7 @@ static void gram_geometry(int nimg, int HW, int C, int* ntiles, int* splits, int
                           int cross = 0) {
   const int T = (C + 127) / 128;
   *ntiles = cross ? T * T : T * (T + 1) / 2;
-  *total_iters = (HW + kRowsPerStage - 1) / kRowsPerStage;
+  *total_iters = (HW + rows_per_stage(C) - 1) / rows_per_stage(C);
   // Aim for about one CTA per SM overall (more slabs only make the fixed-order reduction longer), at least 2
   // pipeline iterations per CTA.
   int want = (148 + (*ntiles) * nimg - 1) / ((*ntiles) * nimg);
@@ -257,7 +282,7 @@ int gram_prepare(GramOp* op, const bf16* feat, int nimg, int HW, int C, float* p
   gram_geometry(nimg, HW, C, &op->ntiles, &op->splits, &op->iters_per_split, &total);
   op->partial = partial;
   const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(HW), static_cast<uint64_t>(nimg)};
-  const uint32_t box[3] = {64u, static_cast<uint32_t>(kRowsPerStage), 1u};
+  const uint32_t box[3] = {64u, static_cast<uint32_t>(rows_per_stage(C)), 1u};
   return encode_tmap_bf16(&op->tmF, feat, 3, dims, box);
 }
 
@@ -282,7 +307,7 @@ int gram_cross_prepare(GramOp* op, const bf16* a, const bf16* b, int nimg, int H
   gram_geometry(nimg, HW, C, &op->ntiles, &op->splits, &op->iters_per_split, &total, 1);
   op->partial = partial;
   const uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(HW), static_cast<uint64_t>(nimg)};
-  const uint32_t box[3] = {64u, static_cast<uint32_t>(kRowsPerStage), 1u};
+  const uint32_t box[3] = {64u, static_cast<uint32_t>(rows_per_stage(C)), 1u};
   STX_TRY(encode_tmap_bf16(&op->tmF, a, 3, dims, box));
   return encode_tmap_bf16(&op->tmU, b, 3, dims, box);
 }
@@ -298,9 +323,9 @@ int gram_launch(const GramOp& op, cudaStream_t stream) {
   p.C = op.C;
   p.splits = op.splits;
   p.iters_per_split = op.iters_per_split;
-  p.total_iters = (op.HW + kRowsPerStage - 1) / kRowsPerStage;
+  p.total_iters = (op.HW + rows_per_stage(op.C) - 1) / rows_per_stage(op.C);
   p.tiles_per_dim = (op.C + 127) / 128;
-  p.lbo = g_debug_gram_lbo ? static_cast<uint32_t>(g_debug_gram_lbo) : static_cast<uint32_t>(kChunkBytes);
+  p.lbo = g_debug_gram_lbo ? static_cast<uint32_t>(g_debug_gram_lbo) : static_cast<uint32_t>(rows_per_stage(op.C) * 128);
   p.sbo = g_debug_gram_sbo ? static_cast<uint32_t>(g_debug_gram_sbo) : 1024u;
   p.partial = op.partial;
   p.cross = op.cross;
@@ -314,6 +339,44 @@ int gram_launch(const GramOp& op, cudaStream_t stream) {
   return STX_OK;
 }
 
+static int finish_kw(int splits) {
+  int kw = 1;
+  while (kw < kFinishWarps && splits > 8 * kw) kw *= 2;      // keep the serial chain per thread <= ~8..37 slabs
+  return kw;
+}
+
+int gram_finish_batch_add(GramFinishBatch* fb, const GramOp& op, float eps, float* G_out, const float* target,
+                          long long target_stride, float dscale, bf16* dscaled, float loss_scale, float* loss_part) {
+  STX_REQUIRE(fb->n < kMaxFinishLayers, "gram_finish_batch: too many layers");
+  GramFinishLayer& f = fb->l[fb->n];
+  f.partial = op.partial;
+  f.C = op.C;
+  f.splits = op.splits;
+  f.kw = finish_kw(op.splits);
+  f.norm = static_cast<float>(op.HW) + eps;
+  f.G_out = G_out;
+  f.target = target;
+  f.target_stride = target_stride;
+  f.dscale = dscale;
+  f.dscaled = dscaled;
+  f.loss_scale = loss_scale;
+  f.loss_part = loss_part;
+  f.block_begin = fb->total_blocks;
+  fb->total_blocks += gram_finish_blocks(op.C);
+  fb->nimg = op.nimg;
+  fb->n += 1;
+  return STX_OK;
+}
+
+int gram_finish_batch_launch(const GramFinishBatch& fb, cudaStream_t stream) {
+  if (fb.n == 0) return STX_OK;
+  dim3 grid(fb.total_blocks, fb.nimg);
+  gram_finish_multi_kernel<<<grid, kFinishThreads, 0, stream>>>(fb);
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
 int gram_finish_blocks(int C) { return (C * C + kFinishElems - 1) / kFinishElems; }
 
 int gram_finish_launch(const GramOp& op, float eps, float* G_out, const float* target, long long target_stride,
@@ -322,8 +385,7 @@ int gram_finish_launch(const GramOp& op, float eps, float* G_out, const float* t
   // fp32 arithmetic as in the reference: normalizer = float32(HW) + float32(eps)  (utils.py:15, :20)
   const float norm = static_cast<float>(op.HW) + eps;
   dim3 grid(gram_finish_blocks(op.C), op.nimg);
-  int kw = 1;
-  while (kw < kFinishWarps && op.splits > 8 * kw) kw *= 2;      // keep the serial chain per thread <= ~8..37 slabs
+  const int kw = finish_kw(op.splits);
   gram_finish_kernel<<<grid, kFinishThreads, 0, stream>>>(op.partial, op.C, op.splits, kw, op.cross, norm, G_out, target,
                                                           target_stride, dscale, dscaled, loss_scale, loss_part, part_stride);
   STX_CUDA(cudaGetLastError());

@@ -85,6 +85,26 @@ int gram_finish_launch(const GramOp& op, float eps, float* G_out /*nullable*/, c
                        float* loss_part /*nullable, [nimg][part_stride], blocks written per image*/, int part_stride,
                        cudaStream_t stream);
 
+// Several layers' finishes in one launch (the f/g plan: five small reductions become one).
+constexpr int kMaxFinishLayers = 8;
+struct GramFinishLayer {
+  const float* partial;
+  int C, splits, kw, block_begin;
+  float norm, dscale, loss_scale;
+  float* G_out;
+  const float* target;
+  long long target_stride;
+  bf16* dscaled;
+  float* loss_part;   // this layer's first column in the [nimg][part_stride] partial-loss table (nullable)
+};
+struct GramFinishBatch {
+  GramFinishLayer l[kMaxFinishLayers];
+  int n = 0, total_blocks = 0, nimg = 0, part_stride = 0;
+};
+int gram_finish_batch_add(GramFinishBatch* fb, const GramOp& op, float eps, float* G_out, const float* target,
+                          long long target_stride, float dscale, bf16* dscaled, float loss_scale, float* loss_part);
+int gram_finish_batch_launch(const GramFinishBatch& fb, cudaStream_t stream);
+
 // ------------------------------------------------------------------ elementwise.cu
 // conv1_1: fp32 image in [0,1] (optionally a pre-image passed through a sigmoid) -> x*255 - mean ->
 // 3x3 SAME conv (3 -> 64) + bias + ReLU -> bf16 NHWC.   w: [27][64] fp32 ((r*3+s)*3+c major), b: [64]

@@ -475,27 +475,58 @@ int Plan::forward(const float* image, int is_preimage, int with_grams, bool with
       {
         cudaStream_t stream = use_side ? side : main_stream;   // STX_LAUNCH records/launches on `stream`
         STX_LAUNCH(kClsGram, gram_launch(ll.gram, stream));
-        // dL/dF = F * (G - T) * coef / (C^2 * n):  loss_overall = sum coef/4 * mean((G-T)^2), G = F^T F / n
-        const float norm = static_cast<float>(ll.HW) + 1e-6f;
-        const float dscale = ll.coef / (static_cast<float>(ll.C) * static_cast<float>(ll.C) * norm);
-        const float lscale = 1.0f / (static_cast<float>(ll.C) * static_cast<float>(ll.C));
-        STX_LAUNCH(kClsGramFinish,
-                   gram_finish_launch(ll.gram, 1e-6f, ll.G, with_loss ? ll.target : nullptr, ll.target_stride, dscale,
-                                      with_loss ? ll.dscaled : nullptr, lscale,
-                                      with_loss ? loss_part + ll.part_offset : nullptr, part_total, stream));
       }
     }
     return STX_OK;
   };
+  // Finishes (split-K reduction, G - T, scaled difference, loss partials) in two launches on the side stream: every
+  // loss layer but the deepest as soon as the last of their Grams has been issued (it hides under the convolutions
+  // of the deepest block), then the deepest one alone - the only finish on the critical path to the backward pass.
+  // Five separate ~10 us launches were mostly launch latency; a single launch at the very end put all of it on the
+  // critical path (measured slower end to end).
+  int deepest = -1;
+  for (const LossLayer& ll : loss) deepest = std::max(deepest, ll.layer);
+  auto launch_finish = [&](bool deepest_only) -> int {
+    GramFinishBatch fb;
+    fb.part_stride = part_total;
+    for (LossLayer& ll : loss) {
+      if ((ll.layer == deepest) != deepest_only) continue;
+      // dL/dF = F * (G - T) * coef / (C^2 * n):  loss_overall = sum coef/4 * mean((G-T)^2), G = F^T F / n
+      const float norm = static_cast<float>(ll.HW) + 1e-6f;
+      const float dscale = ll.coef / (static_cast<float>(ll.C) * static_cast<float>(ll.C) * norm);
+      const float lscale = 1.0f / (static_cast<float>(ll.C) * static_cast<float>(ll.C));
+      STX_TRY(gram_finish_batch_add(&fb, ll.gram, 1e-6f, ll.G, with_loss ? ll.target : nullptr, ll.target_stride, dscale,
+                                    with_loss ? ll.dscaled : nullptr, lscale,
+                                    with_loss ? loss_part + ll.part_offset : nullptr));
+    }
+    if (fb.n == 0) return STX_OK;
+    const bool use_side = (tl == nullptr) && forked;
+    cudaStream_t main_stream = stream;
+    {
+      cudaStream_t stream = use_side ? side : main_stream;
+      STX_LAUNCH(kClsGramFinish, gram_finish_batch_launch(fb, stream));
+    }
+    return STX_OK;
+  };
+  int second_deepest = -1;
+  for (const LossLayer& ll : loss)
+    if (ll.layer != deepest) second_deepest = std::max(second_deepest, ll.layer);
+  auto after_layer = [&](int l) -> int {
+    if (!grams) return STX_OK;
+    STX_TRY(launch_gram(l));
+    if (l == second_deepest) STX_TRY(launch_finish(false));
+    if (l == deepest) STX_TRY(launch_finish(true));
+    return STX_OK;
+  };
   STX_LAUNCH(kClsConv1, conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0], act_lo[0], stream));
-  if (grams) STX_TRY(launch_gram(0));
+  STX_TRY(after_layer(0));
   for (int l = 1; l <= topmost; ++l) {
     if (kLayers[l].is_conv) {
       STX_LAUNCH(kClsConvFwd, conv_launch(fwd[l], stream));
     } else if (!pool_fused[l]) {
       STX_LAUNCH(kClsPool, avgpool2_fwd_launch(act[l - 1], act_lo[l - 1], B, lh[l - 1], lw[l - 1], lc[l - 1], act[l], act_lo[l], stream));
     }
-    if (grams) STX_TRY(launch_gram(l));
+    STX_TRY(after_layer(l));
   }
   if (forked) {
     STX_CUDA(cudaEventRecord(ev_join, side));

@@ -104,6 +104,8 @@ class ProgressiveSynTex(SynTexModelDesc, nn.Module):
         self._loss_scale = args.get("loss_scale", 1.)
         self._pre_act = args.get("pre_act", False)
         self._nn_upsample = not args.get("deconv_upsample", False)
+        # extension (not in the reference parser): run the generator's stock convolutions under bf16 autocast
+        self._generator_bf16 = bool(args.get("generator_bf16", False))
         # The hot path: an object with grams(image) and __call__(image, layers, gram_target, slot, calc_grad) ->
         # (loss_layer, grad_layer). Default: the CUDA plan; tests swap in the CPU oracle to check the training gradient.
         self._texture_fn = texture_fn or CudaTexture(self._vgg19, SynTexModelDesc.DEFAULT_COEFS.keys())
@@ -149,7 +151,12 @@ class ProgressiveSynTex(SynTexModelDesc, nn.Module):
         slot = s if torch.is_grad_enabled() else 0
         loss_layer_input, grad_layer = self._texture_fn(image_input, list(coefs.keys()), gram_target, slot, True)
         loss_overall_input = sum(coefs[k] * 1. / 4 * loss_layer_input[k] for k in coefs)
-        delta_input = self.syn[s](grad_layer)
+        if self._generator_bf16 and image_input.is_cuda:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                delta_input = self.syn[s](grad_layer)
+            delta_input = delta_input.float()
+        else:
+            delta_input = self.syn[s](grad_layer)
         pre_image_output = pre_image_input + delta_input
         return image_input, loss_overall_input, loss_layer_input, pre_image_output
 
