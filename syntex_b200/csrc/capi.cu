@@ -16,6 +16,7 @@ extern int g_debug_no_poolbwd_fusion;
 extern int g_debug_splitk;
 extern int g_debug_tiled_weights;
 extern int g_debug_resident;
+extern int g_lbfgs_no_graph;
 }  // namespace stx
 
 struct stx_vgg {
@@ -46,6 +47,8 @@ int stx_debug_set(int key, int value) {
     case 6: g_debug_splitk = value; return STX_OK;
     case 7: g_debug_tiled_weights = value; return STX_OK;
     case 8: g_debug_resident = value; return STX_OK;
+    case 9: g_pdl = value; return STX_OK;
+    case 10: g_lbfgs_no_graph = value; return STX_OK;
     default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
   }
 }

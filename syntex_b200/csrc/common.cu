@@ -9,6 +9,7 @@ namespace stx {
 
 static thread_local std::string g_last_error;
 static std::atomic<long long> g_launches{0};
+int g_pdl = 1;
 void count_launch(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 

@@ -45,6 +45,30 @@ long long launch_count();
 // dims/box are fastest-first; strides are derived for a dense tensor.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
 
+// Programmatic dependent launch (PDL): a kernel launched through launch_pdl() may start while its predecessor in the
+// stream is still draining - its CTAs become resident as SM resources free up, run their prologue (barrier init,
+// TMEM allocation, descriptor prefetch) and then block in pdl_wait() (griddepcontrol.wait) until the predecessor
+// has completed and flushed. Every kernel launched this way executes pdl_wait() before its first global-memory
+// access, so ordering through memory is unchanged; what disappears is the launch gap and the idle tail between
+// the ~35 dependent launches of one f/g evaluation. g_pdl = 0 (stx_debug_set key 9) restores plain launches.
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx");
+  return 0;
+}
+
 static inline int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;

@@ -93,6 +93,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h)
+  pdl_wait();
 
   const int iters = p.taps * p.cchunks;
 
@@ -222,9 +224,8 @@ int launch_bn(const ConvOp& op, cudaStream_t stream) {
   p.up_mask = op.up_mask;
   p.export_out = op.export_out;
   dim3 grid(op.tiles_w * op.tiles_h * op.tiles_n, op.cout / BN, 1);
-  conv_igemm_kernel<BN, SPLIT><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
-                                                                        SPLIT ? op.tmB2 : op.tmB, p);
-  STX_CUDA(cudaGetLastError());
+  STX_TRY(launch_pdl(conv_igemm_kernel<BN, SPLIT>, grid, dim3(kThreads), L::kTotal, stream, op.tmA, op.tmB,
+                     SPLIT ? op.tmA2 : op.tmA, SPLIT ? op.tmB2 : op.tmB, p));
   count_launch();
   return STX_OK;
 }

@@ -151,6 +151,9 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above overlapped the tail of the previous kernel in the stream; from here on we touch its results.
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int chunks = p.cchunks;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
@@ -611,11 +614,9 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
     STX_REQUIRE(sched.nblocks == 1 && sched.ksplit == 1 && op.cin == 64 * RES,
                 "conv: resident-weight instance on a shape it does not cover");
   }
-  conv_patch_kernel<BN, MT, SPLIT, OCC, RES><<<grid, kThreads, L::kTotal, stream>>>(op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA,
-                                                                           SPLIT ? op.tmB2 : op.tmB,
-                                                                           sched.gram_chunks ? op.tmF : op.tmA,
-                                                                           sched.gram_chunks ? op.tmD : op.tmB, p, sched);
-  STX_CUDA(cudaGetLastError());
+  STX_TRY(launch_pdl(conv_patch_kernel<BN, MT, SPLIT, OCC, RES>, dim3(grid), dim3(kThreads), L::kTotal, stream, op.tmA,
+                     op.tmB, SPLIT ? op.tmA2 : op.tmA, SPLIT ? op.tmB2 : op.tmB, sched.gram_chunks ? op.tmF : op.tmA,
+                     sched.gram_chunks ? op.tmD : op.tmB, p, sched));
   count_launch();
   return STX_OK;
 }

@@ -26,9 +26,11 @@ conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int 
                    bf16* __restrict__ out_lo) {
   __shared__ float sw[27 * 64];
   __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];      // constants: safe before pdl_wait
   if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
   __syncthreads();
+  pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h)
+  pdl_wait();
   const int Wp = (W + 1) >> 1;                                   // pixel pairs per row
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long npairs = static_cast<long long>(nimg) * H * Wp;
@@ -117,6 +119,8 @@ conv1_1_bwd_kernel(const bf16* __restrict__ g, const float* __restrict__ image, 
   __shared__ float sw[27 * 64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long npix = static_cast<long long>(nimg) * H * W;
   long long pix = gid >> 2;
@@ -345,9 +349,8 @@ int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preima
                        const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream) {
   STX_REQUIRE(image && w && b && out && mean3, "conv1_1 fwd: null operand");
   const long long threads = 2LL * nimg * H * ((W + 1) / 2);
-  conv1_1_fwd_kernel<<<blocks_for(threads, 128), 128, 0, stream>>>(image, nimg, H, W, is_preimage, mean3[0], mean3[1],
-                                                                  mean3[2], w, b, out, out_lo);
-  STX_CUDA(cudaGetLastError());
+  STX_TRY(launch_pdl(conv1_1_fwd_kernel, dim3(blocks_for(threads, 128)), dim3(128), 0, stream, image, nimg, H, W,
+                     is_preimage, mean3[0], mean3[1], mean3[2], w, b, out, out_lo));
   count_launch();
   return STX_OK;
 }
@@ -357,8 +360,8 @@ int conv1_1_bwd_launch(const bf16* g, const float* image, int nimg, int H, int W
   STX_REQUIRE(g && w && grad_out, "conv1_1 bwd: null operand");
   STX_REQUIRE(!is_preimage || image, "conv1_1 bwd: pre-image mode needs the input");
   const long long threads = 4LL * nimg * H * W;
-  conv1_1_bwd_kernel<<<blocks_for(threads, 256), 256, 0, stream>>>(g, image, nimg, H, W, is_preimage, w, grad_out);
-  STX_CUDA(cudaGetLastError());
+  STX_TRY(launch_pdl(conv1_1_bwd_kernel, dim3(blocks_for(threads, 256)), dim3(256), 0, stream, g, image, nimg, H, W,
+                     is_preimage, w, grad_out));
   count_launch();
   return STX_OK;
 }

@@ -156,6 +156,14 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUt
         float4* d4 = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        if (!p.cross && ti != tj) {
+          // Mirror of an off-diagonal tile, written here (lane = row: every store of the warp is one coalesced
+          // 128-byte line) so that the finish kernel never has to read a slab transposed (stride-C gathers made it
+          // move 8x the bytes for 3/8 of the elements at C = 512).
+          float* mir = p.partial + ((static_cast<size_t>(img) * p.splits + split) * p.C + n0 + c0) * p.C + i;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mir[static_cast<size_t>(j) * p.C] = v[j];
+        }
       }
     }
   }
@@ -191,11 +199,8 @@ __device__ __forceinline__ void gram_finish_block(int block, const float* __rest
     float s = 0.0f;
     if (e < CC) {
       const int i = e / C, j = e % C;
-      // Only 128x128 tiles with tile(i) <= tile(j) were written; take the mirrored element otherwise.
-      const bool upper = cross || ((i >> 7) <= (j >> 7));
-      const int si = upper ? i : j;
-      const int sj = upper ? j : i;
-      const float* src = partial + static_cast<size_t>(img) * splits * CC + static_cast<size_t>(si) * C + sj;
+      // (the Gram kernel writes the upper-triangle tiles and their mirrors: every slab is a full matrix)
+      const float* src = partial + static_cast<size_t>(img) * splits * CC + e;
       for (int k = sub; k < splits; k += kw) s += src[static_cast<size_t>(k) * CC];
     }
     red[warp][lane] = s;

@@ -17,6 +17,12 @@
 // finished idle through the remaining cycles.
 #include "lbfgs.h"
 
+#include "ptx.cuh"
+
+namespace stx {
+int g_lbfgs_no_graph = 0;   // 1 = launch every optimiser cycle on the stream instead of replaying a CUDA graph (key 10)
+}
+
 #include <algorithm>
 #include <vector>
 
@@ -80,6 +86,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ------------------------------------------------------------------------------------------------ dots
 __global__ void __launch_bounds__(kThreads) lbfgs_dots_kernel(Vecs v) {
+  pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h)
+  pdl_wait();
   const int b = blockIdx.y;
   const Ctrl& c = v.ctrl[b];
   if (c.mode == kDone) return;
@@ -293,6 +301,8 @@ __device__ void solve_direction(Ctrl& c, const double* p1, const double* yp) {
 }
 
 __global__ void __launch_bounds__(512) lbfgs_decide_kernel(Vecs v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   Ctrl& c = v.ctrl[b];
   if (c.mode == kDone) {
@@ -445,6 +455,8 @@ __global__ void __launch_bounds__(512) lbfgs_decide_kernel(Vecs v) {
 
 // ------------------------------------------------------------------------------------------------ update
 __global__ void __launch_bounds__(kThreads) lbfgs_update_kernel(Vecs v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const Ctrl& c = v.ctrl[b];
   const int action = c.action;
@@ -693,10 +705,9 @@ static int launch_cycle(Lbfgs* o, cudaStream_t stream) {
   Vecs& v = im->v;
   STX_TRY(o->plan->step(v.xt, o->is_preimage, v.ft, v.gt, nullptr, stream));
   dim3 grid(v.nblk, im->B);
-  lbfgs_dots_kernel<<<grid, kThreads, 0, stream>>>(v);
-  lbfgs_decide_kernel<<<im->B, 512, 0, stream>>>(v);
-  lbfgs_update_kernel<<<grid, kThreads, 0, stream>>>(v);
-  STX_CUDA(cudaGetLastError());
+  STX_TRY(launch_pdl(lbfgs_dots_kernel, grid, dim3(kThreads), 0, stream, v));
+  STX_TRY(launch_pdl(lbfgs_decide_kernel, dim3(im->B), dim3(512), 0, stream, v));
+  STX_TRY(launch_pdl(lbfgs_update_kernel, grid, dim3(kThreads), 0, stream, v));
   count_launch(3);
   return STX_OK;
 }
@@ -783,8 +794,14 @@ int Lbfgs::run(int maxiter, int max_evals, cudaStream_t caller) {
     if (all_done) break;
     int chunk = std::max(1, maxiter - min_nit);
     chunk = std::min(chunk, max_evals - evals);
-    for (int i = 0; i < chunk; ++i) STX_CUDA(cudaGraphLaunch(im->graph, stream));
-    count_launch(im->graph_nodes * chunk);
+    if (g_lbfgs_no_graph) {
+      // plain stream launches: keeps the programmatic dependent launches between the kernels of a cycle (the host
+      // enqueues a cycle in ~0.1 ms, well ahead of the device)
+      for (int i = 0; i < chunk; ++i) STX_TRY(launch_cycle(this, stream));
+    } else {
+      for (int i = 0; i < chunk; ++i) STX_CUDA(cudaGraphLaunch(im->graph, stream));
+      count_launch(im->graph_nodes * chunk);
+    }
     evals += chunk;
   }
   STX_TRY(fence_out(im, caller));

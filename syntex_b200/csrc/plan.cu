@@ -1,5 +1,7 @@
 #include "plan.h"
 
+#include "ptx.cuh"
+
 #include <algorithm>
 #include <cstring>
 
@@ -139,6 +141,8 @@ namespace {
 __global__ void __launch_bounds__(128)
 loss_reduce_kernel(const float* __restrict__ part, int part_total, const int* __restrict__ offsets, int nloss,
                    const float* __restrict__ coef4, int nimg, float* __restrict__ layer_loss, float* __restrict__ func) {
+  pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h)
+  pdl_wait();
   const int img = blockIdx.x;
   const float* p = part + static_cast<size_t>(img) * part_total;
   __shared__ float red[4];
@@ -608,9 +612,8 @@ int Plan::step(const float* x, int is_preimage, float* func, float* grad, float*
   if (bwd.empty() || (bwd.back().kind != BwdStep::kConv1Bwd && bwd.back().kind != BwdStep::kConv1BwdTensor))
     return fail(STX_ERR_STATE, "step: backward program incomplete");
   STX_TRY(forward(x, is_preimage, 1, true, stream));
-  loss_reduce_kernel<<<B, 128, 0, stream>>>(loss_part, part_total, d_part_offsets, static_cast<int>(loss.size()),
-                                            d_coef, B, layer_loss, func ? func : func_dev);
-  STX_CUDA(cudaGetLastError());
+  STX_TRY(launch_pdl(loss_reduce_kernel, dim3(B), dim3(128), 0, stream, loss_part, part_total, d_part_offsets,
+                     static_cast<int>(loss.size()), d_coef, B, layer_loss, func ? func : func_dev));
   count_launch();
   if (layer_loss_out)
     STX_CUDA(cudaMemcpyAsync(layer_loss_out, layer_loss, loss.size() * B * sizeof(float), cudaMemcpyDeviceToDevice,
