@@ -197,10 +197,9 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION (the image's default): keep stdout to the one
-        # JSON line the contract asks for
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner on STDOUT (NCCL_DEBUG is set in this image): send its log to stderr so that
+        # stdout carries only the one JSON line the contract asks for
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = _lib.lib()
     size, batch = args.size, args.batch
