@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..aparse import ArgParser
-from .layers import PreResBlock, ResBlock, SymConv, UpsampleDeconv, UpsampleNN
+from .layers import PreResBlock, ResBlock, SymConv, UpsampleDeconv, UpsampleNN, instance_norm
 from .model import SynTexModelDesc
 from .texture_op import CudaTexture
 
@@ -52,12 +52,12 @@ class _Stage(nn.Module):
             if deeper is not None:
                 self.up[layer] = up(deeper, chan)
                 if pre_act:
-                    self.pre_inorm[layer] = nn.InstanceNorm2d(deeper, eps=1e-5, affine=True)
+                    self.pre_inorm[layer] = instance_norm(deeper)
             if not pre_act:
-                self.post_inorm[layer] = nn.InstanceNorm2d(chan, eps=1e-5, affine=True)
+                self.post_inorm[layer] = instance_norm(chan)
             self.res[layer] = nn.ModuleList([block(chan) for _ in range(n_block)])
             deeper = chan
-        self.actlast_inorm = nn.InstanceNorm2d(deeper, eps=1e-5, affine=True) if pre_act else None
+        self.actlast_inorm = instance_norm(deeper) if pre_act else None
         self.convlast = SymConv(deeper, 3, 3, act=False, use_bias=True)
 
     def forward(self, grad_layer):
