@@ -92,6 +92,8 @@ int stx_plan_copy_gram(stx_plan* plan, int k, float* out, void* stream);
  * the last forward, or set them from a device array [batch,C,C] (per_image = 1) / [1,C,C] (broadcast). */
 int stx_plan_update_target_from_forward(stx_plan* plan, void* stream);
 int stx_plan_set_target_gram(stx_plan* plan, int k, const float* gram, int per_image, void* stream);
+/* Read the target Gram of loss layer k back as fp32 [batch,C,C] (device; a broadcast target is expanded). */
+int stx_plan_copy_target_gram(stx_plan* plan, int k, float* out, void* stream);
 
 /* Synthesizer.step (synthesizer.py:119-125): one f/g evaluation.
  *   func [batch]         = loss_overall  (build_texture_loss, utils.py:44-49)

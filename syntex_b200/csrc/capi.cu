@@ -131,6 +131,19 @@ int stx_plan_update_target_from_forward(stx_plan* plan, void* stream) {
   return STX_OK;
 }
 
+int stx_plan_copy_target_gram(stx_plan* plan, int k, float* out, void* stream) {
+  STX_REQUIRE(plan && out, "stx_plan_copy_target_gram: null argument");
+  Plan* p = plan->p;
+  STX_REQUIRE(k >= 0 && k < static_cast<int>(p->loss.size()), "loss-layer index out of range");
+  if (!p->have_target) return fail(STX_ERR_STATE, "stx_plan_copy_target_gram: no target Grams set");
+  const LossLayer& ll = p->loss[k];
+  const size_t cc = static_cast<size_t>(ll.C) * ll.C;
+  for (int b = 0; b < p->B; ++b)    // broadcast targets (stride 0) are expanded to [batch,C,C]
+    STX_CUDA(cudaMemcpyAsync(out + b * cc, ll.target + static_cast<size_t>(b) * ll.target_stride, cc * sizeof(float),
+                             cudaMemcpyDeviceToDevice, S(stream)));
+  return STX_OK;
+}
+
 int stx_plan_set_target_gram(stx_plan* plan, int k, const float* gram, int per_image, void* stream) {
   STX_REQUIRE(plan && gram, "stx_plan_set_target_gram: null argument");
   Plan* p = plan->p;

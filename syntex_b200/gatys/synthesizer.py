@@ -87,6 +87,7 @@ class Synthesizer(object):
         self._plan = self.vgg19.get_plan(self.batch, self.image_size, self.image_size, "pool4", coefs,
                                          fast_bf16=(self.precision == "bf16"))
         self._have_target = False
+        self.coef_names = list(coefs.keys())
 
     # ------------------------------------------------------------------ helpers
     def _to_batch(self, image):
@@ -161,6 +162,8 @@ class Synthesizer(object):
         else:
             bounded, lo, hi = (not is_preimage), 0., 1.
         opt = self._get_lbfgs(bounded, lo, hi)
+        if self.verbose:
+            return self._synthesize_device_verbose(opt, x0, is_preimage)
         x = np.empty(self.shape_input, dtype=np.float32)
         fun = np.empty((self.batch,), dtype=np.float32)
         nit = np.empty((self.batch,), dtype=np.int32)
@@ -183,8 +186,7 @@ class Synthesizer(object):
             return [np.sum(ret["func"]), np.array(ret["grad"].ravel(), dtype=np.float64)]
 
         def verbose_callback(x, *args, **kwargs):
-            ret = self.step(x.reshape(self.shape_input), is_preimage=is_preimage)
-            self.verbose_dict["func"].append(np.sum(ret["func"]))
+            self._verbose_record(x.reshape(self.shape_input), is_preimage)
 
         cb = verbose_callback if self.verbose else None
         if bounds is None and (not is_preimage):
@@ -196,6 +198,79 @@ class Synthesizer(object):
         if self.batch == 1:
             return res["x"].reshape(self.shape_input[1:]), res["fun"]
         return res["x"].reshape(self.shape_input), res["fun"]
+
+    def _verbose_record(self, x, is_preimage):
+        """The verbose fetches of the reference graph (synthesizer.py:80-89, :99-107) at `x`, appended to
+        verbose_dict: func, gi_all and, per Gram layer k, l_k (loss), a_k (mean |activation|), gl_k (mean
+        |d loss_k / d feat_k|), gi_k (mean |d loss_k / d input|: one extra back-propagation per layer)."""
+        import torch
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        plan = self._plan
+        xd = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+        B = self.batch
+        K = len(self.coef_names)
+        func = torch.empty((B,), dtype=torch.float32, device="cuda")
+        grad = torch.empty_like(xd)
+        layer_loss = torch.empty((K, B), dtype=torch.float32, device="cuda")
+        pre = int(bool(is_preimage))
+        _lib.check(L.stx_plan_step(plan.handle, xd.data_ptr(), pre, func.data_ptr(), grad.data_ptr(),
+                                   layer_loss.data_ptr(), st))
+        rec = {"func": float(func.sum()), "gi_all": float(grad.abs().mean())}
+        diffs = []
+        for k, name in enumerate(self.coef_names):
+            h, w, c = plan.layer_shape(LAYER_INDEX[name])
+            rec["l_" + name] = float(layer_loss[k].sum())
+            feat = torch.empty((B, h, w, c), dtype=torch.float32, device="cuda")
+            _lib.check(L.stx_plan_copy_feature_f32(plan.handle, LAYER_INDEX[name], feat.data_ptr(), st))
+            rec["a_" + name] = float(feat.abs().mean())
+            g = torch.empty((B, c, c), dtype=torch.float32, device="cuda")
+            t = torch.empty_like(g)
+            _lib.check(L.stx_plan_copy_gram(plan.handle, k, g.data_ptr(), st))
+            _lib.check(L.stx_plan_copy_target_gram(plan.handle, k, t.data_ptr(), st))
+            norm = float(np.float32(h * w) + np.float32(1e-6))
+            diffs.append(((g - t) * (4.0 / (c * c * norm))).contiguous())
+        for k, name in enumerate(self.coef_names):
+            h, w, c = plan.layer_shape(LAYER_INDEX[name])
+            gl = torch.empty((B, h, w, c), dtype=torch.float32, device="cuda")
+            _lib.check(L.stx_plan_layer_grad(plan.handle, k, gl.data_ptr(), st))
+            rec["gl_" + name] = float(gl.abs().mean())
+        for k, name in enumerate(self.coef_names):
+            # d sum(loss_layer[k]) / d input: back-propagate F_k * (alpha (G_k - T_k)) alone
+            mats = [diffs[j] if j == k else torch.zeros_like(diffs[j]) for j in range(K)]
+            Mp = (ctypes.c_void_p * K)(*[m.data_ptr() for m in mats])
+            gk = torch.empty_like(xd)
+            _lib.check(L.stx_plan_backward_custom(plan.handle, xd.data_ptr(), pre, Mp, None, gk.data_ptr(), st))
+            rec["gi_" + name] = float(gk.abs().mean())
+        for key, v in rec.items():
+            self.verbose_dict[key].append(v)
+        return rec
+
+    def _synthesize_device_verbose(self, opt, x0, is_preimage):
+        """The device optimiser advanced one iteration at a time so that the verbose record can be taken after every
+        iteration, as the reference's scipy callback does (diagnostic mode: slower than the resident loop)."""
+        import torch
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        B = self.batch
+        x0d = torch.as_tensor(x0).cuda()
+        xd = torch.empty_like(x0d)
+        fun = torch.empty((B,), dtype=torch.float32, device="cuda")
+        nit = torch.empty((B,), dtype=torch.int32, device="cuda")
+        nfev = torch.empty((B,), dtype=torch.int32, device="cuda")
+        _lib.check(L.stx_lbfgs_reset(opt, x0d.data_ptr(), int(bool(is_preimage)), st))
+        maxiter = int(self.options["maxiter"])
+        for it in range(1, maxiter + 1):
+            _lib.check(L.stx_lbfgs_run(opt, it, 0, st))
+            _lib.check(L.stx_lbfgs_result(opt, xd.data_ptr(), fun.data_ptr(), nit.data_ptr(), nfev.data_ptr(), st))
+            self._verbose_record(xd.cpu().numpy(), is_preimage)
+            if int(nit.min()) < it:      # every job has stopped early (line search could not make progress)
+                break
+        self.last_result = {"nit": nit.cpu().numpy(), "nfev": nfev.cpu().numpy(), "fun": fun.cpu().numpy()}
+        x = xd.cpu().numpy()
+        if self.batch == 1:
+            return x.reshape(self.shape_input[1:]).astype(np.float64), float(fun[0])
+        return x.astype(np.float64), fun.cpu().numpy()
 
     def reset_verbose(self):
         if self.verbose:

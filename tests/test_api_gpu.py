@@ -94,3 +94,57 @@ def test_stage_preparation_gradients_match_autograd(raw_weights):
         assert abs(float(loss_layer[k][0]) - float(ll[k][0])) / float(ll[k][0]) < 5e-3
     want = sum(coefs[k] / 4 * ll[k] for k in list(coefs)[:-1]).detach()
     assert relerr(loss_input, want) < 5e-3
+
+
+@pytest.mark.parametrize("is_preimage", [False, True])
+def test_synthesizer_verbose_record_matches_oracle(raw_weights, is_preimage):
+    """The verbose fetches of gatys/synthesizer.py:80-107: func, gi_all and per Gram layer
+    l_k, a_k, gl_k, gi_k, for the image and for the pre-image (sigmoid) parametrisation."""
+    from syntex_b200.gatys import Synthesizer
+    size = 64
+    syn = Synthesizer({"vgg19_npy_path": raw_weights, "image_size": size, "maxiter": 3, "maxcor": 20, "verbose": True})
+    syn.build()
+    target = so.synthetic_texture(size, seed=31)
+    rng = np.random.RandomState(5)
+    x = rng.uniform(-1, 1, (1, size, size, 3)) if is_preimage else rng.uniform(0.05, 0.95, (1, size, size, 3))
+    syn.compute_gram(target, update=True)
+    syn.reset_verbose()
+    rec = syn._verbose_record(x, is_preimage)
+    # oracle
+    W = so.TorchWeights(so.load_vgg_weights(raw_weights), torch.float64)
+    coefs = Synthesizer.DEFAULT_COEFS
+    gt = OrderedDict((k, so.build_gram(v)) for k, v in so.vgg_build(torch.as_tensor(target[None]).double(), W).items()
+                     if k in coefs)
+    xr = torch.as_tensor(x).double().requires_grad_(True)
+    img = torch.sigmoid(xr) if is_preimage else xr
+    feat = so.vgg_build(img, W)
+    lo, ll, gl = so.build_texture_loss(feat, gt, coefs, calc_grad=True)
+    gi_all = torch.autograd.grad(lo.sum(), xr, retain_graph=True)[0]
+    assert abs(rec["func"] - float(lo.sum())) / float(lo.sum()) < 5e-3
+    assert abs(rec["gi_all"] - float(gi_all.abs().mean())) / float(gi_all.abs().mean()) < 1e-2
+    for k in coefs:
+        assert abs(rec["l_" + k] - float(ll[k].sum())) / float(ll[k].sum()) < 5e-3, k
+        assert abs(rec["a_" + k] - float(feat[k].abs().mean())) / float(feat[k].abs().mean()) < 1e-4, k
+        assert abs(rec["gl_" + k] - float(gl[k].abs().mean())) / float(gl[k].abs().mean()) < 1e-2, k
+        gik = torch.autograd.grad(ll[k].sum(), xr, retain_graph=True)[0]
+        assert abs(rec["gi_" + k] - float(gik.abs().mean())) / float(gik.abs().mean()) < 1e-2, k
+    assert set(syn.verbose_dict.keys()) == {"func", "gi_all"} | {p + k for p in ("l_", "a_", "gl_", "gi_") for k in coefs}
+
+
+@pytest.mark.parametrize("optimizer", ["device", "scipy"])
+def test_synthesize_verbose_collects_one_record_per_iteration(raw_weights, optimizer, tmp_path):
+    from syntex_b200.gatys import Synthesizer
+    size = 64
+    syn = Synthesizer({"vgg19_npy_path": raw_weights, "image_size": size, "maxiter": 4, "maxcor": 20, "verbose": True,
+                       "optimizer": optimizer})
+    syn.build()
+    x0 = np.random.RandomState(0).uniform(1 / 255., 1 - 1 / 255., (size, size, 3))
+    img, fun = syn.synthesize(x0, so.synthetic_texture(size, seed=2))
+    n = len(syn.verbose_dict["func"])
+    assert 1 <= n <= 4 and all(len(v) == n for v in syn.verbose_dict.values())
+    assert syn.verbose_dict["func"][-1] < syn.verbose_dict["func"][0] or n == 1
+    assert abs(syn.verbose_dict["func"][-1] - float(fun)) / float(fun) < 1e-3
+    out = tmp_path / "verbose.npz"
+    syn.save_verbose(str(out))
+    z = np.load(str(out))
+    assert "gi_pool4" in z.files and len(z["func"]) == n
