@@ -59,6 +59,11 @@ int stx_debug_patch_probe(const void* patch_bf16, int rows, const void* b_bf16, 
 int stx_vgg_create(stx_vgg** out, const float* const* weights_hwio, const float* const* biases, int num_convs,
                    const float* mean3, void* stream);
 void stx_vgg_destroy(stx_vgg* vgg);
+/* Device pointers to the packed bf16 weights of conv layer `conv_index` (network order, 1 = conv1_2; conv1_1 runs on
+ * its own fp32 kernel): forward pack [9][cout][cin] high and low halves, input-gradient pack [9][cin][cout]. Any
+ * output may be NULL. Used by callers that drive stx_conv_bf16 themselves with the network's weights (the tangent
+ * sweep of the PO double backward, syntex_b200/po/texture_op.py). */
+int stx_vgg_weights(const stx_vgg* vgg, int conv_index, const void** fwd_hi, const void** fwd_lo, const void** dgrad);
 
 /* ---- plan: the graph that gatys/synthesizer.py:54-107 (Synthesizer.build) and po/model.py:51-69 construct ----
  * topmost: last layer index to compute (15 = pool4, the Vgg19Extractor default, vgg19_extractor.py:5-6).

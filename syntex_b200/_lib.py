@@ -25,6 +25,7 @@ def _declare(lib):
         "stx_vgg_create": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int,
                                    POINTER(c_float), vp]),
         "stx_vgg_destroy": (None, [vp]),
+        "stx_vgg_weights": (c_int, [vp, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
         "stx_plan_create": (c_int, [POINTER(c_void_p), vp, c_int, c_int, c_int, c_int, c_int, POINTER(c_int),
                                     POINTER(c_float), c_int]),
         "stx_plan_destroy": (None, [vp]),

@@ -215,6 +215,16 @@ int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream) {
   return bf16_to_f32_launch(p->gbuf[0], n, out, S(stream));
 }
 
+int stx_vgg_weights(const stx_vgg* vgg, int conv_index, const void** fwd_hi, const void** fwd_lo,
+                    const void** dgrad) {
+  STX_REQUIRE(vgg, "stx_vgg_weights: null handle");
+  STX_REQUIRE(conv_index >= 1 && conv_index < vgg->v->num_convs, "stx_vgg_weights: conv index out of range (1 = conv1_2)");
+  if (fwd_hi) *fwd_hi = vgg->v->wf[conv_index];
+  if (fwd_lo) *fwd_lo = vgg->v->wf_lo[conv_index];
+  if (dgrad) *dgrad = vgg->v->wd[conv_index];
+  return STX_OK;
+}
+
 int stx_plan_feature_bf16(stx_plan* plan, int layer, const void** hi, const void** lo) {
   STX_REQUIRE(plan && hi, "stx_plan_feature_bf16: null argument");
   Plan* p = plan->p;

@@ -138,7 +138,199 @@ def _make_function():
     return VggTextureFunction
 
 
+def _make_prep_function():
+    """Autograd node for the stage preparation of po/improved_model.py:209-232 / po/adaptive_model.py:204-222:
+    (image) -> (feat_k ..., loss_per_layer [K,B], grad_per_layer_k ...) with
+        grad_per_layer = tf.gradients(sum_k coef_k/4 loss_k, [feat_k ...])      (full VGG back-propagation)
+    and, unlike po/prep.py, a backward for ALL outputs - including the second-order term of training through
+    grad_per_layer when --stop-grad is off (the reference's default).
+
+    Second order. With delta_l = dL/da_l, the back-propagation is delta_l = inj_l + Back_{l+1}(delta_{l+1}),
+    inj_l = beta_l a_l D_l at the loss layers (beta = coef / (C^2 n)) and Back_l(d) = W_l^T * (d . mask_l) for a
+    convolution (mask_l = [z_l > 0], piecewise constant) or AvgPoolGrad. An upstream U_k = dl/d delta_k therefore
+    reaches the loss layers through the TRANSPOSED operators, a forward-like "tangent sweep"
+        V_l = U_l + mask_l . (W_l * V_{l-1})          (bias-free masked convolutions; average pooling at the pools)
+    after which l depends on the activations only through the closed forms <V_l, beta_l a_l D_l(a_l)>: the same
+    F M + E injection as in VggTextureFunction with U := V_l, handed to the plan's ordinary backward program."""
+    import torch
+    from ..texture_utils.vgg19 import LAYER_NAMES, PARAM_SHAPE
+
+    def tangent_sweep(plan, vgg_handle, B, loss_idx, U):
+        """U: {layer index: bf16 [B,h,w,C]} -> V: same keys. Masked forward convolutions of the running tangent."""
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        lowest, top = min(loss_idx), max(loss_idx)
+        V, cur = {}, None
+        conv_index = -1
+        for l, name in enumerate(LAYER_NAMES):
+            is_conv = bool(PARAM_SHAPE[name])
+            if is_conv:
+                conv_index += 1
+            if l > top:
+                break
+            h, w, c = plan.layer_shape(l)
+            if cur is not None:
+                out = torch.empty((B, h, w, c), dtype=torch.bfloat16, device="cuda")
+                if is_conv:
+                    wf = ctypes.c_void_p()
+                    _lib.check(L.stx_vgg_weights(vgg_handle, conv_index, ctypes.byref(wf), None, None))
+                    mask, _ = _feature_ptrs(plan, l)
+                    cin = cur.shape[-1]
+                    _lib.check(L.stx_conv_bf16(cur.data_ptr(), B, h, w, cin, wf, c, 9, None, None, mask, 0,
+                                               out.data_ptr(), 0, st))
+                else:
+                    _lib.check(L.stx_avgpool2_fwd(cur.data_ptr(), None, B, cur.shape[1], cur.shape[2], c, out.data_ptr(),
+                                                  None, st))
+                cur = out
+            if l in U:
+                cur = U[l] if cur is None else (cur.float() + U[l].float()).to(torch.bfloat16)
+            if l in loss_idx and l >= lowest and cur is not None:
+                V[l] = cur
+        return V
+
+    class VggStagePreparation(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, image, vgg19, layers, coef_values, slot, *gram_target):
+            _lib.require_cuda()
+            L = _lib.lib()
+            st = _lib.stream_ptr()
+            x = image.detach().to(device="cuda", dtype=torch.float32).contiguous()
+            B, H, W, _ = x.shape
+            K = len(layers)
+            coefs = OrderedDict(zip(layers, coef_values))
+            plan = vgg19.get_plan(B, H, W, topmost=layers[-1], coefs=coefs, export_layer_grads=True,
+                                  full_features=True, slot=slot)
+            targets = []
+            for k, name in enumerate(layers):
+                t = gram_target[k].detach().to(device="cuda", dtype=torch.float32).contiguous()
+                if t.shape[0] not in (1, B):
+                    raise ValueError("gram_target[%s] has batch %d, expected 1 or %d" % (name, t.shape[0], B))
+                _lib.check(L.stx_plan_set_target_gram(plan.handle, k, t.data_ptr(),
+                                                      1 if (t.shape[0] == B and B > 1) else 0, st))
+                targets.append(t)
+            func = torch.empty(B, dtype=torch.float32, device="cuda")
+            grad = torch.empty_like(x)
+            layer_loss = torch.empty((K, B), dtype=torch.float32, device="cuda")
+            _lib.check(L.stx_plan_step(plan.handle, x.data_ptr(), 0, func.data_ptr(), grad.data_ptr(),
+                                       layer_loss.data_ptr(), st))
+            feats, grads, diffs = [], [], []
+            for k, name in enumerate(layers):
+                idx = LAYER_INDEX[name]
+                h, w, c = plan.layer_shape(idx)
+                f = torch.empty((B, h, w, c), dtype=torch.float32, device="cuda")
+                _lib.check(L.stx_plan_copy_feature_f32(plan.handle, idx, f.data_ptr(), st))
+                feats.append(f)
+                g = torch.empty((B, h, w, c), dtype=torch.float32, device="cuda")
+                _lib.check(L.stx_plan_copy_layer_total_grad(plan.handle, k, g.data_ptr(), st))
+                grads.append(g)
+                G = torch.empty((B, c, c), dtype=torch.float32, device="cuda")
+                _lib.check(L.stx_plan_copy_gram(plan.handle, k, G.data_ptr(), st))
+                diffs.append(G - targets[k])
+            ctx.plan, ctx.vgg19 = plan, vgg19
+            ctx.layers, ctx.coef_values = list(layers), [float(v) for v in coef_values]
+            ctx.save_for_backward(x, *diffs)
+            ctx.set_materialize_grads(False)
+            return tuple(feats) + (layer_loss,) + tuple(grads)
+
+        @staticmethod
+        def backward(ctx, *ups):
+            L = _lib.lib()
+            st = _lib.stream_ptr()
+            plan = ctx.plan
+            K = len(ctx.layers)
+            d_feat, d_loss, d_grad = ups[:K], ups[K], ups[K + 1:]
+            saved = ctx.saved_tensors
+            x, diffs = saved[0], saved[1:]
+            B = x.shape[0]
+            loss_idx = [LAYER_INDEX[n] for n in ctx.layers]
+            U = {}
+            for k, u in enumerate(d_grad):
+                if u is not None:
+                    u = u.to(device="cuda", dtype=torch.float32).contiguous()
+                    u16 = torch.empty(u.shape, dtype=torch.bfloat16, device="cuda")
+                    _lib.check(L.stx_f32_to_bf16(u.data_ptr(), u.numel(), u16.data_ptr(), st))
+                    U[loss_idx[k]] = u16
+            V = tangent_sweep(plan, ctx.vgg19._vgg_handle(), B, loss_idx, U) if U else {}
+            mats, extras, keep = [], [], []
+            for k, name in enumerate(ctx.layers):
+                idx = loss_idx[k]
+                h, w, c = plan.layer_shape(idx)
+                n = _norm(h * w)
+                alpha = 4.0 / (c * c * n)
+                beta = ctx.coef_values[k] / (c * c * n)
+                D = diffs[k]
+                M = torch.zeros_like(D)
+                if d_loss is not None:
+                    M = M + (d_loss[k].to(torch.float32).reshape(B, 1, 1) * alpha) * D
+                E = None
+                if d_feat[k] is not None:
+                    E = d_feat[k].to(device="cuda", dtype=torch.float32)
+                if idx in V:
+                    v16 = V[idx].contiguous()
+                    f_hi, _ = _feature_ptrs(plan, idx)
+                    ws = torch.empty(max(L.stx_gram_cross_workspace_bytes(B, h * w, c) // 4, 1), dtype=torch.float32,
+                                     device="cuda")
+                    X = torch.empty((B, c, c), dtype=torch.float32, device="cuda")
+                    _lib.check(L.stx_gram_cross_bf16(f_hi, v16.data_ptr(), B, h * w, c, ctypes.c_float(EPS),
+                                                     X.data_ptr(), ws.data_ptr(), st))
+                    M = M + beta * (X + X.transpose(1, 2))
+                    d16 = torch.empty((B, c, c), dtype=torch.bfloat16, device="cuda")
+                    bD = (beta * D).contiguous()
+                    _lib.check(L.stx_f32_to_bf16(bD.data_ptr(), bD.numel(), d16.data_ptr(), st))
+                    e16 = torch.empty((B, h, w, c), dtype=torch.bfloat16, device="cuda")
+                    for i in range(B):
+                        _lib.check(L.stx_conv_bf16(v16[i].data_ptr(), 1, h, w, c, d16[i].data_ptr(), c, 1, None, None,
+                                                   None, 0, e16[i].data_ptr(), 0, st))
+                    E = e16.float() if E is None else E + e16.float()
+                    keep += [v16, ws, X, d16, bD, e16]
+                E_ptr = None
+                if E is not None:
+                    Ec = E.contiguous()
+                    e_b = torch.empty(Ec.shape, dtype=torch.bfloat16, device="cuda")
+                    _lib.check(L.stx_f32_to_bf16(Ec.data_ptr(), Ec.numel(), e_b.data_ptr(), st))
+                    keep += [Ec, e_b]
+                    E_ptr = e_b.data_ptr()
+                M = M.contiguous()
+                keep.append(M)
+                mats.append(M.data_ptr())
+                extras.append(E_ptr)
+            Mp = (ctypes.c_void_p * K)(*mats)
+            Ep = (ctypes.c_void_p * K)(*extras)
+            grad = torch.empty_like(x)
+            _lib.check(L.stx_plan_backward_custom(plan.handle, x.data_ptr(), 0, Mp, Ep, grad.data_ptr(), st))
+            return (grad, None, None, None, None) + (None,) * K
+
+    return VggStagePreparation
+
+
 _FUNCTION = None
+_PREP_FUNCTION = None
+
+
+def vgg_stage_preparation(image, vgg19, gram_target, coefs, stop_grad=False, slot=0):
+    """Differentiable mirror of ImprovedSynTex.build_stage_preparation (po/improved_model.py:209-232).
+
+    Returns (feat {k: [B,h,w,C]} for the Gram layers, loss_input [B], loss_per_layer {k: [B]},
+    grad_per_layer {k: [B,h,w,C]}); everything is differentiable with respect to `image`, including
+    grad_per_layer unless stop_grad (the reference's --stop-grad) detaches it."""
+    global _PREP_FUNCTION
+    if _PREP_FUNCTION is None:
+        _PREP_FUNCTION = _make_prep_function()
+    layers = list(coefs.keys())
+    K = len(layers)
+    outs = _PREP_FUNCTION.apply(image, vgg19, layers, [float(coefs[k]) for k in layers], slot,
+                                *[gram_target[k] for k in layers])
+    feat = OrderedDict((k, outs[i]) for i, k in enumerate(layers))
+    loss_per_layer = OrderedDict((k, outs[K][i]) for i, k in enumerate(layers))
+    grads = outs[K + 1:]
+    if stop_grad:
+        grads = [g.detach() for g in grads]
+    grad_per_layer = OrderedDict(zip(layers, grads))
+    if K > 1:
+        loss_input = sum(coefs[k] * 1. / 4 * loss_per_layer[k] for k in layers[:-1])
+    else:
+        loss_input = outs[K][0] * 0.
+    return feat, loss_input, loss_per_layer, grad_per_layer
 
 
 def vgg_texture(image, vgg19, layers, gram_target, slot=0, calc_grad=True):

@@ -175,3 +175,47 @@ def test_trainer_step_runs_and_learns(raw_weights):
     assert not torch.equal(p0, trainer.buckets.flat_param)
     assert min(losses[4:]) < losses[0]
     assert _lib.lib().stx_launch_count() > 0
+
+
+@pytest.mark.parametrize("mode", ["second_order", "all"])
+@pytest.mark.parametrize("nlayers", [3, 5])
+def test_stage_preparation_is_differentiable_through_the_vgg_gradients(raw_weights, mode, nlayers):
+    """po/improved_model.py:209-232 with --stop-grad off (the reference's default): training differentiates through
+    grad_per_layer = tf.gradients(loss, feat) - a double backward through VGG19."""
+    from syntex_b200.po import vgg_stage_preparation
+    size, B = 64, 2
+    layers = LAYERS[:nlayers]
+    coefs = OrderedDict((k, 1e5 * (1 + 0.5 * i)) for i, k in enumerate(layers))
+    x, gt, tex = _oracle_case(raw_weights, size, B, layers, 17)
+    ext = Vgg19Extractor(raw_weights)
+    xg = x.cuda().requires_grad_(True)
+    gtg = OrderedDict((k, v.float().cuda()) for k, v in gt.items())
+    feat, loss_input, loss_layer, grads = vgg_stage_preparation(xg, ext, gtg, coefs)
+    # oracle: autograd with create_graph through the same definition
+    xo = x.double().requires_grad_(True)
+    rfeat = so.vgg_build(xo, tex.weights, topmost=layers[-1])
+    _, rll, _ = so.build_texture_loss(rfeat, gt, coefs)
+    loss_grad = sum(coefs[k] / 4 * rll[k] for k in layers)
+    rgrads = torch.autograd.grad(loss_grad.sum(), [rfeat[k] for k in layers], create_graph=True)
+    want_li = sum(coefs[k] / 4 * rll[k] for k in layers[:-1])
+    assert relerr(loss_input, want_li.detach()) < 5e-3
+    gen = torch.Generator().manual_seed(3)
+    total, rtotal = 0.0, 0.0
+    for k, rg in zip(layers, rgrads):
+        assert relerr(feat[k], rfeat[k].detach()) < 1e-4, k
+        assert relerr(grads[k], rg.detach()) < 1e-2, k
+        U = torch.randn(tuple(rg.shape), generator=gen).double()
+        total = total + (grads[k] * U.float().cuda()).sum()
+        rtotal = rtotal + (rg * U).sum()
+        if mode == "all":
+            scale = float(rg.detach().abs().mean())          # keep the three kinds of terms comparable in size
+            w = (torch.rand((B,), generator=gen).double() + 0.5) * scale / float(rll[k].detach().mean()) * rg[0].numel()
+            A = torch.randn(tuple(rg.shape), generator=gen).double() * scale / float(rfeat[k].detach().abs().mean())
+            total = total + (loss_layer[k] * w.float().cuda()).sum() + (feat[k] * A.float().cuda()).sum()
+            rtotal = rtotal + (rll[k] * w).sum() + (rfeat[k] * A).sum()
+    total.backward()
+    rtotal.backward()
+    assert relerr(xg.grad, xo.grad) < 2e-2
+    # --stop-grad: the gradients are constants
+    _, _, _, g2 = vgg_stage_preparation(x.cuda().requires_grad_(True), ext, gtg, coefs, stop_grad=True)
+    assert all(not g.requires_grad for g in g2.values())
