@@ -35,8 +35,8 @@ for name, ds, ci, co in LAYERS:
     dx = torch.empty((batch, H, H, ci), dtype=torch.bfloat16, device="cuda")
     flops = 2.0 * batch * H * H * 9 * ci * co
     line = "%-8s H%-3d %3d->%3d |" % (name, H, ci, co)
-    for label, variants in (("fwd x3", [0, 64, 128, 100064, 100128]), ("fwd bf16", [0, 1128, 21128, 2128, 22128, 2256, 100128]),
-                            ("dgrad", [0, 1064, 21064, 2064, 22064, 1128, 21128, 2128, 22128, 2256, 100064, 100128])):
+    for label, variants in (("fwd x3", [0, 64, 128]), ("fwd bf16", [0, 11128, 21128, 2128, 2256]),
+                            ("dgrad", [0, 11064, 21064, 2064, 11128, 21128, 2128, 2256])):
         res = []
         for v in variants:
             bn = v % 1000

@@ -660,6 +660,10 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
     // at batch 1) the one-CTA layout wins because its 9-stage weight ring covers the L2 latency on its own.
     const int items = ((W + 7) / 8) * ((H + 16 * mt - 1) / (16 * mt)) * nimg * (cout / bn);
     if (items <= 148) occ = 1;
+    // Short K (<= 2 input chunks) with N = 128: tiles are epilogue-heavy and a deeper weight ring pays; one CTA per SM
+    // measured 44 us against 50 us on the conv2_2 input gradient at batch 9
+    // (profiles/r01_conv_variants_b9_256_occ.log), while K >= 4 chunks prefers two (35 vs 38 us).
+    if (!split && bn == 128 && cin <= 128) occ = 1;
     if (force_occ == 1 || force_occ == 2) occ = force_occ;
     if (split || mt == 2) occ = 1;      // only MT = 1 single-MMA instances exist with two CTAs per SM
   }
