@@ -209,6 +209,27 @@ class OracleTexture:
         return loss_layer, grad_layer
 
 
+    def prep(self, image, gram_target, coefs, stop_grad, slot):
+        """ImprovedSynTex / AdaptiveSynTex.build_stage_preparation (po/improved_model.py:209-232,
+        po/adaptive_model.py:204-222): grads = tf.gradients(sum_k coef_k/4 loss_k, [feat_k]), kept differentiable."""
+        layers = list(coefs.keys())
+        image = image.to("cpu", self.dtype)
+        if not image.requires_grad:
+            image = image.detach().requires_grad_(True)
+        feat = vgg_build(image, self.weights, topmost=layers[-1])
+        target = OrderedDict((k, gram_target[k].to("cpu", self.dtype)) for k in layers)
+        _, loss_per_layer, _ = build_texture_loss(feat, target, coefs)
+        loss_grad = sum(coefs[k] * 1.0 / 4 * loss_per_layer[k] for k in layers)
+        grads = torch.autograd.grad(loss_grad.sum(), [feat[k] for k in layers], create_graph=not stop_grad,
+                                    retain_graph=True)
+        if stop_grad:
+            grads = [g.detach() for g in grads]
+        loss_input = sum(coefs[k] * 1.0 / 4 * loss_per_layer[k] for k in layers[:-1]) if len(layers) > 1 \
+            else loss_per_layer[layers[0]] * 0.0
+        return (OrderedDict((k, feat[k]) for k in layers), loss_input, loss_per_layer,
+                OrderedDict(zip(layers, grads)))
+
+
 class SynthesizerOracle:
     """gatys/synthesizer.py:16-159 with the TF session replaced by torch-CPU autograd."""
 

@@ -380,3 +380,7 @@ class CudaTexture(object):
 
     def __call__(self, image, layers, gram_target, slot, calc_grad):
         return vgg_texture(image, self.vgg19, layers, gram_target, slot=slot, calc_grad=calc_grad)
+
+    def prep(self, image, gram_target, coefs, stop_grad, slot):
+        """Stage preparation of the improved / adaptive models: features, losses and full-VGG-backprop gradients."""
+        return vgg_stage_preparation(image, self.vgg19, gram_target, coefs, stop_grad=stop_grad, slot=slot)

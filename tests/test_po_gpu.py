@@ -219,3 +219,35 @@ def test_stage_preparation_is_differentiable_through_the_vgg_gradients(raw_weigh
     # --stop-grad: the gradients are constants
     _, _, _, g2 = vgg_stage_preparation(x.cuda().requires_grad_(True), ext, gtg, coefs, stop_grad=True)
     assert all(not g.requires_grad for g in g2.values())
+
+
+def test_adaptive_model_on_the_cuda_door(raw_weights):
+    """AdaptiveSynTex (po/adaptive_model.py) with the CUDA hot path: stage losses against the float64 oracle graph
+    with the same generator weights, gradients flow to both unfoldings (the first one through the double backward),
+    a few trainer steps reduce the loss."""
+    from syntex_b200.po.adaptive_model import AdaptiveSynTex
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    size = 64
+    torch.manual_seed(2)
+    args = {"vgg19_npy_path": raw_weights, "image_size": size, "n_stage": 2, "lr": 2e-4}
+    cpu = AdaptiveSynTex(args, texture_fn=so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS)).double()
+    gpu = AdaptiveSynTex(args)
+    gpu.load_state_dict({k: v.float() for k, v in cpu.state_dict().items()})
+    gpu = gpu.cuda()
+    rng = np.random.RandomState(0)
+    z = rng.uniform(-1, 1, (1, size, size, 3))
+    t = so.synthetic_texture(size, seed=9)[None] * 255.0
+    lc = cpu.build_graph(torch.as_tensor(z), torch.as_tensor(t))
+    lg = gpu.build_graph(torch.as_tensor(z), torch.as_tensor(t))
+    assert abs(float(cpu.losses[0]) - float(gpu.losses[0])) / float(cpu.losses[0]) < 5e-3
+    for s in (1, 2):     # behind one / two randomly initialised generators (see the progressive test on amplification)
+        assert abs(float(cpu.losses[s]) - float(gpu.losses[s])) / float(cpu.losses[s]) < 0.1, s
+    lg.backward()
+    for s in (0, 1):
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in gpu.syn[s].parameters())
+        assert sum(float(p.grad.abs().sum()) for p in gpu.syn[s].parameters()) > 0
+    trainer = SynTexTrainer(None, gpu, 1)
+    batch = (torch.as_tensor(z, dtype=torch.float32).cuda(), torch.as_tensor(t, dtype=torch.float32).cuda())
+    losses = [float(trainer.run_step(batch)) for _ in range(8)]
+    assert all(np.isfinite(losses)) and min(losses[4:]) < losses[0]

@@ -149,3 +149,50 @@ def test_data_parallel_trainer_gloo_world2(raw_weights):
     # float64 replicas (in float32 the 5-stage graph amplifies summation-order noise to ~10 % of the gradient norm)
     assert np.linalg.norm(r0[1] - mean) / np.linalg.norm(mean) < 1e-3
     assert np.linalg.norm(r0[1] - locals_[0]) / np.linalg.norm(mean) > 1e-2   # ... and is not just one rank's gradient
+
+
+@pytest.mark.parametrize("opts", [{}, {"pad_type": "symmetric", "norm_type": "none", "act_type": "lrelu", "pre_act": True},
+                                  {"pad_type": "zero", "norm_type": "batch", "stop_grad": True, "deconv_upsample": True}])
+def test_adaptive_graph_over_oracle(raw_weights, opts):
+    """po/adaptive_model.py: one shared-structure stage per unfolding, fed by the full-VGG-backprop gradients; with
+    --stop-grad off the training loss reaches stage s through the gradients handed to stage s+1 (double backward)."""
+    from syntex_b200.po.adaptive_model import AdaptiveSynTex
+    torch.manual_seed(0)
+    tex = so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS, torch.float64)
+    args = {"vgg19_npy_path": raw_weights, "image_size": 32, "n_stage": 2}
+    args.update(opts)
+    model = AdaptiveSynTex(args, texture_fn=tex).double()
+    rng = np.random.RandomState(0)
+    z = torch.as_tensor(rng.uniform(-1, 1, (1, 32, 32, 3)))
+    t = torch.as_tensor(so.synthetic_texture(32, seed=1)[None] * 255.0)
+    loss = model.build_graph(z, t)
+    assert torch.isfinite(loss) and len(model.losses) == 3 and len(model.image_outputs) == 3
+    assert torch.allclose(loss, sum(model.losses[1:]))
+    loss.backward()
+    g0 = sum(float(p.grad.abs().sum()) for p in model.syn[0].parameters() if p.grad is not None)
+    g1 = sum(float(p.grad.abs().sum()) for p in model.syn[1].parameters() if p.grad is not None)
+    assert g0 > 0 and g1 > 0
+    opt = model.optimizer()
+    assert opt.defaults["betas"] == (0.5, 0.999) and opt.defaults["eps"] == 1e-3
+    ps = AdaptiveSynTex.get_parser()
+    a = ps.parse_args(["--pad-type", "zero", "--stop-grad"])
+    assert a.get("pad_type") == "zero" and a.get("stop_grad") and a.get("n_stage") == 1
+
+
+def test_adaptive_second_order_path_changes_the_gradient(raw_weights):
+    """Stage 0's parameters influence stage 1's loss also through the gradients stage 1 is fed: --stop-grad removes
+    exactly that path (adaptive_model.py:219-220)."""
+    from syntex_b200.po.adaptive_model import AdaptiveSynTex
+    tex = so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS, torch.float64)
+    rng = np.random.RandomState(0)
+    z = torch.as_tensor(rng.uniform(-1, 1, (1, 32, 32, 3)))
+    t = torch.as_tensor(so.synthetic_texture(32, seed=1)[None] * 255.0)
+    grads = []
+    for stop in (False, True):
+        torch.manual_seed(0)
+        m = AdaptiveSynTex({"vgg19_npy_path": raw_weights, "image_size": 32, "n_stage": 2, "stop_grad": stop},
+                           texture_fn=tex).double()
+        m.build_graph(z, t).backward()
+        grads.append(torch.cat([p.grad.flatten() for p in m.syn[0].parameters()]))
+    rel = float((grads[0] - grads[1]).norm() / grads[0].norm())
+    assert rel > 1e-3
