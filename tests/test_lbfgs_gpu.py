@@ -104,3 +104,26 @@ def test_scipy_optimizer_path_matches_reference_call(raw_weights):
     x, fun = syn.synthesize(x0, tgt)
     assert x.shape == (S, S, 3) and x.min() >= 0 and x.max() <= 1
     assert int(syn.last_result["nit"][0]) == IT
+
+
+def test_launch_modes_give_identical_results(raw_weights):
+    """CUDA-graph replay (default), plain stream launches, and both with / without programmatic dependent launch
+    (stx_debug_set keys 9 and 10) only change how the same kernels are enqueued: bit-identical trajectories."""
+    from syntex_b200 import _lib
+    L = _lib.lib()
+    S, IT = 64, 12
+    tgt = so.synthetic_texture(S, seed=5)
+    x0 = so.init_input((S, S, 3), False, 1)
+    results = []
+    try:
+        for pdl, no_graph in ((1, 0), (0, 0), (1, 1), (0, 1)):
+            L.stx_debug_set(9, pdl)
+            L.stx_debug_set(10, no_graph)
+            syn = make(raw_weights, S, IT)
+            x, fun = syn.synthesize(x0, tgt)
+            results.append((x, fun, int(syn.last_result["nfev"][0])))
+    finally:
+        L.stx_debug_set(9, 1)
+        L.stx_debug_set(10, 0)
+    for x, fun, nfev in results[1:]:
+        assert fun == results[0][1] and nfev == results[0][2] and np.array_equal(x, results[0][0])
