@@ -290,7 +290,12 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"bound": "tensor", "kernel": "conv_patch_kernel (persistent tcgen05 3x3 implicit GEMM, fwd+dgrad, %d launches per f/g evaluation)" % conv_launches,
                     "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops"],
-                    "traffic": "see profiles/r01_ncu_full_conv_patch_b8.md: DRAM bytes per launch equal the compulsory bytes (21-36 MB for the 4.8 GFLOP/image layers at batch 8)",
+                    # dram__bytes_read + dram__bytes_write averaged over the 22 conv launches of one evaluation in the
+                    # ncu --set full capture at batch 9 (profiles/r01_ncu_full_final_b9.md); only meaningful at that batch
+                    "traffic": 61.8e6 if (batch == 9 and size == 256) else None,
+                    "traffic_note": "average DRAM bytes per conv launch, ncu --set full, batch 9 (profiles/r01_ncu_full_final_b9.md): "
+                                    "the deep layers move 24-40 MB per launch (weights + one pass over their activations), "
+                                    "the 64-channel layers 130-220 MB (hi/lo activation planes in and out)",
                     "executed_tflops": exec_total, "executed_frac": exec_total / peaks["bf16_tflops"],
                     "note": "achieved counts algorithmic FLOPs (2*M*N*K once per direction); the bf16x3 forward executes 3 MMAs per MAC, executed_* counts those",
                     "avg_launch_us": 1e3 * conv_ms / max(conv_launches, 1),
