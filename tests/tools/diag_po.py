@@ -1,8 +1,9 @@
-"""Diagnostics for the PO training-graph parity (GPU hot path vs float64 oracle)."""
+"""Diagnostics for the PO training-graph parity (GPU hot path vs float64 oracle). Test tooling: lives under tests/
+because it uses the oracle.  python tests/tools/diag_po.py [size]"""
 import os, sys
 from collections import OrderedDict
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import syntex_oracle as so
 from syntex_b200.synthetic import synthetic_vgg_weights

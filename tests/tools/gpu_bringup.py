@@ -1,5 +1,5 @@
 """Bring-up diagnostics for the CUDA kernels on a B200 (prints errors per kernel; not a test).
-Usage: python scripts/gpu_bringup.py [stage ...]   stages: conv gram elem plan lbfgs
+Usage: python tests/tools/gpu_bringup.py [stage ...]   stages: conv gram elem plan lbfgs
 """
 import ctypes
 import os
@@ -10,8 +10,9 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from syntex_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
