@@ -78,3 +78,40 @@ def build_texture_loss(a, b, coefs, is_gram_a=False, is_gram_b=True,
                                        out16[i].data_ptr(), 0, _lib.stream_ptr()))
         grad_layer[k] = out16.to(torch.float32)
     return loss_overall, loss_layer, grad_layer
+
+
+def gram_grad_double_bwd(feat, gram_diff, upstream, eps=1e-6, name="gram_grad_double_bwd"):
+    """Second-order term of the per-layer style gradient (SURVEY.md section 8 rows a-14 / b): with
+    g = alpha F D, D = F^T F / n - T, alpha = 4 / (C^2 n), n = HW + eps, and U = dl/dg, returns
+
+        dl/dF = alpha [ U D + F (F^T U + U^T F) / n ]
+
+    feat [B,H,W,C] (bf16 or fp32 CUDA), gram_diff = G - T [B,C,C] fp32, upstream U [B,H,W,C].
+    F^T U is the cross-Gram tensor-core kernel, the two products with C x C matrices are 1x1 tensor-core GEMMs."""
+    import torch
+    f = _as_bf16_nhwc(feat)
+    u = _as_bf16_nhwc(upstream)
+    B, H, W, C = f.shape
+    if tuple(u.shape) != (B, H, W, C) or tuple(gram_diff.shape) != (B, C, C):
+        raise ValueError("gram_grad_double_bwd: shape mismatch")
+    L = _lib.lib()
+    st = _lib.stream_ptr()
+    n = float(np.float32(H * W) + np.float32(eps))
+    alpha = 4.0 / (C * C * n)
+    D = gram_diff.to(device="cuda", dtype=torch.float32)
+    ws = torch.empty(max(L.stx_gram_cross_workspace_bytes(B, H * W, C) // 4, 1), dtype=torch.float32, device="cuda")
+    X = torch.empty((B, C, C), dtype=torch.float32, device="cuda")
+    _lib.check(L.stx_gram_cross_bf16(f.data_ptr(), u.data_ptr(), B, H * W, C, ctypes.c_float(eps), X.data_ptr(),
+                                     ws.data_ptr(), st))
+    S = (alpha * (X + X.transpose(1, 2))).contiguous()        # alpha (F^T U + U^T F) / n, symmetric
+    aD = (alpha * D).contiguous()
+    out = torch.zeros((B, H, W, C), dtype=torch.float32, device="cuda")
+    for src, mat in ((u, aD), (f, S)):
+        m16 = torch.empty((B, C, C), dtype=torch.bfloat16, device="cuda")
+        _lib.check(L.stx_f32_to_bf16(mat.data_ptr(), mat.numel(), m16.data_ptr(), st))
+        o16 = torch.empty((B, H, W, C), dtype=torch.bfloat16, device="cuda")
+        for i in range(B):      # per-image weights: both matrices are symmetric, so [cout][cin] = the matrix itself
+            _lib.check(L.stx_conv_bf16(src[i].data_ptr(), 1, H, W, C, m16[i].data_ptr(), C, 1, None, None, None, 0,
+                                       o16[i].data_ptr(), 0, st))
+        out += o16.float()
+    return out

@@ -148,3 +148,23 @@ def test_synthesize_verbose_collects_one_record_per_iteration(raw_weights, optim
     syn.save_verbose(str(out))
     z = np.load(str(out))
     assert "gi_pool4" in z.files and len(z["func"]) == n
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 64), (1, 16, 24, 128), (2, 8, 8, 512)])
+def test_gram_grad_double_bwd_matches_closed_form(B, H, W, C):
+    """d/dF <U, alpha F (F^T F / n - T)> = alpha [U D + F (F^T U + U^T F) / n]."""
+    from syntex_b200.texture_utils import gram_grad_double_bwd
+    g = torch.Generator().manual_seed(C + H)
+    F_ = torch.randn((B, H, W, C), generator=g).relu()
+    F_ = F_.to(torch.bfloat16).float()            # the op consumes bf16 features: compare on the same inputs
+    U = torch.randn((B, H, W, C), generator=g).to(torch.bfloat16).float()
+    T = torch.randn((B, C, C), generator=g)
+    T = 0.5 * (T + T.transpose(1, 2))
+    n = H * W + 1e-6
+    Fd = F_.double().reshape(B, H * W, C).requires_grad_(True)
+    D = Fd.transpose(1, 2) @ Fd / n - T.double()
+    alpha = 4.0 / (C * C * n)
+    obj = ((alpha * Fd @ D) * U.double().reshape(B, H * W, C)).sum()
+    want = torch.autograd.grad(obj, Fd)[0].reshape(B, H, W, C)
+    got = gram_grad_double_bwd(F_.cuda(), D.detach().float().cuda(), U.cuda())
+    assert tuple(got.shape) == (B, H, W, C) and relerr(got, want) < 1e-2

@@ -30,7 +30,7 @@ def make_syn(raw, S, batch=1, precision="bf16x3", **kw):
 
 
 @pytest.mark.parametrize("S,precision", [(64, "bf16x3"), (128, "bf16x3"), (256, "bf16x3"), (256, "bf16"),
-                                         (224, "bf16x3")])
+                                         (224, "bf16x3"), (512, "bf16x3")])     # 512: BASELINE.json config 2
 def test_step_matches_oracle(S, precision, raw_weights, exemplar):
     tgt = so.resize_crop(exemplar / 255.0, S)
     x0 = so.init_input((S, S, 3), False, 0)
