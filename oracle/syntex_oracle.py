@@ -198,6 +198,10 @@ class OracleTexture:
         return OrderedDict((k, build_gram(feat[k]).detach()) for k in layers)
 
     def __call__(self, image, layers, gram_target, slot, calc_grad):
+        with torch.enable_grad():        # grad_layer is itself an autograd.grad result, also in inference
+            return self._call(image, layers, gram_target, slot, calc_grad)
+
+    def _call(self, image, layers, gram_target, slot, calc_grad):
         layers = list(layers)
         image = image.to("cpu", self.dtype)
         if not image.requires_grad:      # first stage: the input is data; autograd.grad still needs a graph
@@ -210,6 +214,10 @@ class OracleTexture:
 
 
     def prep(self, image, gram_target, coefs, stop_grad, slot):
+        with torch.enable_grad():
+            return self._prep(image, gram_target, coefs, stop_grad, slot)
+
+    def _prep(self, image, gram_target, coefs, stop_grad, slot):
         """ImprovedSynTex / AdaptiveSynTex.build_stage_preparation (po/improved_model.py:209-232,
         po/adaptive_model.py:204-222): grads = tf.gradients(sum_k coef_k/4 loss_k, [feat_k]), kept differentiable."""
         layers = list(coefs.keys())

@@ -1,6 +1,6 @@
 """PO configurations of BASELINE.json on the B200.
 
-  python scripts/bench_po.py infer [batch] [size]          config 3: feed-forward synthesis, images/s
+  python scripts/bench_po.py infer [batch] [size] [single|progressive]   config 3: feed-forward synthesis, images/s
   python -m torch.distributed.run --nproc-per-node N ... scripts/bench_po.py train [size] [steps]
                                                             config 5: ProgressiveSynTex training, per-GPU batch 1,
                                                             gradient-mean all-reduce over NCCL, images/s
@@ -18,6 +18,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from syntex_b200 import _lib  # noqa: E402
 from syntex_b200.po.progressive_model import ProgressiveSynTex  # noqa: E402
+from syntex_b200.po.single_model import SingleSynTex  # noqa: E402
 from syntex_b200.po.trainer import SynTexTrainer, SyntheticPOData  # noqa: E402
 from syntex_b200.synthetic import synthetic_vgg_weights  # noqa: E402
 
@@ -38,11 +39,15 @@ def timed(fn, warmup, steps):
 GEN_BF16 = os.environ.get("STX_PO_GENERATOR_BF16", "0") == "1"
 
 
-def infer(batch, size):
+def infer(batch, size, which="progressive"):
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
-    model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size,
-                               "generator_bf16": GEN_BF16}).cuda().eval().to(memory_format=torch.channels_last)
+    if which == "single":
+        model = SingleSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size})
+    else:
+        model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size,
+                                   "generator_bf16": GEN_BF16})
+    model = model.cuda().eval().to(memory_format=torch.channels_last)
     z, t = next(iter(SyntheticPOData(batch, size, seed=0)))
     l0 = _lib.lib().stx_launch_count()
 
@@ -52,11 +57,11 @@ def infer(batch, size):
     ms = timed(step, 2, 5)
     # VGG19 work per image: 6 forwards of the current image (5 stages to their last Gram layer + the final loss) and
     # one of the target, plus the per-layer F*D products
-    print(json.dumps({"workload": "po_progressive_inference", "batch": batch, "size": size, "images_per_s": batch / ms * 1e3,
+    print(json.dumps({"workload": "po_%s_inference" % which, "batch": batch, "size": size, "images_per_s": batch / ms * 1e3,
                       "ms_per_batch": ms, "hot_path_launches_per_batch": (_lib.lib().stx_launch_count() - l0) // 7,
                       "losses": [float(l) for l in model.losses], "generator": "bf16 autocast" if GEN_BF16 else "fp32 (TF32 convs)",
-                      "note": "config 3 measured on ProgressiveSynTex (single_model.py is stale against the current "
-                              "extractor, SURVEY section 2 #8); random generator weights: throughput only"}))
+                      "note": "config 3; single = SingleSynTex on the five Gram layers (single_model.py as shipped is stale "
+                              "against the current extractor, SURVEY section 2 #8); random generator weights: throughput only"}))
 
 
 def train(size, steps):
@@ -114,6 +119,7 @@ def train(size, steps):
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "infer"
     if mode == "infer":
-        infer(int(sys.argv[2]) if len(sys.argv) > 2 else 64, int(sys.argv[3]) if len(sys.argv) > 3 else 256)
+        infer(int(sys.argv[2]) if len(sys.argv) > 2 else 64, int(sys.argv[3]) if len(sys.argv) > 3 else 256,
+              sys.argv[4] if len(sys.argv) > 4 else "progressive")
     else:
         train(int(sys.argv[2]) if len(sys.argv) > 2 else 512, int(sys.argv[3]) if len(sys.argv) > 3 else 10)

@@ -70,10 +70,11 @@ def instance_norm(chan):
 class SymConv(nn.Module):
     """tf.pad(SYMMETRIC) + Conv2D(padding="VALID") (+ InstanceNorm + ReLU when `act`), progressive_model.py:171-175."""
 
-    def __init__(self, cin, cout, ksize=3, act=True, use_bias=False):
+    def __init__(self, cin, cout, ksize=3, act=True, use_bias=False, zero_pad=False):
         super().__init__()
         self.ksize = ksize
-        self.conv = nn.Conv2d(cin, cout, ksize, padding=0, bias=use_bias)
+        self.zero_pad = zero_pad          # Conv2D(padding="SAME") instead of tf.pad(SYMMETRIC) + VALID
+        self.conv = nn.Conv2d(cin, cout, ksize, padding=ksize // 2 if zero_pad else 0, bias=use_bias)
         nn.init.kaiming_normal_(self.conv.weight, mode="fan_in", nonlinearity="relu")
         if use_bias:
             nn.init.zeros_(self.conv.bias)
@@ -81,7 +82,7 @@ class SymConv(nn.Module):
 
     def forward(self, x):
         p0 = self.ksize // 2
-        x = self.conv(symmetric_pad(x, p0, self.ksize - 1 - p0))
+        x = self.conv(x if self.zero_pad else symmetric_pad(x, p0, self.ksize - 1 - p0))
         if self.norm is not None:
             x = F.relu(self.norm(x))
         return x

@@ -32,7 +32,7 @@ class _Stage(nn.Module):
     """The generator of one stage (progressive_model.py:161-206): per Gram layer two gradient convs, merge with the
     up-sampled deeper branch, InstanceNorm, n_block residual blocks; then ReLU + 3x3 conv to an RGB update."""
 
-    def __init__(self, n_loss_layer, n_block, pre_act, nn_upsample):
+    def __init__(self, n_loss_layer, n_block, pre_act, nn_upsample, zero_pad_inputs=False):
         super().__init__()
         self.layers = list(LAYER_CHANNELS.keys())[:n_loss_layer]
         self.pre_act = pre_act
@@ -47,8 +47,10 @@ class _Stage(nn.Module):
         deeper = None
         for layer in reversed(self.layers):
             chan = LAYER_CHANNELS[layer]
-            self.grad_conv1[layer] = SymConv(chan, chan, 3, act=True)
-            self.grad_conv2[layer] = SymConv(chan, chan, 3, act=False)
+            # single_model.py:170-171 feeds the features through plain Conv2D (SAME zero padding); the progressive
+            # model pads its gradient inputs symmetrically (progressive_model.py:171-175)
+            self.grad_conv1[layer] = SymConv(chan, chan, 3, act=True, zero_pad=zero_pad_inputs)
+            self.grad_conv2[layer] = SymConv(chan, chan, 3, act=False, zero_pad=zero_pad_inputs)
             if deeper is not None:
                 self.up[layer] = up(deeper, chan)
                 if pre_act:

@@ -251,3 +251,35 @@ def test_adaptive_model_on_the_cuda_door(raw_weights):
     batch = (torch.as_tensor(z, dtype=torch.float32).cuda(), torch.as_tensor(t, dtype=torch.float32).cuda())
     losses = [float(trainer.run_step(batch)) for _ in range(8)]
     assert all(np.isfinite(losses)) and min(losses[4:]) < losses[0]
+
+
+def test_single_model_on_the_cuda_door(raw_weights):
+    """SingleSynTex (po/single_model.py, BASELINE config 3): inference output against the oracle graph with the same
+    generator weights; training gradients reach both stages; a few trainer steps reduce the loss."""
+    from syntex_b200.po.single_model import SingleSynTex
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    size = 64
+    torch.manual_seed(4)
+    args = {"vgg19_npy_path": raw_weights, "image_size": size, "n_stage": 2, "loss_scale": 1.0, "lr": 2e-4}
+    cpu = SingleSynTex(args, texture_fn=so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS)).double()
+    gpu = SingleSynTex(args)
+    gpu.load_state_dict({k: v.float() for k, v in cpu.state_dict().items()})
+    gpu = gpu.cuda()
+    rng = np.random.RandomState(0)
+    z = rng.uniform(-1, 1, (2, size, size, 3))
+    t = np.stack([so.synthetic_texture(size, seed=9), so.synthetic_texture(size, seed=10)]) * 255.0
+    with torch.no_grad():
+        cpu.build_graph(torch.as_tensor(z), torch.as_tensor(t))
+        gpu.build_graph(torch.as_tensor(z), torch.as_tensor(t))
+    assert abs(float(cpu.losses[0]) - float(gpu.losses[0])) / float(cpu.losses[0]) < 5e-3
+    # the generator reads features (error ~1e-5), not gradients (~3e-3): the first stage output is tight
+    assert relerr(gpu.image_outputs[1], cpu.image_outputs[1]) < 2e-3
+    lg = gpu.build_graph(torch.as_tensor(z), torch.as_tensor(t))
+    lg.backward()
+    for s in (0, 1):
+        assert sum(float(p.grad.abs().sum()) for p in gpu.syn[s].parameters()) > 0
+    trainer = SynTexTrainer(None, gpu, 1)
+    batch = (torch.as_tensor(z, dtype=torch.float32).cuda(), torch.as_tensor(t, dtype=torch.float32).cuda())
+    losses = [float(trainer.run_step(batch)) for _ in range(8)]
+    assert all(np.isfinite(losses)) and min(losses[4:]) < losses[0]

@@ -196,3 +196,25 @@ def test_adaptive_second_order_path_changes_the_gradient(raw_weights):
         grads.append(torch.cat([p.grad.flatten() for p in m.syn[0].parameters()]))
     rel = float((grads[0] - grads[1]).norm() / grads[0].norm())
     assert rel > 1e-3
+
+
+def test_single_model_graph_over_oracle(raw_weights):
+    """po/single_model.py (BASELINE config 3's model): the generator reads the VGG features of the five Gram layers;
+    training reaches the generator of stage 0 through stage 1's features (VGG back-propagation of feature gradients)."""
+    from syntex_b200.po.single_model import SingleSynTex
+    torch.manual_seed(0)
+    tex = so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS, torch.float64)
+    model = SingleSynTex({"vgg19_npy_path": raw_weights, "image_size": 32, "n_stage": 2, "loss_scale": 1.0},
+                         texture_fn=tex).double()
+    rng = np.random.RandomState(0)
+    z = torch.as_tensor(rng.uniform(-1, 1, (1, 32, 32, 3)))
+    t = torch.as_tensor(so.synthetic_texture(32, seed=1)[None] * 255.0)
+    loss = model.build_graph(z, t)
+    assert torch.isfinite(loss) and len(model.losses) == 3
+    loss.backward()
+    for s in (0, 1):
+        assert sum(float(p.grad.abs().sum()) for p in model.syn[s].parameters() if p.grad is not None) > 0
+    opt = model.optimizer()
+    assert opt.defaults["lr"] == 5e-5 and opt.defaults["betas"] == (0.9, 0.999)
+    args = SingleSynTex.get_parser().parse_args([])
+    assert args.get("loss_scale") == 0. and args.get("n_stage") == 1
