@@ -199,6 +199,9 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         # NCCL prints its version banner on STDOUT (NCCL_DEBUG is set in this image): send its log to stderr so that
         # stdout carries only the one JSON line the contract asks for
+        # (NCCL only honours NCCL_DEBUG_FILE above the VERSION level, where the banner is printed straight to stdout)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = _lib.lib()
