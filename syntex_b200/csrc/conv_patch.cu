@@ -162,7 +162,11 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------------------------------------ TMA producer
     // Whole warp in the loops, one elected lane issuing (see the MMA warp for why).
     {
-      int pit = 0, bit = 0;   // ring counters, running across work items
+      // Ring positions are carried as (stage, parity) pairs and advanced incrementally: a modulo by a non-power-of-two
+      // stage count per tap costs a dozen dependent instructions, and the single issuing warp - not the tensor pipe -
+      // paces the single-MMA kernels (measured: 83 SASS instructions and ~800 cycles per tap for 256 cycles of MMA).
+      uint32_t ps = 0, pph = 0, bs = 0, bph = 0;
+      constexpr uint32_t kRing = RES > 0 ? (kDS > 0 ? kDS : 1) : kBS;     // ring used by the weight / Gram tiles
       if (RES > 0) {
         // the whole layer's weights, once: tile (chunk c, tap) -> slot c * 9 + tap
         if (elect_one()) {
@@ -185,19 +189,21 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int n = tm / tiles_per_img;
         const int c_begin = ks * chunks / sched.ksplit, c_end = (ks + 1) * chunks / sched.ksplit;
         const int gram_chunks = (ks == sched.ksplit - 1) ? sched.gram_chunks : 0;
-        for (int c = c_begin; c < c_end; ++c, ++pit) {
-          const int ps = pit % kPS;
-          mbar_wait(&pempty[ps], ((pit / kPS) & 1) ^ 1, 100 + ps);
+        for (int c = c_begin; c < c_end; ++c) {
+          mbar_wait(&pempty[ps], pph ^ 1, 100 + ps);
           uint8_t* pdst = smem + ps * L::kPatchStageBytes;
           if (elect_one()) {
             mbar_arrive_expect_tx(&pfull[ps], (SPLIT ? 2 : 1) * L::kPatchBytes);
             tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
             if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
           }
-          __syncwarp();
-          for (int tap = 0; RES == 0 && tap < 9; ++tap, ++bit) {
-            const int bs = bit % kBS;
-            mbar_wait(&bempty[bs], ((bit / kBS) & 1) ^ 1, 120 + bs);
+          if (++ps == kPS) {
+            ps = 0;
+            pph ^= 1;
+          }
+#pragma unroll
+          for (int tap = 0; RES == 0 && tap < 9; ++tap) {
+            mbar_wait(&bempty[bs], bph ^ 1, 120 + bs);
             uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
             if (elect_one()) {
               mbar_arrive_expect_tx(&bfull[bs], (SPLIT ? 2 : 1) * BN * 128);
@@ -212,19 +218,19 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (SPLIT) tma_load_3d(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, nblk * BN, tap);
               }
             }
-            __syncwarp();
+            if (++bs == kBS) {
+              bs = 0;
+              bph ^= 1;
+            }
           }
         }
         // Fused Gram gradient (utils.py:54): the features of this tile (dense 128-row K-major tiles, staged in a patch
         // buffer) times the per-image scaled Gram difference, accumulated into the same TMEM tile.
-        for (int cf = 0; cf < gram_chunks; ++cf, ++pit, ++bit) {
-          const int ps = pit % kPS;
-          mbar_wait(&pempty[ps], ((pit / kPS) & 1) ^ 1, 140 + ps);
-          constexpr int kRing = RES > 0 ? (kDS > 0 ? kDS : 1) : kBS;
-          const int bs = bit % kRing;
+        for (int cf = 0; cf < gram_chunks; ++cf) {
           uint64_t* ring_empty = RES > 0 ? dempty : bempty;
           uint64_t* ring_full = RES > 0 ? dfull : bfull;
-          mbar_wait(&ring_empty[bs], ((bit / kRing) & 1) ^ 1, 160 + bs);
+          mbar_wait(&pempty[ps], pph ^ 1, 140 + ps);
+          mbar_wait(&ring_empty[bs], bph ^ 1, 160 + bs);
           uint8_t* pdst = smem + ps * L::kPatchStageBytes;
           uint8_t* bdst = RES > 0 ? smem + L::kDOffset + bs * L::kBBytes : smem + L::kBOffset + bs * L::kBStageBytes;
           if (elect_one()) {
@@ -234,7 +240,14 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_arrive_expect_tx(&ring_full[bs], BN * 128);
             tma_load_3d(bdst, &tmD, &ring_full[bs], cf * 64, nblk * BN, n);
           }
-          __syncwarp();
+          if (++ps == kPS) {
+            ps = 0;
+            pph ^= 1;
+          }
+          if (++bs == kRing) {
+            bs = 0;
+            bph ^= 1;
+          }
         }
       }
     }
@@ -249,29 +262,28 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       constexpr uint32_t kGroupStride = kPatchW * 128;     // bytes between consecutive 8-pixel row groups
       constexpr uint32_t kDescHiA = desc_hi_sw128(kGroupStride);   // activations: 8-row groups kGroupStride apart
       constexpr uint32_t kDescHiB = desc_hi_sw128(1024);           // weights: dense 128-byte rows
-      int pit = 0, bit = 0, ait = 0;
+      uint32_t ps = 0, pph = 0, bs = 0, bph = 0, as = 0, aph = 0;     // ring (stage, parity) pairs, see the producer
+      constexpr uint32_t kRing = RES > 0 ? (kDS > 0 ? kDS : 1) : kBS;
+      const uint32_t b_ring = desc_lo_base(smem_u32(smem + L::kBOffset));
+      const uint32_t d_ring = desc_lo_base(smem_u32(smem + L::kDOffset));
       if (RES > 0) {
         mbar_wait(&bfull[0], 0, 219);     // resident weights have landed
         tc_fence_after();
       }
-      for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x, ++ait) {
-        const int as = ait % kAS;
-        mbar_wait(&aempty[as], ((ait / kAS) & 1) ^ 1, 300 + as);    // epilogue has drained this accumulator
+      for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x) {
+        mbar_wait(&aempty[as], aph ^ 1, 300 + as);    // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + as * L::kAccCols;
         const int ks = item % sched.ksplit;
         const int c_begin = ks * chunks / sched.ksplit, c_end = (ks + 1) * chunks / sched.ksplit;
         const int gram_chunks = (ks == sched.ksplit - 1) ? sched.gram_chunks : 0;
-        for (int c = c_begin; c < c_end; ++c, ++pit) {
-          const int ps = pit % kPS;
-          mbar_wait(&pfull[ps], (pit / kPS) & 1, 200 + ps);
+        for (int c = c_begin; c < c_end; ++c) {
+          mbar_wait(&pfull[ps], pph, 200 + ps);
           // Descriptors differ between MMAs only in their 14-bit start-address field (bits 0..13, address >> 4;
           // shared memory ends below 2^18 bytes, so adding offsets never carries out of the field): keep the upper
-          // word constant and do 32-bit adds on the lower one. The issuing lane then spends one or two uniform-ALU
-          // instructions per MMA instead of rebuilding 64-bit descriptors - at N = 64 an MMA executes in 32 cycles
-          // and the issue stream, not the tensor pipe, was the limit (43 % pipe utilisation on conv1_2).
+          // word constant and do 32-bit adds on the lower one.
           const uint32_t patch = smem_u32(smem + ps * L::kPatchStageBytes);
-          const uint32_t a_lo0 = (patch >> 4) & 0x3FFF;
+          const uint32_t a_lo0 = desc_lo_base(patch);
           auto issue_tap = [&](int tap, uint32_t b_lo0, bool first_chunk) {
             const uint32_t tap_off16 = (((tap / 3) * kPatchW + (tap % 3)) * 128) >> 4;
 #pragma unroll
@@ -303,55 +315,66 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (RES > 0) {
             // resident weights: no barrier inside the chunk, nine taps issued as one straight-line block
             tc_fence_after();
-            const uint32_t b_base = ((smem_u32(smem + L::kBOffset) >> 4) & 0x3FFF) + c * 9 * (L::kBStageBytes >> 4);
+            const uint32_t b_base = b_ring + c * 9 * (L::kBStageBytes >> 4);
             if (elect_one()) {
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) issue_tap(tap, b_base + tap * (L::kBStageBytes >> 4), c == c_begin);
               umma_commit(&pempty[ps]);
             }
-            __syncwarp();
           } else {
-            const uint32_t b_ring = (smem_u32(smem + L::kBOffset) >> 4) & 0x3FFF;
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap, ++bit) {
-              const int bs = bit % kBS;
-              mbar_wait(&bfull[bs], (bit / kBS) & 1, 220 + bs);
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&bfull[bs], bph, 220 + bs);
               tc_fence_after();
               if (elect_one()) {
                 issue_tap(tap, b_ring + bs * (L::kBStageBytes >> 4), c == c_begin);
                 umma_commit(&bempty[bs]);
                 if (tap == 8) umma_commit(&pempty[ps]);
               }
-              __syncwarp();
+              if (++bs == kBS) {
+                bs = 0;
+                bph ^= 1;
+              }
             }
           }
+          if (++ps == kPS) {
+            ps = 0;
+            pph ^= 1;
+          }
         }
-        for (int cf = 0; cf < gram_chunks; ++cf, ++pit, ++bit) {
-          constexpr int kRing = RES > 0 ? (kDS > 0 ? kDS : 1) : kBS;
+        for (int cf = 0; cf < gram_chunks; ++cf) {
           uint64_t* ring_empty = RES > 0 ? dempty : bempty;
           uint64_t* ring_full = RES > 0 ? dfull : bfull;
-          const int ps = pit % kPS;
-          const int bs = bit % kRing;
-          mbar_wait(&pfull[ps], (pit / kPS) & 1, 240 + ps);
-          mbar_wait(&ring_full[bs], (bit / kRing) & 1, 260 + bs);
+          mbar_wait(&pfull[ps], pph, 240 + ps);
+          mbar_wait(&ring_full[bs], bph, 260 + bs);
           tc_fence_after();
-          const uint32_t f_addr = smem_u32(smem + ps * L::kPatchStageBytes);
-          const uint64_t bdesc = make_smem_desc_sw128(
-              smem_u32(RES > 0 ? smem + L::kDOffset + bs * L::kBBytes : smem + L::kBOffset + bs * L::kBStageBytes), 16, 1024);
+          const uint32_t f_lo = desc_lo_base(smem_u32(smem + ps * L::kPatchStageBytes));
+          const uint32_t g_lo = RES > 0 ? d_ring + bs * (L::kBBytes >> 4) : b_ring + bs * (L::kBStageBytes >> 4);
           if (elect_one()) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-              const uint64_t adesc = make_smem_desc_sw128(f_addr + mt * 16384, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_bf16(acc + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(acc + mt * BN, desc_pack(f_lo + mt * (16384 >> 4) + 2 * k, kDescHiB),
+                          desc_pack(g_lo + 2 * k, kDescHiB), idesc, 1);
             }
             umma_commit(&ring_empty[bs]);
             umma_commit(&pempty[ps]);
           }
-          __syncwarp();
+          if (++ps == kPS) {
+            ps = 0;
+            pph ^= 1;
+          }
+          if (++bs == kRing) {
+            bs = 0;
+            bph ^= 1;
+          }
         }
         if (elect_one()) umma_commit(&afull[as]);
-        __syncwarp();
+        if (++as == kAS) {
+          as = 0;
+          aph ^= 1;
+        }
       }
     }
   } else {

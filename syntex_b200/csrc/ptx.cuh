@@ -197,8 +197,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
 __host__ __device__ constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
 }
-__device__ __forceinline__ uint64_t desc_pack(uint32_t start_field, uint32_t hi) {
-  return (static_cast<uint64_t>(hi) << 32) | static_cast<uint64_t>(start_field | (1u << 16));
+// `lo` = desc_lo_base(address) + (byte offset >> 4): the LBO bit is part of the base, so every further descriptor
+// is one 32-bit add away.
+__device__ __forceinline__ uint32_t desc_lo_base(uint32_t saddr) { return ((saddr >> 4) & 0x3FFF) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | static_cast<uint64_t>(lo);
 }
 
 // Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
