@@ -101,6 +101,19 @@ class Synthesizer(object):
         # a float64 array fed to the reference's float32 placeholder is rounded to fp32 the same way
         return np.ascontiguousarray(image, dtype=np.float32)
 
+    def _set_target(self, image, is_preimage=False):
+        """compute_gram(image, update=True) without the device-to-host copy of the Grams it returns (12.7 MB at batch
+        9): what synthesize() needs."""
+        import torch
+        if self.gram_only:
+            raise AttributeError("'Synthesizer' object has no attribute 'op_update_gram_target'")
+        img = torch.from_numpy(self._to_batch(image)).cuda()
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        _lib.check(L.stx_plan_forward(self._plan.handle, img.data_ptr(), int(bool(is_preimage)), 1, st))
+        _lib.check(L.stx_plan_update_target_from_forward(self._plan.handle, st))
+        self._have_target = True
+
     def compute_gram(self, image, mask=None, update=False, is_preimage=False):
         """synthesizer.py:109-117. Returns {layer: [B,C,C]} or, with update=True, assigns the target Grams
         (the reference's op_update_gram_target) and returns them as a list."""
@@ -148,7 +161,7 @@ class Synthesizer(object):
         """synthesizer.py:127-151. Returns (image [S,S,3] (or [B,S,S,3] for batch > 1), fun)."""
         if self.verbose:
             self.reset_verbose()
-        self.compute_gram(image_target, update=True)
+        self._set_target(image_target)
         x0 = self._to_batch(input_init)
         if self.optimizer == "scipy":
             return self._synthesize_scipy(x0, bounds, is_preimage)
