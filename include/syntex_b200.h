@@ -195,6 +195,41 @@ int stx_gram_bf16(const void* feat_bf16, int n, int HW, int C, float eps, float*
 size_t stx_gram_cross_workspace_bytes(int n, int HW, int C);
 int stx_gram_cross_bf16(const void* a_bf16, const void* b_bf16, int n, int HW, int C, float eps, float* out,
                         void* workspace, void* stream);
+/* ---- PO generator building blocks (po/progressive_model.py:77-206) -------------
+ * All tensors NHWC bf16 on the device unless noted. These replace, for the generator's trainable 3x3 layers, the
+ * arithmetic of tensorpack Conv2D / InstanceNorm / tf.pad(SYMMETRIC) and of tf.gradients through them. */
+/* 3x3 convolution with an explicit padding mode. H, W are the OUTPUT size; the input is
+ * (H + 2 - 2 pad) x (W + 2 - 2 pad): pad 0 = VALID on an explicitly padded input (tf.pad + Conv2D("VALID"),
+ * progressive_model.py:171-175), 1 = SAME (zero padding), 2 = FULL correlation (the input gradient of the VALID
+ * convolution when w_packed is the dgrad pack of stx_pack_conv_weights). Epilogue as stx_conv_bf16. */
+int stx_conv_bf16_pad(const void* x, int n, int H, int W, int cin, const void* w_packed, int cout, int pad,
+                      const float* bias, const void* addend, int relu, void* out, int variant, void* stream);
+/* Filter gradient (what tf.gradients gives for Conv2D's kernel): dw_hwio fp32 [3][3][cin][cout] (device) =
+ * sum over images and output pixels of x[h + r - pad, w + s - pad, ci] * dy[h, w, co]; x is
+ * [n, H + 2 - 2 pad, W + 2 - 2 pad, cin] (pad 0: explicitly padded; pad 1: taps outside read zeros), dy [n,H,W,cout].
+ * workspace: stx_conv_wgrad_workspace_bytes. Deterministic (fixed-order split-K). */
+size_t stx_conv_wgrad_workspace_bytes(int n, int H, int W, int cin, int cout);
+int stx_conv_wgrad_bf16(const void* x, const void* dy, int n, int H, int W, int cin, int cout, int pad,
+                        float* dw_hwio, void* workspace, void* stream);
+/* tf.pad(mode="SYMMETRIC") by one pixel (= edge replication), optionally of relu(x): out [n,H+2,W+2,C]. */
+int stx_pad_replicate_bf16(const void* x, int n, int H, int W, int C, int relu, void* out, void* stream);
+/* Its gradient: gp [n,H+2,W+2,C] -> dx [n,H,W,C] (ring folded onto the edge pixels); x_or_null non-NULL = the pad
+ * was taken of relu(x): zero where x <= 0. */
+int stx_pad_replicate_bwd_bf16(const void* gp, const void* x_or_null, int n, int H, int W, int C, void* dx,
+                               void* stream);
+/* tensorpack InstanceNorm (per image and channel over H*W, biased variance, affine). mean/rstd fp32 [n,C]. */
+size_t stx_inorm_workspace_bytes(int n, int HW, int C);
+int stx_inorm_stats_bf16(const void* x, int n, int HW, int C, float eps, float* mean, float* rstd, void* workspace,
+                         void* stream);
+/* out = [relu]((x - mean) * rstd * gamma + beta) [+ addend]   (addend: the residual shortcut, nullable) */
+int stx_inorm_apply_bf16(const void* x, int n, int HW, int C, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, int relu, const void* addend, void* out, void* stream);
+/* Backward of the above for upstream dy (w.r.t. the value before the addend): dx, and per image the sums
+ * s1 = sum g, s2 = sum g * xhat with g = dy * [relu mask]  (d beta = sum_n s1, d gamma = sum_n s2), fp32 [n,C]. */
+int stx_inorm_bwd_bf16(const void* x, const void* dy, int n, int HW, int C, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, int relu, float* s1, float* s2, void* dx,
+                       void* workspace, void* stream);
+
 int stx_f32_to_bf16(const float* x, size_t count, void* out_bf16, void* stream);
 int stx_bf16_to_f32(const void* x_bf16, size_t count, float* out, void* stream);
 

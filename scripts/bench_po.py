@@ -6,7 +6,7 @@
                                                             gradient-mean all-reduce over NCCL, images/s
 
 The VGG19 / Gram work (forward, grad_layer, first- and second-order backward) runs on the hand-written kernels; the
-generator runs on stock torch kernels (row f-1: "next"). Synthetic textures, seeded random generator weights."""
+generator runs on the hand-written kernels of po/gen_ops.py (STX_PO_GENERATOR=torch: stock ATen/cuDNN). Synthetic textures, seeded random generator weights."""
 import json
 import os
 import sys
@@ -37,16 +37,23 @@ def timed(fn, warmup, steps):
 
 
 GEN_BF16 = os.environ.get("STX_PO_GENERATOR_BF16", "0") == "1"
+GEN = os.environ.get("STX_PO_GENERATOR", "auto")      # auto / native (hand-written kernels) / torch (stock ATen/cuDNN)
+
+
+def gen_name():
+    if GEN != "torch":
+        return "native (tcgen05 convs incl. wgrad, fused InstanceNorm/ReLU/pad; NHWC bf16)"
+    return "bf16 autocast" if GEN_BF16 else "fp32 (TF32 convs)"
 
 
 def infer(batch, size, which="progressive"):
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
     if which == "single":
-        model = SingleSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size})
+        model = SingleSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size, "generator": GEN})
     else:
         model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size,
-                                   "generator_bf16": GEN_BF16})
+                                   "generator_bf16": GEN_BF16, "generator": GEN})
     model = model.cuda().eval().to(memory_format=torch.channels_last)
     z, t = next(iter(SyntheticPOData(batch, size, seed=0)))
     l0 = _lib.lib().stx_launch_count()
@@ -59,7 +66,7 @@ def infer(batch, size, which="progressive"):
     # one of the target, plus the per-layer F*D products
     print(json.dumps({"workload": "po_%s_inference" % which, "batch": batch, "size": size, "images_per_s": batch / ms * 1e3,
                       "ms_per_batch": ms, "hot_path_launches_per_batch": (_lib.lib().stx_launch_count() - l0) // 7,
-                      "losses": [float(l) for l in model.losses], "generator": "bf16 autocast" if GEN_BF16 else "fp32 (TF32 convs)",
+                      "losses": [float(l) for l in model.losses], "generator": gen_name(),
                       "note": "config 3; single = SingleSynTex on the five Gram layers (single_model.py as shipped is stale "
                               "against the current extractor, SURVEY section 2 #8); random generator weights: throughput only"}))
 
@@ -75,15 +82,16 @@ def train(size, steps):
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = True
     model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size, "n_gpu": world,
-                               "generator_bf16": GEN_BF16}).cuda().to(memory_format=torch.channels_last)
+                               "generator_bf16": GEN_BF16, "generator": GEN}).cuda().to(memory_format=torch.channels_last)
     data = SyntheticPOData(1, size, seed=rank)
     batch = next(iter(data))
-    trainer = SynTexTrainer(data, model, world)
+    graph = os.environ.get("STX_PO_GRAPH", "1" if world == 1 else "0") == "1"
+    trainer = SynTexTrainer(data, model, world, cuda_graph=graph)
     losses = []
 
     def step():
         losses.append(trainer.run_step(batch))
-    for _ in range(3):
+    for _ in range(4):
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -109,7 +117,7 @@ def train(size, steps):
                           "allreduce_bytes": trainer.buckets.allreduce_bytes, "allreduce_alone_ms": ar_ms,
                           "allreduce_share_if_exposed": ar_ms / float(ms),
                           "generator_params": int(trainer.buckets.flat_param.numel()),
-                          "generator": "bf16 autocast" if GEN_BF16 else "fp32 (TF32 convs)",
+                          "generator": gen_name(), "cuda_graph": graph,
                           "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
                           "lr": trainer.opt.param_groups[0]["lr"]}))
     if world > 1:

@@ -63,6 +63,15 @@ def _declare(lib):
         "stx_gram_bf16": (c_int, [vp, c_int, c_int, c_int, c_float, fp, vp, vp]),
         "stx_gram_cross_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
         "stx_gram_cross_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_float, fp, vp, vp]),
+        "stx_conv_bf16_pad": (c_int, [vp, c_int, c_int, c_int, c_int, vp, c_int, c_int, fp, vp, c_int, vp, c_int, vp]),
+        "stx_conv_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+        "stx_conv_wgrad_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, fp, vp, vp]),
+        "stx_pad_replicate_bf16": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, vp]),
+        "stx_pad_replicate_bwd_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, vp]),
+        "stx_inorm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+        "stx_inorm_stats_bf16": (c_int, [vp, c_int, c_int, c_int, c_float, fp, fp, vp, vp]),
+        "stx_inorm_apply_bf16": (c_int, [vp, c_int, c_int, c_int, fp, fp, fp, fp, c_int, vp, vp, vp]),
+        "stx_inorm_bwd_bf16": (c_int, [vp, vp, c_int, c_int, c_int, fp, fp, fp, fp, c_int, fp, fp, vp, vp, vp]),
         "stx_f32_to_bf16": (c_int, [fp, c_size_t, vp, vp]),
         "stx_bf16_to_f32": (c_int, [vp, c_size_t, fp, vp]),
     }

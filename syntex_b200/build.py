@@ -7,9 +7,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsyntex_b200.so")
-SOURCES = ["common.cu", "conv_igemm.cu", "conv_patch.cu", "gram.cu", "elementwise.cu", "plan.cu", "lbfgs.cu", "capi.cu", "probe.cu"]
+SOURCES = ["common.cu", "conv_igemm.cu", "conv_patch.cu", "gram.cu", "elementwise.cu", "plan.cu", "lbfgs.cu", "capi.cu", "probe.cu",
+           "wgrad.cu", "gen_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-t", "0"]
 
 
 def _stale():

@@ -318,6 +318,54 @@ int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_pac
   return conv_launch(op, S(stream));
 }
 
+int stx_conv_bf16_pad(const void* x, int n, int H, int W, int cin, const void* w_packed, int cout, int pad,
+                      const float* bias, const void* addend, int relu, void* out, int variant, void* stream) {
+  STX_REQUIRE(out, "stx_conv_bf16_pad: null output");
+  ConvOp op;
+  // geometry from the OUTPUT size; the activation map is then re-pointed at the (H + 2 - 2 pad)-sized input
+  STX_TRY(conv3x3_prepare(&op, static_cast<const bf16*>(x), nullptr, n, H, W, cin, static_cast<const bf16*>(w_packed),
+                          nullptr, cout, variant));
+  if (pad != 1) STX_TRY(conv_set_input_pad(&op, static_cast<const bf16*>(x), pad));
+  op.bias = bias;
+  op.addend = static_cast<const bf16*>(addend);
+  op.relu = relu;
+  op.out = static_cast<bf16*>(out);
+  return conv_launch(op, S(stream));
+}
+size_t stx_conv_wgrad_workspace_bytes(int n, int H, int W, int cin, int cout) {
+  return wgrad_workspace_bytes(n, H, W, cin, cout);
+}
+int stx_conv_wgrad_bf16(const void* x, const void* dy, int n, int H, int W, int cin, int cout, int pad,
+                        float* dw_hwio, void* workspace, void* stream) {
+  return wgrad_launch(static_cast<const bf16*>(x), static_cast<const bf16*>(dy), n, H, W, cin, cout, pad, dw_hwio,
+                      static_cast<float*>(workspace), S(stream));
+}
+int stx_pad_replicate_bf16(const void* x, int n, int H, int W, int C, int relu, void* out, void* stream) {
+  return pad_rep_launch(static_cast<const bf16*>(x), n, H, W, C, relu, static_cast<bf16*>(out), S(stream));
+}
+int stx_pad_replicate_bwd_bf16(const void* gp, const void* x_or_null, int n, int H, int W, int C, void* dx,
+                               void* stream) {
+  return pad_rep_bwd_launch(static_cast<const bf16*>(gp), static_cast<const bf16*>(x_or_null), n, H, W, C,
+                            static_cast<bf16*>(dx), S(stream));
+}
+size_t stx_inorm_workspace_bytes(int n, int HW, int C) { return inorm_workspace_bytes(n, HW, C); }
+int stx_inorm_stats_bf16(const void* x, int n, int HW, int C, float eps, float* mean, float* rstd, void* workspace,
+                         void* stream) {
+  return inorm_stats_launch(static_cast<const bf16*>(x), n, HW, C, eps, mean, rstd, static_cast<float*>(workspace),
+                            S(stream));
+}
+int stx_inorm_apply_bf16(const void* x, int n, int HW, int C, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, int relu, const void* addend, void* out, void* stream) {
+  return inorm_apply_launch(static_cast<const bf16*>(x), n, HW, C, mean, rstd, gamma, beta, relu,
+                            static_cast<const bf16*>(addend), static_cast<bf16*>(out), S(stream));
+}
+int stx_inorm_bwd_bf16(const void* x, const void* dy, int n, int HW, int C, const float* mean, const float* rstd,
+                       const float* gamma, const float* beta, int relu, float* s1, float* s2, void* dx,
+                       void* workspace, void* stream) {
+  return inorm_bwd_launch(static_cast<const bf16*>(x), static_cast<const bf16*>(dy), n, HW, C, mean, rstd, gamma, beta,
+                          relu, s1, s2, static_cast<bf16*>(dx), static_cast<float*>(workspace), S(stream));
+}
+
 int stx_conv1_1_fwd(const float* image, int n, int H, int W, int is_preimage, const float* mean3_host,
                     const float* w27x64, const float* b64, void* out_bf16, void* out_lo, void* stream) {
   return conv1_1_fwd_launch(image, n, H, W, is_preimage, mean3_host, w27x64, b64, static_cast<bf16*>(out_bf16),

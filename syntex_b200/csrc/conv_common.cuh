@@ -16,6 +16,7 @@ struct ConvKernelParams {
   int n_step;          // images advanced per tile along the batch axis
   int per_image_w;     // weight "tap" index = image index (Gram dF mode); only rows of the first image are stored
   int relu;
+  int pad;             // taps reach from -pad to 2 - pad around the output pixel (1 = SAME)
   const float* bias;   // [cout] or null
   const bf16* addend;  // [nimg,H,W,cout] or null (may alias out)
   const bf16* mask;    // [nimg,H,W,cout] or null: result is zeroed where mask <= 0

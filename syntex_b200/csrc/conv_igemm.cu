@@ -110,8 +110,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int cc = it - tap * p.cchunks;
       int dy = 0, dx = 0;
       if (p.taps == 9) {
-        dy = tap / 3 - 1;
-        dx = tap % 3 - 1;
+        dy = tap / 3 - p.pad;
+        dx = tap % 3 - p.pad;
       }
       uint8_t* a_dst = smem + s * L::kStageBytes;
       uint8_t* b_dst = a_dst + kABytes;
@@ -210,6 +210,7 @@ int launch_bn(const ConvOp& op, cudaStream_t stream) {
   p.n_step = op.n_step;
   p.per_image_w = op.per_image_w;
   p.relu = op.relu;
+  p.pad = op.pad;
   p.bias = op.bias;
   p.addend = op.addend;
   p.mask = op.mask;
@@ -314,6 +315,7 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->export_out = nullptr;
   op->split = 0;
   op->relu = 0;
+  op->pad = 1;
   return STX_OK;
 }
 
@@ -331,6 +333,26 @@ int conv3x3_prepare(ConvOp* op, const bf16* x, const bf16* x_lo, int nimg, int H
   }
   STX_TRY(conv_prepare(op, x, nimg, H, W, cin, w, cout, 9, 0, force_bn == 256 ? 128 : force_bn));
   return split ? conv_prepare_split(op, x_lo, w_lo) : STX_OK;
+}
+
+int conv_set_input_pad(ConvOp* op, const bf16* x, int pad) {
+  STX_REQUIRE(pad >= 0 && pad <= 2, "conv: pad must be 0 (VALID), 1 (SAME) or 2 (FULL)");
+  STX_REQUIRE(op->taps == 9 && !op->split && !op->per_image_w, "conv: input padding modes exist for the plain 3x3 op only");
+  const int Hin = op->H + 2 - 2 * pad, Win = op->W + 2 - 2 * pad;
+  STX_REQUIRE(Hin > 0 && Win > 0, "conv: input smaller than the filter");
+  const uint64_t adims[4] = {static_cast<uint64_t>(op->cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                             static_cast<uint64_t>(op->nimg)};
+  uint32_t abox[4];
+  if (op->patch) {
+    abox[0] = 64u; abox[1] = 10u; abox[2] = static_cast<uint32_t>(16 * op->mt + 2); abox[3] = 1u;
+  } else {
+    const int bw = 1 << op->bw_log2, bh = 1 << op->bh_log2;
+    abox[0] = 64u; abox[1] = static_cast<uint32_t>(bw); abox[2] = static_cast<uint32_t>(bh);
+    abox[3] = static_cast<uint32_t>(kTileM / (bw * bh));
+  }
+  STX_TRY(encode_tmap_bf16(&op->tmA, x, 4, adims, abox));
+  op->pad = pad;
+  return STX_OK;
 }
 
 int conv_launch(const ConvOp& op, cudaStream_t stream) {

@@ -194,8 +194,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* pdst = smem + ps * L::kPatchStageBytes;
           if (elect_one()) {
             mbar_arrive_expect_tx(&pfull[ps], (SPLIT ? 2 : 1) * L::kPatchBytes);
-            tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
-            if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - 1, h0 - 1, n);
+            tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - p.pad, h0 - p.pad, n);
+            if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - p.pad, h0 - p.pad, n);
           }
           if (++ps == kPS) {
             ps = 0;
@@ -600,6 +600,7 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.n_step = 1;
   p.per_image_w = 0;
   p.relu = op.relu;
+  p.pad = op.pad;
   p.bias = op.bias;
   p.addend = op.addend;
   p.mask = op.mask;
@@ -741,6 +742,7 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->export_out = nullptr;
   op->split = 0;
   op->relu = 0;
+  op->pad = 1;
   return STX_OK;
 }
 

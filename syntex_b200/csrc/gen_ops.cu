@@ -1,0 +1,395 @@
+// HBM-bound building blocks of the PO generator, NHWC bf16 with fp32 arithmetic:
+//   * tf.pad(mode="SYMMETRIC") by one pixel (= edge replication) and its gradient, optionally fused with ReLU
+//     (po/progressive_model.py:171-175: pad -> Conv2D(VALID); :77-99 relu before the first conv of a block)
+//   * tensorpack InstanceNorm (per image and channel over H x W, biased variance, affine), forward and backward, with
+//     the ReLU that follows it and the residual shortcut that is added to it fused into the same pass
+//     (po/progressive_model.py:77-121).
+// Every kernel moves 16-byte vectors (8 channels) with consecutive threads on consecutive addresses; reductions are
+// two-level (per-block partials in a fixed order, then one small finishing kernel): deterministic, no atomics.
+#include "ops.h"
+#include "ptx.cuh"
+
+namespace stx {
+
+namespace {
+
+union Vec8 {
+  uint4 u;
+  __nv_bfloat162 h2[4];
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  Vec8 v;
+  v.u = u;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __bfloat1622float2(v.h2[e]);
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  Vec8 v;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v.h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  return v.u;
+}
+
+// out [n, H+2, W+2, C] <- x [n, H, W, C], edge pixels replicated; optional ReLU on the way.
+__global__ void __launch_bounds__(256)
+pad_rep_kernel(const uint4* __restrict__ x, int nimg, int H, int W, int c8, int relu, uint4* __restrict__ out) {
+  const int Hp = H + 2, Wp = W + 2;
+  const size_t total = static_cast<size_t>(nimg) * Hp * Wp * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8);
+    size_t t = i / c8;
+    const int wp = static_cast<int>(t % Wp);
+    t /= Wp;
+    const int hp = static_cast<int>(t % Hp);
+    const int n = static_cast<int>(t / Hp);
+    const int h = min(max(hp - 1, 0), H - 1), w = min(max(wp - 1, 0), W - 1);
+    uint4 v = __ldg(x + ((static_cast<size_t>(n) * H + h) * W + w) * c8 + c);
+    if (relu) {
+      float f[8];
+      unpack8(v, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+      v = pack8(f);
+    }
+    out[i] = v;
+  }
+}
+
+// dx [n, H, W, C] <- gradient w.r.t. the padded tensor gp [n, H+2, W+2, C]: the ring folds onto the edge pixels;
+// with `x` (the forward input) given, ReluGrad is applied as well (zero where x <= 0).
+__global__ void __launch_bounds__(256)
+pad_rep_bwd_kernel(const uint4* __restrict__ gp, const uint4* __restrict__ x, int nimg, int H, int W, int c8,
+                   uint4* __restrict__ dx) {
+  const int Wp = W + 2, Hp = H + 2;
+  const size_t total = static_cast<size_t>(nimg) * H * W * c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8);
+    size_t t = i / c8;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    const int h_lo = (h == 0) ? 0 : h + 1, h_hi = (h == H - 1) ? H + 1 : h + 1;
+    const int w_lo = (w == 0) ? 0 : w + 1, w_hi = (w == W - 1) ? W + 1 : w + 1;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    for (int hp = h_lo; hp <= h_hi; ++hp) {
+      for (int wp = w_lo; wp <= w_hi; ++wp) {
+        float f[8];
+        unpack8(__ldg(gp + ((static_cast<size_t>(n) * Hp + hp) * Wp + wp) * c8 + c), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    }
+    if (x) {
+      float f[8];
+      unpack8(__ldg(x + i), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (!(f[e] > 0.0f)) acc[e] = 0.0f;
+    }
+    dx[i] = pack8(acc);
+  }
+}
+
+// ---------------------------------------------------------------- instance norm
+// Per-(image, channel) sums over the pixels. One block = one slab of pixels of one image; thread t owns the channel
+// group t % c8 and walks pixels t / c8, t / c8 + 256 / c8, ... of the slab.
+//   MODE 0: a = sum x,                b = sum x^2
+//   MODE 1: a = sum g,                b = sum g * xhat       with g = dy * [relu: xhat * gamma + beta > 0]
+constexpr int kInThreads = 256;
+
+struct InParams {
+  int HW, C, c8, slabs, pix_per_slab;
+  int relu;
+  float eps;
+  const float* mean;    // [n][C]
+  const float* rstd;    // [n][C]
+  const float* gamma;   // [C]
+  const float* beta;    // [C]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kInThreads)
+in_partial_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, const InParams p, float* __restrict__ part) {
+  __shared__ float red[2][kInThreads][8 + 1];
+  const int img = blockIdx.y, slab = blockIdx.x;
+  const int cg = threadIdx.x % p.c8, pl = threadIdx.x / p.c8, lanes = kInThreads / p.c8;
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = b[e] = 0.0f;
+  float mu[8], rs[8], ga[8], be[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = cg * 8 + e;
+      mu[e] = p.mean[img * p.C + ch];
+      rs[e] = p.rstd[img * p.C + ch];
+      ga[e] = p.gamma[ch];
+      be[e] = p.beta[ch];
+    }
+  }
+  const int p_begin = slab * p.pix_per_slab;
+  const int p_end = min(p_begin + p.pix_per_slab, p.HW);
+  const uint4* xi = x + static_cast<size_t>(img) * p.HW * p.c8;
+  const uint4* di = (MODE == 1) ? dy + static_cast<size_t>(img) * p.HW * p.c8 : nullptr;
+#pragma unroll 4
+  for (int px = p_begin + pl; px < p_end; px += lanes) {
+    float f[8];
+    unpack8(__ldg(xi + static_cast<size_t>(px) * p.c8 + cg), f);
+    if (MODE == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a[e] += f[e];
+        b[e] += f[e] * f[e];
+      }
+    } else {
+      float g[8];
+      unpack8(__ldg(di + static_cast<size_t>(px) * p.c8 + cg), g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (f[e] - mu[e]) * rs[e];
+        float gg = g[e];
+        if (p.relu && !(xh * ga[e] + be[e] > 0.0f)) gg = 0.0f;
+        a[e] += gg;
+        b[e] += gg * xh;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    red[0][threadIdx.x][e] = a[e];
+    red[1][threadIdx.x][e] = b[e];
+  }
+  __syncthreads();
+  // thread (cg, e) of the first C threads sums the pixel lanes in a fixed order
+  for (int ch = threadIdx.x; ch < p.C; ch += kInThreads) {
+    const int g8 = ch >> 3, e = ch & 7;
+    float sa = 0.0f, sb = 0.0f;
+    for (int l = 0; l < lanes; ++l) {
+      sa += red[0][l * p.c8 + g8][e];
+      sb += red[1][l * p.c8 + g8][e];
+    }
+    float* dst = part + ((static_cast<size_t>(img) * p.slabs + slab) * p.C + ch) * 2;
+    dst[0] = sa;
+    dst[1] = sb;
+  }
+}
+
+// MODE 0: (mean, rstd) from the slab sums; MODE 1: the two sums themselves. One warp per (image, channel): lane l sums
+// slabs l, l + 32, ... and the lanes meet in a fixed-order shuffle tree (deterministic).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+in_finish_kernel(const float* __restrict__ part, int nimg, int C, int slabs, int HW, float eps, float* __restrict__ o0,
+                 float* __restrict__ o1) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= nimg * C) return;
+  const int img = i / C, ch = i - img * C;
+  float sa = 0.0f, sb = 0.0f;
+  for (int s = lane; s < slabs; s += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(part + ((static_cast<size_t>(img) * slabs + s) * C + ch) * 2);
+    sa += v.x;
+    sb += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  if (lane != 0) return;
+  if (MODE == 0) {
+    const float m = sa / static_cast<float>(HW);
+    const float var = fmaxf(sb / static_cast<float>(HW) - m * m, 0.0f);
+    o0[i] = m;
+    o1[i] = rsqrtf(var + eps);
+  } else {
+    o0[i] = sa;
+    o1[i] = sb;
+  }
+}
+
+// out = [relu]((x - mean) * rstd * gamma + beta) [+ addend]
+__global__ void __launch_bounds__(256)
+in_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ addend, const InParams p, size_t total,
+                uint4* __restrict__ out) {
+  const size_t per_img = static_cast<size_t>(p.HW) * p.c8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % p.c8);
+    const int img = static_cast<int>(i / per_img);
+    float f[8];
+    unpack8(__ldg(x + i), f);
+    // scalar parameter loads: gamma / beta may live at any 4-byte offset of a flat parameter buffer (po/trainer.py)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = cg * 8 + e;
+      f[e] = (f[e] - __ldg(p.mean + img * p.C + ch)) * __ldg(p.rstd + img * p.C + ch) * __ldg(p.gamma + ch) +
+             __ldg(p.beta + ch);
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+    }
+    if (addend) {
+      float a[8];
+      unpack8(__ldg(addend + i), a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += a[e];
+    }
+    out[i] = pack8(f);
+  }
+}
+
+// dx = rstd * gamma * (g - s1 / HW - xhat * s2 / HW),  g = dy * [relu mask], s1 = sum g, s2 = sum g * xhat
+__global__ void __launch_bounds__(256)
+in_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, const InParams p,
+                    const float* __restrict__ s1, const float* __restrict__ s2, size_t total, uint4* __restrict__ dx) {
+  const size_t per_img = static_cast<size_t>(p.HW) * p.c8;
+  const float inv = 1.0f / static_cast<float>(p.HW);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % p.c8);
+    const int img = static_cast<int>(i / per_img);
+    float f[8], g[8];
+    unpack8(__ldg(x + i), f);
+    unpack8(__ldg(dy + i), g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = cg * 8 + e;
+      const float mu = __ldg(p.mean + img * p.C + ch), rs = __ldg(p.rstd + img * p.C + ch);
+      const float ga = __ldg(p.gamma + ch), be = __ldg(p.beta + ch);
+      const float xh = (f[e] - mu) * rs;
+      float gg = g[e];
+      if (p.relu && !(xh * ga + be > 0.0f)) gg = 0.0f;
+      f[e] = rs * ga * (gg - inv * __ldg(s1 + img * p.C + ch) - xh * inv * __ldg(s2 + img * p.C + ch));
+    }
+    dx[i] = pack8(f);
+  }
+}
+
+int ew_blocks(size_t total) {
+  size_t b = (total + 255) / 256;
+  const size_t cap = 148 * 16;
+  return static_cast<int>(b < cap ? (b ? b : 1) : cap);
+}
+
+int in_slabs(int nimg, int HW) {
+  int slabs = (148 * 8 + nimg - 1) / nimg;              // ~8 blocks per SM over the whole batch
+  const int max_slabs = (HW + 63) / 64;                 // at least 64 pixels per slab
+  if (slabs > max_slabs) slabs = max_slabs;
+  return slabs < 1 ? 1 : slabs;
+}
+
+}  // namespace
+
+int pad_rep_launch(const bf16* x, int nimg, int H, int W, int C, int relu, bf16* out, cudaStream_t stream) {
+  STX_REQUIRE(x && out, "pad: null operand");
+  STX_REQUIRE(nimg > 0 && H > 0 && W > 0 && C % 8 == 0, "pad: C must be a multiple of 8");
+  const size_t total = static_cast<size_t>(nimg) * (H + 2) * (W + 2) * (C / 8);
+  pad_rep_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), nimg, H, W, C / 8, relu,
+                                                      reinterpret_cast<uint4*>(out));
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+int pad_rep_bwd_launch(const bf16* gp, const bf16* x_or_null, int nimg, int H, int W, int C, bf16* dx,
+                       cudaStream_t stream) {
+  STX_REQUIRE(gp && dx, "pad backward: null operand");
+  STX_REQUIRE(nimg > 0 && H > 0 && W > 0 && C % 8 == 0, "pad backward: C must be a multiple of 8");
+  const size_t total = static_cast<size_t>(nimg) * H * W * (C / 8);
+  pad_rep_bwd_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(gp),
+                                                          reinterpret_cast<const uint4*>(x_or_null), nimg, H, W, C / 8,
+                                                          reinterpret_cast<uint4*>(dx));
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+size_t inorm_workspace_bytes(int nimg, int HW, int C) {
+  if (nimg <= 0 || HW <= 0 || C <= 0) return 0;
+  return static_cast<size_t>(nimg) * in_slabs(nimg, HW) * C * 2 * sizeof(float);
+}
+
+static int in_check(int nimg, int HW, int C) {
+  STX_REQUIRE(nimg > 0 && HW > 0, "instance norm: empty tensor");
+  STX_REQUIRE(C % 8 == 0 && C >= 8 && (kInThreads % (C / 8) == 0) && C <= 8 * kInThreads,
+              "instance norm: C must be 8 * a divisor of 256");
+  return STX_OK;
+}
+
+static InParams in_params(int nimg, int HW, int C, int relu, float eps, const float* mean, const float* rstd,
+                          const float* gamma, const float* beta) {
+  InParams p;
+  p.HW = HW;
+  p.C = C;
+  p.c8 = C / 8;
+  p.slabs = in_slabs(nimg, HW);
+  p.pix_per_slab = (HW + p.slabs - 1) / p.slabs;
+  p.relu = relu;
+  p.eps = eps;
+  p.mean = mean;
+  p.rstd = rstd;
+  p.gamma = gamma;
+  p.beta = beta;
+  return p;
+}
+
+int inorm_stats_launch(const bf16* x, int nimg, int HW, int C, float eps, float* mean, float* rstd, float* workspace,
+                       cudaStream_t stream) {
+  STX_REQUIRE(x && mean && rstd && workspace, "instance norm: null operand");
+  STX_TRY(in_check(nimg, HW, C));
+  const InParams p = in_params(nimg, HW, C, 0, eps, nullptr, nullptr, nullptr, nullptr);
+  in_partial_kernel<0><<<dim3(p.slabs, nimg), kInThreads, 0, stream>>>(reinterpret_cast<const uint4*>(x), nullptr, p,
+                                                                      workspace);
+  STX_CUDA(cudaGetLastError());
+  in_finish_kernel<0><<<(nimg * C + 7) / 8, 256, 0, stream>>>(workspace, nimg, C, p.slabs, HW, eps, mean, rstd);
+  STX_CUDA(cudaGetLastError());
+  count_launch(2);
+  return STX_OK;
+}
+
+int inorm_apply_launch(const bf16* x, int nimg, int HW, int C, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, int relu, const bf16* addend, bf16* out, cudaStream_t stream) {
+  STX_REQUIRE(x && mean && rstd && gamma && beta && out, "instance norm: null operand");
+  STX_TRY(in_check(nimg, HW, C));
+  const InParams p = in_params(nimg, HW, C, relu, 0.0f, mean, rstd, gamma, beta);
+  const size_t total = static_cast<size_t>(nimg) * HW * p.c8;
+  in_apply_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                       reinterpret_cast<const uint4*>(addend), p, total,
+                                                       reinterpret_cast<uint4*>(out));
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+int inorm_bwd_launch(const bf16* x, const bf16* dy, int nimg, int HW, int C, const float* mean, const float* rstd,
+                     const float* gamma, const float* beta, int relu, float* s1, float* s2, bf16* dx, float* workspace,
+                     cudaStream_t stream) {
+  STX_REQUIRE(x && dy && mean && rstd && gamma && beta && s1 && s2 && dx && workspace, "instance norm: null operand");
+  STX_TRY(in_check(nimg, HW, C));
+  const InParams p = in_params(nimg, HW, C, relu, 0.0f, mean, rstd, gamma, beta);
+  in_partial_kernel<1><<<dim3(p.slabs, nimg), kInThreads, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                                      reinterpret_cast<const uint4*>(dy), p, workspace);
+  STX_CUDA(cudaGetLastError());
+  in_finish_kernel<1><<<(nimg * C + 7) / 8, 256, 0, stream>>>(workspace, nimg, C, p.slabs, HW, 0.0f, s1, s2);
+  STX_CUDA(cudaGetLastError());
+  const size_t total = static_cast<size_t>(nimg) * HW * p.c8;
+  in_bwd_apply_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
+                                                           reinterpret_cast<const uint4*>(dy), p, s1, s2, total,
+                                                           reinterpret_cast<uint4*>(dx));
+  STX_CUDA(cudaGetLastError());
+  count_launch(3);
+  return STX_OK;
+}
+
+}  // namespace stx

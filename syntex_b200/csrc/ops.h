@@ -37,6 +37,8 @@ struct ConvOp {
   int nimg, H, W, cin, cout, taps, per_image_w;
   int bw_log2, bh_log2, tiles_w, tiles_h, tiles_n, n_step, bn;
   int relu;
+  int pad;             // rows/columns of (zero) padding the taps reach into: 1 = SAME (default), 0 = VALID on an input two
+                       // pixels larger than the output, 2 = FULL on an input two pixels smaller (see conv_set_input_pad)
   const float* bias;
   const bf16* addend;
   const bf16* mask;
@@ -57,6 +59,10 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream);
 int conv3x3_prepare(ConvOp* op, const bf16* x, const bf16* x_lo, int nimg, int H, int W, int cin, const bf16* w,
                     const bf16* w_lo, int cout, int variant);
 int conv_launch(const ConvOp& op, cudaStream_t stream);
+// Re-point a prepared 3x3 op (geometry = OUTPUT H x W) at an input of (H + 2 - 2 pad) x (W + 2 - 2 pad) pixels:
+// pad 0 = VALID convolution of an explicitly padded input (the generator's symmetric padding), pad 2 = FULL
+// correlation (the input gradient of a VALID convolution). Out-of-range taps read zeros (TMA fill).
+int conv_set_input_pad(ConvOp* op, const bf16* x, int pad);
 
 // ------------------------------------------------------------------ gram.cu
 struct GramOp {
@@ -136,5 +142,26 @@ int pack_weights_tiled_launch(const float* w_hwio, int cin, int cout, bf16* f_hi
                               cudaStream_t stream);
 int pack_conv1_1_dgrad_launch(const float* w27x64, bf16* out, cudaStream_t stream);
 int sum_partials_launch(const float* part, int nimg, int count, int stride, float* out, cudaStream_t stream);
+
+
+// ------------------------------------------------------------------ wgrad.cu
+// Filter gradient of a 3x3 convolution: dw_hwio fp32 [3][3][cin][cout] = sum over images/pixels of
+// X[h + r - pad, w + s - pad] (x) dY[h, w]; x is [nimg, H + 2 - 2 pad, W + 2 - 2 pad, cin], dy [nimg, H, W, cout].
+size_t wgrad_workspace_bytes(int nimg, int H, int W, int cin, int cout);
+int wgrad_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin, int cout, int pad, float* dw_hwio,
+                 float* workspace, cudaStream_t stream);
+
+// ------------------------------------------------------------------ gen_ops.cu
+int pad_rep_launch(const bf16* x, int nimg, int H, int W, int C, int relu, bf16* out, cudaStream_t stream);
+int pad_rep_bwd_launch(const bf16* gp, const bf16* x_or_null, int nimg, int H, int W, int C, bf16* dx,
+                       cudaStream_t stream);
+size_t inorm_workspace_bytes(int nimg, int HW, int C);
+int inorm_stats_launch(const bf16* x, int nimg, int HW, int C, float eps, float* mean, float* rstd, float* workspace,
+                       cudaStream_t stream);
+int inorm_apply_launch(const bf16* x, int nimg, int HW, int C, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, int relu, const bf16* addend, bf16* out, cudaStream_t stream);
+int inorm_bwd_launch(const bf16* x, const bf16* dy, int nimg, int HW, int C, const float* mean, const float* rstd,
+                     const float* gamma, const float* beta, int relu, float* s1, float* s2, bf16* dx, float* workspace,
+                     cudaStream_t stream);
 
 }  // namespace stx

@@ -4,7 +4,9 @@ The reference builds these from tensorpack 0.9.8 layers (Conv2D, InstanceNorm) a
 (po/progressive_model.py:24-143). tensorpack is absent from /root/reference, so its defaults are restated from
 its published source and are UNVERIFIED here: Conv2D kernels He-normal on fan-in (variance_scaling 2.0), zero biases;
 InstanceNorm per (image, channel) over H x W with eps 1e-5 and an affine gamma = 1 / beta = 0.
-These layers run on stock ATen/cuDNN kernels: the generator is the "next" row, outside the hand-written hot path.
+Two routes share these modules and their parameters: `forward` on stock ATen/cuDNN kernels (NCHW fp32; also what
+the CPU tests run over the oracle door), and `forward_native` on the hand-written kernels of po/gen_ops.py (NHWC bf16
+activations: tcgen05 convolutions incl. the filter gradient, fused InstanceNorm / ReLU / padding passes).
 """
 import torch
 import torch.nn as nn
@@ -62,6 +64,10 @@ class InstanceNormAffine(nn.Module):
             return F.group_norm(x, self.chan, self.weight, self.bias, self.eps)
         return F.instance_norm(x, None, None, self.weight, self.bias, True, 0.0, self.eps)
 
+    def forward_native(self, x, relu=False, shortcut=None):
+        from . import gen_ops
+        return gen_ops.instance_norm(x, self.weight, self.bias, self.eps, relu, shortcut)
+
 
 def instance_norm(chan):
     return InstanceNormAffine(chan)
@@ -87,6 +93,18 @@ class SymConv(nn.Module):
             x = F.relu(self.norm(x))
         return x
 
+    def forward_native(self, x, relu_in=False):
+        """x NHWC bf16; relu_in: the ReLU the caller applies to x first, fused into the padding pass."""
+        from . import gen_ops
+        if self.ksize != 3:
+            raise NotImplementedError("native generator route: 3x3 layers only (5x5 runs as 4 phase filters)")
+        if self.zero_pad and relu_in:
+            x, relu_in = torch.relu(x), False
+        x = gen_ops.conv3x3(x, self.conv.weight, self.conv.bias, "zero" if self.zero_pad else "rep", relu_in)
+        if self.norm is not None:
+            x = self.norm.forward_native(x, relu=True)
+        return x
+
 
 class ResBlock(nn.Module):
     """build_res_block (progressive_model.py:77-99): relu -> conv0 (IN+ReLU) -> conv1 -> IN, plus the shortcut."""
@@ -99,6 +117,10 @@ class ResBlock(nn.Module):
 
     def forward(self, x):
         return self.inorm(self.conv1(self.conv0(F.relu(x)))) + x
+
+    def forward_native(self, x):
+        return self.inorm.forward_native(self.conv1.forward_native(self.conv0.forward_native(x, relu_in=True)),
+                                         relu=False, shortcut=x)
 
 
 class PreResBlock(nn.Module):
@@ -113,6 +135,9 @@ class PreResBlock(nn.Module):
     def forward(self, x):
         return self.conv1(self.conv0(F.relu(self.inorm(x)))) + x
 
+    def forward_native(self, x):
+        return self.conv1.forward_native(self.conv0.forward_native(self.inorm.forward_native(x, relu=True))) + x
+
 
 class UpsampleNN(nn.Module):
     """build_upsampling_nn (progressive_model.py:123-134): nearest x2, symmetric pad, (2*scale+1)^2 conv, no bias."""
@@ -124,6 +149,17 @@ class UpsampleNN(nn.Module):
 
     def forward(self, x):
         return self.conv(F.interpolate(x, scale_factor=self.scale, mode="nearest"))
+
+    def forward_native(self, x, relu_in=False):
+        """Nearest x2 + symmetric pad 2 + 5x5 conv == edge-replicated 3x3 conv of the low-resolution map with four
+        phase filters (gen_ops.upsample_weights), then a pixel shuffle: 36 tap-GEMMs on h x w pixels instead of 25 on
+        4 h x w."""
+        from . import gen_ops
+        if self.scale != 2:
+            raise NotImplementedError("native generator route: x2 up-sampling only")
+        w5 = self.conv.conv.weight
+        y = gen_ops.conv3x3(x, gen_ops.upsample_weights(w5), None, "rep", relu_in)
+        return gen_ops.pixel_shuffle_nhwc(y, w5.shape[0])
 
 
 class UpsampleDeconv(nn.Module):

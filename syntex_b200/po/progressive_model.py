@@ -4,7 +4,8 @@ Five stages; stage s looks at the current image through VGG19, takes the closed-
 s+1 Gram layers (build_texture_loss(calc_grad=True), utils.py:50-55) and lets a small generator turn them into a
 pre-image update. Everything VGG / Gram - forward, the gradients handed to the generator, and the back-propagation
 of the training loss through them (first- and second-order) - runs on the hand-written kernels through
-`po.texture_op.vgg_texture`; the generator itself is stock torch (row f-1 of SURVEY.md section 8).
+`po.texture_op.vgg_texture`; the generator (row f-1 of SURVEY.md section 8) runs on the hand-written kernels of
+po/gen_ops.py (`generator="native"`, the default on the CUDA door) or on stock torch (`generator="torch"`).
 """
 from collections import OrderedDict
 
@@ -80,6 +81,32 @@ class _Stage(nn.Module):
         delta = F.relu(self.actlast_inorm(delta)) if self.pre_act else F.relu(delta)
         return self.convlast(delta).permute(0, 2, 3, 1)
 
+    def native_supported(self):
+        return all(hasattr(m, "forward_native") for m in self.up.values())
+
+    def forward_native(self, grad_layer):
+        """The same graph on the hand-written kernels (po/gen_ops.py): NHWC bf16 activations end to end, ReLUs fused
+        into the padding pass of the convolution that follows, InstanceNorm + ReLU / + shortcut in one pass."""
+        delta = None
+        for layer in reversed(self.layers):
+            g = grad_layer[layer].to(torch.bfloat16)
+            g = self.grad_conv2[layer].forward_native(self.grad_conv1[layer].forward_native(g))
+            if delta is None:
+                delta = g
+            elif self.pre_act:
+                delta = g + self.up[layer].forward_native(self.pre_inorm[layer].forward_native(delta, relu=True))
+            else:
+                delta = g + self.up[layer].forward_native(delta, relu_in=True)
+            if not self.pre_act:
+                delta = self.post_inorm[layer].forward_native(delta)
+            for blk in self.res[layer]:
+                delta = blk.forward_native(delta)
+        if self.pre_act:
+            out = self.convlast.forward_native(self.actlast_inorm.forward_native(delta, relu=True))
+        else:
+            out = self.convlast.forward_native(delta, relu_in=True)
+        return out.to(torch.float32)
+
 
 class ProgressiveSynTex(SynTexModelDesc, nn.Module):
     def __init__(self, args, texture_fn=None):
@@ -108,6 +135,12 @@ class ProgressiveSynTex(SynTexModelDesc, nn.Module):
         self._nn_upsample = not args.get("deconv_upsample", False)
         # extension (not in the reference parser): run the generator's stock convolutions under bf16 autocast
         self._generator_bf16 = bool(args.get("generator_bf16", False))
+        # extension: "native" = the generator on the hand-written kernels (po/gen_ops.py), "torch" = stock ATen/cuDNN,
+        # "auto" = native when the door is the CUDA plan and the configuration is covered (nearest-neighbour up-sampling)
+        self._generator = args.get("generator", "auto")
+        if self._generator not in ("auto", "native", "torch"):
+            raise ValueError("generator must be auto, native or torch")
+        self._door_is_cuda = texture_fn is None
         # The hot path: an object with grams(image) and __call__(image, layers, gram_target, slot, calc_grad) ->
         # (loss_layer, grad_layer). Default: the CUDA plan; tests swap in the CPU oracle to check the training gradient.
         self._texture_fn = texture_fn or CudaTexture(self._vgg19, SynTexModelDesc.DEFAULT_COEFS.keys())
@@ -153,14 +186,29 @@ class ProgressiveSynTex(SynTexModelDesc, nn.Module):
         slot = s if torch.is_grad_enabled() else 0
         loss_layer_input, grad_layer = self._texture_fn(image_input, list(coefs.keys()), gram_target, slot, True)
         loss_overall_input = sum(coefs[k] * 1. / 4 * loss_layer_input[k] for k in coefs)
-        if self._generator_bf16 and image_input.is_cuda:
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                delta_input = self.syn[s](grad_layer)
-            delta_input = delta_input.float()
-        else:
-            delta_input = self.syn[s](grad_layer)
+        delta_input = self.run_generator(self.syn[s], grad_layer, image_input.is_cuda)
         pre_image_output = pre_image_input + delta_input
         return image_input, loss_overall_input, loss_layer_input, pre_image_output
+
+    def use_native_generator(self, stage):
+        if self._generator == "torch":
+            return False
+        ok = self._nn_upsample and stage.native_supported()
+        if self._generator == "native":
+            if not ok:
+                raise NotImplementedError("generator='native' covers nearest-neighbour up-sampling only")
+            return True
+        return ok and self._door_is_cuda
+
+    def run_generator(self, stage, inputs, on_cuda):
+        if on_cuda and self.use_native_generator(stage):
+            return stage.forward_native(inputs)
+        if self._generator == "native":
+            raise RuntimeError("generator='native' needs CUDA tensors; there is no CPU route")
+        if self._generator_bf16 and on_cuda:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return stage(inputs).float()
+        return stage(inputs)
 
     def build_graph(self, pre_image_input, image_target):
         """progressive_model.py:208-266. pre_image_input: values before the activation; image_target in [0, 255].

@@ -5,7 +5,8 @@ provided by final loss", single_model.py:157-158). As shipped the reference loop
 current extractor (`for layer in reversed(feat_input)`, :165) and cannot build (its up-sampling chain assumes the
 five Gram layers; po/README.md:58 marks the file stale): this mirror follows the diagram at single_model.py:156-162
 - the five DEFAULT_COEFS layers. Training back-propagates through the features, i.e. through VGG19
-(`texture_op.vgg_stage_preparation`, direct feature gradients); the generator is stock torch (row f-1).
+(`texture_op.vgg_stage_preparation`, direct feature gradients); the generator runs on the hand-written kernels of
+po/gen_ops.py (or stock torch: `generator="torch"`).
 """
 from collections import OrderedDict
 
@@ -15,7 +16,7 @@ import torch.nn as nn
 
 from ..aparse import ArgParser
 from .model import SynTexModelDesc
-from .progressive_model import _Stage
+from .progressive_model import ProgressiveSynTex, _Stage
 from .texture_op import CudaTexture
 
 IMAGESIZE = 224
@@ -48,10 +49,19 @@ class SingleSynTex(SynTexModelDesc, nn.Module):
         self._loss_scale = args.get("loss_scale", 0.)
         self._pre_act = args.get("pre_act", False)
         self._nn_upsample = not args.get("deconv_upsample", False)
+        # generator route, as in ProgressiveSynTex: hand-written kernels ("native") or stock torch
+        self._generator_bf16 = bool(args.get("generator_bf16", False))
+        self._generator = args.get("generator", "auto")
+        if self._generator not in ("auto", "native", "torch"):
+            raise ValueError("generator must be auto, native or torch")
+        self._door_is_cuda = texture_fn is None
         self._texture_fn = texture_fn or CudaTexture(self._vgg19, SynTexModelDesc.DEFAULT_COEFS.keys())
         self.syn = nn.ModuleList([_Stage(5, self._n_block, self._pre_act, self._nn_upsample, zero_pad_inputs=True)
                                   for _ in range(self._n_stage)])
         self.image_outputs, self.losses, self.loss_layer_output = [], [], OrderedDict()
+
+    use_native_generator = ProgressiveSynTex.use_native_generator
+    run_generator = ProgressiveSynTex.run_generator
 
     def inputs(self):
         s = self._image_size
@@ -84,7 +94,7 @@ class SingleSynTex(SynTexModelDesc, nn.Module):
         slot = stage_index if torch.is_grad_enabled() else 0
         feat_input, _, loss_layer_input, _ = self._texture_fn.prep(image_input, gram_target, coefs, True, slot)
         loss_overall_input = sum(coefs[k] * 1. / 4 * loss_layer_input[k] for k in coefs)
-        delta_input = self.syn[stage_index](feat_input)
+        delta_input = self.run_generator(self.syn[stage_index], feat_input, image_input.is_cuda)
         pre_image_output = pre_image_input + delta_input
         return image_input, loss_overall_input, loss_layer_input, pre_image_output
 

@@ -1,0 +1,45 @@
+"""Host logic of the hand-written generator route (po/gen_ops.py) that needs no GPU: the phase decomposition that
+turns "nearest x2 + symmetric pad 2 + 5x5 conv" (build_upsampling_nn, po/progressive_model.py:123-134) into one
+edge-replicated 3x3 convolution of the low-resolution map plus a pixel shuffle, and the loud failure without CUDA."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from syntex_b200.po import gen_ops
+from syntex_b200.po.layers import UpsampleNN, symmetric_pad
+
+
+@pytest.mark.parametrize("cin,cout,h,w", [(3, 2, 5, 7), (8, 4, 6, 6), (1, 1, 1, 1)])
+def test_upsample_phase_filters_equal_the_5x5_convolution(cin, cout, h, w):
+    torch.manual_seed(0)
+    m = UpsampleNN(cin, cout).double()
+    x = torch.randn(2, cin, h, w, dtype=torch.float64, requires_grad=True)
+    ref = m(x)
+    w3 = gen_ops.upsample_weights(m.conv.conv.weight)
+    assert w3.shape == (4 * cout, cin, 3, 3)
+    y = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="replicate"), w3)               # [B, 4*cout, h, w]
+    y = gen_ops.pixel_shuffle_nhwc(y.permute(0, 2, 3, 1).contiguous(), cout)   # [B, 2h, 2w, cout]
+    assert torch.allclose(y.permute(0, 3, 1, 2), ref, atol=1e-12)
+    # ... and so are the gradients that flow back to the 5x5 parameters through the phase combination
+    g = torch.randn_like(ref)
+    gw_ref, gx_ref = torch.autograd.grad(ref, [m.conv.conv.weight, x], g)
+    gw, gx = torch.autograd.grad(y.permute(0, 3, 1, 2), [m.conv.conv.weight, x], g)
+    assert torch.allclose(gw, gw_ref, atol=1e-10) and torch.allclose(gx, gx_ref, atol=1e-10)
+
+
+def test_symmetric_pad_of_upsampled_map_is_edge_replication_of_the_low_resolution_map():
+    x = torch.arange(2 * 3 * 4 * 5, dtype=torch.float32).reshape(2, 3, 4, 5)
+    up = F.interpolate(x, scale_factor=2, mode="nearest")
+    a = symmetric_pad(up, 2)
+    b = F.interpolate(F.pad(x, (1, 1, 1, 1), mode="replicate"), scale_factor=2, mode="nearest")
+    assert torch.equal(a, b)
+
+
+def test_native_operators_fail_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    x = torch.zeros((1, 8, 8, 64), dtype=torch.bfloat16)
+    with pytest.raises(Exception):
+        gen_ops.conv3x3(x, torch.zeros(64, 64, 3, 3))
+    with pytest.raises(Exception):
+        gen_ops.instance_norm(x, torch.ones(64), torch.zeros(64))

@@ -1,0 +1,229 @@
+"""Hand-written PO generator kernels on the B200 against a plain PyTorch fp32 reference of
+the same operator: padded-mode tcgen05 convolutions (VALID / SAME / FULL), the filter-gradient contraction, the fused
+InstanceNorm / ReLU / edge-replication passes, and a whole generator stage native vs stock torch (shared parameters).
+
+Tolerances: inputs are bf16-exact in both arms; the kernels accumulate in fp32 and round their OUTPUT to bf16
+(relative 2^-9 per element), the filter gradient stays fp32."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import L, relerr, st  # noqa: E402
+from syntex_b200 import _lib  # noqa: E402
+from syntex_b200.po import gen_ops  # noqa: E402
+from syntex_b200.po.layers import ResBlock, SymConv, UpsampleNN  # noqa: E402
+from syntex_b200.po.progressive_model import _Stage  # noqa: E402
+
+
+def _rand_bf16(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def _nchw(x):
+    return x.float().permute(0, 3, 1, 2)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1)
+
+
+def _pack(w_oihw):
+    cout, cin = w_oihw.shape[:2]
+    w_hwio = w_oihw.float().permute(2, 3, 1, 0).contiguous()
+    wf = torch.empty((9, cout, cin), dtype=torch.bfloat16, device="cuda")
+    wd = torch.empty((9, cin, cout), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L().stx_pack_conv_weights(w_hwio.data_ptr(), cin, cout, wf.data_ptr(), wd.data_ptr(), st()))
+    return wf, wd
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 32, 32, 64, 64), (2, 16, 24, 128, 64), (1, 8, 8, 64, 256),
+                                            (1, 4, 4, 64, 64), (1, 64, 64, 64, 128)])
+@pytest.mark.parametrize("pad", [0, 1, 2])
+def test_conv_padding_modes_match_torch(n, h, w, cin, cout, pad):
+    """H, W are the OUTPUT size; the input is (H + 2 - 2 pad) x (W + 2 - 2 pad). Covers both kernels (W < 8 goes to
+    the per-tap one)."""
+    hin, win = h + 2 - 2 * pad, w + 2 - 2 * pad
+    if hin <= 0 or win <= 0:
+        pytest.skip("input smaller than the filter")
+    x = _rand_bf16((n, hin, win, cin), 1)
+    wt = _rand_bf16((cout, cin, 3, 3), 2, (2.0 / (9 * cin)) ** 0.5)
+    bias = torch.linspace(-1, 1, cout, device="cuda")
+    wf, _ = _pack(wt)
+    out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L().stx_conv_bf16_pad(x.data_ptr(), n, h, w, cin, wf.data_ptr(), cout, pad, bias.data_ptr(), None, 0,
+                                     out.data_ptr(), 0, st()))
+    ref = _nhwc(F.conv2d(_nchw(x), wt.float(), bias, padding=pad))
+    assert ref.shape == out.shape
+    assert relerr(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 32, 32, 64, 64), (2, 16, 16, 128, 256), (1, 64, 64, 64, 64),
+                                            (1, 8, 8, 512, 512), (3, 12, 20, 64, 128), (1, 128, 128, 64, 64)])
+@pytest.mark.parametrize("pad", [0, 1])
+def test_conv_wgrad_matches_torch(n, h, w, cin, cout, pad):
+    """pad 0: x is the explicitly padded input [n, h+2, w+2, cin]; pad 1: x is [n, h, w, cin], taps outside read 0."""
+    hx, wx = h + 2 - 2 * pad, w + 2 - 2 * pad
+    x = _rand_bf16((n, hx, wx, cin), 3)
+    dy = _rand_bf16((n, h, w, cout), 4)
+    ws = torch.empty(max(L().stx_conv_wgrad_workspace_bytes(n, h, w, cin, cout) // 4, 1), dtype=torch.float32,
+                     device="cuda")
+    dw = torch.full((3, 3, cin, cout), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(L().stx_conv_wgrad_bf16(x.data_ptr(), dy.data_ptr(), n, h, w, cin, cout, pad, dw.data_ptr(),
+                                       ws.data_ptr(), st()))
+    ref = torch.nn.grad.conv2d_weight(_nchw(x).double(), (cout, cin, 3, 3), _nchw(dy).double(), padding=pad)
+    ref = ref.permute(2, 3, 1, 0)          # OIHW -> HWIO
+    assert torch.isfinite(dw).all()
+    assert relerr(dw, ref) < 1e-5          # exact bf16 products, fp32 accumulation
+    # deterministic: fixed-order split-K
+    dw2 = torch.empty_like(dw)
+    _lib.check(L().stx_conv_wgrad_bf16(x.data_ptr(), dy.data_ptr(), n, h, w, cin, cout, pad, dw2.data_ptr(),
+                                       ws.data_ptr(), st()))
+    assert torch.equal(dw, dw2)
+
+
+@pytest.mark.parametrize("relu", [0, 1])
+def test_replicate_pad_forward_and_backward(relu):
+    n, h, w, c = 2, 9, 13, 64
+    x = _rand_bf16((n, h, w, c), 5)
+    out = torch.empty((n, h + 2, w + 2, c), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L().stx_pad_replicate_bf16(x.data_ptr(), n, h, w, c, relu, out.data_ptr(), st()))
+    xr = _nchw(x).requires_grad_(True)
+    ref = F.pad(F.relu(xr) if relu else xr, (1, 1, 1, 1), mode="replicate")
+    assert torch.equal(out.float(), _nhwc(ref).detach())
+    gp = _rand_bf16((n, h + 2, w + 2, c), 6)
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L().stx_pad_replicate_bwd_bf16(gp.data_ptr(), x.data_ptr() if relu else None, n, h, w, c, dx.data_ptr(),
+                                              st()))
+    ref.backward(_nchw(gp))
+    assert relerr(dx.float(), _nhwc(xr.grad)) < 4e-3
+
+
+@pytest.mark.parametrize("n,h,w,c", [(1, 32, 32, 64), (2, 16, 16, 128), (1, 8, 8, 512), (3, 20, 12, 256)])
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("shortcut", [False, True])
+def test_instance_norm_function_matches_torch(n, h, w, c, relu, shortcut):
+    x = (_rand_bf16((n, h, w, c), 7).float() * 1.5 + 0.3).to(torch.bfloat16).requires_grad_(True)
+    gamma = torch.linspace(0.5, 1.5, c, device="cuda").requires_grad_(True)
+    beta = torch.linspace(-0.5, 0.5, c, device="cuda").requires_grad_(True)
+    sc = _rand_bf16((n, h, w, c), 8).requires_grad_(True) if shortcut else None
+    out = gen_ops.instance_norm(x, gamma, beta, 1e-5, relu, sc)
+    xr = _nchw(x.detach()).requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    ref = F.instance_norm(xr, None, None, gr, br, True, 0.0, 1e-5)
+    if relu:
+        ref = F.relu(ref)
+    if shortcut:
+        ref = ref + _nchw(sc.detach())
+    assert relerr(out.float(), _nhwc(ref).detach()) < 4e-3
+    dy = _rand_bf16((n, h, w, c), 9)
+    out.backward(dy)
+    ref.backward(_nchw(dy))
+    assert relerr(x.grad.float(), _nhwc(xr.grad)) < 1e-2
+    assert relerr(gamma.grad, gr.grad) < 1e-2
+    assert relerr(beta.grad, br.grad) < 1e-2
+    if shortcut:
+        assert torch.equal(sc.grad, dy)
+
+
+@pytest.mark.parametrize("mode,relu_in,cout", [("rep", False, 64), ("rep", True, 128), ("zero", False, 64),
+                                               ("rep", True, 3)])
+def test_conv3x3_function_gradients_match_torch(mode, relu_in, cout):
+    n, h, w, cin = 2, 16, 16, 64
+    x = _rand_bf16((n, h, w, cin), 10).requires_grad_(True)
+    wt = (_rand_bf16((cout, cin, 3, 3), 11, (2.0 / (9 * cin)) ** 0.5).float()).requires_grad_(True)
+    bias = torch.linspace(-0.1, 0.1, cout, device="cuda").requires_grad_(True)
+    y = gen_ops.conv3x3(x, wt, bias, mode, relu_in)
+    xr = _nchw(x.detach()).requires_grad_(True)
+    wr, br = wt.detach().clone().requires_grad_(True), bias.detach().clone().requires_grad_(True)
+    xin = F.relu(xr) if relu_in else xr
+    if mode == "rep":
+        ref = F.conv2d(F.pad(xin, (1, 1, 1, 1), mode="replicate"), wr, br)
+    else:
+        ref = F.conv2d(xin, wr, br, padding=1)
+    assert y.shape == (n, h, w, cout)
+    assert relerr(y.float(), _nhwc(ref).detach()) < 4e-3
+    dy = _rand_bf16((n, h, w, cout), 12)
+    y.backward(dy)
+    ref.backward(_nchw(dy))
+    assert relerr(x.grad.float(), _nhwc(xr.grad)) < 1e-2
+    assert relerr(wt.grad, wr.grad) < 1e-2       # weights rounded to bf16 inside the kernel; dW itself is fp32
+    assert relerr(bias.grad, br.grad) < 1e-3
+
+
+def test_upsample_native_matches_stock():
+    """Nearest x2 + symmetric pad 2 + 5x5 conv == four 3x3 phase filters on the low-resolution map."""
+    torch.manual_seed(0)
+    m = UpsampleNN(128, 64).cuda()
+    x = _rand_bf16((1, 16, 16, 128), 13).requires_grad_(True)
+    y = m.forward_native(x, relu_in=True)
+    xr = _nchw(x.detach()).requires_grad_(True)
+    ref = m(F.relu(xr))
+    assert y.shape == (1, 32, 32, 64)
+    assert relerr(y.float(), _nhwc(ref).detach()) < 1e-2
+    dy = _rand_bf16((1, 32, 32, 64), 14)
+    y.backward(dy)
+    g_native = m.conv.conv.weight.grad.clone()
+    m.zero_grad()
+    ref.backward(_nchw(dy))
+    assert relerr(x.grad.float(), _nhwc(xr.grad)) < 2e-2
+    assert relerr(g_native, m.conv.conv.weight.grad) < 2e-2
+
+
+def _cos(a, b):
+    a, b = a.flatten().double(), b.flatten().double()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+@pytest.mark.parametrize("n_loss_layer,pre_act", [(2, False), (3, True), (5, False)])
+def test_generator_stage_native_matches_stock(n_loss_layer, pre_act):
+    """A whole stage generator (progressive_model.py:161-206) on the hand-written kernels vs stock torch fp32 with the
+    SAME parameters: output, input gradients and every parameter gradient."""
+    torch.manual_seed(1)
+    stage = _Stage(n_loss_layer, 2, pre_act, True).cuda()
+    size = 128
+    chans = {"conv1_1": 64, "pool1": 64, "pool2": 128, "pool3": 256, "pool4": 512}
+    inputs, refs = {}, {}
+    s = size
+    for i, k in enumerate(stage.layers):
+        if k != "conv1_1":
+            s = s // 2
+        v = _rand_bf16((1, s, s, chans[k]), 20 + i).float()
+        inputs[k] = v.clone().requires_grad_(True)
+        refs[k] = v.clone().requires_grad_(True)
+    out = stage.forward_native(inputs)
+    ref = stage(refs)
+    assert out.shape == ref.shape == (1, size, size, 3)
+    assert relerr(out, ref.detach()) < 5e-2
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    g_native = {n: p.grad.clone() for n, p in stage.named_parameters()}
+    stage.zero_grad()
+    ref.backward(dy)
+    for k in stage.layers:
+        assert _cos(inputs[k].grad, refs[k].grad) > 0.99, k
+    bad = [(n, _cos(g_native[n], p.grad)) for n, p in stage.named_parameters() if _cos(g_native[n], p.grad) < 0.98]
+    assert not bad, bad
+
+
+def test_res_block_native_matches_stock():
+    torch.manual_seed(2)
+    blk = ResBlock(64).cuda()
+    x = _rand_bf16((2, 24, 24, 64), 30).requires_grad_(True)
+    y = blk.forward_native(x)
+    xr = _nchw(x.detach()).requires_grad_(True)
+    ref = blk(xr)
+    assert relerr(y.float(), _nhwc(ref).detach()) < 2e-2
+    dy = _rand_bf16((2, 24, 24, 64), 31)
+    y.backward(dy)
+    g_native = {n: p.grad.clone() for n, p in blk.named_parameters()}
+    blk.zero_grad()
+    ref.backward(_nchw(dy))
+    # three bf16-rounded stages and two ReLU masks between this gradient and the fp32 arm
+    assert relerr(x.grad.float(), _nhwc(xr.grad)) < 5e-2
+    for n, p in blk.named_parameters():
+        assert relerr(g_native[n], p.grad) < 5e-2, n
