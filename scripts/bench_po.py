@@ -5,8 +5,9 @@
                                                             config 5: ProgressiveSynTex training, per-GPU batch 1,
                                                             gradient-mean all-reduce over NCCL, images/s
 
-The VGG19 / Gram work (forward, grad_layer, first- and second-order backward) runs on the hand-written kernels; the
-generator runs on the hand-written kernels of po/gen_ops.py (STX_PO_GENERATOR=torch: stock ATen/cuDNN). Synthetic textures, seeded random generator weights."""
+The VGG19 / Gram work (forward, grad_layer, first- and second-order backward) and the generator (po/gen_ops.py) run
+on the hand-written kernels; STX_PO_GENERATOR=torch selects the stock ATen/cuDNN generator, STX_PO_GRAPH=0/1 the
+eager / CUDA-graph training step (default: graph on one GPU). Synthetic textures, seeded random generator weights."""
 import json
 import os
 import sys
@@ -119,8 +120,15 @@ def train(size, steps):
                           "generator_params": int(trainer.buckets.flat_param.numel()),
                           "generator": gen_name(), "cuda_graph": graph,
                           "loss_first": float(losses[0]), "loss_last": float(losses[-1]),
-                          "lr": trainer.opt.param_groups[0]["lr"]}))
+                          "lr": float(trainer.opt.param_groups[0]["lr"])}))
     if world > 1:
+        if graph:
+            # a captured NCCL all-reduce keeps the communicator busy at teardown (destroy_process_group was seen to
+            # hang until the launcher's timeout): results are out, leave without the collective shutdown
+            sys.stdout.flush()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
         dist.destroy_process_group()
 
 

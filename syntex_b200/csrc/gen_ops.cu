@@ -156,11 +156,11 @@ in_partial_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, con
       unpack8(__ldg(di + static_cast<size_t>(px) * p.c8 + cg), g);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float xh = (f[e] - mu[e]) * rs[e];
+        const float t = f[e] - mu[e];
         float gg = g[e];
-        if (p.relu && !(xh * ga[e] + be[e] > 0.0f)) gg = 0.0f;
+        if (p.relu && !(t * (rs[e] * ga[e]) + be[e] > 0.0f)) gg = 0.0f;   // the forward's expression, bit for bit
         a[e] += gg;
-        b[e] += gg * xh;
+        b[e] += gg * (t * rs[e]);
       }
     }
   }
@@ -217,68 +217,93 @@ in_finish_kernel(const float* __restrict__ part, int nimg, int C, int slabs, int
   }
 }
 
-// out = [relu]((x - mean) * rstd * gamma + beta) [+ addend]
+// out = [relu]((x - mean) * (rstd * gamma) + beta) [+ addend]. Grid (slabs, images): a thread keeps its channel group
+// for the whole image (the grid stride is a multiple of C / 8), so the eight per-channel constants live in registers
+// and the loop body is one 16-byte load, eight FMAs and one 16-byte store.
 __global__ void __launch_bounds__(256)
-in_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ addend, const InParams p, size_t total,
-                uint4* __restrict__ out) {
+in_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ addend, const InParams p, uint4* __restrict__ out) {
+  const int img = blockIdx.y;
   const size_t per_img = static_cast<size_t>(p.HW) * p.c8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % p.c8);
-    const int img = static_cast<int>(i / per_img);
+  const size_t first = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const int cg = static_cast<int>(first % p.c8);
+  float mu[8], a[8], be[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ch = cg * 8 + e;
+    mu[e] = __ldg(p.mean + img * p.C + ch);
+    a[e] = __ldg(p.rstd + img * p.C + ch) * __ldg(p.gamma + ch);
+    be[e] = __ldg(p.beta + ch);
+  }
+  const uint4* xi = x + img * per_img;
+  const uint4* ai = addend ? addend + img * per_img : nullptr;
+  uint4* oi = out + img * per_img;
+#pragma unroll 2
+  for (size_t i = first; i < per_img; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float f[8];
-    unpack8(__ldg(x + i), f);
-    // scalar parameter loads: gamma / beta may live at any 4-byte offset of a flat parameter buffer (po/trainer.py)
+    unpack8(__ldg(xi + i), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int ch = cg * 8 + e;
-      f[e] = (f[e] - __ldg(p.mean + img * p.C + ch)) * __ldg(p.rstd + img * p.C + ch) * __ldg(p.gamma + ch) +
-             __ldg(p.beta + ch);
+      f[e] = (f[e] - mu[e]) * a[e] + be[e];
+      if (p.relu) f[e] = fmaxf(f[e], 0.0f);
     }
-    if (p.relu) {
+    if (ai) {
+      float s[8];
+      unpack8(__ldg(ai + i), s);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+      for (int e = 0; e < 8; ++e) f[e] += s[e];
     }
-    if (addend) {
-      float a[8];
-      unpack8(__ldg(addend + i), a);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] += a[e];
-    }
-    out[i] = pack8(f);
+    oi[i] = pack8(f);
   }
 }
 
 // dx = rstd * gamma * (g - s1 / HW - xhat * s2 / HW),  g = dy * [relu mask], s1 = sum g, s2 = sum g * xhat
 __global__ void __launch_bounds__(256)
 in_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, const InParams p,
-                    const float* __restrict__ s1, const float* __restrict__ s2, size_t total, uint4* __restrict__ dx) {
+                    const float* __restrict__ s1, const float* __restrict__ s2, uint4* __restrict__ dx) {
+  const int img = blockIdx.y;
   const size_t per_img = static_cast<size_t>(p.HW) * p.c8;
+  const size_t first = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const int cg = static_cast<int>(first % p.c8);
   const float inv = 1.0f / static_cast<float>(p.HW);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % p.c8);
-    const int img = static_cast<int>(i / per_img);
+  float mu[8], rs[8], a[8], be[8], c1[8], c2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ch = cg * 8 + e;
+    mu[e] = __ldg(p.mean + img * p.C + ch);
+    rs[e] = __ldg(p.rstd + img * p.C + ch);
+    a[e] = rs[e] * __ldg(p.gamma + ch);
+    be[e] = __ldg(p.beta + ch);
+    c1[e] = inv * __ldg(s1 + img * p.C + ch);
+    c2[e] = inv * __ldg(s2 + img * p.C + ch);
+  }
+  const uint4* xi = x + img * per_img;
+  const uint4* di = dy + img * per_img;
+  uint4* oi = dx + img * per_img;
+#pragma unroll 2
+  for (size_t i = first; i < per_img; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float f[8], g[8];
-    unpack8(__ldg(x + i), f);
-    unpack8(__ldg(dy + i), g);
+    unpack8(__ldg(xi + i), f);
+    unpack8(__ldg(di + i), g);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int ch = cg * 8 + e;
-      const float mu = __ldg(p.mean + img * p.C + ch), rs = __ldg(p.rstd + img * p.C + ch);
-      const float ga = __ldg(p.gamma + ch), be = __ldg(p.beta + ch);
-      const float xh = (f[e] - mu) * rs;
+      const float t = f[e] - mu[e];
       float gg = g[e];
-      if (p.relu && !(xh * ga + be > 0.0f)) gg = 0.0f;
-      f[e] = rs * ga * (gg - inv * __ldg(s1 + img * p.C + ch) - xh * inv * __ldg(s2 + img * p.C + ch));
+      if (p.relu && !(t * a[e] + be[e] > 0.0f)) gg = 0.0f;
+      f[e] = a[e] * (gg - c1[e] - (t * rs[e]) * c2[e]);
     }
-    dx[i] = pack8(f);
+    oi[i] = pack8(f);
   }
 }
 
 int ew_blocks(size_t total) {
   size_t b = (total + 255) / 256;
   const size_t cap = 148 * 16;
+  return static_cast<int>(b < cap ? (b ? b : 1) : cap);
+}
+
+int in_apply_blocks(int nimg, size_t per_img) {
+  size_t b = (per_img + 255) / 256;                      // one vector per thread ...
+  const size_t cap = (148 * 16 + nimg - 1) / nimg;       // ... up to ~16 blocks per SM over the batch, then grid-stride
   return static_cast<int>(b < cap ? (b ? b : 1) : cap);
 }
 
@@ -363,10 +388,9 @@ int inorm_apply_launch(const bf16* x, int nimg, int HW, int C, const float* mean
   STX_REQUIRE(x && mean && rstd && gamma && beta && out, "instance norm: null operand");
   STX_TRY(in_check(nimg, HW, C));
   const InParams p = in_params(nimg, HW, C, relu, 0.0f, mean, rstd, gamma, beta);
-  const size_t total = static_cast<size_t>(nimg) * HW * p.c8;
-  in_apply_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
-                                                       reinterpret_cast<const uint4*>(addend), p, total,
-                                                       reinterpret_cast<uint4*>(out));
+  const size_t per_img = static_cast<size_t>(HW) * p.c8;
+  in_apply_kernel<<<dim3(in_apply_blocks(nimg, per_img), nimg), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(addend), p, reinterpret_cast<uint4*>(out));
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;
@@ -383,10 +407,9 @@ int inorm_bwd_launch(const bf16* x, const bf16* dy, int nimg, int HW, int C, con
   STX_CUDA(cudaGetLastError());
   in_finish_kernel<1><<<(nimg * C + 7) / 8, 256, 0, stream>>>(workspace, nimg, C, p.slabs, HW, 0.0f, s1, s2);
   STX_CUDA(cudaGetLastError());
-  const size_t total = static_cast<size_t>(nimg) * HW * p.c8;
-  in_bwd_apply_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x),
-                                                           reinterpret_cast<const uint4*>(dy), p, s1, s2, total,
-                                                           reinterpret_cast<uint4*>(dx));
+  const size_t per_img = static_cast<size_t>(HW) * p.c8;
+  in_bwd_apply_kernel<<<dim3(in_apply_blocks(nimg, per_img), nimg), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy), p, s1, s2, reinterpret_cast<uint4*>(dx));
   STX_CUDA(cudaGetLastError());
   count_launch(3);
   return STX_OK;

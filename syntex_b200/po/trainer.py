@@ -82,8 +82,7 @@ class SynTexTrainer(object):
         self.graph_warmup = max(int(graph_warmup), 1)
         self._graph = None
         self._static = None
-        if self.cuda_graph and self.num_gpu > 1:
-            raise ValueError("cuda_graph=True covers single-GPU training (the NCCL hooks are not captured)")
+        self._stream = None
         if self.num_gpu > 1:
             if not dist.is_initialized():
                 raise RuntimeError("SynTexTrainer(num_gpu=%d): torch.distributed is not initialised (launch with "
@@ -120,9 +119,20 @@ class SynTexTrainer(object):
         if batch is None:
             batch = next(self._iter())
         pre_image_input, image_target = batch
-        if self.cuda_graph and self.global_step >= self.graph_warmup:
+        if not self.cuda_graph:
+            return self._step_eager(pre_image_input, image_target)
+        if self.global_step >= self.graph_warmup:
             return self._run_step_graphed(pre_image_input, image_target)
-        return self._step_eager(pre_image_input, image_target)
+        # Warm-up steps of the graph mode run on the stream the capture will use: autograd binds every parameter's
+        # AccumulateGrad node to the stream of its first forward, and a node bound to the legacy default stream
+        # invalidates a capture on any other stream.
+        if self._stream is None:
+            self._stream = torch.cuda.Stream()
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):
+            loss = self._step_eager(pre_image_input, image_target)
+        torch.cuda.current_stream().wait_stream(self._stream)
+        return loss
 
     def _step_eager(self, pre_image_input, image_target):
         self.buckets.zero_grad()
@@ -142,7 +152,9 @@ class SynTexTrainer(object):
             self._graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             step0 = self.global_step
-            with torch.cuda.graph(self._graph):
+            if self._stream is None:
+                self._stream = torch.cuda.Stream()
+            with torch.cuda.graph(self._graph, stream=self._stream):
                 self._static[2] = self._step_eager(self._static[0], self._static[1])
             self.global_step = step0          # capturing does not execute the step
         elif z.shape != self._static[0].shape:

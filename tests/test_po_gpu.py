@@ -106,7 +106,9 @@ def _models(raw_weights, size, seed):
     torch.manual_seed(seed)
     cpu = ProgressiveSynTex({"vgg19_npy_path": raw_weights, "image_size": size},
                             texture_fn=so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS)).double()
-    gpu = ProgressiveSynTex({"vgg19_npy_path": raw_weights, "image_size": size})
+    # the stock fp32 generator: this test measures the DOOR against the oracle (the bf16 generator kernels have their
+    # own tests, tests/test_po_native_gpu.py)
+    gpu = ProgressiveSynTex({"vgg19_npy_path": raw_weights, "image_size": size, "generator": "torch"})
     gpu.load_state_dict({k: v.float() for k, v in cpu.state_dict().items()})
     return cpu, gpu.cuda()
 
@@ -263,9 +265,12 @@ def test_single_model_on_the_cuda_door(raw_weights):
     torch.manual_seed(4)
     args = {"vgg19_npy_path": raw_weights, "image_size": size, "n_stage": 2, "loss_scale": 1.0, "lr": 2e-4}
     cpu = SingleSynTex(args, texture_fn=so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS)).double()
-    gpu = SingleSynTex(args)
+    gpu = SingleSynTex(dict(args, generator="torch"))      # fp32 generator: the door is what is compared here
     gpu.load_state_dict({k: v.float() for k, v in cpu.state_dict().items()})
     gpu = gpu.cuda()
+    native = SingleSynTex(dict(args, generator="native"))
+    native.load_state_dict({k: v.float() for k, v in cpu.state_dict().items()})
+    native = native.cuda()
     rng = np.random.RandomState(0)
     z = rng.uniform(-1, 1, (2, size, size, 3))
     t = np.stack([so.synthetic_texture(size, seed=9), so.synthetic_texture(size, seed=10)]) * 255.0
@@ -275,6 +280,11 @@ def test_single_model_on_the_cuda_door(raw_weights):
     assert abs(float(cpu.losses[0]) - float(gpu.losses[0])) / float(cpu.losses[0]) < 5e-3
     # the generator reads features (error ~1e-5), not gradients (~3e-3): the first stage output is tight
     assert relerr(gpu.image_outputs[1], cpu.image_outputs[1]) < 2e-3
+    # the same model on the hand-written generator kernels (bf16 activations): same picture, bf16-sized differences
+    with torch.no_grad():
+        native.build_graph(torch.as_tensor(z), torch.as_tensor(t))
+    assert relerr(native.image_outputs[1], cpu.image_outputs[1]) < 0.1
+    assert abs(float(native.losses[1]) - float(cpu.losses[1])) / float(cpu.losses[1]) < 0.25
     lg = gpu.build_graph(torch.as_tensor(z), torch.as_tensor(t))
     lg.backward()
     for s in (0, 1):
