@@ -213,7 +213,7 @@ class OracleTexture:
         return loss_layer, grad_layer
 
 
-    def prep(self, image, gram_target, coefs, stop_grad, slot):
+    def prep(self, image, gram_target, coefs, stop_grad, slot, need_grads=True):
         with torch.enable_grad():
             return self._prep(image, gram_target, coefs, stop_grad, slot)
 

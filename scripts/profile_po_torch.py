@@ -11,10 +11,11 @@ torch.backends.cudnn.benchmark = True
 model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size}).cuda().to(memory_format=torch.channels_last)
 data = SyntheticPOData(1, size, seed=0)
 batch = next(iter(data))
-trainer = SynTexTrainer(data, model, 1)
-for _ in range(3): trainer.run_step(batch)
+graph = os.environ.get('STX_PO_GRAPH', '0') == '1'
+trainer = SynTexTrainer(data, model, 1, cuda_graph=graph)
+for _ in range(5): trainer.run_step(batch)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(2): trainer.run_step(batch)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get('ROWS', '28')), max_name_column_width=70))

@@ -141,7 +141,7 @@ in_partial_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, con
   const int p_end = min(p_begin + p.pix_per_slab, p.HW);
   const uint4* xi = x + static_cast<size_t>(img) * p.HW * p.c8;
   const uint4* di = (MODE == 1) ? dy + static_cast<size_t>(img) * p.HW * p.c8 : nullptr;
-#pragma unroll 4
+#pragma unroll 8
   for (int px = p_begin + pl; px < p_end; px += lanes) {
     float f[8];
     unpack8(__ldg(xi + static_cast<size_t>(px) * p.c8 + cg), f);
@@ -195,8 +195,9 @@ in_finish_kernel(const float* __restrict__ part, int nimg, int C, int slabs, int
   if (i >= nimg * C) return;
   const int img = i / C, ch = i - img * C;
   float sa = 0.0f, sb = 0.0f;
+#pragma unroll 4
   for (int s = lane; s < slabs; s += 32) {
-    const float2 v = *reinterpret_cast<const float2*>(part + ((static_cast<size_t>(img) * slabs + s) * C + ch) * 2);
+    const float2 v = __ldg(reinterpret_cast<const float2*>(part + ((static_cast<size_t>(img) * slabs + s) * C + ch) * 2));
     sa += v.x;
     sb += v.y;
   }
@@ -308,8 +309,10 @@ int in_apply_blocks(int nimg, size_t per_img) {
 }
 
 int in_slabs(int nimg, int HW) {
-  int slabs = (148 * 8 + nimg - 1) / nimg;              // ~8 blocks per SM over the whole batch
-  const int max_slabs = (HW + 63) / 64;                 // at least 64 pixels per slab
+  // ~4 blocks per SM over the whole batch (more slabs only lengthen the finishing reduction: with 1184 of them the
+  // 8-block finish kernel took 15 us at 512x512, longer than the 13 us streaming pass it follows), >= 64 pixels each
+  int slabs = (148 * 4 + nimg - 1) / nimg;
+  const int max_slabs = (HW + 63) / 64;
   if (slabs > max_slabs) slabs = max_slabs;
   return slabs < 1 ? 1 : slabs;
 }

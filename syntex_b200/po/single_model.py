@@ -92,7 +92,8 @@ class SingleSynTex(SynTexModelDesc, nn.Module):
         coefs = SynTexModelDesc.DEFAULT_COEFS
         image_input = self._act(pre_image_input)
         slot = stage_index if torch.is_grad_enabled() else 0
-        feat_input, _, loss_layer_input, _ = self._texture_fn.prep(image_input, gram_target, coefs, True, slot)
+        feat_input, _, loss_layer_input, _ = self._texture_fn.prep(image_input, gram_target, coefs, True, slot,
+                                                                   need_grads=False)
         loss_overall_input = sum(coefs[k] * 1. / 4 * loss_layer_input[k] for k in coefs)
         delta_input = self.run_generator(self.syn[stage_index], feat_input, image_input.is_cuda)
         pre_image_output = pre_image_input + delta_input

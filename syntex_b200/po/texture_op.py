@@ -381,6 +381,36 @@ class CudaTexture(object):
     def __call__(self, image, layers, gram_target, slot, calc_grad):
         return vgg_texture(image, self.vgg19, layers, gram_target, slot=slot, calc_grad=calc_grad)
 
-    def prep(self, image, gram_target, coefs, stop_grad, slot):
-        """Stage preparation of the improved / adaptive models: features, losses and full-VGG-backprop gradients."""
+    def prep(self, image, gram_target, coefs, stop_grad, slot, need_grads=True):
+        """Stage preparation of the improved / adaptive models: features, losses and full-VGG-backprop gradients.
+        need_grads=False (SingleSynTex reads the features only) under torch.no_grad() skips the VGG back-propagation:
+        feed-forward synthesis then costs one VGG forward per stage instead of a forward and a backward."""
+        import torch
+        if not need_grads and not torch.is_grad_enabled():
+            return self._features_and_losses(image, gram_target, coefs, slot)
         return vgg_stage_preparation(image, self.vgg19, gram_target, coefs, stop_grad=stop_grad, slot=slot)
+
+    def _features_and_losses(self, image, gram_target, coefs, slot):
+        import torch
+        layers = list(coefs.keys())
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        x = image.detach().to(device="cuda", dtype=torch.float32).contiguous()
+        B, H, W, _ = x.shape
+        plan = self.vgg19.get_plan(B, H, W, topmost=layers[-1], coefs=OrderedDict((k, float(coefs[k])) for k in layers),
+                                   export_layer_grads=True, full_features=True, slot=slot)
+        _lib.check(L.stx_plan_forward(plan.handle, x.data_ptr(), 0, 1, st))
+        feat, loss_per_layer = OrderedDict(), OrderedDict()
+        for k, name in enumerate(layers):
+            idx = LAYER_INDEX[name]
+            h, w, c = plan.layer_shape(idx)
+            f = torch.empty((B, h, w, c), dtype=torch.float32, device="cuda")
+            _lib.check(L.stx_plan_copy_feature_f32(plan.handle, idx, f.data_ptr(), st))
+            feat[name] = f
+            g = torch.empty((B, c, c), dtype=torch.float32, device="cuda")
+            _lib.check(L.stx_plan_copy_gram(plan.handle, k, g.data_ptr(), st))
+            d = g - gram_target[name].to(device="cuda", dtype=torch.float32)
+            loss_per_layer[name] = torch.mean(d * d, dim=(1, 2))
+        loss_input = sum(coefs[k] * 1. / 4 * loss_per_layer[k] for k in layers[:-1]) if len(layers) > 1 \
+            else loss_per_layer[layers[0]] * 0.
+        return feat, loss_input, loss_per_layer, None
