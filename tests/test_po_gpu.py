@@ -293,3 +293,36 @@ def test_single_model_on_the_cuda_door(raw_weights):
     batch = (torch.as_tensor(z, dtype=torch.float32).cuda(), torch.as_tensor(t, dtype=torch.float32).cuda())
     losses = [float(trainer.run_step(batch)) for _ in range(8)]
     assert all(np.isfinite(losses)) and min(losses[4:]) < losses[0]
+
+
+def test_improved_model_on_the_cuda_door(raw_weights):
+    """ImprovedSynTex (po/improved_model.py: five progressive stages on full-VGG-backprop gradients) with the CUDA hot
+    path: the first stage losses against the float64 oracle graph with the same generator weights, gradients reach
+    every stage (the earlier ones through the double backward), a few trainer steps reduce the loss."""
+    from syntex_b200.po.improved_model import ImprovedSynTex
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    size = 64
+    torch.manual_seed(3)
+    args = {"vgg19_npy_path": raw_weights, "image_size": size, "lr": 2e-4, "pad_type": "zero", "norm_type": "batch",
+            "act_type": "lrelu"}
+    cpu = ImprovedSynTex(args, texture_fn=so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS)).double()
+    gpu = ImprovedSynTex(args)
+    gpu.load_state_dict({k: v.float() for k, v in cpu.state_dict().items()})
+    gpu = gpu.cuda()
+    rng = np.random.RandomState(0)
+    z = rng.uniform(-1, 1, (1, size, size, 3))
+    t = so.synthetic_texture(size, seed=9)[None] * 255.0
+    cpu.build_graph(torch.as_tensor(z), torch.as_tensor(t))
+    lg = gpu.build_graph(torch.as_tensor(z), torch.as_tensor(t))
+    assert float(gpu.losses[0]) == 0.0 and float(cpu.losses[0]) == 0.0
+    # stage 1's loss_input: the conv1_1 term of an image one generator away from the input
+    assert abs(float(cpu.losses[1]) - float(gpu.losses[1])) / float(cpu.losses[1]) < 0.1
+    lg.backward()
+    for s in range(5):
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in gpu.syn[s].parameters())
+        assert sum(float(p.grad.abs().sum()) for p in gpu.syn[s].parameters()) > 0
+    trainer = SynTexTrainer(None, gpu, 1)
+    batch = (torch.as_tensor(z, dtype=torch.float32).cuda(), torch.as_tensor(t, dtype=torch.float32).cuda())
+    losses = [float(trainer.run_step(batch)) for _ in range(8)]
+    assert all(np.isfinite(losses)) and min(losses[4:]) < losses[0]

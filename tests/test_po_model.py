@@ -218,3 +218,60 @@ def test_single_model_graph_over_oracle(raw_weights):
     assert opt.defaults["lr"] == 5e-5 and opt.defaults["betas"] == (0.9, 0.999)
     args = SingleSynTex.get_parser().parse_args([])
     assert args.get("loss_scale") == 0. and args.get("n_stage") == 1
+
+
+@pytest.mark.parametrize("opts", [{}, {"pad_type": "zero", "norm_type": "batch", "act_type": "lrelu"},
+                                  {"pad_type": "symmetric", "norm_type": "none", "pre_act": True, "stop_grad": True}])
+def test_improved_graph_over_oracle(raw_weights, opts):
+    """po/improved_model.py: five progressive stages fed by the full-VGG-backprop gradients of their first s+1 Gram
+    layers; loss_input of a stage leaves out its last layer (:218-226); --stop-grad also cuts the pre-image path."""
+    from syntex_b200.po.improved_model import ImprovedSynTex, test_only
+    torch.manual_seed(0)
+    tex = so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS, torch.float64)
+    args = {"vgg19_npy_path": raw_weights, "image_size": 32}
+    args.update(opts)
+    model = ImprovedSynTex(args, texture_fn=tex).double()
+    assert [len(s.layers) for s in model.syn] == [1, 2, 3, 4, 5]
+    rng = np.random.RandomState(0)
+    z = torch.as_tensor(rng.uniform(-1, 1, (1, 32, 32, 3)))
+    t = torch.as_tensor(so.synthetic_texture(32, seed=1)[None] * 255.0)
+    loss = model.build_graph(z, t)
+    assert torch.isfinite(loss) and len(model.losses) == 6 and len(model.image_outputs) == 6
+    assert float(model.losses[0]) == 0.0                      # one layer: nothing left after dropping the last
+    assert torch.allclose(loss, sum(model.losses[1:]))
+    # stage 1's loss_input is the conv1_1 term of ITS input image only
+    x1 = model.image_outputs[1].detach()
+    ll, _ = tex(x1, LAYERS[:1], tex.grams(t / 255.), 0, False)
+    assert torch.allclose(model.losses[1], (1e5 / 4 * ll["conv1_1"]).mean(), rtol=1e-9)
+    loss.backward()
+    g = [sum(float(p.grad.abs().sum()) for p in st.parameters() if p.grad is not None) for st in model.syn]
+    assert all(v > 0 for v in g)
+    # BatchNorm uses batch statistics in every phase (improved_model.py:353-360): eval() changes nothing
+    with torch.no_grad():
+        a = model.build_graph(z, t)
+        model.eval()
+        b = model.build_graph(z, t)
+    assert torch.equal(a, b)
+    opt = model.optimizer()
+    assert opt.defaults["betas"] == (0.5, 0.999) and opt.defaults["eps"] == 1e-3 and opt.defaults["lr"] == 2e-4
+    ps = ImprovedSynTex.get_parser()
+    a = ps.parse_args([])
+    assert a.get("pad_type") == "zero" and a.get("norm_type") == "batch" and a.get("act_type") == "lrelu"
+    outs, losses = test_only(model, [(z, t)])
+    assert outs[0].shape == (1, 32, 32 * 7, 3) and outs[0].dtype == np.uint8 and np.isfinite(losses[0])
+
+
+def test_improved_stop_grad_cuts_the_cross_stage_paths(raw_weights):
+    from syntex_b200.po.improved_model import ImprovedSynTex
+    tex = so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS, torch.float64)
+    rng = np.random.RandomState(0)
+    z = torch.as_tensor(rng.uniform(-1, 1, (1, 32, 32, 3)))
+    t = torch.as_tensor(so.synthetic_texture(32, seed=1)[None] * 255.0)
+    grads = []
+    for stop in (False, True):
+        torch.manual_seed(0)
+        m = ImprovedSynTex({"vgg19_npy_path": raw_weights, "image_size": 32, "stop_grad": stop}, texture_fn=tex).double()
+        m.build_graph(z, t).backward()
+        grads.append(torch.cat([p.grad.flatten() for p in m.syn[0].parameters()]))
+    rel = float((grads[0] - grads[1]).norm() / grads[0].norm())
+    assert rel > 1e-3
