@@ -12,7 +12,9 @@ no communication - weak scaling; at N = 8, batch = 8 this
 One JSON line is printed by rank 0. `value` is device-timed with the state resident in HBM; `e2e` is the same
 metric through Synthesizer.synthesize() with host buffers (H2D of x0 and exemplars, target Grams, optimisation,
 D2H of the result). `--impl reference` times the CPU oracle (torch-CPU fp32 restatement of the TF graph + the
-reference's own scipy L-BFGS-B call) on the host cores instead.
+reference's own scipy L-BFGS-B call) on the host cores instead. At N = 1 the line also carries `po`: the PO half of
+BASELINE.json's metric (ProgressiveSynTex training images/s at 512x512, SingleSynTex inference images/s at batch 64
+of 256x256) measured in the same process after the Gatys timing (`--no-po` skips it).
 """
 import argparse
 import ctypes
@@ -326,6 +328,58 @@ def run_ours(args, rank, world, local_rank):
     return out
 
 
+def po_sample():
+    """The PO half of BASELINE.json's metric ("PO imgs/sec"), measured beside the Gatys line on one GPU: config 5
+    (ProgressiveSynTex training at 512x512, per-GPU batch 1, whole step replayed as a CUDA graph) and config 3
+    (SingleSynTex feed-forward synthesis, batch 64 of 256x256). Synthetic textures, seeded random generator weights,
+    generator on the hand-written kernels (syntex_b200/po/gen_ops.py). scripts/bench_po.py is the stand-alone /
+    multi-GPU version. Never raises: a failure is reported in the returned dict."""
+    import torch
+    out = {}
+    try:
+        from syntex_b200.po.progressive_model import ProgressiveSynTex
+        from syntex_b200.po.single_model import SingleSynTex
+        from syntex_b200.po.trainer import SynTexTrainer, SyntheticPOData
+        from syntex_b200.synthetic import synthetic_vgg_weights
+
+        def timed(fn, warmup, steps):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / steps
+
+        torch.manual_seed(0)
+        model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": 512}).cuda()
+        data = SyntheticPOData(1, 512, seed=0)
+        batch = next(iter(data))
+        trainer = SynTexTrainer(data, model, 1, cuda_graph=True)
+        ms = timed(lambda: trainer.run_step(batch), 4, 10)
+        out["progressive_training_512"] = {"images_per_s": 1e3 / ms, "ms_per_step": ms, "per_gpu_batch": 1,
+                                           "generator_params": int(trainer.buckets.flat_param.numel()),
+                                           "step": "door + generator + backward + fused Adam as one CUDA graph"}
+        del trainer, model
+        torch.cuda.empty_cache()
+        single = SingleSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": 256}).cuda().eval()
+        z, t = next(iter(SyntheticPOData(64, 256, seed=0)))
+
+        def infer():
+            with torch.no_grad():
+                single.build_graph(z, t)
+        ms = timed(infer, 2, 5)
+        out["single_inference_b64_256"] = {"images_per_s": 64e3 / ms, "ms_per_batch": ms}
+        del single
+        torch.cuda.empty_cache()
+    except Exception as e:      # the Gatys line above is the contract; this leg is a report beside it
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +392,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--maxcor", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-po", action="store_true", help="skip the PO images/s report beside the Gatys line (N = 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -356,6 +411,8 @@ def main():
             out["cpu_baseline"] = cpu_baseline_sample(args)
         else:
             out["cpu_baseline"] = None
+        if world == 1 and not args.no_po:
+            out["po"] = po_sample()
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist

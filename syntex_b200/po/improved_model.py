@@ -33,14 +33,31 @@ BATCH = 1
 TEST_BATCH = 1
 
 
+class _BatchStatsNorm(nn.Module):
+    """tensorpack BatchNorm under argscope(BatchNorm, training=True) (improved_model.py:353-360): batch statistics in
+    every phase, biased variance, eps 1e-5, affine (with the per-GPU batch of 1 the reference trains with, this is
+    InstanceNorm). Plain tensor arithmetic: cuDNN's batch-norm entry point fails on the channels-last views this
+    generator passes around (CUDNN_STATUS_EXECUTION_FAILED_CUDART, measured)."""
+
+    def __init__(self, chan, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(chan))
+        self.bias = nn.Parameter(torch.zeros(chan))
+
+    def forward(self, x):
+        mean = x.mean(dim=(0, 2, 3), keepdim=True)
+        var = x.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
+        return (x - mean) * torch.rsqrt(var + self.eps) * self.weight.view(1, -1, 1, 1) + self.bias.view(1, -1, 1, 1)
+
+
 def _always_batch_stats(module):
-    """improved_model.py:353-360 builds every stage under argscope(BatchNorm, training=True): batch statistics in
-    every phase (with the per-GPU batch of 1 the reference trains with, BatchNorm is InstanceNorm)."""
-    for m in module.modules():
-        if isinstance(m, nn.BatchNorm2d):
-            m.track_running_stats = False
-            m.running_mean = None
-            m.running_var = None
+    """Swap every nn.BatchNorm2d the shared layer modules (po/adaptive_model.py) created for _BatchStatsNorm."""
+    for name, child in list(module.named_children()):
+        if isinstance(child, nn.BatchNorm2d):
+            setattr(module, name, _BatchStatsNorm(child.num_features, child.eps))
+        else:
+            _always_batch_stats(child)
     return module
 
 
