@@ -217,17 +217,26 @@ int stx_pad_replicate_bf16(const void* x, int n, int H, int W, int C, int relu, 
  * was taken of relu(x): zero where x <= 0. */
 int stx_pad_replicate_bwd_bf16(const void* gp, const void* x_or_null, int n, int H, int W, int C, void* dx,
                                void* stream);
+/* General form: mode 0 = SYMMETRIC by one pixel, 1 = REFLECT (tf.pad modes of po/improved_model.py:49-55; CONSTANT
+ * needs no copy: stx_conv_bf16_pad with pad = 1); act 0 = none, 1 = x > 0 ? x : slope * x applied on the way (slope 0
+ * = ReLU, 0.2 = the LeakyReLU of po/improved_model.py:30-47). The backward applies the activation's derivative when
+ * x_or_null is the forward input. */
+int stx_pad2d_bf16(const void* x, int n, int H, int W, int C, int mode, int act, float slope, void* out, void* stream);
+int stx_pad2d_bwd_bf16(const void* gp, const void* x_or_null, int n, int H, int W, int C, int mode, float slope,
+                       void* dx, void* stream);
 /* tensorpack InstanceNorm (per image and channel over H*W, biased variance, affine). mean/rstd fp32 [n,C]. */
 size_t stx_inorm_workspace_bytes(int n, int HW, int C);
 int stx_inorm_stats_bf16(const void* x, int n, int HW, int C, float eps, float* mean, float* rstd, void* workspace,
                          void* stream);
-/* out = [relu]((x - mean) * rstd * gamma + beta) [+ addend]   (addend: the residual shortcut, nullable) */
+/* out = act((x - mean) * rstd * gamma + beta) [+ addend]   (addend: the residual shortcut, nullable)
+ * act 0 = none, 1 = v > 0 ? v : slope * v  (slope 0 = ReLU) */
 int stx_inorm_apply_bf16(const void* x, int n, int HW, int C, const float* mean, const float* rstd,
-                         const float* gamma, const float* beta, int relu, const void* addend, void* out, void* stream);
+                         const float* gamma, const float* beta, int act, float slope, const void* addend, void* out,
+                         void* stream);
 /* Backward of the above for upstream dy (w.r.t. the value before the addend): dx, and per image the sums
- * s1 = sum g, s2 = sum g * xhat with g = dy * [relu mask]  (d beta = sum_n s1, d gamma = sum_n s2), fp32 [n,C]. */
+ * s1 = sum g, s2 = sum g * xhat with g = dy * act'  (d beta = sum_n s1, d gamma = sum_n s2), fp32 [n,C]. */
 int stx_inorm_bwd_bf16(const void* x, const void* dy, int n, int HW, int C, const float* mean, const float* rstd,
-                       const float* gamma, const float* beta, int relu, float* s1, float* s2, void* dx,
+                       const float* gamma, const float* beta, int act, float slope, float* s1, float* s2, void* dx,
                        void* workspace, void* stream);
 
 int stx_f32_to_bf16(const float* x, size_t count, void* out_bf16, void* stream);

@@ -64,8 +64,8 @@ def main():
         ws = torch.empty(max(L.stx_inorm_workspace_bytes(1, s * s, c) // 4, 1), dtype=torch.float32, device="cuda")
         nb = x.numel() * 2
         t_s = timed(lambda: _lib.check(L.stx_inorm_stats_bf16(x.data_ptr(), 1, s * s, c, ctypes.c_float(1e-5), mean.data_ptr(), rstd.data_ptr(), ws.data_ptr(), st())))
-        t_a = timed(lambda: _lib.check(L.stx_inorm_apply_bf16(x.data_ptr(), 1, s * s, c, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, o.data_ptr(), st())))
-        t_b = timed(lambda: _lib.check(L.stx_inorm_bwd_bf16(x.data_ptr(), dy.data_ptr(), 1, s * s, c, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, s1.data_ptr(), s2.data_ptr(), o.data_ptr(), ws.data_ptr(), st())))
+        t_a = timed(lambda: _lib.check(L.stx_inorm_apply_bf16(x.data_ptr(), 1, s * s, c, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, ctypes.c_float(0.0), None, o.data_ptr(), st())))
+        t_b = timed(lambda: _lib.check(L.stx_inorm_bwd_bf16(x.data_ptr(), dy.data_ptr(), 1, s * s, c, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, ctypes.c_float(0.0), s1.data_ptr(), s2.data_ptr(), o.data_ptr(), ws.data_ptr(), st())))
         t_p = timed(lambda: _lib.check(L.stx_pad_replicate_bf16(x.data_ptr(), 1, s, s, c, 1, xp.data_ptr(), st())))
         t_q = timed(lambda: _lib.check(L.stx_pad_replicate_bwd_bf16(xp.data_ptr(), x.data_ptr(), 1, s, s, c, o.data_ptr(), st())))
         out.append({"op": "elementwise", "size": s, "c": c, "tensor_mb": nb / 1e6,

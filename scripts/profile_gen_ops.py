@@ -36,8 +36,8 @@ for s, cin, cout in [(512, 64, 64), (64, 256, 256)]:
         gamma, beta = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
         wsn = torch.empty(max(L.stx_inorm_workspace_bytes(1, s * s, c) // 4, 1), dtype=torch.float32, device="cuda")
         _lib.check(L.stx_inorm_stats_bf16(xi.data_ptr(), 1, s * s, c, ctypes.c_float(1e-5), mean.data_ptr(), rstd.data_ptr(), wsn.data_ptr(), st()))
-        _lib.check(L.stx_inorm_apply_bf16(xi.data_ptr(), 1, s * s, c, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, None, o.data_ptr(), st()))
-        _lib.check(L.stx_inorm_bwd_bf16(xi.data_ptr(), dy.data_ptr(), 1, s * s, c, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, s1.data_ptr(), s2.data_ptr(), o.data_ptr(), wsn.data_ptr(), st()))
+        _lib.check(L.stx_inorm_apply_bf16(xi.data_ptr(), 1, s * s, c, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, ctypes.c_float(0.0), None, o.data_ptr(), st()))
+        _lib.check(L.stx_inorm_bwd_bf16(xi.data_ptr(), dy.data_ptr(), 1, s * s, c, mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1, ctypes.c_float(0.0), s1.data_ptr(), s2.data_ptr(), o.data_ptr(), wsn.data_ptr(), st()))
         _lib.check(L.stx_pad_replicate_bf16(xi.data_ptr(), 1, s, s, c, 1, xp.data_ptr(), st()))
         _lib.check(L.stx_pad_replicate_bwd_bf16(xp.data_ptr(), xi.data_ptr(), 1, s, s, c, o.data_ptr(), st()))
         torch.cuda.synchronize()

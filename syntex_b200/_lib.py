@@ -70,8 +70,11 @@ def _declare(lib):
         "stx_pad_replicate_bwd_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, vp]),
         "stx_inorm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
         "stx_inorm_stats_bf16": (c_int, [vp, c_int, c_int, c_int, c_float, fp, fp, vp, vp]),
-        "stx_inorm_apply_bf16": (c_int, [vp, c_int, c_int, c_int, fp, fp, fp, fp, c_int, vp, vp, vp]),
-        "stx_inorm_bwd_bf16": (c_int, [vp, vp, c_int, c_int, c_int, fp, fp, fp, fp, c_int, fp, fp, vp, vp, vp]),
+        "stx_pad2d_bf16": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, c_int, c_float, vp, vp]),
+        "stx_pad2d_bwd_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_float, vp, vp]),
+        "stx_inorm_apply_bf16": (c_int, [vp, c_int, c_int, c_int, fp, fp, fp, fp, c_int, c_float, vp, vp, vp]),
+        "stx_inorm_bwd_bf16": (c_int, [vp, vp, c_int, c_int, c_int, fp, fp, fp, fp, c_int, c_float, fp, fp, vp, vp,
+                                       vp]),
         "stx_f32_to_bf16": (c_int, [fp, c_size_t, vp, vp]),
         "stx_bf16_to_f32": (c_int, [vp, c_size_t, fp, vp]),
     }

@@ -341,11 +341,19 @@ int stx_conv_wgrad_bf16(const void* x, const void* dy, int n, int H, int W, int 
                       static_cast<float*>(workspace), S(stream));
 }
 int stx_pad_replicate_bf16(const void* x, int n, int H, int W, int C, int relu, void* out, void* stream) {
-  return pad_rep_launch(static_cast<const bf16*>(x), n, H, W, C, relu, static_cast<bf16*>(out), S(stream));
+  return pad_rep_launch(static_cast<const bf16*>(x), n, H, W, C, 0, relu, 0.0f, static_cast<bf16*>(out), S(stream));
 }
 int stx_pad_replicate_bwd_bf16(const void* gp, const void* x_or_null, int n, int H, int W, int C, void* dx,
                                void* stream) {
-  return pad_rep_bwd_launch(static_cast<const bf16*>(gp), static_cast<const bf16*>(x_or_null), n, H, W, C,
+  return pad_rep_bwd_launch(static_cast<const bf16*>(gp), static_cast<const bf16*>(x_or_null), n, H, W, C, 0, 0.0f,
+                            static_cast<bf16*>(dx), S(stream));
+}
+int stx_pad2d_bf16(const void* x, int n, int H, int W, int C, int mode, int act, float slope, void* out, void* stream) {
+  return pad_rep_launch(static_cast<const bf16*>(x), n, H, W, C, mode, act, slope, static_cast<bf16*>(out), S(stream));
+}
+int stx_pad2d_bwd_bf16(const void* gp, const void* x_or_null, int n, int H, int W, int C, int mode, float slope,
+                       void* dx, void* stream) {
+  return pad_rep_bwd_launch(static_cast<const bf16*>(gp), static_cast<const bf16*>(x_or_null), n, H, W, C, mode, slope,
                             static_cast<bf16*>(dx), S(stream));
 }
 size_t stx_inorm_workspace_bytes(int n, int HW, int C) { return inorm_workspace_bytes(n, HW, C); }
@@ -355,15 +363,16 @@ int stx_inorm_stats_bf16(const void* x, int n, int HW, int C, float eps, float* 
                             S(stream));
 }
 int stx_inorm_apply_bf16(const void* x, int n, int HW, int C, const float* mean, const float* rstd,
-                         const float* gamma, const float* beta, int relu, const void* addend, void* out, void* stream) {
-  return inorm_apply_launch(static_cast<const bf16*>(x), n, HW, C, mean, rstd, gamma, beta, relu,
+                         const float* gamma, const float* beta, int act, float slope, const void* addend, void* out,
+                         void* stream) {
+  return inorm_apply_launch(static_cast<const bf16*>(x), n, HW, C, mean, rstd, gamma, beta, act, slope,
                             static_cast<const bf16*>(addend), static_cast<bf16*>(out), S(stream));
 }
 int stx_inorm_bwd_bf16(const void* x, const void* dy, int n, int HW, int C, const float* mean, const float* rstd,
-                       const float* gamma, const float* beta, int relu, float* s1, float* s2, void* dx,
+                       const float* gamma, const float* beta, int act, float slope, float* s1, float* s2, void* dx,
                        void* workspace, void* stream) {
   return inorm_bwd_launch(static_cast<const bf16*>(x), static_cast<const bf16*>(dy), n, HW, C, mean, rstd, gamma, beta,
-                          relu, s1, s2, static_cast<bf16*>(dx), static_cast<float*>(workspace), S(stream));
+                          act, slope, s1, s2, static_cast<bf16*>(dx), static_cast<float*>(workspace), S(stream));
 }
 
 int stx_conv1_1_fwd(const float* image, int n, int H, int W, int is_preimage, const float* mean3_host,

@@ -1,5 +1,5 @@
 // HBM-bound building blocks of the PO generator, NHWC bf16 with fp32 arithmetic:
-//   * tf.pad(mode="SYMMETRIC") by one pixel (= edge replication) and its gradient, optionally fused with ReLU
+//   * tf.pad(mode="SYMMETRIC" / "REFLECT") by one pixel and its gradient, optionally fused with ReLU / LeakyReLU
 //     (po/progressive_model.py:171-175: pad -> Conv2D(VALID); :77-99 relu before the first conv of a block)
 //   * tensorpack InstanceNorm (per image and channel over H x W, biased variance, affine), forward and backward, with
 //     the ReLU that follows it and the residual shortcut that is added to it fused into the same pass
@@ -35,9 +35,20 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v.u;
 }
 
-// out [n, H+2, W+2, C] <- x [n, H, W, C], edge pixels replicated; optional ReLU on the way.
+// Source index of padded position p (0 .. n + 1) along an axis of n pixels.
+//   mode 0: SYMMETRIC by one pixel = edge replication (p = 0 -> 0, p = n + 1 -> n - 1)
+//   mode 1: REFLECT (p = 0 -> 1, p = n + 1 -> n - 2; needs n >= 2)
+__device__ __forceinline__ int pad_src(int p, int n, int mode) {
+  if (p == 0) return mode;
+  if (p == n + 1) return n - 1 - mode;
+  return p - 1;
+}
+
+// out [n, H+2, W+2, C] <- act(x [n, H, W, C]) with a one-pixel SYMMETRIC / REFLECT ring.
+// act: 0 none, 1 = x > 0 ? x : slope * x  (slope 0 = ReLU, 0.2 = the reference's LeakyReLU).
 __global__ void __launch_bounds__(256)
-pad_rep_kernel(const uint4* __restrict__ x, int nimg, int H, int W, int c8, int relu, uint4* __restrict__ out) {
+pad_rep_kernel(const uint4* __restrict__ x, int nimg, int H, int W, int c8, int mode, int act, float slope,
+               uint4* __restrict__ out) {
   const int Hp = H + 2, Wp = W + 2;
   const size_t total = static_cast<size_t>(nimg) * Hp * Wp * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -48,24 +59,36 @@ pad_rep_kernel(const uint4* __restrict__ x, int nimg, int H, int W, int c8, int 
     t /= Wp;
     const int hp = static_cast<int>(t % Hp);
     const int n = static_cast<int>(t / Hp);
-    const int h = min(max(hp - 1, 0), H - 1), w = min(max(wp - 1, 0), W - 1);
+    const int h = pad_src(hp, H, mode), w = pad_src(wp, W, mode);
     uint4 v = __ldg(x + ((static_cast<size_t>(n) * H + h) * W + w) * c8 + c);
-    if (relu) {
+    if (act) {
       float f[8];
       unpack8(v, f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+      for (int e = 0; e < 8; ++e) f[e] = f[e] > 0.0f ? f[e] : slope * f[e];
       v = pack8(f);
     }
     out[i] = v;
   }
 }
 
-// dx [n, H, W, C] <- gradient w.r.t. the padded tensor gp [n, H+2, W+2, C]: the ring folds onto the edge pixels;
-// with `x` (the forward input) given, ReluGrad is applied as well (zero where x <= 0).
+// Padded positions that read source pixel h along an axis of n pixels: always h + 1, plus one ring position for the
+// pixels the ring copies (mode 0: pixel 0 <- ring 0, pixel n-1 <- ring n+1; mode 1: pixel 1 <- ring 0,
+// pixel n-2 <- ring n+1). Returns the count (1..3) and fills idx.
+__device__ __forceinline__ int pad_readers(int h, int n, int mode, int (&idx)[3]) {
+  int k = 0;
+  idx[k++] = h + 1;
+  if (h == mode) idx[k++] = 0;
+  if (h == n - 1 - mode) idx[k++] = n + 1;
+  return k;
+}
+
+// dx [n, H, W, C] <- gradient w.r.t. the padded tensor gp [n, H+2, W+2, C]: the ring folds back onto the pixels it
+// copied; with `x` (the forward input) given, the activation's derivative is applied as well (1 where x > 0, else
+// slope).
 __global__ void __launch_bounds__(256)
-pad_rep_bwd_kernel(const uint4* __restrict__ gp, const uint4* __restrict__ x, int nimg, int H, int W, int c8,
-                   uint4* __restrict__ dx) {
+pad_rep_bwd_kernel(const uint4* __restrict__ gp, const uint4* __restrict__ x, int nimg, int H, int W, int c8, int mode,
+                   float slope, uint4* __restrict__ dx) {
   const int Wp = W + 2, Hp = H + 2;
   const size_t total = static_cast<size_t>(nimg) * H * W * c8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -76,15 +99,15 @@ pad_rep_bwd_kernel(const uint4* __restrict__ gp, const uint4* __restrict__ x, in
     t /= W;
     const int h = static_cast<int>(t % H);
     const int n = static_cast<int>(t / H);
-    const int h_lo = (h == 0) ? 0 : h + 1, h_hi = (h == H - 1) ? H + 1 : h + 1;
-    const int w_lo = (w == 0) ? 0 : w + 1, w_hi = (w == W - 1) ? W + 1 : w + 1;
+    int hs[3], ws[3];
+    const int nh = pad_readers(h, H, mode, hs), nw = pad_readers(w, W, mode, ws);
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
-    for (int hp = h_lo; hp <= h_hi; ++hp) {
-      for (int wp = w_lo; wp <= w_hi; ++wp) {
+    for (int a = 0; a < nh; ++a) {
+      for (int b = 0; b < nw; ++b) {
         float f[8];
-        unpack8(__ldg(gp + ((static_cast<size_t>(n) * Hp + hp) * Wp + wp) * c8 + c), f);
+        unpack8(__ldg(gp + ((static_cast<size_t>(n) * Hp + hs[a]) * Wp + ws[b]) * c8 + c), f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += f[e];
       }
@@ -94,7 +117,7 @@ pad_rep_bwd_kernel(const uint4* __restrict__ gp, const uint4* __restrict__ x, in
       unpack8(__ldg(x + i), f);
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (!(f[e] > 0.0f)) acc[e] = 0.0f;
+        if (!(f[e] > 0.0f)) acc[e] *= slope;
     }
     dx[i] = pack8(acc);
   }
@@ -104,12 +127,13 @@ pad_rep_bwd_kernel(const uint4* __restrict__ gp, const uint4* __restrict__ x, in
 // Per-(image, channel) sums over the pixels. One block = one slab of pixels of one image; thread t owns the channel
 // group t % c8 and walks pixels t / c8, t / c8 + 256 / c8, ... of the slab.
 //   MODE 0: a = sum x,                b = sum x^2
-//   MODE 1: a = sum g,                b = sum g * xhat       with g = dy * [relu: xhat * gamma + beta > 0]
+//   MODE 1: a = sum g,                b = sum g * xhat       with g = dy * act'(xhat * gamma + beta)
 constexpr int kInThreads = 256;
 
 struct InParams {
   int HW, C, c8, slabs, pix_per_slab;
-  int relu;
+  int relu;             // activation after the affine: 0 none, 1 = v > 0 ? v : slope * v
+  float slope;          // 0 = ReLU, 0.2 = LeakyReLU of po/improved_model.py:30-47
   float eps;
   const float* mean;    // [n][C]
   const float* rstd;    // [n][C]
@@ -158,7 +182,7 @@ in_partial_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, con
       for (int e = 0; e < 8; ++e) {
         const float t = f[e] - mu[e];
         float gg = g[e];
-        if (p.relu && !(t * (rs[e] * ga[e]) + be[e] > 0.0f)) gg = 0.0f;   // the forward's expression, bit for bit
+        if (p.relu && !(t * (rs[e] * ga[e]) + be[e] > 0.0f)) gg *= p.slope;   // the forward's expression, bit for bit
         a[e] += gg;
         b[e] += gg * (t * rs[e]);
       }
@@ -245,7 +269,7 @@ in_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ addend, c
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       f[e] = (f[e] - mu[e]) * a[e] + be[e];
-      if (p.relu) f[e] = fmaxf(f[e], 0.0f);
+      if (p.relu) f[e] = f[e] > 0.0f ? f[e] : p.slope * f[e];
     }
     if (ai) {
       float s[8];
@@ -289,7 +313,7 @@ in_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, c
     for (int e = 0; e < 8; ++e) {
       const float t = f[e] - mu[e];
       float gg = g[e];
-      if (p.relu && !(t * a[e] + be[e] > 0.0f)) gg = 0.0f;
+      if (p.relu && !(t * a[e] + be[e] > 0.0f)) gg *= p.slope;
       f[e] = a[e] * (gg - c1[e] - (t * rs[e]) * c2[e]);
     }
     oi[i] = pack8(f);
@@ -319,25 +343,28 @@ int in_slabs(int nimg, int HW) {
 
 }  // namespace
 
-int pad_rep_launch(const bf16* x, int nimg, int H, int W, int C, int relu, bf16* out, cudaStream_t stream) {
+int pad_rep_launch(const bf16* x, int nimg, int H, int W, int C, int mode, int act, float slope, bf16* out,
+                   cudaStream_t stream) {
   STX_REQUIRE(x && out, "pad: null operand");
   STX_REQUIRE(nimg > 0 && H > 0 && W > 0 && C % 8 == 0, "pad: C must be a multiple of 8");
+  STX_REQUIRE(mode == 0 || (mode == 1 && H >= 2 && W >= 2), "pad: mode must be 0 (symmetric) or 1 (reflect, H, W >= 2)");
   const size_t total = static_cast<size_t>(nimg) * (H + 2) * (W + 2) * (C / 8);
-  pad_rep_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), nimg, H, W, C / 8, relu,
-                                                      reinterpret_cast<uint4*>(out));
+  pad_rep_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), nimg, H, W, C / 8, mode, act,
+                                                      slope, reinterpret_cast<uint4*>(out));
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;
 }
 
-int pad_rep_bwd_launch(const bf16* gp, const bf16* x_or_null, int nimg, int H, int W, int C, bf16* dx,
-                       cudaStream_t stream) {
+int pad_rep_bwd_launch(const bf16* gp, const bf16* x_or_null, int nimg, int H, int W, int C, int mode, float slope,
+                       bf16* dx, cudaStream_t stream) {
   STX_REQUIRE(gp && dx, "pad backward: null operand");
   STX_REQUIRE(nimg > 0 && H > 0 && W > 0 && C % 8 == 0, "pad backward: C must be a multiple of 8");
+  STX_REQUIRE(mode == 0 || (mode == 1 && H >= 2 && W >= 2), "pad backward: mode must be 0 (symmetric) or 1 (reflect)");
   const size_t total = static_cast<size_t>(nimg) * H * W * (C / 8);
   pad_rep_bwd_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const uint4*>(gp),
                                                           reinterpret_cast<const uint4*>(x_or_null), nimg, H, W, C / 8,
-                                                          reinterpret_cast<uint4*>(dx));
+                                                          mode, slope, reinterpret_cast<uint4*>(dx));
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;
@@ -355,9 +382,10 @@ static int in_check(int nimg, int HW, int C) {
   return STX_OK;
 }
 
-static InParams in_params(int nimg, int HW, int C, int relu, float eps, const float* mean, const float* rstd,
-                          const float* gamma, const float* beta) {
+static InParams in_params(int nimg, int HW, int C, int relu, float slope, float eps, const float* mean,
+                          const float* rstd, const float* gamma, const float* beta) {
   InParams p;
+  p.slope = slope;
   p.HW = HW;
   p.C = C;
   p.c8 = C / 8;
@@ -376,7 +404,7 @@ int inorm_stats_launch(const bf16* x, int nimg, int HW, int C, float eps, float*
                        cudaStream_t stream) {
   STX_REQUIRE(x && mean && rstd && workspace, "instance norm: null operand");
   STX_TRY(in_check(nimg, HW, C));
-  const InParams p = in_params(nimg, HW, C, 0, eps, nullptr, nullptr, nullptr, nullptr);
+  const InParams p = in_params(nimg, HW, C, 0, 0.0f, eps, nullptr, nullptr, nullptr, nullptr);
   in_partial_kernel<0><<<dim3(p.slabs, nimg), kInThreads, 0, stream>>>(reinterpret_cast<const uint4*>(x), nullptr, p,
                                                                       workspace);
   STX_CUDA(cudaGetLastError());
@@ -387,10 +415,10 @@ int inorm_stats_launch(const bf16* x, int nimg, int HW, int C, float eps, float*
 }
 
 int inorm_apply_launch(const bf16* x, int nimg, int HW, int C, const float* mean, const float* rstd, const float* gamma,
-                       const float* beta, int relu, const bf16* addend, bf16* out, cudaStream_t stream) {
+                       const float* beta, int relu, float slope, const bf16* addend, bf16* out, cudaStream_t stream) {
   STX_REQUIRE(x && mean && rstd && gamma && beta && out, "instance norm: null operand");
   STX_TRY(in_check(nimg, HW, C));
-  const InParams p = in_params(nimg, HW, C, relu, 0.0f, mean, rstd, gamma, beta);
+  const InParams p = in_params(nimg, HW, C, relu, slope, 0.0f, mean, rstd, gamma, beta);
   const size_t per_img = static_cast<size_t>(HW) * p.c8;
   in_apply_kernel<<<dim3(in_apply_blocks(nimg, per_img), nimg), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(addend), p, reinterpret_cast<uint4*>(out));
@@ -400,11 +428,11 @@ int inorm_apply_launch(const bf16* x, int nimg, int HW, int C, const float* mean
 }
 
 int inorm_bwd_launch(const bf16* x, const bf16* dy, int nimg, int HW, int C, const float* mean, const float* rstd,
-                     const float* gamma, const float* beta, int relu, float* s1, float* s2, bf16* dx, float* workspace,
-                     cudaStream_t stream) {
+                     const float* gamma, const float* beta, int relu, float slope, float* s1, float* s2, bf16* dx,
+                     float* workspace, cudaStream_t stream) {
   STX_REQUIRE(x && dy && mean && rstd && gamma && beta && s1 && s2 && dx && workspace, "instance norm: null operand");
   STX_TRY(in_check(nimg, HW, C));
-  const InParams p = in_params(nimg, HW, C, relu, 0.0f, mean, rstd, gamma, beta);
+  const InParams p = in_params(nimg, HW, C, relu, slope, 0.0f, mean, rstd, gamma, beta);
   in_partial_kernel<1><<<dim3(p.slabs, nimg), kInThreads, 0, stream>>>(reinterpret_cast<const uint4*>(x),
                                                                       reinterpret_cast<const uint4*>(dy), p, workspace);
   STX_CUDA(cudaGetLastError());

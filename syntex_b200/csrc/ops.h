@@ -152,16 +152,18 @@ int wgrad_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin,
                  float* workspace, cudaStream_t stream);
 
 // ------------------------------------------------------------------ gen_ops.cu
-int pad_rep_launch(const bf16* x, int nimg, int H, int W, int C, int relu, bf16* out, cudaStream_t stream);
-int pad_rep_bwd_launch(const bf16* gp, const bf16* x_or_null, int nimg, int H, int W, int C, bf16* dx,
-                       cudaStream_t stream);
+// mode: 0 = SYMMETRIC (edge replication), 1 = REFLECT; act: 0 none, 1 = leaky ReLU with `slope` (0 = ReLU)
+int pad_rep_launch(const bf16* x, int nimg, int H, int W, int C, int mode, int act, float slope, bf16* out,
+                   cudaStream_t stream);
+int pad_rep_bwd_launch(const bf16* gp, const bf16* x_or_null, int nimg, int H, int W, int C, int mode, float slope,
+                       bf16* dx, cudaStream_t stream);
 size_t inorm_workspace_bytes(int nimg, int HW, int C);
 int inorm_stats_launch(const bf16* x, int nimg, int HW, int C, float eps, float* mean, float* rstd, float* workspace,
                        cudaStream_t stream);
 int inorm_apply_launch(const bf16* x, int nimg, int HW, int C, const float* mean, const float* rstd, const float* gamma,
-                       const float* beta, int relu, const bf16* addend, bf16* out, cudaStream_t stream);
+                       const float* beta, int relu, float slope, const bf16* addend, bf16* out, cudaStream_t stream);
 int inorm_bwd_launch(const bf16* x, const bf16* dy, int nimg, int HW, int C, const float* mean, const float* rstd,
-                     const float* gamma, const float* beta, int relu, float* s1, float* s2, bf16* dx, float* workspace,
-                     cudaStream_t stream);
+                     const float* gamma, const float* beta, int relu, float slope, float* s1, float* s2, bf16* dx,
+                     float* workspace, cudaStream_t stream);
 
 }  // namespace stx

@@ -54,6 +54,33 @@ def _act(act_type, x):
     return F.relu(x) if act_type == "relu" else F.leaky_relu(x, 0.2)
 
 
+# ---- the same modules on the hand-written kernels (po/gen_ops.py): NHWC bf16 activations ------------------------
+_NATIVE_PAD = {"SYMMETRIC": "symmetric", "REFLECT": "reflect", "CONSTANT": "zero"}
+
+
+def _act_arg(act_type):
+    """Activation argument of the fused kernels: True = ReLU, a float = LeakyReLU slope."""
+    return True if act_type == "relu" else 0.2
+
+
+def _norm_is_native(norm, batch):
+    """InstanceNorm always; BatchNorm with batch statistics only at batch 1, where it IS InstanceNorm (the reference's
+    per-GPU batch, po/improved_model.py:24); nothing to do for Identity."""
+    from .layers import InstanceNormAffine
+    if norm is None or isinstance(norm, (nn.Identity, InstanceNormAffine)):
+        return True
+    return type(norm).__name__ == "_BatchStatsNorm" and batch == 1
+
+
+def _norm_native(norm, x, act=None, shortcut=None):
+    from . import gen_ops
+    if norm is None or isinstance(norm, nn.Identity):
+        if act is not None:
+            x = torch.relu(x) if act is True else F.leaky_relu(x, float(act))
+        return x if shortcut is None else x + shortcut
+    return gen_ops.instance_norm(x, norm.weight, norm.bias, norm.eps, act if act is not None else False, shortcut)
+
+
 class PadConv2D(nn.Module):
     """adaptive_model.py:50-56: tf.pad + Conv2D(VALID); norm_act=True appends norm + activation (the argscope
     default), False leaves it linear."""
@@ -74,6 +101,20 @@ class PadConv2D(nn.Module):
             x = _act(self.act_type, self.norm(x))
         return x
 
+    def forward_native(self, x, act_in=None):
+        """x NHWC bf16; act_in: the activation the caller applies to x first (True = ReLU, float = LeakyReLU slope),
+        fused into the padding pass."""
+        from . import gen_ops
+        if self.ksize != 3:
+            raise NotImplementedError("native generator route: 3x3 layers only")
+        mode = _NATIVE_PAD[self.pad_type]
+        if mode == "zero" and act_in is not None:
+            x, act_in = _norm_native(None, x, act=act_in), None
+        x = gen_ops.conv3x3(x, self.conv.weight, self.conv.bias, mode, act_in if act_in is not None else False)
+        if self.norm is not None:
+            x = _norm_native(self.norm, x, act=_act_arg(self.act_type))
+        return x
+
 
 class _ResBlock(nn.Module):
     def __init__(self, chan, pad_type, norm_type, act_type, pre_act):
@@ -87,6 +128,12 @@ class _ResBlock(nn.Module):
         if self.pre_act:       # build_pre_res_block (adaptive_model.py:149-176)
             return self.conv1(self.conv0(_act(self.act_type, self.norm(x)))) + x
         return self.norm(self.conv1(self.conv0(_act(self.act_type, x)))) + x      # build_res_block (:121-147)
+
+    def forward_native(self, x):
+        a = _act_arg(self.act_type)
+        if self.pre_act:
+            return self.conv1.forward_native(self.conv0.forward_native(_norm_native(self.norm, x, act=a))) + x
+        return _norm_native(self.norm, self.conv1.forward_native(self.conv0.forward_native(x, act_in=a)), shortcut=x)
 
 
 class _Upsample(nn.Module):
@@ -103,6 +150,20 @@ class _Upsample(nn.Module):
         if self.nn_upsample:
             x = F.interpolate(x, scale_factor=self.scale, mode="nearest")
         return self.conv(x)
+
+    def forward_native(self, x, act_in=None):
+        """Tile x2 + pad 1 + 3x3 conv == one 3x3 conv of the LOW-resolution map with four phase filters
+        (gen_ops.upsample_weights) + a pixel shuffle. One pixel of SYMMETRIC or REFLECT padding of the tiled map both
+        read low-resolution edge pixel 0 (tiled rows 0 and 1 are copies of it): edge replication; CONSTANT stays zero."""
+        from . import gen_ops
+        if not self.nn_upsample or self.scale != 2:
+            raise NotImplementedError("native generator route: nearest-neighbour x2 up-sampling only")
+        mode = "zero" if self.conv.pad_type == "CONSTANT" else "symmetric"
+        if mode == "zero" and act_in is not None:
+            x, act_in = _norm_native(None, x, act=act_in), None
+        w = self.conv.conv.weight
+        y = gen_ops.conv3x3(x, gen_ops.upsample_weights(w), None, mode, act_in if act_in is not None else False)
+        return gen_ops.pixel_shuffle_nhwc(y, w.shape[0])
 
 
 class _Stage(nn.Module):
@@ -146,6 +207,67 @@ class _Stage(nn.Module):
         delta = _act(self.act_type, self.last_norm(delta) if self.pre_act else delta)
         return self.convlast(delta).permute(0, 2, 3, 1)
 
+    def native_supported(self, batch):
+        return stage_native_supported(self, batch)
+
+    def forward_native(self, grad_per_layer):
+        return stage_forward_native(self, grad_per_layer)
+
+
+def stage_native_supported(stage, batch):
+    """Does the hand-written route cover this generator stage (shared by the adaptive and improved mirrors)?"""
+    for m in stage.modules():
+        if isinstance(m, PadConv2D) and m.ksize != 3:
+            return False
+        if isinstance(m, _Upsample) and (not m.nn_upsample or m.scale != 2):
+            return False
+        if isinstance(m, nn.BatchNorm2d):
+            return False
+        if type(m).__name__ == "_BatchStatsNorm" and batch != 1:
+            return False
+    return True
+
+
+def stage_forward_native(stage, grad_per_layer):
+    """The graph of _Stage.forward on the kernels of po/gen_ops.py: activations fused into the padding pass of the
+    convolution that follows or into the normalisation that precedes, shortcut adds fused into the normalisation."""
+    a = _act_arg(stage.act_type)
+    delta = None
+    for layer in reversed(stage.layers):
+        g = grad_per_layer[layer].to(torch.bfloat16)
+        g = stage.grad_conv2[layer].forward_native(stage.grad_conv1[layer].forward_native(g))
+        if delta is None:
+            delta = g
+        elif stage.pre_act:
+            delta = g + stage.up[layer].forward_native(_norm_native(stage.pre_norm[layer], delta, act=a))
+        else:
+            delta = g + stage.up[layer].forward_native(delta, act_in=a)
+        if not stage.pre_act:
+            delta = _norm_native(stage.post_norm[layer], delta)
+        for blk in stage.res[layer]:
+            delta = blk.forward_native(delta)
+    if stage.pre_act:
+        out = stage.convlast.forward_native(_norm_native(stage.last_norm, delta, act=a))
+    else:
+        out = stage.convlast.forward_native(delta, act_in=a)
+    return out.to(torch.float32)
+
+
+def run_generator(model, stage, inputs):
+    """Route a stage through the hand-written kernels or stock torch (`generator` = auto / native / torch, as in
+    po/progressive_model.py)."""
+    first = next(iter(inputs.values()))
+    ok = first.is_cuda and stage.native_supported(first.shape[0])
+    if model._generator == "native":
+        if not ok:
+            raise NotImplementedError("generator='native': this configuration is not covered by the hand-written "
+                                      "kernels (needs CUDA, 3x3 gradient convolutions, nearest-neighbour up-sampling, "
+                                      "instance / no normalisation or batch statistics at batch 1)")
+        return stage.forward_native(inputs)
+    if model._generator == "auto" and ok and model._door_is_cuda:
+        return stage.forward_native(inputs)
+    return stage(inputs)
+
 
 class AdaptiveSynTex(SynTexModelDesc, nn.Module):
     def __init__(self, args, texture_fn=None):
@@ -180,6 +302,10 @@ class AdaptiveSynTex(SynTexModelDesc, nn.Module):
         self._act_type = args.get("act_type") or "relu"
         self._grad_ksize = args.get("grad_ksize") or 3
         self._stop_grad = args.get("stop_grad") or False
+        self._generator = args.get("generator", "auto")       # extension: auto / native / torch (po/gen_ops.py)
+        if self._generator not in ("auto", "native", "torch"):
+            raise ValueError("generator must be auto, native or torch")
+        self._door_is_cuda = texture_fn is None
         self._texture_fn = texture_fn or CudaTexture(self._vgg19, SynTexModelDesc.DEFAULT_COEFS.keys())
         self.syn = nn.ModuleList([_Stage(self._n_block, self._pre_act, self._nn_upsample, self._pad_type,
                                          self._norm_type, self._act_type, self._grad_ksize)
@@ -233,7 +359,7 @@ class AdaptiveSynTex(SynTexModelDesc, nn.Module):
         slot = s if torch.is_grad_enabled() else 0
         feat_input, loss_input, loss_per_layer, grad_per_layer = \
             self.build_stage_preparation(image_input, gram_target, coefs, slot=slot)
-        delta_input = self.syn[s](grad_per_layer)
+        delta_input = run_generator(self, self.syn[s], grad_per_layer)
         pre_image_output = pre_image_input + delta_input
         return image_input, loss_input, loss_per_layer, pre_image_output
 

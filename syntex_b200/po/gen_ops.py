@@ -33,12 +33,22 @@ def _phase_matrices(device):
     return _PHASE
 
 
-def upsample_weights(w5):
-    """[Cout, Cin, 5, 5] -> [4 * Cout, Cin, 3, 3]: output channel (py * 2 + px) * Cout + o holds the filter that
-    produces up-sampled pixel (2 j + py, 2 i + px) from the low-resolution neighbourhood of (j, i). Differentiable."""
-    P = _phase_matrices(w5.device).to(w5.dtype)
-    w3 = torch.einsum("yat,xbu,oitu->yxoiab", P, P, w5)
-    return w3.reshape(4 * w5.shape[0], w5.shape[1], 3, 3)
+def upsample_weights(w):
+    """[Cout, Cin, k, k] (k = 5: build_upsampling_nn, po/progressive_model.py:123-134; k = 3:
+    build_upsampling_nnconv, po/improved_model.py:185-199) -> [4 * Cout, Cin, 3, 3]: output channel
+    (py * 2 + px) * Cout + o holds the filter that produces up-sampled pixel (2 j + py, 2 i + px) from the
+    low-resolution neighbourhood of (j, i). Differentiable."""
+    k = w.shape[-1]
+    if k == 5:
+        P = _phase_matrices(w.device).to(w.dtype)
+    elif k == 3:
+        # three taps on the up-sampled map: even pixel 2j reads x[j-1], x[j], x[j]; odd pixel 2j+1 reads x[j], x[j], x[j+1]
+        P = torch.tensor([[[1, 0, 0], [0, 1, 1], [0, 0, 0]], [[0, 0, 0], [1, 1, 0], [0, 0, 1]]], dtype=w.dtype,
+                         device=w.device)
+    else:
+        raise NotImplementedError("upsample_weights: kernel size %d" % k)
+    w3 = torch.einsum("yat,xbu,oitu->yxoiab", P, P, w)
+    return w3.reshape(4 * w.shape[0], w.shape[1], 3, 3)
 
 
 def pixel_shuffle_nhwc(y, cout):
@@ -55,19 +65,26 @@ def _f32(shape):
     return torch.empty(shape, dtype=torch.float32, device="cuda")
 
 
+_PAD_MODES = {"rep": 0, "symmetric": 0, "reflect": 1}
+
+
 class Conv3x3Function(torch.autograd.Function):
-    """y = conv3x3(pad(relu?(x)), W) + b on NHWC bf16. pad: "rep" = tf.pad(SYMMETRIC) by one pixel + VALID
-    (progressive_model.py:171-175), "zero" = Conv2D(padding="SAME") (single_model.py:170-171)."""
+    """y = conv3x3(pad(act?(x)), W) + b on NHWC bf16. mode: "rep" / "symmetric" = tf.pad(SYMMETRIC) by one pixel +
+    VALID (progressive_model.py:171-175), "reflect" = tf.pad(REFLECT) + VALID (improved_model.py:49-55), "zero" =
+    Conv2D(padding="SAME") (single_model.py:170-171). relu_in: False / None = no activation, True = ReLU, a float =
+    LeakyReLU with that slope, applied to x on the way into the padded copy."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, mode, relu_in):
         _lib.require_cuda()
         L = _lib.lib()
         st = _lib.stream_ptr()
-        if mode not in ("rep", "zero"):
+        if mode not in _PAD_MODES and mode != "zero":
             raise ValueError("Conv3x3Function: unknown padding mode %r" % (mode,))
-        if relu_in and mode != "rep":
-            raise ValueError("Conv3x3Function: the fused input ReLU exists for the replicated-edge mode only")
+        act_in = relu_in is not None and relu_in is not False
+        slope = 0.0 if relu_in is True or not act_in else float(relu_in)
+        if act_in and mode == "zero":
+            raise ValueError("Conv3x3Function: the fused input activation needs a padded copy (not the zero mode)")
         x = x.contiguous()
         if x.dtype != torch.bfloat16 or not x.is_cuda:
             raise ValueError("Conv3x3Function expects a CUDA bf16 NHWC tensor")
@@ -90,17 +107,18 @@ class Conv3x3Function(torch.autograd.Function):
             b = b.contiguous()
             if b.data_ptr() % 16:           # the epilogue reads the bias as float4; a flat parameter buffer need not align
                 b = b.clone()
-        if mode == "rep":
+        if mode != "zero":
             xin = _bf16((B, H + 2, W + 2, cin))
-            _lib.check(L.stx_pad_replicate_bf16(x.data_ptr(), B, H, W, cin, 1 if relu_in else 0, xin.data_ptr(), st))
+            _lib.check(L.stx_pad2d_bf16(x.data_ptr(), B, H, W, cin, _PAD_MODES[mode], 1 if act_in else 0,
+                                        ctypes.c_float(slope), xin.data_ptr(), st))
             pad = 0
         else:
             xin, pad = x, 1
         y = _bf16((B, H, W, coutp))
         _lib.check(L.stx_conv_bf16_pad(xin.data_ptr(), B, H, W, cin, w_fwd.data_ptr(), coutp, pad,
                                        b.data_ptr() if b is not None else None, None, 0, y.data_ptr(), 0, st))
-        ctx.mode, ctx.relu_in, ctx.cout, ctx.has_bias = mode, relu_in, cout, bias is not None
-        ctx.save_for_backward(xin, w_dgrad, x if relu_in else None)
+        ctx.mode, ctx.slope, ctx.cout, ctx.has_bias = mode, slope, cout, bias is not None
+        ctx.save_for_backward(xin, w_dgrad, x if act_in else None)
         return y if coutp == cout else y[..., :cout].contiguous()
 
     @staticmethod
@@ -118,13 +136,14 @@ class Conv3x3Function(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = _bf16((B, H, W, cin))
-            if ctx.mode == "rep":
+            if ctx.mode != "zero":
                 # gradient w.r.t. the padded input = FULL correlation with the rotated filter; the ring then folds back
                 gp = _bf16((B, H + 2, W + 2, cin))
                 _lib.check(L.stx_conv_bf16_pad(dy.data_ptr(), B, H + 2, W + 2, coutp, w_dgrad.data_ptr(), cin, 2, None,
                                                None, 0, gp.data_ptr(), 0, st))
-                _lib.check(L.stx_pad_replicate_bwd_bf16(gp.data_ptr(), x_mask.data_ptr() if x_mask is not None else None,
-                                                        B, H, W, cin, dx.data_ptr(), st))
+                _lib.check(L.stx_pad2d_bwd_bf16(gp.data_ptr(), x_mask.data_ptr() if x_mask is not None else None,
+                                                B, H, W, cin, _PAD_MODES[ctx.mode], ctypes.c_float(ctx.slope),
+                                                dx.data_ptr(), st))
             else:
                 _lib.check(L.stx_conv_bf16_pad(dy.data_ptr(), B, H, W, coutp, w_dgrad.data_ptr(), cin, 1, None, None, 0,
                                                dx.data_ptr(), 0, st))
@@ -133,7 +152,7 @@ class Conv3x3Function(torch.autograd.Function):
                              device="cuda")
             dw_hwio = _f32((3, 3, cin, coutp))
             _lib.check(L.stx_conv_wgrad_bf16(xin.data_ptr(), dy.data_ptr(), B, H, W, cin, coutp,
-                                             0 if ctx.mode == "rep" else 1, dw_hwio.data_ptr(), ws.data_ptr(), st))
+                                             1 if ctx.mode == "zero" else 0, dw_hwio.data_ptr(), ws.data_ptr(), st))
             dw = dw_hwio[..., :cout].permute(3, 2, 0, 1)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy[..., :cout].to(torch.float32).sum(dim=(0, 1, 2))
@@ -141,11 +160,14 @@ class Conv3x3Function(torch.autograd.Function):
 
 
 class InstanceNormFunction(torch.autograd.Function):
-    """out = relu?(InstanceNorm(x) * gamma + beta) (+ shortcut): tensorpack InstanceNorm over H x W per image and
-    channel, with the ReLU after it and the residual add of build_res_block (progressive_model.py:77-99) fused."""
+    """out = act?(InstanceNorm(x) * gamma + beta) (+ shortcut): tensorpack InstanceNorm over H x W per image and
+    channel, with the activation after it (relu: False / None = none, True = ReLU, a float = LeakyReLU slope) and the
+    residual add of build_res_block (progressive_model.py:77-99) fused."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, eps, relu, shortcut):
+        act = relu is not None and relu is not False
+        slope = 0.0 if relu is True or not act else float(relu)
         _lib.require_cuda()
         L = _lib.lib()
         st = _lib.stream_ptr()
@@ -166,9 +188,9 @@ class InstanceNormFunction(torch.autograd.Function):
                 raise ValueError("InstanceNormFunction: shortcut must match the input")
         out = _bf16((B, H, W, C))
         _lib.check(L.stx_inorm_apply_bf16(x.data_ptr(), B, H * W, C, mean.data_ptr(), rstd.data_ptr(), g.data_ptr(),
-                                          b.data_ptr(), 1 if relu else 0, sc.data_ptr() if sc is not None else None,
-                                          out.data_ptr(), st))
-        ctx.relu, ctx.has_shortcut = bool(relu), shortcut is not None
+                                          b.data_ptr(), 1 if act else 0, ctypes.c_float(slope),
+                                          sc.data_ptr() if sc is not None else None, out.data_ptr(), st))
+        ctx.relu, ctx.slope, ctx.has_shortcut = act, slope, shortcut is not None
         ctx.save_for_backward(x, mean, rstd, g, b)
         return out
 
@@ -183,8 +205,8 @@ class InstanceNormFunction(torch.autograd.Function):
         dx = _bf16((B, H, W, C))
         ws = torch.empty(max(L.stx_inorm_workspace_bytes(B, H * W, C) // 4, 1), dtype=torch.float32, device="cuda")
         _lib.check(L.stx_inorm_bwd_bf16(x.data_ptr(), dy.data_ptr(), B, H * W, C, mean.data_ptr(), rstd.data_ptr(),
-                                        g.data_ptr(), b.data_ptr(), 1 if ctx.relu else 0, s1.data_ptr(), s2.data_ptr(),
-                                        dx.data_ptr(), ws.data_ptr(), st))
+                                        g.data_ptr(), b.data_ptr(), 1 if ctx.relu else 0, ctypes.c_float(ctx.slope),
+                                        s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), ws.data_ptr(), st))
         dgamma = s2.sum(0) if ctx.needs_input_grad[1] else None
         dbeta = s1.sum(0) if ctx.needs_input_grad[2] else None
         return dx, dgamma, dbeta, None, None, (dy if ctx.has_shortcut else None)

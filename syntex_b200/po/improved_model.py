@@ -7,7 +7,8 @@ trained THROUGH those gradients unless --stop-grad: the double backward through 
 differs from progressive_model.py in its options (padding reflect / symmetric / zero, instance / batch / no
 normalisation - BatchNorm always with batch statistics, :353-360 -, ReLU / LeakyReLU(0.2), gradient-conv kernel size,
 3x3 convolution after the nearest-neighbour up-sampling, :185-199) and shares its layer modules with the
-AdaptiveSynTex mirror (po/adaptive_model.py); it runs on stock torch kernels. tensorpack layer defaults restated from
+AdaptiveSynTex mirror (po/adaptive_model.py); it runs on the hand-written kernels of po/gen_ops.py (reflect /
+symmetric / zero padding, InstanceNorm or batch-1 BatchNorm, ReLU / LeakyReLU fused) or on stock torch. tensorpack layer defaults restated from
 its published source, unverified.
 """
 from collections import OrderedDict
@@ -18,7 +19,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..aparse import ArgParser
-from .adaptive_model import PadConv2D, _ResBlock, _Upsample, _act, _norm
+from .adaptive_model import (PadConv2D, _ResBlock, _Upsample, _act, _norm, run_generator, stage_forward_native,
+                             stage_native_supported)
 from .model import SynTexModelDesc
 from .progressive_model import LAYER_CHANNELS
 from .texture_op import CudaTexture
@@ -106,6 +108,12 @@ class _Stage(nn.Module):
         delta = _act(self.act_type, self.last_norm(delta) if self.pre_act else delta)
         return self.convlast(delta).permute(0, 2, 3, 1)
 
+    def native_supported(self, batch):
+        return stage_native_supported(self, batch)
+
+    def forward_native(self, grad_per_layer):
+        return stage_forward_native(self, grad_per_layer)
+
 
 class ImprovedSynTex(SynTexModelDesc, nn.Module):
     def __init__(self, args, texture_fn=None):
@@ -142,6 +150,10 @@ class ImprovedSynTex(SynTexModelDesc, nn.Module):
         self._grad_ksize = args.get("grad_ksize") or 3
         self._stop_grad = args.get("stop_grad") or False
         self._sync_stats = args.get("sync_stats")          # accepted; the reference has the sync variant commented out
+        self._generator = args.get("generator", "auto")       # extension: auto / native / torch (po/gen_ops.py)
+        if self._generator not in ("auto", "native", "torch"):
+            raise ValueError("generator must be auto, native or torch")
+        self._door_is_cuda = texture_fn is None
         self._texture_fn = texture_fn or CudaTexture(self._vgg19, SynTexModelDesc.DEFAULT_COEFS.keys())
         self.syn = nn.ModuleList([_Stage(s + 1, self._n_block, self._pre_act, self._nn_upsample, self._pad_type,
                                          self._norm_type, self._act_type, self._grad_ksize)
@@ -196,7 +208,7 @@ class ImprovedSynTex(SynTexModelDesc, nn.Module):
         slot = s if torch.is_grad_enabled() else 0
         _, loss_input, loss_per_layer, grad_per_layer = \
             self.build_stage_preparation(image_input, gram_target, coefs, slot=slot)
-        delta_input = self.syn[s](grad_per_layer)
+        delta_input = run_generator(self, self.syn[s], grad_per_layer)
         if self._stop_grad:
             pre_image_output = pre_image_input.detach() + delta_input
         else:

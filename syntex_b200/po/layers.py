@@ -65,6 +65,7 @@ class InstanceNormAffine(nn.Module):
         return F.instance_norm(x, None, None, self.weight, self.bias, True, 0.0, self.eps)
 
     def forward_native(self, x, relu=False, shortcut=None):
+        """relu: False = none, True = ReLU, a float = LeakyReLU slope (fused into the normalisation pass)."""
         from . import gen_ops
         return gen_ops.instance_norm(x, self.weight, self.bias, self.eps, relu, shortcut)
 

@@ -27,6 +27,20 @@ def test_upsample_phase_filters_equal_the_5x5_convolution(cin, cout, h, w):
     assert torch.allclose(gw, gw_ref, atol=1e-10) and torch.allclose(gx, gx_ref, atol=1e-10)
 
 
+@pytest.mark.parametrize("pad_type", ["SYMMETRIC", "REFLECT", "CONSTANT"])
+def test_upsample_phase_filters_equal_the_3x3_convolution_after_tiling(pad_type):
+    """build_upsampling_nnconv (po/improved_model.py:185-199): tile x2, pad 1 (any tf.pad mode), 3x3 conv."""
+    from syntex_b200.po.adaptive_model import _Upsample
+    torch.manual_seed(0)
+    m = _Upsample(6, 4, pad_type, True).double()
+    x = torch.randn(2, 6, 5, 7, dtype=torch.float64)
+    ref = m(x)
+    w3 = gen_ops.upsample_weights(m.conv.conv.weight)
+    xp = F.pad(x, (1, 1, 1, 1)) if pad_type == "CONSTANT" else F.pad(x, (1, 1, 1, 1), mode="replicate")
+    y = gen_ops.pixel_shuffle_nhwc(F.conv2d(xp, w3).permute(0, 2, 3, 1).contiguous(), 4)
+    assert torch.allclose(y.permute(0, 3, 1, 2), ref, atol=1e-12)
+
+
 def test_symmetric_pad_of_upsampled_map_is_edge_replication_of_the_low_resolution_map():
     x = torch.arange(2 * 3 * 4 * 5, dtype=torch.float32).reshape(2, 3, 4, 5)
     up = F.interpolate(x, scale_factor=2, mode="nearest")

@@ -234,7 +234,7 @@ def test_adaptive_model_on_the_cuda_door(raw_weights):
     torch.manual_seed(2)
     args = {"vgg19_npy_path": raw_weights, "image_size": size, "n_stage": 2, "lr": 2e-4}
     cpu = AdaptiveSynTex(args, texture_fn=so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS)).double()
-    gpu = AdaptiveSynTex(args)
+    gpu = AdaptiveSynTex(dict(args, generator="torch"))     # fp32 generator: the door is what is compared here
     gpu.load_state_dict({k: v.float() for k, v in cpu.state_dict().items()})
     gpu = gpu.cuda()
     rng = np.random.RandomState(0)
@@ -307,7 +307,7 @@ def test_improved_model_on_the_cuda_door(raw_weights):
     args = {"vgg19_npy_path": raw_weights, "image_size": size, "lr": 2e-4, "pad_type": "zero", "norm_type": "batch",
             "act_type": "lrelu"}
     cpu = ImprovedSynTex(args, texture_fn=so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS)).double()
-    gpu = ImprovedSynTex(args)
+    gpu = ImprovedSynTex(dict(args, generator="torch"))     # fp32 generator: the door is what is compared here
     gpu.load_state_dict({k: v.float() for k, v in cpu.state_dict().items()})
     gpu = gpu.cuda()
     rng = np.random.RandomState(0)

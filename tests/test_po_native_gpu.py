@@ -103,6 +103,69 @@ def test_replicate_pad_forward_and_backward(relu):
     assert relerr(dx.float(), _nhwc(xr.grad)) < 4e-3
 
 
+@pytest.mark.parametrize("mode,slope", [(1, 0.0), (1, 0.2), (0, 0.2)])
+def test_pad2d_reflect_and_leaky_forward_and_backward(mode, slope):
+    """tf.pad(REFLECT / SYMMETRIC) by one pixel of LeakyReLU(x) (po/improved_model.py:49-55, :136-143)."""
+    n, h, w, c = 2, 7, 10, 64
+    x = _rand_bf16((n, h, w, c), 40)
+    out = torch.empty((n, h + 2, w + 2, c), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L().stx_pad2d_bf16(x.data_ptr(), n, h, w, c, mode, 1, ctypes.c_float(slope), out.data_ptr(), st()))
+    xr = _nchw(x).requires_grad_(True)
+    ref = F.pad(F.leaky_relu(xr, slope), (1, 1, 1, 1), mode="reflect" if mode == 1 else "replicate")
+    assert relerr(out.float(), _nhwc(ref).detach()) < 4e-3
+    gp = _rand_bf16((n, h + 2, w + 2, c), 41)
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L().stx_pad2d_bwd_bf16(gp.data_ptr(), x.data_ptr(), n, h, w, c, mode, ctypes.c_float(slope),
+                                      dx.data_ptr(), st()))
+    ref.backward(_nchw(gp))
+    assert relerr(dx.float(), _nhwc(xr.grad)) < 4e-3
+
+
+def test_instance_norm_function_with_leaky_relu():
+    n, h, w, c = 2, 16, 16, 128
+    x = (_rand_bf16((n, h, w, c), 42).float() * 1.5 + 0.3).to(torch.bfloat16).requires_grad_(True)
+    gamma = torch.linspace(0.5, 1.5, c, device="cuda").requires_grad_(True)
+    beta = torch.linspace(-0.5, 0.5, c, device="cuda").requires_grad_(True)
+    out = gen_ops.instance_norm(x, gamma, beta, 1e-5, 0.2, None)
+    xr = _nchw(x.detach()).requires_grad_(True)
+    gr, br = gamma.detach().clone().requires_grad_(True), beta.detach().clone().requires_grad_(True)
+    ref = F.leaky_relu(F.instance_norm(xr, None, None, gr, br, True, 0.0, 1e-5), 0.2)
+    assert relerr(out.float(), _nhwc(ref).detach()) < 4e-3
+    dy = _rand_bf16((n, h, w, c), 43)
+    out.backward(dy)
+    ref.backward(_nchw(dy))
+    assert relerr(x.grad.float(), _nhwc(xr.grad)) < 1e-2
+    assert relerr(gamma.grad, gr.grad) < 1e-2 and relerr(beta.grad, br.grad) < 1e-2
+
+
+@pytest.mark.parametrize("opts", [{"pad_type": "REFLECT", "norm_type": "batch", "act_type": "lrelu", "pre_act": False},
+                                  {"pad_type": "CONSTANT", "norm_type": "instance", "act_type": "relu", "pre_act": True},
+                                  {"pad_type": "SYMMETRIC", "norm_type": "none", "act_type": "lrelu", "pre_act": False}])
+def test_improved_stage_native_matches_stock(opts):
+    """A two-layer stage of the improved model (po/improved_model.py:234-318) on the hand-written kernels vs stock
+    torch fp32 with the same parameters: output and the parameter gradients' direction."""
+    from syntex_b200.po.improved_model import _Stage as ImprovedStage
+    torch.manual_seed(5)
+    stage = ImprovedStage(2, 2, opts["pre_act"], True, opts["pad_type"], opts["norm_type"], opts["act_type"], 3).cuda()
+    assert stage.native_supported(1)
+    vals = {"conv1_1": _rand_bf16((1, 64, 64, 64), 50).float(), "pool1": _rand_bf16((1, 32, 32, 64), 51).float()}
+    a = {k: v.clone().requires_grad_(True) for k, v in vals.items()}
+    b = {k: v.clone().requires_grad_(True) for k, v in vals.items()}
+    out = stage.forward_native(a)
+    ref = stage(b)
+    assert out.shape == ref.shape == (1, 64, 64, 3)
+    assert relerr(out, ref.detach()) < 5e-2
+    dy = torch.randn_like(out)
+    out.backward(dy)
+    g_native = {n: p.grad.clone() for n, p in stage.named_parameters()}
+    stage.zero_grad()
+    ref.backward(dy)
+    cos = [_cos(g_native[n], p.grad) for n, p in stage.named_parameters()]
+    assert min(cos) > 0.9 and sum(cos) / len(cos) > 0.97, (min(cos), sum(cos) / len(cos))
+    for k in vals:
+        assert _cos(a[k].grad, b[k].grad) > 0.95, k
+
+
 @pytest.mark.parametrize("n,h,w,c", [(1, 32, 32, 64), (2, 16, 16, 128), (1, 8, 8, 512), (3, 20, 12, 256)])
 @pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("shortcut", [False, True])
