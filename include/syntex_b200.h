@@ -124,6 +124,9 @@ int stx_plan_copy_layer_total_grad(stx_plan* plan, int k, float* out, void* stre
 /* Per-layer gradients of build_texture_loss(calc_grad=True) (utils.py:50-55): d loss_layer[k] / d feat[k],
  * fp32 [batch,h,w,c] device, for the features of the last forward and the current targets. */
 int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream);
+/* The same in the kernels' own precision, bf16 [batch,h,w,c] (device): what the hand-written PO generator consumes
+ * (syntex_b200/po/gen_ops.py), without the fp32 round trip. */
+int stx_plan_layer_grad_bf16(stx_plan* plan, int k, void* out_bf16, void* stream);
 
 /* Zero-copy view of a recorded layer of the last forward: device pointers to the bf16 planes [batch,h,w,c] the
  * plan owns (hi = bf16(value); lo = bf16(value - hi) in the accurate mode, NULL in STX_PLAN_FAST_BF16 mode; `lo` may

@@ -41,6 +41,7 @@ def _declare(lib):
         "stx_plan_step_timed": (c_int, [vp, fp, c_int, fp, fp, POINTER(c_float), POINTER(c_int), vp]),
         "stx_plan_step_host": (c_int, [vp, fp, c_int, fp, fp, vp]),
         "stx_plan_layer_grad": (c_int, [vp, c_int, fp, vp]),
+        "stx_plan_layer_grad_bf16": (c_int, [vp, c_int, vp, vp]),
         "stx_plan_copy_layer_total_grad": (c_int, [vp, c_int, fp, vp]),
         "stx_plan_feature_bf16": (c_int, [vp, c_int, POINTER(c_void_p), POINTER(c_void_p)]),
         "stx_plan_backward_custom": (c_int, [vp, fp, c_int, POINTER(c_void_p), POINTER(c_void_p), fp, vp]),

@@ -215,6 +215,23 @@ int stx_plan_layer_grad(stx_plan* plan, int k, float* out, void* stream) {
   return bf16_to_f32_launch(p->gbuf[0], n, out, S(stream));
 }
 
+int stx_plan_layer_grad_bf16(stx_plan* plan, int k, void* out_bf16, void* stream) {
+  STX_REQUIRE(plan && out_bf16, "stx_plan_layer_grad_bf16: null argument");
+  Plan* p = plan->p;
+  STX_REQUIRE(k >= 0 && k < static_cast<int>(p->loss.size()), "loss-layer index out of range");
+  if (!p->have_grams || !p->have_target)
+    return fail(STX_ERR_STATE, "stx_plan_layer_grad_bf16: needs a forward with Grams and target Grams");
+  LossLayer& ll = p->loss[k];
+  const float norm = static_cast<float>(ll.HW) + 1e-6f;
+  const float dscale = 4.0f / (static_cast<float>(ll.C) * static_cast<float>(ll.C) * norm);
+  STX_TRY(gram_finish_launch(ll.gram, 1e-6f, nullptr, ll.target, ll.target_stride, dscale, ll.dscaled, 0.0f, nullptr, 0,
+                             S(stream)));
+  STX_TRY(conv_launch(ll.layer_grad_op, S(stream)));
+  const size_t n = static_cast<size_t>(p->B) * ll.HW * ll.C;
+  STX_CUDA(cudaMemcpyAsync(out_bf16, p->gbuf[0], n * sizeof(bf16), cudaMemcpyDeviceToDevice, S(stream)));
+  return STX_OK;
+}
+
 int stx_vgg_weights(const stx_vgg* vgg, int conv_index, const void** fwd_hi, const void** fwd_lo,
                     const void** dgrad) {
   STX_REQUIRE(vgg, "stx_vgg_weights: null handle");

@@ -20,93 +20,116 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 // sigmoid pre-image (gatys/synthesizer.py:59). Each thread computes 32 output channels of TWO horizontally adjacent
 // pixels, so every shared-memory weight vector (broadcast LDS.128) feeds 8 FMAs and the 3x4 input patch is shared.
 // Zero padding applies to the *preprocessed* image, as in the TF graph.
+// Packed fp32 FMA (FFMA2 on sm_100): d.{x,y} += a.{x,y} * b.{x,y} in one issue slot.
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+// The kernel is issue-bound on the 1728 FMAs per pixel (27 taps x 64 channels): the packed FFMA2 form halves that, and
+// a grid-stride loop over pixel pairs lets a block load the 7 KB of weights once instead of once per 128 pixels
+// (4608 blocks at batch 9 spent ~40 % of their life in that prologue; 120 us per launch, profiles/r01_ncu_full_final_b9.md).
 __global__ void __launch_bounds__(128, 4)
 conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int is_preimage, float m0, float m1,
                    float m2, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
                    bf16* __restrict__ out_lo) {
-  __shared__ float sw[27 * 64];
-  __shared__ float sb[64];
+  __shared__ __align__(16) float sw[27 * 64];
+  __shared__ __align__(16) float sb[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];      // constants: safe before pdl_wait
   if (threadIdx.x < 64) sb[threadIdx.x] = b[threadIdx.x];
   __syncthreads();
   pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h)
   pdl_wait();
   const int Wp = (W + 1) >> 1;                                   // pixel pairs per row
-  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long npairs = static_cast<long long>(nimg) * H * Wp;
-  const long long pair = gid >> 1;
-  const int half = static_cast<int>(gid & 1);
-  if (pair >= npairs) return;
-  const int x = static_cast<int>(pair % Wp) * 2;
-  const int y = static_cast<int>((pair / Wp) % H);
-  const long long img_base = (pair / (static_cast<long long>(Wp) * H)) * H * W;
   const float mean[3] = {m0, m1, m2};
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; (gid >> 1) < npairs;
+       gid += stride) {
+    const long long pair = gid >> 1;
+    const int half = static_cast<int>(gid & 1);
+    const int x = static_cast<int>(pair % Wp) * 2;
+    const int y = static_cast<int>((pair / Wp) % H);
+    const long long img_base = (pair / (static_cast<long long>(Wp) * H)) * H * W;
 
-  float patch[3][4][3];                                          // rows y-1..y+1, columns x-1..x+2
+    float patch[3][4][3];                                          // rows y-1..y+1, columns x-1..x+2
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
+    for (int r = 0; r < 3; ++r) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int yy = y + r - 1, xx = x + s - 1;
-      const bool in = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
-      const float* src = image + (img_base + static_cast<long long>(yy) * W + xx) * 3;
+      for (int s = 0; s < 4; ++s) {
+        const int yy = y + r - 1, xx = x + s - 1;
+        const bool in = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+        const float* src = image + (img_base + static_cast<long long>(yy) * W + xx) * 3;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = 0.0f;
-        if (in) {
-          v = __ldg(src + c);
-          if (is_preimage) v = sigmoidf_(v);
-          v = v * 255.0f - mean[c];
-        }
-        patch[r][s][c] = v;
-      }
-    }
-  }
-  float acc0[32], acc1[32];
-#pragma unroll
-  for (int k = 0; k < 32; ++k) acc0[k] = acc1[k] = sb[half * 32 + k];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-#pragma unroll
-    for (int s = 0; s < 3; ++s) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float4* w4 = reinterpret_cast<const float4*>(sw + ((r * 3 + s) * 3 + c) * 64 + half * 32);
-        const float p0 = patch[r][s][c], p1 = patch[r][s + 1][c];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 ww = w4[k];
-          acc0[4 * k + 0] = fmaf(p0, ww.x, acc0[4 * k + 0]);
-          acc0[4 * k + 1] = fmaf(p0, ww.y, acc0[4 * k + 1]);
-          acc0[4 * k + 2] = fmaf(p0, ww.z, acc0[4 * k + 2]);
-          acc0[4 * k + 3] = fmaf(p0, ww.w, acc0[4 * k + 3]);
-          acc1[4 * k + 0] = fmaf(p1, ww.x, acc1[4 * k + 0]);
-          acc1[4 * k + 1] = fmaf(p1, ww.y, acc1[4 * k + 1]);
-          acc1[4 * k + 2] = fmaf(p1, ww.z, acc1[4 * k + 2]);
-          acc1[4 * k + 3] = fmaf(p1, ww.w, acc1[4 * k + 3]);
+        for (int c = 0; c < 3; ++c) {
+          float v = 0.0f;
+          if (in) {
+            v = __ldg(src + c);
+            if (is_preimage) v = sigmoidf_(v);
+            v = v * 255.0f - mean[c];
+          }
+          patch[r][s][c] = v;
         }
       }
     }
-  }
+    unsigned long long acc0[16], acc1[16];                         // channel pairs (2k, 2k+1) of the two pixels
+    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(sb + half * 32);
 #pragma unroll
-  for (int px = 0; px < 2; ++px) {
-    if (x + px >= W) break;
-    const float* acc = px ? acc1 : acc0;
-    const long long pix = img_base + static_cast<long long>(y) * W + x + px;
-    uint4* o4 = reinterpret_cast<uint4*>(out + pix * 64 + half * 32);
-    uint4* l4 = out_lo ? reinterpret_cast<uint4*>(out_lo + pix * 64 + half * 32) : nullptr;
+    for (int k = 0; k < 8; ++k) {
+      const ulonglong2 bb = b2[k];
+      acc0[2 * k] = acc1[2 * k] = bb.x;
+      acc0[2 * k + 1] = acc1[2 * k + 1] = bb.y;
+    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      Pack8 pk, pl;
+    for (int r = 0; r < 3; ++r) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float a = fmaxf(acc[8 * j + 2 * e], 0.0f), bb = fmaxf(acc[8 * j + 2 * e + 1], 0.0f);
-        pk.h2[e] = __floats2bfloat162_rn(a, bb);
-        const float2 h = __bfloat1622float2(pk.h2[e]);
-        pl.h2[e] = __floats2bfloat162_rn(a - h.x, bb - h.y);
+      for (int s = 0; s < 3; ++s) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(sw + ((r * 3 + s) * 3 + c) * 64 + half * 32);
+          const unsigned long long p0 = pack2(patch[r][s][c], patch[r][s][c]);
+          const unsigned long long p1 = pack2(patch[r][s + 1][c], patch[r][s + 1][c]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const ulonglong2 ww = w2[k];                           // one LDS.128 = two channel pairs
+            ffma2(acc0[2 * k], p0, ww.x);
+            ffma2(acc0[2 * k + 1], p0, ww.y);
+            ffma2(acc1[2 * k], p1, ww.x);
+            ffma2(acc1[2 * k + 1], p1, ww.y);
+          }
+        }
       }
-      o4[j] = pk.u;
-      if (l4) l4[j] = pl.u;
+    }
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      if (x + px >= W) break;
+      const unsigned long long* acc = px ? acc1 : acc0;
+      const long long pix = img_base + static_cast<long long>(y) * W + x + px;
+      uint4* o4 = reinterpret_cast<uint4*>(out + pix * 64 + half * 32);
+      uint4* l4 = out_lo ? reinterpret_cast<uint4*>(out_lo + pix * 64 + half * 32) : nullptr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        Pack8 pk, pl;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 v = unpack2(acc[4 * j + e]);
+          const float a = fmaxf(v.x, 0.0f), bb = fmaxf(v.y, 0.0f);
+          pk.h2[e] = __floats2bfloat162_rn(a, bb);
+          const float2 h = __bfloat1622float2(pk.h2[e]);
+          pl.h2[e] = __floats2bfloat162_rn(a - h.x, bb - h.y);
+        }
+        o4[j] = pk.u;
+        if (l4) l4[j] = pl.u;
+      }
     }
   }
 }
@@ -349,7 +372,9 @@ int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preima
                        const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream) {
   STX_REQUIRE(image && w && b && out && mean3, "conv1_1 fwd: null operand");
   const long long threads = 2LL * nimg * H * ((W + 1) / 2);
-  STX_TRY(launch_pdl(conv1_1_fwd_kernel, dim3(blocks_for(threads, 128)), dim3(128), 0, stream, image, nimg, H, W,
+  unsigned blocks = blocks_for(threads, 128);
+  if (blocks > 148u * 4u * 4u) blocks = 148u * 4u * 4u;      // four resident blocks per SM, ~four rounds each
+  STX_TRY(launch_pdl(conv1_1_fwd_kernel, dim3(blocks), dim3(128), 0, stream, image, nimg, H, W,
                      is_preimage, mean3[0], mean3[1], mean3[2], w, b, out, out_lo));
   count_launch();
   return STX_OK;

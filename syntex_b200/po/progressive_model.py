@@ -184,7 +184,10 @@ class ProgressiveSynTex(SynTexModelDesc, nn.Module):
         image_input = self._act(pre_image_input)
         # every stage keeps its own plan alive until backward; inference can reuse one
         slot = s if torch.is_grad_enabled() else 0
-        loss_layer_input, grad_layer = self._texture_fn(image_input, list(coefs.keys()), gram_target, slot, True)
+        # the hand-written generator consumes the gradients in the kernels' own bf16: skip the fp32 round trip
+        native = image_input.is_cuda and self._door_is_cuda and self.use_native_generator(self.syn[s])
+        loss_layer_input, grad_layer = self._texture_fn(image_input, list(coefs.keys()), gram_target, slot,
+                                                        "bf16" if native else True)
         loss_overall_input = sum(coefs[k] * 1. / 4 * loss_layer_input[k] for k in coefs)
         delta_input = self.run_generator(self.syn[s], grad_layer, image_input.is_cuda)
         pre_image_output = pre_image_input + delta_input

@@ -70,7 +70,12 @@ def _make_function():
                 d = g - targets[k]
                 diffs.append(d)
                 losses.append(torch.mean(d * d, dim=(1, 2)))
-                if calc_grad:
+                if calc_grad == "bf16":
+                    # the kernels' own precision, for the hand-written generator: no fp32 round trip either way
+                    out = torch.empty((B, h, w, c), dtype=torch.bfloat16, device="cuda")
+                    _lib.check(L.stx_plan_layer_grad_bf16(plan.handle, k, out.data_ptr(), st))
+                    grads.append(out)
+                elif calc_grad:
                     out = torch.empty((B, h, w, c), dtype=torch.float32, device="cuda")
                     _lib.check(L.stx_plan_layer_grad(plan.handle, k, out.data_ptr(), st))
                     grads.append(out)
@@ -104,9 +109,12 @@ def _make_function():
                 U = d_grads[k] if (ctx.calc_grad and k < len(d_grads)) else None
                 E_ptr = None
                 if U is not None:
-                    U = U.to(device="cuda", dtype=torch.float32).contiguous()
-                    u16 = torch.empty((B, h, w, c), dtype=torch.bfloat16, device="cuda")
-                    _lib.check(L.stx_f32_to_bf16(U.data_ptr(), U.numel(), u16.data_ptr(), st))
+                    if U.dtype == torch.bfloat16 and U.is_cuda:
+                        u16 = U.contiguous()
+                    else:
+                        U = U.to(device="cuda", dtype=torch.float32).contiguous()
+                        u16 = torch.empty((B, h, w, c), dtype=torch.bfloat16, device="cuda")
+                        _lib.check(L.stx_f32_to_bf16(U.data_ptr(), U.numel(), u16.data_ptr(), st))
                     f_hi, _ = _feature_ptrs(plan, idx)
                     # X = F^T U / n  (tensor cores, split-K over the pixels)
                     ws = torch.empty(max(L.stx_gram_cross_workspace_bytes(B, h * w, c) // 4, 1), dtype=torch.float32,
@@ -340,6 +348,7 @@ def vgg_texture(image, vgg19, layers, gram_target, slot=0, calc_grad=True):
     vgg19        Vgg19Extractor
     layers       Gram layer names, shallow to deep; VGG is evaluated up to layers[-1]
     gram_target  {layer: [B or 1, C, C]}
+    calc_grad    False / True (fp32 gradients, as the reference) / "bf16" (the kernels' own precision)
     slot         plan slot: every VGG evaluation that must stay alive until backward needs its own
     Returns (loss_layer OrderedDict {k: [B]}, grad_layer OrderedDict {k: [B,h,w,C]} or None); both differentiable
     with respect to `image` (utils.py:44-55 semantics: grad_layer[k] = d loss_layer[k] / d feat[k], unweighted)."""
@@ -347,7 +356,8 @@ def vgg_texture(image, vgg19, layers, gram_target, slot=0, calc_grad=True):
     if _FUNCTION is None:
         _FUNCTION = _make_function()
     layers = list(layers)
-    outs = _FUNCTION.apply(image, vgg19, layers, slot, bool(calc_grad), *[gram_target[k] for k in layers])
+    outs = _FUNCTION.apply(image, vgg19, layers, slot, calc_grad if calc_grad == "bf16" else bool(calc_grad),
+                           *[gram_target[k] for k in layers])
     loss_layer = OrderedDict((k, outs[0][i]) for i, k in enumerate(layers))
     grad_layer = OrderedDict((k, outs[1 + i]) for i, k in enumerate(layers)) if calc_grad else None
     return loss_layer, grad_layer
