@@ -296,11 +296,13 @@ def run_ours(args, rank, world, local_rank):
                     "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops"],
                     # dram__bytes_read + dram__bytes_write averaged over the 22 conv launches of one evaluation in the
-                    # ncu --set full capture at batch 9 (profiles/r01_ncu_full_final_b9.md); only meaningful at that batch
-                    "traffic": 61.8e6 if (batch == 9 and size == 256) else None,
-                    "traffic_note": "average DRAM bytes per conv launch, ncu --set full, batch 9 (profiles/r01_ncu_full_final_b9.md): "
-                                    "the deep layers move 24-40 MB per launch (weights + one pass over their activations), "
-                                    "the 64-channel layers 130-220 MB (hi/lo activation planes in and out)",
+                    # ncu --set full captures at batch 18 (profiles/r01_ncu_full_b18.md) and batch 9
+                    # (profiles/r01_ncu_full_final_b9.md); only meaningful at those batches
+                    "traffic": {18: 139.8e6, 9: 61.8e6}.get(batch) if size == 256 else None,
+                    "traffic_note": "average DRAM bytes per conv launch, ncu --set full (profiles/r01_ncu_full_b18.md, "
+                                    "r01_ncu_full_final_b9.md): at batch 18 the deep layers move 47-80 MB per launch "
+                                    "(weights + one pass over their activations), the 64-channel layers 300-490 MB "
+                                    "(hi/lo activation planes in and out)",
                     "executed_tflops": exec_total, "executed_frac": exec_total / peaks["bf16_tflops"],
                     "note": "achieved counts algorithmic FLOPs (2*M*N*K once per direction); the bf16x3 forward executes 3 MMAs per MAC, executed_* counts those",
                     "avg_launch_us": 1e3 * conv_ms / max(conv_launches, 1),
@@ -386,9 +388,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=9,
-                    help="independent synthesis jobs per GPU (9: the deep layers then have 288 and 576 work items for "
-                         "the 148 persistent CTAs, 97 % full waves; 8 leaves the last wave 46 % empty)")
+    ap.add_argument("--batch", type=int, default=18,
+                    help="independent synthesis jobs per GPU (a multiple of 9: the deep layers then have 32 and 64 work "
+                         "items per job for the 148 / 296 persistent CTAs, 97 %% full waves; 18 measured 4 %% above 9 - "
+                         "4584 vs 4401 job-iterations/s, conv roofline 0.45 vs 0.40 - and 27 another 0.5 %%)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--maxcor", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
