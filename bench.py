@@ -3,10 +3,13 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--size S]
 
-A *step* is one L-BFGS iteration of every job in flight (`nit` of scipy / of the device optimiser; each costs
-~1.08 f/g evaluations = VGG19 forward + Gram loss + input-gradient backward). The workload per GPU is `batch`
-independent synthesis jobs (own exemplar, own seed, own history) run side by side; N GPUs run N x batch jobs with
-no communication - weak scaling; at N = 8, batch = 8 this is BASELINE.json's config 4
+A *step* is one cycle of the device-resident optimiser over the batch: ONE f/g evaluation of every job in flight
+(VGG19 forward + Gram loss + input-gradient backward) followed by the L-BFGS update of every job. `value` is the
+number of L-BFGS iterations (`nit` of scipy / of the device optimiser) the jobs complete per second over exactly K
+such steps; a job in a line search spends a step without completing an iteration (`fg_evals_per_iteration`, ~1.06).
+No job reaches its iteration limit inside the timed region, so every job is busy in every step. The workload per GPU
+is `batch` independent synthesis jobs (own exemplar, own seed, own history) run side by side; N GPUs run N x batch
+jobs with no communication - weak scaling; at N = 8, batch = 8 this is BASELINE.json's config 4
 (64 independent 256^2 jobs). Weights are seeded synthetic VGG19 weights, exemplars seeded synthetic textures.
 
 One JSON line is printed by rank 0. `value` is device-timed with the state resident in HBM; `e2e` is the same
@@ -236,8 +239,23 @@ def run_ours(args, rank, world, local_rank):
     xd = torch.from_numpy(x0).cuda()
     syn.compute_gram(targets, update=True)
     opt = syn._get_lbfgs(True, 0.0, 1.0)
+    fun = torch.empty(batch, dtype=torch.float32, device="cuda")
+    nit = torch.empty(batch, dtype=torch.int32, device="cuda")
+    nfev = torch.empty(batch, dtype=torch.int32, device="cuda")
+
+    def counters():
+        _lib.check(L.stx_lbfgs_result(opt, None, fun.data_ptr(), nit.data_ptr(), nfev.data_ptr(), stream))
+        torch.cuda.synchronize()
+        return nit.cpu().numpy().astype(np.int64), nfev.cpu().numpy().astype(np.int64)
+
+    # A step is one cycle of the device optimiser: ONE f/g evaluation of every job in flight (VGG19 forward, Gram
+    # loss, input-gradient backward) followed by the L-BFGS update of every job. No job ever reaches its iteration
+    # limit inside the timed region, so all jobs are busy in every cycle; the throughput is the number of L-BFGS
+    # iterations the jobs completed over those K cycles (a job in a line search spends a cycle without completing one).
+    never = 1 << 30
     _lib.check(L.stx_lbfgs_reset(opt, xd.data_ptr(), 0, stream))
-    _lib.check(L.stx_lbfgs_run(opt, args.warmup, 0, stream))          # W untimed warm-up iterations
+    _lib.check(L.stx_lbfgs_run(opt, never, max(args.warmup, 1), stream))      # W untimed warm-up cycles
+    nit0, nfev0 = counters()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -247,26 +265,26 @@ def run_ours(args, rank, world, local_rank):
     launches0 = L.stx_launch_count()
     t_mark0 = time.time()
     ev0.record()
-    _lib.check(L.stx_lbfgs_run(opt, args.warmup + args.steps, 0, stream))   # exactly K more iterations per job
+    _lib.check(L.stx_lbfgs_run(opt, never, args.steps, stream))              # exactly K cycles
     ev1.record()
     barrier()
     t_mark1 = time.time()
     launches = L.stx_launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop(t_mark0, t_mark1) if rank == 0 else None
-    fun = torch.empty(batch, dtype=torch.float32, device="cuda")
-    nit = torch.empty(batch, dtype=torch.int32, device="cuda")
-    nfev = torch.empty(batch, dtype=torch.int32, device="cuda")
-    _lib.check(L.stx_lbfgs_result(opt, None, fun.data_ptr(), nit.data_ptr(), nfev.data_ptr(), stream))
-    torch.cuda.synchronize()
-    nit_h, nfev_h, fun_h = nit.cpu().numpy(), nfev.cpu().numpy(), fun.cpu().numpy()
-    if int(nit_h.min()) < args.warmup + args.steps:
-        raise RuntimeError("optimiser stopped early: nit %s" % nit_h)
+    nit1, nfev1 = counters()
+    fun_h = fun.cpu().numpy()
+    if int((nfev1 - nfev0).min()) != args.steps or int((nfev1 - nfev0).max()) != args.steps:
+        raise RuntimeError("expected exactly %d evaluations per job in the timed region, got %s" % (args.steps, nfev1 - nfev0))
+    iters_done = int((nit1 - nit0).sum())                  # L-BFGS iterations completed by this rank's jobs
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    it_all = torch.tensor([iters_done], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(it_all, op=dist.ReduceOp.SUM)
     ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    iters_all = float(it_all[0])                           # over all ranks
 
     # ---- roofline of the dominant kernel family (tcgen05 conv), measured live with CUDA events ------------
     roofline, kernel_ms = None, None
@@ -312,9 +330,9 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return None
     jobs = batch * world
-    value = jobs * args.steps / (ms_max * 1e-3)
+    value = iters_all / (ms_max * 1e-3)                    # job-iterations completed per second, whole job
     e2e_value = jobs * nit_e2e / (e2e_ms_max * 1e-3)
-    evals_per_it = float(nfev_h.max() - 1) / max(int(nit_h.min()), 1)
+    evals_per_it = float(batch * args.steps) / max(iters_done, 1)      # this rank: f/g evaluations per completed iteration
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
