@@ -207,8 +207,9 @@ class InstanceNormFunction(torch.autograd.Function):
         _lib.check(L.stx_inorm_bwd_bf16(x.data_ptr(), dy.data_ptr(), B, H * W, C, mean.data_ptr(), rstd.data_ptr(),
                                         g.data_ptr(), b.data_ptr(), 1 if ctx.relu else 0, ctypes.c_float(ctx.slope),
                                         s1.data_ptr(), s2.data_ptr(), dx.data_ptr(), ws.data_ptr(), st))
-        dgamma = s2.sum(0) if ctx.needs_input_grad[1] else None
-        dbeta = s1.sum(0) if ctx.needs_input_grad[2] else None
+        # per-image sums -> parameter gradients (at the reference's per-GPU batch of 1 there is nothing to add up)
+        dgamma = (s2[0] if B == 1 else s2.sum(0)) if ctx.needs_input_grad[1] else None
+        dbeta = (s1[0] if B == 1 else s1.sum(0)) if ctx.needs_input_grad[2] else None
         return dx, dgamma, dbeta, None, None, (dy if ctx.has_shortcut else None)
 
 
