@@ -349,6 +349,20 @@ def run_ours(args, rank, world, local_rank):
 
 
 def po_sample():
+    """po_sample_inprocess() in a child process: a failure there (even a crash of the CUDA context) cannot take the
+    Gatys line with it."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--po-child"], capture_output=True, text=True,
+                           timeout=420)
+        lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": "PO child exited %d: %s" % (r.returncode, (r.stderr or "").strip()[-300:])}
+        return json.loads(lines[-1])
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def po_sample_inprocess():
     """The PO half of BASELINE.json's metric ("PO imgs/sec"), measured beside the Gatys line on one GPU: config 5
     (ProgressiveSynTex training at 512x512, per-GPU batch 1, whole step replayed as a CUDA graph) and config 3
     (SingleSynTex feed-forward synthesis, batch 64 of 256x256). Synthetic textures, seeded random generator weights,
@@ -414,7 +428,11 @@ def main():
     ap.add_argument("--maxcor", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-po", action="store_true", help="skip the PO images/s report beside the Gatys line (N = 1)")
+    ap.add_argument("--po-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.po_child:
+        print(json.dumps(po_sample_inprocess()), flush=True)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
