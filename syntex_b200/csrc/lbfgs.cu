@@ -300,39 +300,11 @@ __device__ void solve_direction(Ctrl& c, const double* p1, const double* yp) {
   }
 }
 
-__global__ void __launch_bounds__(512) lbfgs_decide_kernel(Vecs v) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int b = blockIdx.x;
-  Ctrl& c = v.ctrl[b];
-  if (c.mode == kDone) {
-    if (threadIdx.x == 0) c.action = kNone;
-    return;
-  }
-  __shared__ double sums[kNP + 1];
-  const int nh = c.nh;
-  const int np = 6 + 4 * nh;
-  // Sum the block partials in a fixed order: one warp per quantity, lane l takes blocks l, l+32, ... (a serial chain
-  // of nblk dependent L2 round trips per quantity used to make this kernel the longest of the optimiser, ~57 us),
-  // then a butterfly over the lanes. Deterministic: the summation tree depends only on nblk.
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int k = warp; k <= np; k += nwarps) {
-      double t = 0.0;
-      if (k < np) {
-        const float* src = v.part + static_cast<size_t>(b) * v.nblk * kNP + k;
-        for (int j = lane; j < v.nblk; j += 32) t += static_cast<double>(src[static_cast<size_t>(j) * kNP]);
-      } else {
-        const float* src = v.part2 + static_cast<size_t>(b) * v.nblk;
-        for (int j = lane; j < v.nblk; j += 32) t += static_cast<double>(src[j]);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) sums[k < np ? k : kNP] = t;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+// The serial part of a cycle's decision (line search, history bookkeeping, the m x m solves), run by ONE thread on a
+// SHARED-MEMORY copy of the job's control block: on the global copy every one of the ~1500 dependent accesses to
+// S'Y / Y'Y (shifting the 20 x 20 tables when the oldest pair is dropped, three triangular passes) was an L2 round
+// trip, and this kernel - 57-70 us with a full history - was as long as the two streaming kernels around it.
+__device__ void decide_body(Ctrl& c, const double* sums, const Vecs& v, int b) {
 
   const double ft = static_cast<double>(v.ft[b]);
   const double dphi = sums[0], ys = sums[1], yy = sums[2], ppn = sums[3], spg = sums[4], ypg = sums[5];
@@ -450,6 +422,54 @@ __global__ void __launch_bounds__(512) lbfgs_decide_kernel(Vecs v) {
   } else {
     c.stp = static_cast<float>(c.ls.stp);
     c.action = kRetry;
+  }
+}
+
+__global__ void __launch_bounds__(512) lbfgs_decide_kernel(Vecs v) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  Ctrl& cg = v.ctrl[b];
+  if (cg.mode == kDone) {
+    if (threadIdx.x == 0) cg.action = kNone;
+    return;
+  }
+  __shared__ double sums[kNP + 1];
+  __shared__ Ctrl sc;
+  static_assert(sizeof(Ctrl) % 4 == 0, "Ctrl is copied word by word");
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&cg);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sc);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(Ctrl) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  const int nh = cg.nh;
+  const int np = 6 + 4 * nh;
+  // Sum the block partials in a fixed order: one warp per quantity, lane l takes blocks l, l+32, ... (a serial chain
+  // of nblk dependent L2 round trips per quantity used to make this kernel the longest of the optimiser, ~57 us),
+  // then a butterfly over the lanes. Deterministic: the summation tree depends only on nblk.
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int k = warp; k <= np; k += nwarps) {
+      double t = 0.0;
+      if (k < np) {
+        const float* src = v.part + static_cast<size_t>(b) * v.nblk * kNP + k;
+        for (int j = lane; j < v.nblk; j += 32) t += static_cast<double>(src[static_cast<size_t>(j) * kNP]);
+      } else {
+        const float* src = v.part2 + static_cast<size_t>(b) * v.nblk;
+        for (int j = lane; j < v.nblk; j += 32) t += static_cast<double>(src[j]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) sums[k < np ? k : kNP] = t;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) decide_body(sc, sums, v, b);
+  __syncthreads();
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&sc);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&cg);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(Ctrl) / 4); i += blockDim.x) dst[i] = src[i];
   }
 }
 
