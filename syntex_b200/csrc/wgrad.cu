@@ -26,6 +26,7 @@ constexpr int kWgChunkBytes = 64 * 128;             // 64 pixels x 64 channels b
 constexpr int kWgStageBytes = 64 * 1024;            // 6 A chunks + up to 2 B chunks
 constexpr int kWgThreads = 192;                     // warp 0: TMA, warp 1: MMA, warps 2..5: epilogue
 constexpr int kWgSmemTotal = kWgStages * kWgStageBytes + 128 + 1024;
+constexpr int kWgMaxGroups = 16;                    // 9 * (Cin / 64) / 6 groups: Cin <= 640
 
 struct WgradKernelParams {
   int cchunks;          // Cin / 64
@@ -35,8 +36,13 @@ struct WgradKernelParams {
   int bw_log2, bh_log2; // pixel box of one K stage (bw * bh = 64)
   int tiles_w, tiles_h;
   int total_iters;      // nimg * tiles_h * tiles_w
-  int iters_per_split;
-  float* partial;       // [splits][nq * 64][cout]
+  int groups;           // CTA groups along M (six A chunks each)
+  // Pixel slabs per group: a group with fewer valid chunks (the tail of the chunk list: 3 of 6 for a 64-channel
+  // layer) stages fewer bytes per iteration, so it gets proportionally fewer, longer slabs and every CTA of the launch
+  // finishes at the same time. split_begin[g] = first blockIdx.x of group g (prefix sums, groups + 1 entries).
+  int split_begin[kWgMaxGroups + 1];
+  int iters_per_split[kWgMaxGroups];
+  float* partial;       // [max splits][nq * 64][cout]
 };
 
 template <int BN>
@@ -55,15 +61,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kWgAChunks;
+  int grp = 0;
+  while (grp + 1 < p.groups && static_cast<int>(blockIdx.x) >= p.split_begin[grp + 1]) ++grp;
+  const int q0 = grp * kWgAChunks;
   const int n0 = blockIdx.y * BN;
-  const int split = blockIdx.z;
+  const int split = blockIdx.x - p.split_begin[grp];
   int valid = p.nq - q0;
   if (valid > kWgAChunks) valid = kWgAChunks;
   const int n_acc = (valid + 1) >> 1;
 
-  const int it_begin = split * p.iters_per_split;
-  const int it_end = min(it_begin + p.iters_per_split, p.total_iters);
+  const int it_begin = split * p.iters_per_split[grp];
+  const int it_end = min(it_begin + p.iters_per_split[grp], p.total_iters);
   const int iters = max(it_end - it_begin, 0);
 
   if (warp == 0 && lane == 0) {
@@ -175,11 +183,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-// out[e] = scale * sum_s partial[s][e], slabs in a fixed order.
+struct WgradSplits {
+  int n[kWgMaxGroups];   // slabs written by group g
+};
+
+// out[e] = sum_s partial[s][e], the slabs of the element's group in a fixed order.
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float4* __restrict__ partial, size_t count4, int splits, float4* __restrict__ out) {
+wgrad_reduce_kernel(const float4* __restrict__ partial, size_t count4, int cout4, const WgradSplits sp,
+                    float4* __restrict__ out) {
   for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < count4;
        e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int chunk = static_cast<int>(e / (static_cast<size_t>(64) * cout4));
+    const int splits = sp.n[chunk / kWgAChunks];
     float4 a = partial[e];
     for (int s = 1; s < splits; ++s) {
       const float4 b = partial[static_cast<size_t>(s) * count4 + e];
@@ -193,7 +208,8 @@ wgrad_reduce_kernel(const float4* __restrict__ partial, size_t count4, int split
 }
 
 struct WgradGeom {
-  int bw, bh, tiles_w, tiles_h, total_iters, groups, nblocks, bn, splits, iters_per_split;
+  int bw, bh, tiles_w, tiles_h, total_iters, groups, nblocks, bn;
+  int splits[kWgMaxGroups], iters_per_split[kWgMaxGroups], max_splits, total_splits;
 };
 
 int wgrad_geometry(int nimg, int H, int W, int cin, int cout, WgradGeom* g) {
@@ -208,14 +224,30 @@ int wgrad_geometry(int nimg, int H, int W, int cin, int cout, WgradGeom* g) {
   g->total_iters = nimg * g->tiles_w * g->tiles_h;
   const int nq = 9 * (cin / 64);
   g->groups = (nq + kWgAChunks - 1) / kWgAChunks;
+  STX_REQUIRE(g->groups <= kWgMaxGroups, "wgrad: too many input channels");
   g->bn = (cout % 128 == 0) ? 128 : 64;
   g->nblocks = cout / g->bn;
-  const int ctas = g->groups * g->nblocks;
-  int want = (148 + ctas - 1) / ctas;
-  if (want > g->total_iters) want = g->total_iters;
-  if (want < 1) want = 1;
-  g->iters_per_split = (g->total_iters + want - 1) / want;
-  g->splits = (g->total_iters + g->iters_per_split - 1) / g->iters_per_split;
+  // About one CTA per SM over the launch, shared among the groups in proportion to the bytes a group stages per
+  // iteration (its valid A chunks + the dY chunks): the kernel is bound by L2 -> SMEM delivery.
+  int weight[kWgMaxGroups], wsum = 0;
+  for (int i = 0; i < g->groups; ++i) {
+    int valid = nq - i * kWgAChunks;
+    if (valid > kWgAChunks) valid = kWgAChunks;
+    weight[i] = valid + g->bn / 64;
+    wsum += weight[i];
+  }
+  const int budget = (148 + g->nblocks - 1) / g->nblocks;      // CTAs along x
+  g->max_splits = 0;
+  g->total_splits = 0;
+  for (int i = 0; i < g->groups; ++i) {
+    int want = (budget * weight[i] + wsum / 2) / wsum;
+    if (want > g->total_iters) want = g->total_iters;
+    if (want < 1) want = 1;
+    g->iters_per_split[i] = (g->total_iters + want - 1) / want;
+    g->splits[i] = (g->total_iters + g->iters_per_split[i] - 1) / g->iters_per_split[i];
+    g->total_splits += g->splits[i];
+    if (g->splits[i] > g->max_splits) g->max_splits = g->splits[i];
+  }
   return STX_OK;
 }
 
@@ -224,7 +256,7 @@ int wgrad_geometry(int nimg, int H, int W, int cin, int cout, WgradGeom* g) {
 size_t wgrad_workspace_bytes(int nimg, int H, int W, int cin, int cout) {
   WgradGeom g;
   if (wgrad_geometry(nimg, H, W, cin, cout, &g) != STX_OK) return 0;
-  return static_cast<size_t>(g.splits) * 9 * cin * cout * sizeof(float);
+  return static_cast<size_t>(g.max_splits) * 9 * cin * cout * sizeof(float);
 }
 
 int wgrad_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin, int cout, int pad, float* dw_hwio,
@@ -258,9 +290,17 @@ int wgrad_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin,
   p.tiles_w = g.tiles_w;
   p.tiles_h = g.tiles_h;
   p.total_iters = g.total_iters;
-  p.iters_per_split = g.iters_per_split;
+  p.groups = g.groups;
+  WgradSplits sp;
+  p.split_begin[0] = 0;
+  for (int i = 0; i < kWgMaxGroups; ++i) {
+    const bool live = i < g.groups;
+    sp.n[i] = live ? g.splits[i] : 0;
+    p.iters_per_split[i] = live ? g.iters_per_split[i] : 1;
+    p.split_begin[i + 1] = p.split_begin[i] + sp.n[i];
+  }
   p.partial = workspace;
-  dim3 grid(g.groups, g.nblocks, g.splits);
+  dim3 grid(g.total_splits, g.nblocks, 1);
   if (g.bn == 64)
     wgrad_kernel<64><<<grid, kWgThreads, kWgSmemTotal, stream>>>(tmX, tmY, p);
   else
@@ -270,7 +310,7 @@ int wgrad_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin,
   const size_t count4 = static_cast<size_t>(9) * cin * cout / 4;
   int blocks = static_cast<int>((count4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(workspace), count4, g.splits,
+  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(workspace), count4, cout / 4, sp,
                                                   reinterpret_cast<float4*>(dw_hwio));
   STX_CUDA(cudaGetLastError());
   count_launch();
