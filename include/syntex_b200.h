@@ -214,6 +214,14 @@ int stx_conv_bf16_pad(const void* x, int n, int H, int W, int cin, const void* w
 size_t stx_conv_wgrad_workspace_bytes(int n, int H, int W, int cin, int cout);
 int stx_conv_wgrad_bf16(const void* x, const void* dy, int n, int H, int W, int cin, int cout, int pad,
                         float* dw_hwio, void* workspace, void* stream);
+/* The same with the result in torch's OIHW layout [cout_real][cin][3][3] (cout_real <= cout: the zero-padded filters
+ * of a narrow layer are dropped), so that it adds straight into an nn.Parameter's .grad. */
+int stx_conv_wgrad_oihw_bf16(const void* x, const void* dy, int n, int H, int W, int cin, int cout, int pad,
+                             int cout_real, float* dw_oihw, void* workspace, void* stream);
+/* OIHW fp32 [cout][cin][3][3] (device) -> the forward pack [9][cout_padded][cin] and dgrad pack [9][cin][cout_padded]
+ * of stx_pack_conv_weights, output channels >= cout zero. Any output may be NULL. */
+int stx_pack_conv_weights_oihw(const float* w_oihw, int cin, int cout, int cout_padded, void* w_fwd_bf16,
+                               void* w_dgrad_bf16, void* stream);
 /* tf.pad(mode="SYMMETRIC") by one pixel (= edge replication), optionally of relu(x): out [n,H+2,W+2,C]. */
 int stx_pad_replicate_bf16(const void* x, int n, int H, int W, int C, int relu, void* out, void* stream);
 /* Its gradient: gp [n,H+2,W+2,C] -> dx [n,H,W,C] (ring folded onto the edge pixels); x_or_null non-NULL = the pad

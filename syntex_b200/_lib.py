@@ -67,6 +67,8 @@ def _declare(lib):
         "stx_conv_bf16_pad": (c_int, [vp, c_int, c_int, c_int, c_int, vp, c_int, c_int, fp, vp, c_int, vp, c_int, vp]),
         "stx_conv_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
         "stx_conv_wgrad_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, fp, vp, vp]),
+        "stx_conv_wgrad_oihw_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, fp, vp, vp]),
+        "stx_pack_conv_weights_oihw": (c_int, [fp, c_int, c_int, c_int, vp, vp, vp]),
         "stx_pad_replicate_bf16": (c_int, [vp, c_int, c_int, c_int, c_int, c_int, vp, vp]),
         "stx_pad_replicate_bwd_bf16": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, vp]),
         "stx_inorm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

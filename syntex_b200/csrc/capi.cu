@@ -357,6 +357,16 @@ int stx_conv_wgrad_bf16(const void* x, const void* dy, int n, int H, int W, int 
   return wgrad_launch(static_cast<const bf16*>(x), static_cast<const bf16*>(dy), n, H, W, cin, cout, pad, dw_hwio,
                       static_cast<float*>(workspace), S(stream));
 }
+int stx_conv_wgrad_oihw_bf16(const void* x, const void* dy, int n, int H, int W, int cin, int cout, int pad,
+                             int cout_real, float* dw_oihw, void* workspace, void* stream) {
+  return wgrad_oihw_launch(static_cast<const bf16*>(x), static_cast<const bf16*>(dy), n, H, W, cin, cout, pad, cout_real,
+                           dw_oihw, static_cast<float*>(workspace), S(stream));
+}
+int stx_pack_conv_weights_oihw(const float* w_oihw, int cin, int cout, int cout_padded, void* w_fwd_bf16,
+                               void* w_dgrad_bf16, void* stream) {
+  return pack_weights_oihw_launch(w_oihw, cin, cout, cout_padded, static_cast<bf16*>(w_fwd_bf16),
+                                  static_cast<bf16*>(w_dgrad_bf16), S(stream));
+}
 int stx_pad_replicate_bf16(const void* x, int n, int H, int W, int C, int relu, void* out, void* stream) {
   return pad_rep_launch(static_cast<const bf16*>(x), n, H, W, C, 0, relu, 0.0f, static_cast<bf16*>(out), S(stream));
 }

@@ -312,6 +312,24 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cin, int co
   if (wd) wd[(static_cast<long long>(8 - tap) * cin + ci) * cout + co] = v;
 }
 
+// The same from torch's OIHW layout [cout][cin][3][3] (the generator's nn.Parameters), with the filter bank zero-padded
+// to cout_p outputs (the 64 -> 3 colour layer runs as one 64-channel tile). One thread per element of the forward
+// pack (coalesced bf16 writes; the fp32 reads are 36-byte-strided but L2-resident: at most 9.4 MB).
+__global__ void pack_weights_oihw_kernel(const float* __restrict__ w, int cin, int cout, int cout_p,
+                                         bf16* __restrict__ wf, bf16* __restrict__ wd) {
+  const long long total = 9LL * cin * cout_p;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // forward pack index: i = ((tap * cout_p) + co) * cin + ci
+  const int ci = static_cast<int>(i % cin);
+  const int co = static_cast<int>((i / cin) % cout_p);
+  const int tap = static_cast<int>(i / (static_cast<long long>(cin) * cout_p));
+  const float x = co < cout ? w[(static_cast<long long>(co) * cin + ci) * 9 + tap] : 0.0f;
+  const bf16 v = __float2bfloat16_rn(x);
+  if (wf) wf[i] = v;
+  if (wd) wd[(static_cast<long long>(8 - tap) * cin + ci) * cout_p + co] = v;
+}
+
 // Tiled, pre-swizzled packs for the halo-patch kernel: [tap][K/64][N/64] blocks of 64 rows x 128 bytes laid out
 // exactly as a 128B-swizzled shared-memory tile (16-byte chunk j of row r stored at chunk j ^ (r & 7)), so that a
 // [BN x 64] weight tile is ONE contiguous BN*128-byte run and lands with a single 1-D bulk copy instead of BN
@@ -441,6 +459,17 @@ int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf1
   STX_REQUIRE(w_hwio, "pack_weights: null weights");
   const long long total = 9LL * cin * cout;
   pack_weights_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_hwio, cin, cout, w_fwd, w_fwd_lo, w_dgrad);
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+int pack_weights_oihw_launch(const float* w_oihw, int cin, int cout, int cout_p, bf16* w_fwd, bf16* w_dgrad,
+                             cudaStream_t stream) {
+  STX_REQUIRE(w_oihw, "pack_weights_oihw: null weights");
+  STX_REQUIRE(cin > 0 && cout > 0 && cout_p >= cout, "pack_weights_oihw: bad channel counts");
+  const long long total = 9LL * cin * cout_p;
+  pack_weights_oihw_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_oihw, cin, cout, cout_p, w_fwd, w_dgrad);
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;

@@ -134,6 +134,9 @@ int bf16pair_to_f32_launch(const bf16* hi, const bf16* lo, size_t n, float* out,
 // w_fwd_lo (nullable): low halves bf16(w - bf16(w)) in the forward layout.
 int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf16* w_fwd_lo, bf16* w_dgrad,
                         cudaStream_t stream);
+// OIHW fp32 [cout][cin][3][3] (torch layout) -> the same two packs with cout zero-padded to cout_p.
+int pack_weights_oihw_launch(const float* w_oihw, int cin, int cout, int cout_p, bf16* w_fwd, bf16* w_dgrad,
+                             cudaStream_t stream);
 // Sum loss partials: out[img] = sum_k part[img*stride + k], fixed order (deterministic).
 // conv1_1 weights fp32 [27][64] -> dgrad pack for the tensor-core path: [9][16][64] bf16, rows 0..2 = colours
 // (taps rotated 180 degrees), rows 3..15 zero.
@@ -150,6 +153,10 @@ int sum_partials_launch(const float* part, int nimg, int count, int stride, floa
 size_t wgrad_workspace_bytes(int nimg, int H, int W, int cin, int cout);
 int wgrad_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin, int cout, int pad, float* dw_hwio,
                  float* workspace, cudaStream_t stream);
+// Same contraction, result written in torch's OIHW layout [cout_real][cin][3][3] (output channels >= cout_real, the
+// zero-padded filters of a narrow layer, are dropped).
+int wgrad_oihw_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin, int cout, int pad, int cout_real,
+                      float* dw_oihw, float* workspace, cudaStream_t stream);
 
 // ------------------------------------------------------------------ gen_ops.cu
 // mode: 0 = SYMMETRIC (edge replication), 1 = REFLECT; act: 0 none, 1 = leaky ReLU with `slope` (0 = ReLU)

@@ -207,6 +207,34 @@ wgrad_reduce_kernel(const float4* __restrict__ partial, size_t count4, int cout4
   }
 }
 
+// The same reduction written out in torch's OIHW layout: e runs over the HWIO partial layout (coalesced float4 reads
+// along co), each of the four sums goes to out[(co * cin + ci) * 9 + tap] for co < cout_real.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_oihw_kernel(const float4* __restrict__ partial, size_t count4, int cout4, int cin, int cout_real,
+                         const WgradSplits sp, float* __restrict__ out) {
+  for (size_t e = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; e < count4;
+       e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t row = e / cout4;                        // tap * cin + ci
+    const int co0 = static_cast<int>(e - row * cout4) * 4;
+    if (co0 >= cout_real) continue;
+    const int chunk = static_cast<int>(row >> 6);
+    const int splits = sp.n[chunk / kWgAChunks];
+    float4 a = partial[e];
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = partial[static_cast<size_t>(s) * count4 + e];
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+    }
+    const int tap = static_cast<int>(row / cin), ci = static_cast<int>(row - static_cast<size_t>(tap) * cin);
+    const float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (co0 + j < cout_real) out[(static_cast<size_t>(co0 + j) * cin + ci) * 9 + tap] = v[j];
+  }
+}
+
 struct WgradGeom {
   int bw, bh, tiles_w, tiles_h, total_iters, groups, nblocks, bn;
   int splits[kWgMaxGroups], iters_per_split[kWgMaxGroups], max_splits, total_splits;
@@ -259,8 +287,22 @@ size_t wgrad_workspace_bytes(int nimg, int H, int W, int cin, int cout) {
   return static_cast<size_t>(g.max_splits) * 9 * cin * cout * sizeof(float);
 }
 
+static int wgrad_run(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin, int cout, int pad, float* dw,
+                     int cout_real_or_0, float* workspace, cudaStream_t stream);
+
 int wgrad_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin, int cout, int pad, float* dw_hwio,
                  float* workspace, cudaStream_t stream) {
+  return wgrad_run(x, dy, nimg, H, W, cin, cout, pad, dw_hwio, 0, workspace, stream);
+}
+
+int wgrad_oihw_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin, int cout, int pad, int cout_real,
+                      float* dw_oihw, float* workspace, cudaStream_t stream) {
+  STX_REQUIRE(cout_real > 0 && cout_real <= cout, "wgrad: cout_real out of range");
+  return wgrad_run(x, dy, nimg, H, W, cin, cout, pad, dw_oihw, cout_real, workspace, stream);
+}
+
+static int wgrad_run(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin, int cout, int pad, float* dw_hwio,
+                     int cout_real_or_0, float* workspace, cudaStream_t stream) {
   STX_REQUIRE(x && dy && dw_hwio && workspace, "wgrad: null operand");
   STX_REQUIRE(pad == 0 || pad == 1, "wgrad: pad must be 0 (explicitly padded input) or 1 (zero padding)");
   WgradGeom g;
@@ -310,8 +352,12 @@ int wgrad_launch(const bf16* x, const bf16* dy, int nimg, int H, int W, int cin,
   const size_t count4 = static_cast<size_t>(9) * cin * cout / 4;
   int blocks = static_cast<int>((count4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(workspace), count4, cout / 4, sp,
-                                                  reinterpret_cast<float4*>(dw_hwio));
+  if (cout_real_or_0 > 0)
+    wgrad_reduce_oihw_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(workspace), count4, cout / 4,
+                                                         cin, cout_real_or_0, sp, dw_hwio);
+  else
+    wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(workspace), count4, cout / 4, sp,
+                                                    reinterpret_cast<float4*>(dw_hwio));
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;

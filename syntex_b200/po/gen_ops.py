@@ -93,12 +93,10 @@ class Conv3x3Function(torch.autograd.Function):
         if tuple(weight.shape[1:]) != (cin, 3, 3):
             raise ValueError("Conv3x3Function: weight %s does not match %d input channels" % (tuple(weight.shape), cin))
         coutp = (cout + 63) // 64 * 64          # convlast (3 colours) runs as a 64-channel tile, extra filters zero
-        w_hwio = weight.detach().to(torch.float32).permute(2, 3, 1, 0)
-        if coutp != cout:
-            w_hwio = torch.nn.functional.pad(w_hwio, (0, coutp - cout))
-        w_hwio = w_hwio.contiguous()
+        w_oihw = weight.detach().to(torch.float32).contiguous()
         w_fwd, w_dgrad = _bf16((9, coutp, cin)), _bf16((9, cin, coutp))
-        _lib.check(L.stx_pack_conv_weights(w_hwio.data_ptr(), cin, coutp, w_fwd.data_ptr(), w_dgrad.data_ptr(), st))
+        _lib.check(L.stx_pack_conv_weights_oihw(w_oihw.data_ptr(), cin, cout, coutp, w_fwd.data_ptr(), w_dgrad.data_ptr(),
+                                                st))
         b = None
         if bias is not None:
             b = bias.detach().to(torch.float32)
@@ -150,10 +148,9 @@ class Conv3x3Function(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             ws = torch.empty(max(L.stx_conv_wgrad_workspace_bytes(B, H, W, cin, coutp) // 4, 1), dtype=torch.float32,
                              device="cuda")
-            dw_hwio = _f32((3, 3, cin, coutp))
-            _lib.check(L.stx_conv_wgrad_bf16(xin.data_ptr(), dy.data_ptr(), B, H, W, cin, coutp,
-                                             1 if ctx.mode == "zero" else 0, dw_hwio.data_ptr(), ws.data_ptr(), st))
-            dw = dw_hwio[..., :cout].permute(3, 2, 0, 1)
+            dw = _f32((cout, cin, 3, 3))          # torch's layout: adds straight into the parameter's .grad
+            _lib.check(L.stx_conv_wgrad_oihw_bf16(xin.data_ptr(), dy.data_ptr(), B, H, W, cin, coutp,
+                                                  1 if ctx.mode == "zero" else 0, cout, dw.data_ptr(), ws.data_ptr(), st))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy[..., :cout].to(torch.float32).sum(dim=(0, 1, 2))
         return dx, dw, db, None, None
