@@ -57,3 +57,30 @@ def test_native_operators_fail_loudly_without_cuda():
         gen_ops.conv3x3(x, torch.zeros(64, 64, 3, 3))
     with pytest.raises(Exception):
         gen_ops.instance_norm(x, torch.ones(64), torch.zeros(64))
+
+
+def test_native_route_selection_rules():
+    """Which generator stages the hand-written route claims (po/adaptive_model.py:stage_native_supported) and what
+    happens off the GPU: `auto` falls back to stock torch, `native` refuses - there is no CPU route."""
+    from syntex_b200.po.adaptive_model import _Stage as AdaptiveStage, run_generator
+    from syntex_b200.po.improved_model import _Stage as ImprovedStage
+    from syntex_b200.po.progressive_model import _Stage as ProgressiveStage
+
+    ok = ImprovedStage(2, 1, False, True, "REFLECT", "batch", "lrelu", 3)
+    assert ok.native_supported(1) and not ok.native_supported(2)          # batch statistics == instance only at batch 1
+    assert ImprovedStage(2, 1, True, True, "CONSTANT", "instance", "relu", 3).native_supported(4)
+    assert ImprovedStage(2, 1, False, True, "SYMMETRIC", "none", "relu", 3).native_supported(4)
+    assert not ImprovedStage(2, 1, False, True, "REFLECT", "instance", "relu", 5).native_supported(1)   # 5x5 gradient convs
+    assert not ImprovedStage(2, 1, False, False, "REFLECT", "instance", "relu", 3).native_supported(1)  # deconvolution
+    assert not AdaptiveStage(1, False, True, "REFLECT", "batch", "relu", 3).native_supported(1)         # running statistics
+    assert ProgressiveStage(3, 1, False, True).native_supported() and not ProgressiveStage(3, 1, False, False).native_supported()
+
+    class _Model:
+        _generator, _door_is_cuda = "auto", True
+    stage = ImprovedStage(1, 1, False, True, "REFLECT", "instance", "relu", 3)
+    x = {"conv1_1": torch.randn(1, 8, 8, 64)}
+    out = run_generator(_Model(), stage, x)                                # CPU tensors: the stock route
+    assert out.shape == (1, 8, 8, 3)
+    _Model._generator = "native"
+    with pytest.raises(NotImplementedError):
+        run_generator(_Model(), stage, x)
