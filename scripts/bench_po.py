@@ -7,7 +7,7 @@
 
 The VGG19 / Gram work (forward, grad_layer, first- and second-order backward) and the generator (po/gen_ops.py) run
 on the hand-written kernels; STX_PO_GENERATOR=torch selects the stock ATen/cuDNN generator, STX_PO_GRAPH=0/1 the
-eager / CUDA-graph training step (default: graph on one GPU). Synthetic textures, seeded random generator weights."""
+eager / CUDA-graph training step (default: graph; the NCCL all-reduce is captured with it). Synthetic textures, seeded random generator weights."""
 import json
 import os
 import sys
@@ -86,7 +86,7 @@ def train(size, steps):
                                "generator_bf16": GEN_BF16, "generator": GEN}).cuda().to(memory_format=torch.channels_last)
     data = SyntheticPOData(1, size, seed=rank)
     batch = next(iter(data))
-    graph = os.environ.get("STX_PO_GRAPH", "1" if world == 1 else "0") == "1"
+    graph = os.environ.get("STX_PO_GRAPH", "1") == "1"
     trainer = SynTexTrainer(data, model, world, cuda_graph=graph)
     losses = []
 
@@ -124,11 +124,13 @@ def train(size, steps):
     if world > 1:
         if graph:
             # a captured NCCL all-reduce keeps the communicator busy at teardown (destroy_process_group was seen to
-            # hang until the launcher's timeout): results are out, leave without the collective shutdown
+            # hang until the launcher's timeout): drop the graph first; STX_PO_HARD_EXIT=1 skips the shutdown altogether
             sys.stdout.flush()
+            trainer.release_graph()
             dist.barrier()
             torch.cuda.synchronize()
-            os._exit(0)
+            if os.environ.get("STX_PO_HARD_EXIT", "0") == "1":
+                os._exit(0)
         dist.destroy_process_group()
 
 

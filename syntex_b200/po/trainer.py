@@ -165,6 +165,18 @@ class SynTexTrainer(object):
         self.global_step += 1
         return self._static[2].clone()
 
+    def release_graph(self):
+        """Drop the captured step (and the NCCL work it references). Call before torch.distributed is shut down: a
+        live CUDA graph holding captured all-reduces keeps the communicator busy and destroy_process_group() waits
+        for it."""
+        if self._graph is not None:
+            torch.cuda.synchronize()
+            self._graph = None
+            self._static = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+
     def _iter(self):
         if not hasattr(self, "_it"):
             self._it = iter(self.input)
