@@ -38,8 +38,9 @@ TEST_BATCH = 1
 class _BatchStatsNorm(nn.Module):
     """tensorpack BatchNorm under argscope(BatchNorm, training=True) (improved_model.py:353-360): batch statistics in
     every phase, biased variance, eps 1e-5, affine (with the per-GPU batch of 1 the reference trains with, this is
-    InstanceNorm). Plain tensor arithmetic: cuDNN's batch-norm entry point fails on the channels-last views this
-    generator passes around (CUDNN_STATUS_EXECUTION_FAILED_CUDART, measured)."""
+    InstanceNorm). Plain tensor arithmetic rather than nn.BatchNorm2d with its running statistics stripped: that
+    combination failed inside cuDNN on the B200 (CUDNN_STATUS_EXECUTION_FAILED_CUDART on this generator's permuted
+    views), while nn.BatchNorm2d as shipped - which the adaptive mirror uses - works."""
 
     def __init__(self, chan, eps=1e-5):
         super().__init__()
