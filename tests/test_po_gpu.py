@@ -326,3 +326,26 @@ def test_improved_model_on_the_cuda_door(raw_weights):
     batch = (torch.as_tensor(z, dtype=torch.float32).cuda(), torch.as_tensor(t, dtype=torch.float32).cuda())
     losses = [float(trainer.run_step(batch)) for _ in range(8)]
     assert all(np.isfinite(losses)) and min(losses[4:]) < losses[0]
+
+
+def test_vgg_texture_bf16_gradients_equal_the_fp32_ones_rounded(raw_weights):
+    """calc_grad="bf16" hands the per-layer gradients over in the kernels' own precision (stx_plan_layer_grad_bf16,
+    what the hand-written generator consumes): the same numbers as calc_grad=True, rounded to bf16, and the backward
+    accepts bf16 upstream gradients without the fp32 round trip."""
+    size, B = 64, 2
+    x, gt, _ = _oracle_case(raw_weights, size, B, LAYERS, 21)
+    ext = Vgg19Extractor(raw_weights)
+    gtg = OrderedDict((k, v.float().cuda()) for k, v in gt.items())
+    grads = {}
+    for mode in (True, "bf16"):
+        xg = x.cuda().requires_grad_(True)
+        ll, gl = vgg_texture(xg, ext, LAYERS, gtg, slot=0, calc_grad=mode)
+        ups = {k: torch.randn(gl[k].shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+               for k in LAYERS}
+        total = sum((gl[k].float() * ups[k]).sum() for k in LAYERS)
+        total.backward()
+        grads[mode] = (OrderedDict((k, gl[k].detach()) for k in LAYERS), xg.grad.clone())
+    for k in LAYERS:
+        assert grads["bf16"][0][k].dtype == torch.bfloat16 and grads[True][0][k].dtype == torch.float32
+        assert torch.equal(grads["bf16"][0][k], grads[True][0][k].to(torch.bfloat16)), k
+    assert relerr(grads["bf16"][1], grads[True][1]) < 5e-3
