@@ -178,11 +178,24 @@ def cpu_baseline_sample(args, seconds_budget=25.0):
     iters = 12
     stamps = []
     orc.synthesize(x0[0], targets[0], maxiter=iters + 2, callback=lambda xk: stamps.append(time.time()))
-    torch.set_num_threads(old)
     dt = stamps[-1] - stamps[1]
     n = len(stamps) - 2
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "1 job x %d L-BFGS-B iterations at %dx%d after 2 warm-up iterations (torch-CPU fp32 oracle + scipy)" % (n, size, size)}
+    out = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "1 job x %d L-BFGS-B iterations at %dx%d after 2 warm-up iterations (torch-CPU fp32 oracle + scipy)" % (n, size, size)}
+    # ... and once with the reference's own thread setting: gatys/synthesizer.py:211-216 runs its TF session with
+    # intra_op_parallelism_threads = inter_op_parallelism_threads = 2
+    try:
+        torch.set_num_threads(2)
+        stamps2 = []
+        orc2 = so.SynthesizerOracle(weights, size, dtype=torch.float32, maxcor=args.maxcor)
+        orc2.synthesize(x0[0], targets[0], maxiter=6, callback=lambda xk: stamps2.append(time.time()))
+        if len(stamps2) > 2:
+            out["reference_thread_setting"] = {"value": (len(stamps2) - 2) / (stamps2[-1] - stamps2[1]), "unit": UNIT,
+                                               "cores": 2, "sample": "%d iterations after 2 warm-up iterations" % (len(stamps2) - 2)}
+    except Exception as e:      # a report beside the report: never fatal
+        out["reference_thread_setting"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    torch.set_num_threads(old)
+    return out
 
 
 def workload_config(args):
