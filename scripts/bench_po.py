@@ -63,10 +63,17 @@ def infer(batch, size, which="progressive"):
         with torch.no_grad():
             model.build_graph(z, t)
     ms = timed(step, 2, 5)
+    ms_images_only = None
+    if hasattr(model, "synthesize"):
+        ms_images_only = timed(lambda: model.synthesize(z, t), 2, 5)
     # VGG19 work per image: 6 forwards of the current image (5 stages to their last Gram layer + the final loss) and
     # one of the target, plus the per-layer F*D products
     print(json.dumps({"workload": "po_%s_inference" % which, "batch": batch, "size": size, "images_per_s": batch / ms * 1e3,
-                      "ms_per_batch": ms, "hot_path_launches_per_batch": (_lib.lib().stx_launch_count() - l0) // 7,
+                      "ms_per_batch": ms,
+                      "images_only": None if ms_images_only is None else {
+                          "images_per_s": batch / ms_images_only * 1e3, "ms_per_batch": ms_images_only,
+                          "call": "model.synthesize(): the output image without the loss of the result"},
+                      "hot_path_launches_per_batch": (_lib.lib().stx_launch_count() - l0) // 7,
                       "losses": [float(l) for l in model.losses], "generator": gen_name(),
                       "note": "config 3; single = SingleSynTex on the five Gram layers (single_model.py as shipped is stale "
                               "against the current extractor, SURVEY section 2 #8); random generator weights: throughput only"}))

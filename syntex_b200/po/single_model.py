@@ -131,3 +131,17 @@ class SingleSynTex(SynTexModelDesc, nn.Module):
 
     def optimizer(self):
         return torch.optim.Adam(self.vars, lr=self._lr, betas=(self._beta1, self._beta2), eps=1e-3)
+
+    @torch.no_grad()
+    def synthesize(self, pre_image_input, image_target):
+        """Feed-forward synthesis only: the output image [B,H,W,3] in [0,1], without the loss of the result that
+        build_graph evaluates for the summaries (one VGG19 forward less per call; the reference's predictor fetches
+        'stages-target/viz' and 'loss_output' from the same graph, po/improved_model.py:453-484)."""
+        dev = next(self.syn.parameters()).device
+        dtype = next(self.syn.parameters()).dtype
+        pre = torch.as_tensor(pre_image_input).to(device=dev, dtype=dtype)
+        target = torch.as_tensor(image_target).to(device=dev, dtype=dtype) / 255.
+        gram_target = self._texture_fn.grams(target)
+        for s in range(self._n_stage):
+            _, _, _, pre = self.build_stage(pre, gram_target, name="stage%d" % s, stage_index=s)
+        return self._act(pre)

@@ -275,3 +275,20 @@ def test_improved_stop_grad_cuts_the_cross_stage_paths(raw_weights):
         grads.append(torch.cat([p.grad.flatten() for p in m.syn[0].parameters()]))
     rel = float((grads[0] - grads[1]).norm() / grads[0].norm())
     assert rel > 1e-3
+
+
+def test_single_model_synthesize_returns_the_output_image_of_the_graph(raw_weights):
+    """SingleSynTex.synthesize(): feed-forward synthesis without the loss of the result - the same image as the last
+    entry of build_graph's image_outputs."""
+    from syntex_b200.po.single_model import SingleSynTex
+    torch.manual_seed(0)
+    tex = so.OracleTexture(so.load_vgg_weights(raw_weights), LAYERS, torch.float64)
+    model = SingleSynTex({"vgg19_npy_path": raw_weights, "image_size": 32, "n_stage": 2}, texture_fn=tex).double()
+    rng = np.random.RandomState(0)
+    z = torch.as_tensor(rng.uniform(-1, 1, (1, 32, 32, 3)))
+    t = torch.as_tensor(so.synthetic_texture(32, seed=1)[None] * 255.0)
+    with torch.no_grad():
+        model.build_graph(z, t)
+    out = model.synthesize(z, t)
+    assert out.shape == (1, 32, 32, 3) and not out.requires_grad
+    assert torch.equal(out, model.image_outputs[-1])
