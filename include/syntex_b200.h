@@ -97,6 +97,14 @@ int stx_plan_copy_gram(stx_plan* plan, int k, float* out, void* stream);
  * the last forward, or set them from a device array [batch,C,C] (per_image = 1) / [1,C,C] (broadcast). */
 int stx_plan_update_target_from_forward(stx_plan* plan, void* stream);
 int stx_plan_set_target_gram(stx_plan* plan, int k, const float* gram, int per_image, void* stream);
+/* A target is complete only once every loss layer has been set (or update_target_from_forward has run); until then
+ * stx_plan_step / stx_lbfgs_* / stx_plan_layer_grad return STX_ERR_STATE. stx_plan_clear_target invalidates the
+ * current target set (call it before re-using a plan for a new set of targets). */
+int stx_plan_clear_target(stx_plan* plan);
+/* Number of forward passes this plan has run. A caller that keeps a plan's activations for a later backward
+ * (po/texture_op.py) records it at forward time and compares before the backward: a mismatch means another forward
+ * has overwritten the activations. */
+long long stx_plan_generation(const stx_plan* plan);
 /* Read the target Gram of loss layer k back as fp32 [batch,C,C] (device; a broadcast target is expanded). */
 int stx_plan_copy_target_gram(stx_plan* plan, int k, float* out, void* stream);
 
@@ -249,6 +257,13 @@ int stx_inorm_apply_bf16(const void* x, int n, int HW, int C, const float* mean,
 int stx_inorm_bwd_bf16(const void* x, const void* dy, int n, int HW, int C, const float* mean, const float* rstd,
                        const float* gamma, const float* beta, int act, float slope, float* s1, float* s2, void* dx,
                        void* workspace, void* stream);
+
+/* tf.train.AdamOptimizer(lr, beta1, beta2, epsilon) as the PO trainers use it (po/progressive_model.py:268-271):
+ *   lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t);  param -= lr_t m / (sqrt(v) + eps)     ("epsilon hat")
+ * over flat fp32 device buffers of `count` elements (16-byte aligned); lr_dev and step_dev (t as a float, already
+ * incremented for this step) are device scalars so that a CUDA-graph replay sees the current values. */
+int stx_adam_tf(float* param, const float* grad, float* m, float* v, size_t count, const float* lr_dev,
+                const float* step_dev, float beta1, float beta2, float eps, void* stream);
 
 int stx_f32_to_bf16(const float* x, size_t count, void* out_bf16, void* stream);
 int stx_bf16_to_f32(const void* x_bf16, size_t count, float* out, void* stream);

@@ -37,6 +37,9 @@ def _declare(lib):
         "stx_plan_update_target_from_forward": (c_int, [vp, vp]),
         "stx_plan_set_target_gram": (c_int, [vp, c_int, fp, c_int, vp]),
         "stx_plan_copy_target_gram": (c_int, [vp, c_int, fp, vp]),
+        "stx_plan_clear_target": (c_int, [vp]),
+        "stx_adam_tf": (c_int, [fp, fp, fp, fp, c_size_t, fp, fp, c_float, c_float, c_float, vp]),
+        "stx_plan_generation": (ctypes.c_longlong, [vp]),
         "stx_plan_step": (c_int, [vp, fp, c_int, fp, fp, fp, vp]),
         "stx_plan_step_timed": (c_int, [vp, fp, c_int, fp, fp, POINTER(c_float), POINTER(c_int), vp]),
         "stx_plan_step_host": (c_int, [vp, fp, c_int, fp, fp, vp]),

@@ -126,10 +126,20 @@ int stx_plan_update_target_from_forward(stx_plan* plan, void* stream) {
     STX_CUDA(cudaMemcpyAsync(ll.target, ll.G, static_cast<size_t>(p->B) * ll.C * ll.C * sizeof(float),
                              cudaMemcpyDeviceToDevice, S(stream)));
     ll.target_stride = static_cast<long long>(ll.C) * ll.C;
+    ll.target_set = true;
   }
   p->have_target = true;
   return STX_OK;
 }
+
+int stx_plan_clear_target(stx_plan* plan) {
+  STX_REQUIRE(plan, "stx_plan_clear_target: null plan");
+  for (LossLayer& ll : plan->p->loss) ll.target_set = false;
+  plan->p->have_target = false;
+  return STX_OK;
+}
+
+long long stx_plan_generation(const stx_plan* plan) { return plan ? plan->p->generation : -1; }
 
 int stx_plan_copy_target_gram(stx_plan* plan, int k, float* out, void* stream) {
   STX_REQUIRE(plan && out, "stx_plan_copy_target_gram: null argument");
@@ -153,7 +163,11 @@ int stx_plan_set_target_gram(stx_plan* plan, int k, const float* gram, int per_i
   STX_CUDA(cudaMemcpyAsync(ll.target, gram, (per_image ? p->B : 1) * cc * sizeof(float), cudaMemcpyDeviceToDevice,
                            S(stream)));
   ll.target_stride = per_image ? static_cast<long long>(cc) : 0;
+  // A target is complete only when EVERY loss layer has one: step / the optimiser / layer_grad refuse to run on a
+  // partially set target instead of silently using zeros (or a previous target set) for the other layers.
+  ll.target_set = true;
   bool all = true;
+  for (const LossLayer& other : p->loss) all = all && other.target_set;
   p->have_target = all;
   return STX_OK;
 }
@@ -400,6 +414,11 @@ int stx_inorm_bwd_bf16(const void* x, const void* dy, int n, int HW, int C, cons
                        void* workspace, void* stream) {
   return inorm_bwd_launch(static_cast<const bf16*>(x), static_cast<const bf16*>(dy), n, HW, C, mean, rstd, gamma, beta,
                           act, slope, s1, s2, static_cast<bf16*>(dx), static_cast<float*>(workspace), S(stream));
+}
+
+int stx_adam_tf(float* param, const float* grad, float* m, float* v, size_t count, const float* lr_dev,
+                const float* step_dev, float beta1, float beta2, float eps, void* stream) {
+  return adam_tf_launch(param, grad, m, v, count, lr_dev, step_dev, beta1, beta2, eps, S(stream));
 }
 
 int stx_conv1_1_fwd(const float* image, int n, int H, int W, int is_preimage, const float* mean3_host,

@@ -446,4 +446,60 @@ int inorm_bwd_launch(const bf16* x, const bf16* dy, int nimg, int HW, int C, con
   return STX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ Adam (TF rule)
+// tf.train.AdamOptimizer as the reference's trainers use it (po/progressive_model.py:268-271, epsilon 1e-3):
+//   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  lr_t = lr sqrt(1 - b2^t) / (1 - b1^t);  p -= lr_t m / (sqrt(v) + eps)
+// ("epsilon hat": eps is added to sqrt(v), NOT to sqrt(v / (1 - b2^t)) as torch.optim.Adam does - with eps = 1e-3 the
+// two differ by up to 30x in the effective epsilon over the first thousand steps.)
+// lr and the step count t (already incremented, as a float) live on the device so that a captured step replays
+// with the current schedule value.
+namespace {
+__global__ void __launch_bounds__(256) adam_tf_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                      float* __restrict__ m, float* __restrict__ v, size_t n,
+                                                      const float* __restrict__ lr, const float* __restrict__ step,
+                                                      float b1, float b2, float eps) {
+  const float t = *step;
+  const float lr_t = *lr * sqrtf(1.0f - powf(b2, t)) / (1.0f - powf(b1, t));
+  const size_t i4 = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    float4 pp = *reinterpret_cast<const float4*>(p + i4);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float4 mm = *reinterpret_cast<const float4*>(m + i4);
+    float4 vv = *reinterpret_cast<const float4*>(v + i4);
+#define STX_ADAM1(c)                                 \
+    mm.c = b1 * mm.c + (1.0f - b1) * gg.c;             \
+    vv.c = b2 * vv.c + (1.0f - b2) * gg.c * gg.c;      \
+    pp.c -= lr_t * mm.c / (sqrtf(vv.c) + eps);
+    STX_ADAM1(x) STX_ADAM1(y) STX_ADAM1(z) STX_ADAM1(w)
+#undef STX_ADAM1
+    *reinterpret_cast<float4*>(p + i4) = pp;
+    *reinterpret_cast<float4*>(m + i4) = mm;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+  } else {
+    for (size_t i = i4; i < n; ++i) {
+      const float gi = g[i];
+      const float mi = b1 * m[i] + (1.0f - b1) * gi;
+      const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+  }
+}
+}  // namespace
+
+int adam_tf_launch(float* p, const float* g, float* m, float* v, size_t n, const float* lr_dev, const float* step_dev,
+                   float b1, float b2, float eps, cudaStream_t stream) {
+  STX_REQUIRE(p && g && m && v && lr_dev && step_dev, "adam: null argument");
+  STX_REQUIRE((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+               reinterpret_cast<uintptr_t>(v)) % 16 == 0, "adam: buffers must be 16-byte aligned");
+  if (n == 0) return STX_OK;
+  const size_t threads = (n + 3) / 4;
+  adam_tf_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(p, g, m, v, n, lr_dev, step_dev, b1,
+                                                                                  b2, eps);
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
 }  // namespace stx

@@ -173,4 +173,8 @@ int inorm_bwd_launch(const bf16* x, const bf16* dy, int nimg, int HW, int C, con
                      const float* gamma, const float* beta, int relu, float slope, float* s1, float* s2, bf16* dx,
                      float* workspace, cudaStream_t stream);
 
+// tf.train.AdamOptimizer update over flat fp32 buffers (see gen_ops.cu); lr_dev / step_dev: device scalars.
+int adam_tf_launch(float* p, const float* g, float* m, float* v, size_t n, const float* lr_dev, const float* step_dev,
+                   float b1, float b2, float eps, cudaStream_t stream);
+
 }  // namespace stx

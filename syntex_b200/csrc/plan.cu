@@ -462,6 +462,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
 
 int Plan::forward(const float* image, int is_preimage, int with_grams, bool with_loss, cudaStream_t stream) {
   STX_REQUIRE(image, "forward: null image");
+  ++generation;
   const bool grams = with_grams || with_loss;
   bool forked = false;
   // Gram + finish of loss layer `l`, on the side stream, as soon as act[l] exists.

@@ -53,6 +53,7 @@ struct LossLayer {
   float* G = nullptr;         // [B,C,C]
   float* target = nullptr;    // [B,C,C]
   long long target_stride = 0;
+  bool target_set = false;    // this layer's target has been written since the last stx_plan_clear_target
   bf16* dscaled = nullptr;    // [B,C,C]
   bf16* dfeat = nullptr;      // [B,h,w,C] total gradient dL/dF_k (only with STX_PLAN_EXPORT_LAYER_GRADS)
   int part_offset = 0;        // into loss_part rows
@@ -94,6 +95,7 @@ struct Plan {
   float* d_coef = nullptr;         // [nloss] coef/4
   int* d_part_offsets = nullptr;   // [nloss+1]
   bool have_target = false, have_grams = false;
+  long long generation = 0;        // bumped by every forward(): a backward may check that its activations are still there
   // Gram + finish launches run on a side stream, forked right after their layer is produced and joined before the
   // loss reduction: they are bandwidth-bound and hide under the tensor-bound convolutions of the deeper layers.
   cudaStream_t side = nullptr;

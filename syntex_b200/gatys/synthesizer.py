@@ -277,7 +277,7 @@ class Synthesizer(object):
             _lib.check(L.stx_lbfgs_run(opt, it, 0, st))
             _lib.check(L.stx_lbfgs_result(opt, xd.data_ptr(), fun.data_ptr(), nit.data_ptr(), nfev.data_ptr(), st))
             self._verbose_record(xd.cpu().numpy(), is_preimage)
-            if int(nit.min()) < it:      # every job has stopped early (line search could not make progress)
+            if int(nit.max()) < it:      # every job has stopped early (line search could not make progress)
                 break
         self.last_result = {"nit": nit.cpu().numpy(), "nfev": nfev.cpu().numpy(), "fun": fun.cpu().numpy()}
         x = xd.cpu().numpy()

@@ -13,8 +13,8 @@ def save_checkpoint(folder, model, trainer=None, global_step=None):
     step = int(global_step if global_step is not None else (trainer.global_step if trainer is not None else 0))
     state = {"global_step": step, "model": {k: v.detach().cpu() for k, v in model.state_dict().items()}}
     if trainer is not None:
-        state["optimizer"] = trainer.opt.state_dict()
-        state["learning_rate"] = trainer.opt.param_groups[0]["lr"]
+        state["optimizer"] = trainer.opt.state_dict()       # plain tensors and floats only (see restore)
+        state["learning_rate"] = float(trainer.opt.param_groups[0]["lr"])
     path = os.path.join(folder, "model-%d" % step)
     torch.save(state, path)
     with open(os.path.join(folder, "checkpoint"), "w") as f:
@@ -34,7 +34,8 @@ def restore_checkpoint(path, model, trainer=None):
         if found is None:
             raise IOError("no model-<step> checkpoint in %s" % path)
         path = found
-    state = torch.load(path, map_location="cpu", weights_only=False)
+    # tensors, floats and strings only: nothing in a checkpoint needs unpickling arbitrary objects
+    state = torch.load(path, map_location="cpu", weights_only=True)
     with torch.no_grad():
         own = model.state_dict()
         for k, v in state["model"].items():

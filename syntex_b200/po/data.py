@@ -51,9 +51,13 @@ class ImageFolderData(object):
             raise IOError("no *.jpg under %s" % os.path.join(datadir, sub))
         self.size, self.isTrain = size, isTrain
         self.batch = batch or (BATCH if isTrain else TEST_BATCH)
-        self.rng = np.random.RandomState(seed if seed is None else seed + rank)
+        # crops and flips: a stream per rank; the epoch permutation: ONE stream shared by all ranks (seed, epoch), so
+        # that the strided shards below partition the same permutation and an epoch covers the dataset exactly once
+        self.rng = np.random.RandomState(seed if seed is None else seed + 7919 * (rank + 1))
+        self.shuffle_seed = 0 if seed is None else int(seed)
+        self.epoch = 0
         self.rank, self.world = rank, world
-        self.z = iter(RandomZData([size, size, 3], -1, 1))
+        self.z = iter(RandomZData([size, size, 3], -1, 1, seed=None if seed is None else seed + 104729 * (rank + 1)))
 
     def _load(self, path):
         import cv2
@@ -72,7 +76,8 @@ class ImageFolderData(object):
     def _order(self):
         idx = np.arange(len(self.files))
         if self.isTrain:
-            self.rng.shuffle(idx)
+            np.random.RandomState([self.shuffle_seed, self.epoch]).shuffle(idx)
+            self.epoch += 1
         return idx[self.rank::self.world] if self.world > 1 and len(idx) >= self.world else idx
 
     def __iter__(self):

@@ -65,11 +65,13 @@ class SynTexModelDesc(object):
 class RandomZData(object):
     """po/model.py:138-147: endless uniform noise source."""
 
-    def __init__(self, shape, minv=0., maxv=1.):
+    def __init__(self, shape, minv=0., maxv=1., seed=None):
         self.shape = shape
         self.minv = minv
         self.maxv = maxv
+        # the reference draws from the global numpy state; `seed` (an extension) gives a private, reproducible stream
+        self.rng = np.random if seed is None else np.random.RandomState(seed)
 
     def __iter__(self):
         while True:
-            yield [np.random.uniform(self.minv, self.maxv, size=self.shape)]
+            yield [self.rng.uniform(self.minv, self.maxv, size=self.shape)]

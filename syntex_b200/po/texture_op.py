@@ -38,6 +38,17 @@ def _feature_ptrs(plan, layer_idx):
     return hi.value, lo.value
 
 
+def _check_generation(L, plan, generation):
+    """The backward of these nodes reads the plan's activations, Gram partials and scaled differences. Plans are
+    cached per (shape, layers, slot) by Vgg19.get_plan, so a second forward with the same key - two graphs alive at
+    once, or an evaluation sharing the slot - overwrites them: refuse instead of returning wrong gradients."""
+    now = L.stx_plan_generation(plan.handle)
+    if now != generation:
+        raise RuntimeError("VGG plan was re-run since this graph's forward (generation %d -> %d): a plan keeps the "
+                           "activations of its LAST forward only; give concurrent graphs distinct `slot`s"
+                           % (generation, now))
+
+
 def _make_function():
     import torch
 
@@ -80,6 +91,7 @@ def _make_function():
                     _lib.check(L.stx_plan_layer_grad(plan.handle, k, out.data_ptr(), st))
                     grads.append(out)
             ctx.plan = plan
+            ctx.generation = L.stx_plan_generation(plan.handle)
             ctx.layers = list(layers)
             ctx.calc_grad = calc_grad
             ctx.save_for_backward(x, *diffs)
@@ -91,6 +103,7 @@ def _make_function():
             L = _lib.lib()
             st = _lib.stream_ptr()
             plan = ctx.plan
+            _check_generation(L, plan, ctx.generation)
             saved = ctx.saved_tensors
             x, diffs = saved[0], saved[1:]
             B = x.shape[0]
@@ -150,7 +163,7 @@ def _make_prep_function():
     """Autograd node for the stage preparation of po/improved_model.py:209-232 / po/adaptive_model.py:204-222:
     (image) -> (feat_k ..., loss_per_layer [K,B], grad_per_layer_k ...) with
         grad_per_layer = tf.gradients(sum_k coef_k/4 loss_k, [feat_k ...])      (full VGG back-propagation)
-    and, unlike po/prep.py, a backward for ALL outputs - including the second-order term of training through
+    and a backward for ALL outputs - including the second-order term of training through
     grad_per_layer when --stop-grad is off (the reference's default).
 
     Second order. With delta_l = dL/da_l, the back-propagation is delta_l = inj_l + Back_{l+1}(delta_{l+1}),
@@ -235,6 +248,7 @@ def _make_prep_function():
                 _lib.check(L.stx_plan_copy_gram(plan.handle, k, G.data_ptr(), st))
                 diffs.append(G - targets[k])
             ctx.plan, ctx.vgg19 = plan, vgg19
+            ctx.generation = L.stx_plan_generation(plan.handle)
             ctx.layers, ctx.coef_values = list(layers), [float(v) for v in coef_values]
             ctx.save_for_backward(x, *diffs)
             ctx.set_materialize_grads(False)
@@ -245,6 +259,7 @@ def _make_prep_function():
             L = _lib.lib()
             st = _lib.stream_ptr()
             plan = ctx.plan
+            _check_generation(L, plan, ctx.generation)
             K = len(ctx.layers)
             d_feat, d_loss, d_grad = ups[:K], ups[K], ups[K + 1:]
             saved = ctx.saved_tensors
@@ -339,6 +354,13 @@ def vgg_stage_preparation(image, vgg19, gram_target, coefs, stop_grad=False, slo
     else:
         loss_input = outs[K][0] * 0.
     return feat, loss_input, loss_per_layer, grad_per_layer
+
+
+def build_stage_preparation(vgg19, image_input, gram_target, coefs, stop_grad=False, name="prep", slot=0):
+    """ImprovedSynTex.build_stage_preparation (po/improved_model.py:209-232) with the reference's argument order
+    (the VGG extractor is `self.vgg19` there) and its default: `--stop-grad` is OFF (po/improved_model.py:117), so
+    the per-layer gradients stay differentiable. Thin wrapper over vgg_stage_preparation."""
+    return vgg_stage_preparation(image_input, vgg19, gram_target, coefs, stop_grad=stop_grad, slot=slot)
 
 
 def vgg_texture(image, vgg19, layers, gram_target, slot=0, calc_grad=True):

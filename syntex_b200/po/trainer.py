@@ -68,6 +68,50 @@ class _FlatBuckets(object):
             self.flat_grad.mul_(1.0 / self.world_size)
 
 
+class TfAdam(object):
+    """tf.train.AdamOptimizer(lr, beta1, beta2, epsilon) over the trainer's flat parameter / gradient buffers
+    (po/progressive_model.py:268-271): lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), p -= lr_t m / (sqrt(v) + eps).
+    NOT torch.optim.Adam, whose eps is added to sqrt(v / (1 - b2^t)): with the reference's eps = 1e-3 the effective
+    epsilon differs by 1 / sqrt(1 - b2^t) (30x at t = 1). On CUDA one hand-written kernel (stx_adam_tf) updates the
+    whole generator; the learning rate and step count are device scalars, so a captured step replays with the current
+    schedule value. On CPU (the gloo tests) the same rule in torch ops."""
+
+    def __init__(self, flat_param, flat_grad, lr, betas=(0.9, 0.999), eps=1e-3):
+        self.p, self.g = flat_param, flat_grad
+        self.m = torch.zeros_like(flat_param)
+        self.v = torch.zeros_like(flat_param)
+        self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
+        self.lr_t = torch.tensor(float(lr), dtype=torch.float32, device=flat_param.device)
+        self.step_t = torch.zeros((), dtype=torch.float32, device=flat_param.device)
+        self.param_groups = [{"lr": self.lr_t, "betas": self.betas, "eps": self.eps}]
+
+    def step(self):
+        b1, b2 = self.betas
+        self.step_t.add_(1.0)
+        if self.p.is_cuda:
+            from .. import _lib
+            _lib.check(_lib.lib().stx_adam_tf(self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(),
+                                              self.v.data_ptr(), self.p.numel(), self.lr_t.data_ptr(),
+                                              self.step_t.data_ptr(), b1, b2, self.eps, _lib.stream_ptr()))
+            return
+        with torch.no_grad():
+            t = self.step_t
+            self.m.mul_(b1).add_(self.g, alpha=1.0 - b1)
+            self.v.mul_(b2).addcmul_(self.g, self.g, value=1.0 - b2)
+            lr_t = self.lr_t * torch.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+            self.p.sub_(lr_t * self.m / (self.v.sqrt() + self.eps))
+
+    def state_dict(self):
+        return {"m": self.m.detach().cpu(), "v": self.v.detach().cpu(), "step": float(self.step_t),
+                "lr": float(self.lr_t)}
+
+    def load_state_dict(self, state):
+        self.m.copy_(state["m"])
+        self.v.copy_(state["v"])
+        self.step_t.fill_(float(state["step"]))
+        self.lr_t.fill_(float(state["lr"]))
+
+
 class SynTexTrainer(object):
     def __init__(self, input, model, num_gpu=1, cuda_graph=False, graph_warmup=2):
         """input: iterable of (pre_image_input, image_target) batches for THIS rank; model: a PO model
@@ -93,17 +137,11 @@ class SynTexTrainer(object):
                 dist.broadcast(p.data, src=0)
         groups = [list(stage.parameters()) for stage in model.syn] if hasattr(model, "syn") else [list(model.vars)]
         self.buckets = _FlatBuckets(groups, self.num_gpu)
-        self.opt = model.optimizer()
-        self.base_lr = self.opt.param_groups[0]["lr"]
-        if self.buckets.flat_param.is_cuda:
-            # one fused multi-tensor Adam launch over the generator (same update rule and eps; the per-parameter
-            # launches cost 2.8 ms of a 512x512 step against ~0.3 ms of HBM time); capturable for the graph mode,
-            # where the learning rate lives on the device so that the schedule still applies to the replayed step
-            lr = torch.tensor(float(self.base_lr), device=self.buckets.flat_param.device) if self.cuda_graph \
-                else self.base_lr
-            g0 = self.opt.param_groups[0]
-            self.opt = torch.optim.Adam(model.vars, lr=lr, betas=g0["betas"], eps=g0["eps"], fused=True,
-                                        capturable=self.cuda_graph)
+        # The model's optimizer() states the hyper-parameters (Adam, epsilon 1e-3); the update itself runs as ONE
+        # launch over the flat buffers with TensorFlow's rule (see TfAdam).
+        g0 = model.optimizer().param_groups[0]
+        self.base_lr = float(g0["lr"])
+        self.opt = TfAdam(self.buckets.flat_param, self.buckets.flat_grad, self.base_lr, g0["betas"], g0["eps"])
         self.global_step = 0
         self.allreduce_wait_s = 0.0
 
@@ -191,8 +229,10 @@ class SynTexTrainer(object):
         if start_dec_epoch is None:
             start_dec_epoch = max_epoch // 2
         for epoch in range(1, int(max_epoch) + 1):
-            if epoch > start_dec_epoch and max_epoch > start_dec_epoch:
-                frac = (max_epoch - epoch) / float(max_epoch - start_dec_epoch)
+            # tensorpack's ScheduledHyperParamSetter applies the value scheduled for epoch e AFTER epoch e has run,
+            # i.e. epoch e trains with the value of epoch e - 1: the last epoch still has a non-zero rate.
+            if epoch - 1 > start_dec_epoch and max_epoch > start_dec_epoch:
+                frac = (max_epoch - (epoch - 1)) / float(max_epoch - start_dec_epoch)
                 self.set_learning_rate(self.base_lr * max(frac, 0.0))
             t0 = time.time()
             last = None

@@ -114,7 +114,7 @@ def _dp_worker(rank, world, port, raw_weights, out):
         p0 = trainer.buckets.flat_param.clone()
         trainer.run_step((z, t))
         out[rank] = (p0.numpy(), trainer.buckets.flat_grad.clone().numpy(), trainer.buckets.flat_param.clone().numpy(),
-                     trainer.opt.param_groups[0]["lr"])
+                     float(trainer.opt.param_groups[0]["lr"]))
     finally:
         dist.destroy_process_group()
 
