@@ -1,24 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the SynTex hot path on B200: Gatys L-BFGS synthesis at 256x256.
+"""Benchmark of the SynTex hot path on B200: BASELINE.json's config 4 - 64 independent Gatys L-BFGS-B synthesis jobs
+at 256x256, split 64 / N per GPU with no communication (strong scaling).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--size S]
 
-A *step* is one cycle of the device-resident optimiser over the batch: ONE f/g evaluation of every job in flight
-(VGG19 forward + Gram loss + input-gradient backward) followed by the L-BFGS update of every job. `value` is the
-number of L-BFGS iterations (`nit` of scipy / of the device optimiser) the jobs complete per second over exactly K
-such steps; a job in a line search spends a step without completing an iteration (`fg_evals_per_iteration`, ~1.06).
-No job reaches an iteration limit inside the timed region; after JOB_LEN = 200 steps every job is replaced by a fresh
-one (restart from x0 with an empty history), so every job is busy in every step however long the run. The workload per GPU
-is `batch` independent synthesis jobs (own exemplar, own seed, own history) run side by side; N GPUs run N x batch
-jobs with no communication - weak scaling; at N = 8, batch = 8 this is BASELINE.json's config 4
-(64 independent 256^2 jobs). Weights are seeded synthetic VGG19 weights, exemplars seeded synthetic textures.
+A *step* is one cycle of the device-resident optimiser over this rank's jobs: ONE f/g evaluation of every job in
+flight (VGG19 forward + Gram loss + input-gradient backward) followed by the L-BFGS-B update of every job. `value` is
+the number of L-BFGS-B iterations (`nit` of scipy / of the device optimiser) all jobs of all ranks complete per second
+over exactly K such steps; a job in a line search spends a step without completing an iteration
+(`fg_evals_per_iteration`, ~1.06). The warm-up runs at least maxcor + 5 cycles, so the timed cycles see a full
+L-BFGS history. No job reaches an iteration limit inside the timed region; after JOB_LEN = 200 steps every job is
+replaced by a fresh one (restart from x0 with an empty history, inside the timed region), so every job is busy in
+every step however long the run. `--batch B` overrides the 64 / N split (B jobs per GPU, weak scaling).
+Weights are seeded synthetic VGG19 weights, exemplars seeded synthetic textures.
 
 One JSON line is printed by rank 0. `value` is device-timed with the state resident in HBM; `e2e` is the same
 metric through Synthesizer.synthesize() with host buffers (H2D of x0 and exemplars, target Grams, optimisation,
 D2H of the result). `--impl reference` times the CPU oracle (torch-CPU fp32 restatement of the TF graph + the
-reference's own scipy L-BFGS-B call) on the host cores instead. At N = 1 the line also carries `po`: the PO half of
-BASELINE.json's metric (ProgressiveSynTex training images/s at 512x512, SingleSynTex inference images/s at batch 64
-of 256x256) measured in the same process after the Gatys timing (`--no-po` skips it).
+reference's own scipy L-BFGS-B call) on the host cores instead. Beside the headline, every N carries
+  config1_b1            BASELINE.json config 1 (ONE 256x256 job, 100 iterations) on rank 0: iterations/s
+  po_config5            ProgressiveSynTex training at 512x512, per-GPU batch 1, data parallel over the N ranks (NCCL
+                        gradient-mean all-reduce): images/s and the all-reduce's share of the step
+  gpu_library_baseline  the same f/g evaluation through stock torch (cuDNN / cuBLAS, TF32 and bf16) on this GPU
+and N = 1 also `po_config3` (SingleSynTex inference, batch 64 of 256x256) and `cpu_baseline`.
 """
 import argparse
 import ctypes
@@ -35,6 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "gatys_lbfgs_job_iterations_per_sec_256"
+TOTAL_JOBS = 64     # BASELINE.json config 4: 64 independent 256x256 jobs, 64 / N per GPU
 JOB_LEN = 200       # optimiser cycles a synthesis job stays in flight before a fresh one takes its place (see run_ours)
 UNIT = "iterations/s"
 
@@ -60,9 +65,13 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
-                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernels timed inside a long step)"}
-    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback of B200_PROFILING.md"}
+        # the roofline leg times its kernels one launch at a time in a burst of a few hundred ms at full clocks: the
+        # like-for-like denominator is the BURST cuBLAS figure, not the power-capped sustained one
+        return {"bf16_tflops": d.get("bf16_tflops", d.get("bf16_tflops_sustained")),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "hbm_gbs": d.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (bf16_tflops, the burst figure: kernels timed alone in a short leg)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback of B200_PROFILING.md (burst)"}
 
 
 class ClockSampler(object):
@@ -156,7 +165,7 @@ def run_reference(args, rank, world):
     sample = "1 job x %d timed L-BFGS-B iterations at %dx%d (jobs are independent: job-iterations/s does not depend on the job count)" % (steps, size, size)
     return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,10 +208,13 @@ def cpu_baseline_sample(args, seconds_budget=25.0):
 
 
 def workload_config(args):
-    return {"workload": "gatys_lbfgs_%d" % args.size, "image_size": args.size, "jobs_per_gpu": args.batch,
+    return {"workload": ("config4_%d_gatys_jobs_%d" % (args.jobs_total, args.size)) if args.strong
+            else "gatys_lbfgs_%d" % args.size, "image_size": args.size, "jobs_total": args.jobs_total,
+            "jobs_per_gpu": args.batch,
             "gram_layers": "conv1_1,pool1,pool2,pool3,pool4", "maxcor": args.maxcor, "bounds": "[0,1]",
             "weights": "seeded synthetic VGG19 (He-normal, mean activation ~1)",
-            "parallelism": "independent jobs per GPU, no collective",
+            "parallelism": "independent jobs, %s, no collective" % (
+                "64 / N per GPU (strong scaling)" if args.strong else "--batch per GPU (weak scaling)"),
             "l2": "inputs larger than L2: %d jobs x ~95 MB of activations + L-BFGS history per GPU" % args.batch}
 
 
@@ -271,7 +283,10 @@ def run_ours(args, rank, world, local_rank):
     # iterations the jobs completed over those K cycles (a job in a line search spends a cycle without completing one).
     never = 1 << 30
     _lib.check(L.stx_lbfgs_reset(opt, xd.data_ptr(), 0, stream))
-    _lib.check(L.stx_lbfgs_run(opt, never, max(args.warmup, 1), stream))      # W untimed warm-up cycles
+    # W untimed warm-up cycles, never fewer than maxcor + 5: the timed cycles see a FULL L-BFGS history (the optimiser's
+    # passes over S / Y are at their steady-state cost)
+    warm_cycles = max(args.warmup, args.maxcor + 5)
+    _lib.check(L.stx_lbfgs_run(opt, never, warm_cycles, stream))
     nit0, nfev0 = counters()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -329,7 +344,7 @@ def run_ours(args, rank, world, local_rank):
         g = torch.empty_like(xd)
         f = torch.empty(batch, dtype=torch.float32, device="cuda")
         acc = np.zeros(8)
-        reps = 5
+        reps = 10
         for _ in range(reps):
             _lib.check(L.stx_plan_step_timed(syn._plan.handle, xd.data_ptr(), 0, f.data_ptr(), g.data_ptr(), ms_cls,
                                              cnt_cls, stream))
@@ -360,6 +375,7 @@ def run_ours(args, rank, world, local_rank):
                     "note": "achieved counts algorithmic FLOPs (2*M*N*K once per direction); the bf16x3 forward executes 3 MMAs per MAC, executed_* counts those",
                     "avg_launch_us": 1e3 * conv_ms / max(conv_launches, 1),
                     "algorithmic_gflop_per_launch_avg": flops / 1e9 / max(conv_launches, 1),
+                    "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
                     "peak_source": peaks["source"] + " of measured"}
 
     if rank != 0:
@@ -369,7 +385,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = jobs * nit_e2e / (e2e_ms_max * 1e-3)
     evals_per_it = float(batch * args.steps) / max(iters_done, 1)      # this rank: f/g evaluations per completed iteration
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "warmup_cycles_run": warm_cycles, "ms_per_step": ms_max / args.steps,
+           "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(nit_e2e, 1),
@@ -383,96 +400,231 @@ def run_ours(args, rank, world, local_rank):
     return out
 
 
-def po_sample():
-    """po_sample_inprocess() in a child process: a failure there (even a crash of the CUDA context) cannot take the
-    Gatys line with it."""
+def _timed_ms(fn, warmup, steps):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def config1_b1(args):
+    """BASELINE.json config 1 on one GPU: ONE 256x256 job, 100 L-BFGS-B iterations (rank 0). Device-timed through the
+    optimiser's C entry points and end to end through Synthesizer.synthesize() with host arrays."""
+    import torch
+    from syntex_b200 import _lib
+    from syntex_b200.gatys import Synthesizer
+    from syntex_b200.synthetic import synthetic_vgg_weights
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--po-child"], capture_output=True, text=True,
-                           timeout=420)
-        lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
-        if r.returncode != 0 or not lines:
-            return {"error": "PO child exited %d: %s" % (r.returncode, (r.stderr or "").strip()[-300:])}
-        return json.loads(lines[-1])
+        L = _lib.lib()
+        stream = _lib.stream_ptr()
+        size, IT = args.size, 100
+        x0, targets = make_inputs(size, 1, 0)
+        syn = Synthesizer({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size, "maxiter": IT,
+                           "maxcor": args.maxcor, "batch": 1})
+        syn.build()
+        syn.synthesize(x0[0], targets[0])                 # warm-up of the whole path (graph capture included)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, fun = syn.synthesize(x0[0], targets[0])
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        nit_e2e, nfev_e2e = int(syn.last_result["nit"][0]), int(syn.last_result["nfev"][0])
+        xd = torch.from_numpy(x0).cuda()
+        opt = syn._get_lbfgs(True, 0.0, 1.0)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.check(L.stx_lbfgs_reset(opt, xd.data_ptr(), 0, stream))
+        torch.cuda.synchronize()
+        ev0.record()
+        _lib.check(L.stx_lbfgs_run(opt, IT, 0, stream))
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        return {"workload": "config1: 1 job, %dx%d, %d L-BFGS-B iterations" % (size, size, IT),
+                "iterations_per_s": nit_e2e / (ms * 1e-3), "ms_per_iteration": ms / max(nit_e2e, 1),
+                "e2e_iterations_per_s": nit_e2e / e2e_s, "nit": nit_e2e, "nfev": nfev_e2e, "final_loss": float(fun)}
     except Exception as e:
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
-def po_sample_inprocess():
-    """The PO half of BASELINE.json's metric ("PO imgs/sec"), measured beside the Gatys line on one GPU: config 5
-    (ProgressiveSynTex training at 512x512, per-GPU batch 1, whole step replayed as a CUDA graph) and config 3
-    (SingleSynTex feed-forward synthesis, batch 64 of 256x256). Synthetic textures, seeded random generator weights,
-    generator on the hand-written kernels (syntex_b200/po/gen_ops.py). scripts/bench_po.py is the stand-alone /
-    multi-GPU version. Never raises: a failure is reported in the returned dict."""
+def gpu_library_baseline(args, evals_per_iteration):
+    """The same f/g evaluation (VGG19 forward to pool4, five Gram losses, input gradient by autograd) through STOCK
+    torch on this GPU - cuDNN convolutions, cuBLAS batched GEMMs, eager launches - in TF32 (torch's fp32 default for
+    convolutions on this part) and under bf16 autocast. The reference has no GPU kernels of its own; this is the
+    GPU-library baseline SURVEY.md section 8d asks for beside the CPU one. Reported per job; iterations/s uses the
+    evaluations per iteration measured in the headline run."""
+    import torch
+    import torch.nn.functional as F
+    from syntex_b200.synthetic import synthetic_vgg_weights
+    try:
+        dev = "cuda"
+        size = args.size
+        batch = min(args.batch, 16)
+        torch.backends.cudnn.benchmark = True
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        raw = synthetic_vgg_weights(0)
+        order = ["conv1_1", "conv1_2", "P", "conv2_1", "conv2_2", "P", "conv3_1", "conv3_2", "conv3_3", "conv3_4", "P",
+                 "conv4_1", "conv4_2", "conv4_3", "conv4_4", "P"]
+        gram_after = {0, 2, 5, 10, 15}                  # conv1_1, pool1, pool2, pool3, pool4
+        W = {}
+        for k, (w, b) in raw.items():
+            w = np.asarray(w)
+            if k == "conv1_1":
+                w = w[:, :, ::-1, :]
+            W[k] = (torch.as_tensor(np.ascontiguousarray(w)).permute(3, 2, 0, 1).contiguous().to(dev)
+                    .to(memory_format=torch.channels_last), torch.as_tensor(np.asarray(b)).to(dev))
+        mean = torch.tensor([123.68, 116.779, 103.939], device=dev)
+        x0, _ = make_inputs(size, batch, 0)
+        x = torch.from_numpy(x0).to(dev)
+        targets = None
+
+        def grams(img):
+            h = (img * 255.0 - mean).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+            out = []
+            for i, name in enumerate(order):
+                if name == "P":
+                    h = F.avg_pool2d(h, 2, 2)
+                else:
+                    h = F.relu(F.conv2d(h, W[name][0].to(h.dtype), W[name][1].to(h.dtype), padding=1))
+                if i in gram_after:
+                    f = h.flatten(2).float()                       # [B, C, HW]
+                    out.append(torch.bmm(f, f.transpose(1, 2)) / f.shape[2])
+            return out
+
+        with torch.no_grad():
+            targets = [g * 0.9 for g in grams(x)]
+
+        def fg(autocast):
+            xi = x.detach().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                gs = grams(xi)
+            loss = sum(1e5 / 4 * ((g - t) ** 2).mean(dim=(1, 2)) for g, t in zip(gs, targets)).sum()
+            (grad,) = torch.autograd.grad(loss, xi)
+            return grad
+
+        out = {"batch": batch, "what": "torch %s eager: F.conv2d (cuDNN, channels_last) + torch.bmm Grams + autograd, "
+                                        "per f/g evaluation of %d jobs" % (torch.__version__, batch)}
+        for name, ac in (("tf32", False), ("bf16_autocast", True)):
+            ms = _timed_ms(lambda: fg(ac), 3, 10)
+            out[name] = {"ms_per_eval_per_job": ms / batch,
+                         "job_iterations_per_s": batch / (ms * 1e-3) / evals_per_iteration}
+        return out
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
+def po_config5(rank, world, local_rank):
+    """BASELINE.json config 5: ProgressiveSynTex training at 512x512, per-GPU batch 1, synchronous data parallel over
+    the N ranks of this run (po/model.py:114-136: mean of the tower losses; NCCL gradient-mean all-reduce, bucketed
+    per stage and overlapped with the backward pass; learning rate x N, po/progressive_model.py:36-37). The whole
+    step - VGG19 door, generator on the hand-written kernels, back-propagation, all-reduce, Adam - replays as one
+    CUDA graph. Returns images/s (max over ranks of the device time) and the all-reduce's share of the step:
+    `allreduce_alone_ms` is the exchange timed alone on the same buffer, `exposed_ms` the step time minus the step time
+    of the same replica without the exchange (N = 1 of this run's record)."""
     import torch
     out = {}
+    trainer = None
     try:
+        import torch.distributed as dist
         from syntex_b200.po.progressive_model import ProgressiveSynTex
-        from syntex_b200.po.single_model import SingleSynTex
         from syntex_b200.po.trainer import SynTexTrainer, SyntheticPOData
         from syntex_b200.synthetic import synthetic_vgg_weights
-
-        def timed(fn, warmup, steps):
-            for _ in range(warmup):
-                fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(steps):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / steps
-
         torch.manual_seed(0)
-        model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": 512}).cuda()
-        data = SyntheticPOData(1, 512, seed=0)
+        model = ProgressiveSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": 512, "n_gpu": world}).cuda()
+        data = SyntheticPOData(1, 512, seed=rank)
         batch = next(iter(data))
-        trainer = SynTexTrainer(data, model, 1, cuda_graph=True)
-        ms = timed(lambda: trainer.run_step(batch), 4, 10)
-        out["progressive_training_512"] = {"images_per_s": 1e3 / ms, "ms_per_step": ms, "per_gpu_batch": 1,
-                                           "generator_params": int(trainer.buckets.flat_param.numel()),
-                                           "step": "door + generator + backward + fused Adam as one CUDA graph"}
-        del trainer, model
-        torch.cuda.empty_cache()
+        trainer = SynTexTrainer(data, model, world, cuda_graph=True)
+        for _ in range(4):
+            trainer.run_step(batch)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        steps = 10
+        ms_local = _timed_ms(lambda: trainer.run_step(batch), 0, steps)
+        t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        ar_ms = 0.0
+        if world > 1:
+            g = trainer.buckets.flat_grad
+            ar_ms = _timed_ms(lambda: dist.all_reduce(g), 2, 5)
+        out = {"workload": "config5: ProgressiveSynTex training 512x512, per-GPU batch 1, data parallel",
+               "n_gpus": world, "images_per_s": world / ms * 1e3, "ms_per_step": ms,
+               "allreduce_bytes": int(trainer.buckets.allreduce_bytes) if world > 1 else 0,
+               "allreduce_alone_ms": ar_ms, "allreduce_share_of_step": ar_ms / ms,
+               "generator_params": int(trainer.buckets.flat_param.numel()),
+               "step": "door + generator + backward + all-reduce + Adam (TF rule) as one CUDA graph"}
+    except Exception as e:      # the Gatys line is the contract; this leg is a report beside it
+        out = {"error": "%s: %s" % (type(e).__name__, e)}
+    finally:
+        # a captured NCCL all-reduce keeps the communicator busy at teardown: drop the graph before the group goes
+        try:
+            if trainer is not None:
+                trainer.release_graph()
+            if world > 1:
+                import torch.distributed as dist
+                dist.barrier()
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+    return out
+
+
+def po_config3():
+    """BASELINE.json config 3: SingleSynTex feed-forward synthesis, batch 64 of 256x256 (N = 1 only)."""
+    import torch
+    try:
+        from syntex_b200.po.single_model import SingleSynTex
+        from syntex_b200.po.trainer import SyntheticPOData
+        from syntex_b200.synthetic import synthetic_vgg_weights
+        torch.manual_seed(0)
         single = SingleSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": 256}).cuda().eval()
         z, t = next(iter(SyntheticPOData(64, 256, seed=0)))
 
         def infer():
             with torch.no_grad():
                 single.build_graph(z, t)
-        ms = timed(infer, 2, 5)
-        out["single_inference_b64_256"] = {"images_per_s": 64e3 / ms, "ms_per_batch": ms}
-        del single
-        torch.cuda.empty_cache()
-    except Exception as e:      # the Gatys line above is the contract; this leg is a report beside it
-        out["error"] = "%s: %s" % (type(e).__name__, e)
-    return out
+        ms = _timed_ms(infer, 2, 5)
+        return {"workload": "config3: SingleSynTex inference, batch 64 of 256x256", "images_per_s": 64e3 / ms,
+                "ms_per_batch": ms}
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=25)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=18,
-                    help="independent synthesis jobs per GPU (a multiple of 9: the deep layers then have 32 and 64 work "
-                         "items per job for the 148 / 296 persistent CTAs, 97 %% full waves; 18 measured 4 %% above 9 - "
-                         "4584 vs 4401 job-iterations/s, conv roofline 0.45 vs 0.40 - and 27 another 0.5 %%)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="jobs per GPU; 0 (default) = BASELINE.json config 4: 64 jobs in total, 64 / N per GPU (strong "
+                         "scaling). A value B > 0 runs B jobs on every GPU instead (weak scaling)")
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--maxcor", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-po", action="store_true", help="skip the PO images/s report beside the Gatys line (N = 1)")
-    ap.add_argument("--po-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-po", action="store_true", help="skip the PO sub-records (config 5, config 3)")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: no config1_b1 / gpu_library_baseline / PO")
     args = ap.parse_args()
-    if args.po_child:
-        print(json.dumps(po_sample_inprocess()), flush=True)
-        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE %d" % (args.gpus, world))
+    args.strong = args.batch <= 0
+    if args.strong:
+        if TOTAL_JOBS % max(world, 1) != 0:
+            raise SystemExit("config 4 splits %d jobs evenly: --gpus must divide it" % TOTAL_JOBS)
+        args.batch = TOTAL_JOBS // max(world, 1)
+    args.jobs_total = args.batch * max(world, 1)
 
     if args.impl == "reference":
         out = run_reference(args, rank, world)
@@ -480,13 +632,18 @@ def main():
             print(json.dumps(out), flush=True)
         return
     out = run_ours(args, rank, world, local_rank)
+    extras = not args.no_extras
+    if extras and rank == 0:
+        out["config1_b1"] = config1_b1(args)
+        out["gpu_library_baseline"] = gpu_library_baseline(args, out["fg_evals_per_iteration"])
+    if extras and not args.no_po:
+        po = po_config5(rank, world, local_rank)          # every rank takes part (NCCL)
+        if rank == 0:
+            out["po_config5"] = po
+            if world == 1:
+                out["po_config3"] = po_config3()
     if out is not None:
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_sample(args)
-        else:
-            out["cpu_baseline"] = None
-        if world == 1 and not args.no_po:
-            out["po"] = po_sample()
+        out["cpu_baseline"] = cpu_baseline_sample(args) if (world == 1 and not args.no_cpu_baseline) else None
         print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist

@@ -152,10 +152,14 @@ int stx_plan_feature_bf16(stx_plan* plan, int layer, const void** hi, const void
 int stx_plan_backward_custom(stx_plan* plan, const float* image, int is_preimage, const float* const* M,
                              const void* const* E, float* grad, void* stream);
 
-/* ---- device-resident L-BFGS with box bounds: the optimiser loop of synthesizer.py:127-151 ----------------
+/* ---- device-resident L-BFGS-B: the optimiser loop of synthesizer.py:127-151 ------------------------------
  * Replaces scipy.optimize.minimize(method="L-BFGS-B", jac=True, bounds=[0,1]^n, options={maxiter, maxcor,
- * ftol=0, gtol=0}) with a projected L-BFGS whose state (x, history, line search) never leaves the GPU.
- * Each of the `batch` images of the plan is an independent problem with its own history and line search. */
+ * ftol=0, gtol=0}) with the same algorithm on the GPU (subspace minimisation over the free variables by the direct
+ * primal method, projected step, More'-Thuente line search along the feasible segment with lnsrlb's constants and
+ * termination rules; the one omission is the breakpoint walk of the generalized Cauchy point - csrc/lbfgs.cu,
+ * DESIGN.md section 6) whose state (x, history, line search) never leaves the device.
+ * Each of the `batch` images of the plan is an independent problem with its own history and line search. A problem
+ * stops before `maxiter` when f does not decrease (L-BFGS-B's test at factr = 0) or a line search fails twice. */
 int stx_lbfgs_create(stx_lbfgs** out, stx_plan* plan, int maxcor, int bounded, float lower, float upper);
 void stx_lbfgs_destroy(stx_lbfgs* opt);
 /* x0: device [batch,H,W,3]. Resets the history. */

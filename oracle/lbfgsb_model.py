@@ -35,14 +35,20 @@ class LbfgsB:
     """One bound-constrained problem, reverse communication: opt.start(x0, f0, g0); while not opt.done:
     f, g = fg(opt.xt); opt.feed(f, g).  Vectors float64 (as scipy) unless `vec_dtype` says otherwise."""
 
-    def __init__(self, n, m=20, lo=0.0, hi=1.0, bounded=True, vec_dtype=np.float64, gcp="exact", subspace=True):
+    def __init__(self, n, m=20, lo=0.0, hi=1.0, bounded=True, vec_dtype=np.float64, gcp="exact", subspace=True,
+                 x_dtype=np.float64, backtrack="lbfgsb"):
         self.n, self.m = n, m
         self.bounded = bounded
         self.lo = np.full(n, lo, np.float64)
         self.hi = np.full(n, hi, np.float64)
         self.vt = vec_dtype
-        self.gcp = gcp              # "exact": algorithm CP; "first": first segment only (no breakpoint walk)
+        self.gcp = gcp              # "exact": algorithm CP; "first": first segment only (no breakpoint walk);
+                                    # "none": no Cauchy step once there is a history (xcp = x, active set = variables at a
+                                    # bound whose gradient points outwards) - what the CUDA optimiser does
         self.subspace = subspace
+        self.xdt = x_dtype          # dtype of x, g, d and the trial point (float32 on the device)
+        self.backtrack = backtrack  # "lbfgsb": truncate at the first bound when the projected step is not a descent
+                                    # direction (subsm of version 3.0); "reset": drop the memory instead (device)
         self.S = np.zeros((m, n), vec_dtype)
         self.Y = np.zeros((m, n), vec_dtype)
         self.col = 0
@@ -212,6 +218,8 @@ class LbfgsB:
             if float((xs - x) @ g) > 0.0:
                 # projected point is not a descent direction: classic truncation of the step at the first bound
                 self.nbacktrack += 1
+                if self.backtrack == "reset":
+                    return None
                 xf = xcp[free]
                 with np.errstate(divide="ignore", invalid="ignore"):
                     a = np.where(d < 0.0, (self.lo[free] - xf) / d, np.where(d > 0.0, (self.hi[free] - xf) / d, np.inf))
@@ -227,17 +235,19 @@ class LbfgsB:
     # ------------------------------------------------------------------ one iteration set-up
     def _direction(self):
         x, g = self.x, self.g
+        x64, g64 = x.astype(np.float64), g.astype(np.float64)
         while True:
             if not self.bounded and self.col > 0:
-                xcp, c, fixed = x.copy(), np.zeros(2 * self.col), np.zeros(self.n, bool)
+                xcp, c, fixed = x64.copy(), np.zeros(2 * self.col), np.zeros(self.n, bool)
             else:
-                xcp, c, fixed = self._cauchy(x, g)
-            z = self._subspace(x, g, xcp, c, fixed)
+                xcp, c, fixed = self._cauchy(x64, g64)
+            z = self._subspace(x64, g64, xcp, c, fixed)
             if z is None:
                 self._reset()
                 continue
+            z = z.astype(self.xdt)
             d = z - x
-            gd = float(g @ d)
+            gd = float(g.astype(np.float64) @ d.astype(np.float64))
             if not (gd < 0.0):
                 if self.col > 0:
                     self._reset()
@@ -254,10 +264,13 @@ class LbfgsB:
                 stpmx = 1.0
             else:
                 with np.errstate(divide="ignore", invalid="ignore"):
-                    a = np.where(d < 0.0, (self.lo - x) / d, np.where(d > 0.0, (self.hi - x) / d, np.inf))
+                    d64 = d.astype(np.float64)
+                    a = np.where(d64 < 0.0, (self.lo - x64) / d64, np.where(d64 > 0.0, (self.hi - x64) / d64, np.inf))
                 a = np.where(np.isnan(a), np.inf, a)
                 stpmx = min(stpmx, max(float(a.min()), 0.0))
-        dnorm = float(np.sqrt(d @ d))
+                if self.xdt != np.float64:
+                    stpmx = max(stpmx, 1.0)     # d = z - x is feasible at step 1 by construction; rounding may say 0.9999999
+        dnorm = float(np.sqrt(d.astype(np.float64) @ d.astype(np.float64)))
         stp = min(1.0 / dnorm, stpmx) if (self.nit == 0 and not self.bounded) else 1.0
         self.ls = ls_init(self.f, gd, stp)
         self.ls["stmax_user"] = stpmx
@@ -266,7 +279,11 @@ class LbfgsB:
 
     def _trial(self, stp):
         self.stp = stp
-        self.xt = self.z.copy() if stp == 1.0 else self.x + stp * self.d
+        if stp == 1.0:
+            self.xt = self.z.copy()
+        else:
+            xt = self.x + self.xdt(stp) * self.d
+            self.xt = np.clip(xt, self.lo.astype(self.xdt), self.hi.astype(self.xdt)) if self.bounded else xt
 
     def _reset(self):
         self.col = 0
@@ -275,17 +292,17 @@ class LbfgsB:
 
     # ------------------------------------------------------------------ driver interface
     def start(self, x0, f0, g0):
-        x = np.asarray(x0, np.float64).ravel().copy()
+        x = np.asarray(x0, self.xdt).ravel().copy()
         if self.bounded:
-            x = np.clip(x, self.lo, self.hi)
-        self.x, self.f, self.g = x, float(f0), np.asarray(g0, np.float64).ravel().copy()
+            x = np.clip(x, self.lo.astype(self.xdt), self.hi.astype(self.xdt))
+        self.x, self.f, self.g = x, float(f0), np.asarray(g0, self.xdt).ravel().copy()
         self.nfev = 1
         self._direction()
 
     def feed(self, ft, gt):
-        gt = np.asarray(gt, np.float64).ravel()
+        gt = np.asarray(gt, self.xdt).ravel()
         self.nfev += 1
-        gdt = float(gt @ self.d)
+        gdt = float(gt.astype(np.float64) @ self.d.astype(np.float64))
         res = ls_update_bounded(self.ls, float(ft), gdt, self.stpmx)
         if res == "again":
             self._trial(self.ls["stp"])
@@ -300,7 +317,11 @@ class LbfgsB:
             return
         # accept (CONVERGENCE or WARNING of dcsrch: lnsrlb takes both as the new iterate)
         stp = self.stp
-        r = gt - self.g
+        r = (gt - self.g).astype(np.float64)
+        if self.xdt != np.float64:
+            # the device forms s = xt - x (after rounding and clipping) and takes s'y from the stored vectors
+            s_dev = (self.xt - self.x).astype(np.float64)
+            dr_dev = float(s_dev @ r)
         if stp == 1.0:
             dr = gdt - self.gd
             ddum = -self.gd
@@ -309,6 +330,8 @@ class LbfgsB:
             dr = (gdt - self.gd) * stp
             s = self.d * stp
             ddum = -self.gd * stp
+        if self.xdt != np.float64:
+            s, dr = s_dev, dr_dev
         fold = self.f
         self.x, self.f, self.g = self.xt, float(ft), gt.copy()
         self.nit += 1
@@ -322,6 +345,10 @@ class LbfgsB:
         else:
             self._update(s, r, dr)
         self._direction()
+
+    @property
+    def nh(self):
+        return self.col
 
     def _update(self, s, y, dr):
         m = self.m
@@ -394,6 +421,13 @@ def ls_update_bounded(st, f, g, stpmx):
         new = st["stx"]
     st["stp"] = new
     return "again"
+
+
+DEVICE = dict(gcp="none", vec_dtype=np.float32, x_dtype=np.float32, backtrack="reset")
+"""The variant syntex_b200/csrc/lbfgs.cu implements (keyword arguments of LbfgsB): float32 vectors, the subspace step
+taken from x itself with the active set of the current point (no breakpoint walk: measured on the texture objective,
+tests/test_lbfgsb_model.py, final losses are indistinguishable from the exact generalized Cauchy point), and a
+memory reset in the (never observed) case that the projected step is not a descent direction."""
 
 
 def minimize(fg, x0, maxiter, m=20, lo=0.0, hi=1.0, bounded=True, max_evals=None, callback=None, **kw):

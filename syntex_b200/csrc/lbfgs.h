@@ -1,4 +1,4 @@
-// Device-resident projected L-BFGS (see lbfgs.cu).
+// Device-resident L-BFGS-B (see lbfgs.cu).
 #pragma once
 #include "plan.h"
 

@@ -3,7 +3,7 @@
 Same class, method names, argument order and defaults as the reference (gatys/synthesizer.py:16-159). The TF
 session/graph is replaced by one prepared CUDA plan (syntex_b200/csrc/plan.cu); `sess` is accepted and ignored.
 Two optimisers drive the same f/g evaluation:
-  args["optimizer"] = "device" (default)  the GPU-resident projected L-BFGS (csrc/lbfgs.cu): x, history and line
+  args["optimizer"] = "device" (default)  the GPU-resident L-BFGS-B (csrc/lbfgs.cu): x, history and line
                                           search stay in HBM, no host round trip per iteration;
   args["optimizer"] = "scipy"             the reference's own call, scipy L-BFGS-B over Synthesizer.step with host
                                           buffers (synthesizer.py:149-150), for like-for-like comparisons.

@@ -84,4 +84,4 @@ if __name__ == "__main__":
     if "config1" in which:
         run(256, 100, list(range(8)), os.path.join(HERE, "optimizer_config1.npz"))
     if "config2" in which:
-        run(512, 500, [0, 1], os.path.join(HERE, "optimizer_config2.npz"))
+        run(512, 500, [0, 1], os.path.join(HERE, "optimizer_config2.npz"), with_model=False)

@@ -1,5 +1,5 @@
-"""The numpy model of the device optimiser (oracle/lbfgs_model.py): line-search conditions, agreement with
-scipy L-BFGS-B on problems whose solution is unique, bound handling."""
+"""The numpy model of the device optimiser (oracle/lbfgs_model.py over oracle/lbfgsb_model.py): line-search
+conditions, agreement with scipy L-BFGS-B on problems whose solution is unique, bound handling."""
 import numpy as np
 import pytest
 from scipy.optimize import minimize as sp_minimize
