@@ -79,6 +79,12 @@ int stx_vgg_weights(const stx_vgg* vgg, int conv_index, const void** fwd_hi, con
  * convolutions that only feed a pooling layer (conv1_2, conv2_2, conv3_4, conv4_4): nothing on the f/g path reads it,
  * and stx_plan_copy_feature_f32 then returns those four layers rounded to bf16. Vgg19.build sets this flag. */
 #define STX_PLAN_FULL_FEATURES 4
+/* f16 + f8 forward: activations as fp16 planes plus e4m3 correction planes ([A8 | A_lo8] per 64-channel chunk), weights
+ * as an fp16 pack plus e4m3 correction rows; per K step ONE kind::f16 MMA and ONE kind::f8f6f4 MMA (twice the MACs in
+ * the same tensor-pipe time) instead of the three bf16 MMAs of the default forward - two MMAs' time per algorithmic
+ * MAC at the same (bf16x3-class) accuracy of the pre-activations. Needs every convolution's map >= 8 pixels wide
+ * (image side >= 64); such a plan does not serve stx_plan_feature_bf16. */
+#define STX_PLAN_F16F8 8
 int stx_plan_create(stx_plan** out, const stx_vgg* vgg, int batch, int height, int width, int topmost,
                     int num_loss_layers, const int* loss_layers, const float* coefs, int flags);
 void stx_plan_destroy(stx_plan* plan);

@@ -103,6 +103,9 @@ int stx_plan_copy_feature_f32(stx_plan* plan, int layer, float* out, void* strea
   Plan* p = plan->p;
   STX_REQUIRE(layer >= 0 && layer <= p->topmost, "layer index out of range for this plan");
   const size_t n = static_cast<size_t>(p->B) * p->lh[layer] * p->lw[layer] * p->lc[layer];
+  if (p->split == 2)
+    return f16f8_to_f32_launch(p->act[layer], p->lo_valid[layer] ? p->act_lo[layer] : nullptr, n, p->lc[layer], out,
+                               S(stream));
   if (p->split && p->lo_valid[layer]) return bf16pair_to_f32_launch(p->act[layer], p->act_lo[layer], n, out, S(stream));
   return bf16_to_f32_launch(p->act[layer], n, out, S(stream));
 }
@@ -260,6 +263,7 @@ int stx_plan_feature_bf16(stx_plan* plan, int layer, const void** hi, const void
   STX_REQUIRE(plan && hi, "stx_plan_feature_bf16: null argument");
   Plan* p = plan->p;
   STX_REQUIRE(layer >= 0 && layer <= p->topmost, "stx_plan_feature_bf16: layer out of range");
+  if (p->split == 2) return fail(STX_ERR_STATE, "stx_plan_feature_bf16: an f16+f8 plan keeps fp16 / e4m3 planes, not bf16");
   *hi = p->act[layer];
   if (lo) *lo = p->lo_valid[layer] ? p->act_lo[layer] : nullptr;
   return STX_OK;

@@ -1,6 +1,9 @@
 // Shared by the two convolution kernels (conv_igemm.cu: one TMA box per filter tap; conv_patch.cu: one halo patch
 // per channel chunk): kernel parameters and the epilogue that turns fp32 accumulators into the stored result.
 #pragma once
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -36,12 +39,99 @@ struct ConvKernelParams {
   float* rgb_out;
   const float* rgb_image;
   int rgb_preimage;
+  // f16+f8 forward (plan precision 2, see kF8*): the correction accumulator is multiplied by corr_scale before it
+  // is added to the main one. aux_out / pool_aux (nullable): a bf16 copy of the stored / pooled result, kept for the
+  // loss layers - their features are the A operand of the Gram gradient against bf16 matrices, and kind::f16 does
+  // NOT take an fp16 A with a bf16 B (measured on the B200: illegal instruction).
+  float corr_scale;
+  bf16* aux_out;
+  bf16* pool_aux;
 };
 
 union Pack8 {
   uint4 u;
   __nv_bfloat162 h2[4];
 };
+
+// ---- f16 + f8 activation format (plan precision 2) ----------------------------------------------------------
+// A recorded layer is TWO planes of 2 bytes per element:
+//   hi   [n,H,W,C] fp16: A16 = fp16(A)                        (main MMA operand, Gram operand, ReLU mask)
+//   corr [n,H,W,C/64][128 B]: per pixel and 64-channel chunk, 64 bytes e4m3(A * kF8ScaleA) followed by 64 bytes
+//        e4m3((A - A16) * kF8ScaleLo)
+// so that one K = 128-byte row of the correction MMA (kind::f8f6f4) is [A8 | Alo8] against a weight row [Wlo8 | W8]:
+//   A8 * Wlo8 + Alo8 * W8  =  2^S (A * W_lo + A_lo * W)   up to e4m3 rounding of quantities that are already 2^-11
+//   of the main term (relative error ~2^-15: bf16x3 class, measured tests/tools/precision_emulation.py).
+// The scales are powers of two: activations are data, so theirs are fixed (A / 8 covers 2^-12 .. 3584, A_lo * 512
+// the same range relative to A's half-ulp); the weights' are chosen per layer from max |W| (vgg_create), with
+// scale(W_lo) = 4096 * scale(W) so that both products carry the same factor 2^S = 512 * scale(W).
+constexpr float kF8ScaleA = 0.125f;
+constexpr float kF8ScaleLo = 512.0f;
+
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+
+union Pack8h {
+  uint4 u;
+  __half2 h2[4];
+};
+
+// 32 consecutive channels (ch0 a multiple of 32) of one pixel -> fp16 plane and correction plane.
+// pix = pixel index, C = channels of the layer; lo_plane may be null (layer whose low half nothing reads).
+__device__ __forceinline__ void store_f16f8_32(const float (&v)[32], bf16* hi_plane, bf16* corr_plane, size_t pix, int C,
+                                               int ch0) {
+  uint4* o4 = reinterpret_cast<uint4*>(hi_plane + pix * C + ch0);
+  uint32_t a8[8], l8[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    Pack8h pk;
+    float lo[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = fminf(v[8 * j + 2 * e], 65504.0f), b = fminf(v[8 * j + 2 * e + 1], 65504.0f);
+      pk.h2[e] = __floats2half2_rn(a, b);
+      const float2 hh = __half22float2(pk.h2[e]);
+      lo[2 * e] = (a - hh.x) * kF8ScaleLo;
+      lo[2 * e + 1] = (b - hh.y) * kF8ScaleLo;
+    }
+    o4[j] = pk.u;
+    a8[2 * j] = pack_e4m3x4(v[8 * j] * kF8ScaleA, v[8 * j + 1] * kF8ScaleA, v[8 * j + 2] * kF8ScaleA,
+                            v[8 * j + 3] * kF8ScaleA);
+    a8[2 * j + 1] = pack_e4m3x4(v[8 * j + 4] * kF8ScaleA, v[8 * j + 5] * kF8ScaleA, v[8 * j + 6] * kF8ScaleA,
+                                v[8 * j + 7] * kF8ScaleA);
+    l8[2 * j] = pack_e4m3x4(lo[0], lo[1], lo[2], lo[3]);
+    l8[2 * j + 1] = pack_e4m3x4(lo[4], lo[5], lo[6], lo[7]);
+  }
+  if (corr_plane) {
+    uint8_t* cb = reinterpret_cast<uint8_t*>(corr_plane) + pix * C * 2 + static_cast<size_t>(ch0 >> 6) * 128 + (ch0 & 63);
+    uint4* c4 = reinterpret_cast<uint4*>(cb);
+    c4[0] = make_uint4(a8[0], a8[1], a8[2], a8[3]);
+    c4[1] = make_uint4(a8[4], a8[5], a8[6], a8[7]);
+    uint4* d4 = reinterpret_cast<uint4*>(cb + 64);
+    d4[0] = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+    d4[1] = make_uint4(l8[4], l8[5], l8[6], l8[7]);
+  }
+}
+
+// 32 consecutive channels of one pixel -> bf16
+__device__ __forceinline__ void store_bf16_32(const float (&v)[32], bf16* dst) {
+  uint4* o4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    Pack8 pk;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pk.h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+    o4[j] = pk.u;
+  }
+}
+
+// Sign test of a stored activation, valid for bf16 AND fp16 bit patterns: positive <=> the 16 bits, read as a signed
+// integer, are > 0 (the ReLU masks of the backward pass only need the sign of the recorded activation).
+__device__ __forceinline__ bool pos16_lo(uint32_t w) { return static_cast<short>(w & 0xffffu) > 0; }
+__device__ __forceinline__ bool pos16_hi(uint32_t w) { return static_cast<int>(w) >> 16 > 0; }
+
 
 // Epilogue for 32 consecutive output channels of one pixel: v[] are the fp32 accumulators.
 //   v += bias; v += addend; relu; zero where mask <= 0; then one of
@@ -50,7 +140,8 @@ union Pack8 {
 // Called by all 32 lanes of the warp (the pooling uses shuffles); `valid` guards the memory operations.
 // Pooling relies on the patch kernel's row mapping: lane = 8 * (h & 3) + (w & 7), so a 2x2 window is
 // {lane, lane ^ 1, lane ^ 8, lane ^ 9}.
-template <bool SPLIT>
+// FMT: 0 = bf16 planes (hi, and lo in split mode), 2 = fp16 + e4m3 correction planes (see kF8*)
+template <bool SPLIT, int FMT = 0>
 __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, float (&v)[32], bool valid, int n, int h,
                                                     int w, int ch0) {
   const size_t off = ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.cout + ch0;
@@ -98,13 +189,12 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
       const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        Pack8 pk;
-        pk.u = __ldg(m4 + j);
+        const uint4 mk = __ldg(m4 + j);
+        const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(pk.h2[e]);
-          if (!(f.x > 0.0f)) v[8 * j + 2 * e] = 0.0f;
-          if (!(f.y > 0.0f)) v[8 * j + 2 * e + 1] = 0.0f;
+          if (!pos16_lo(mw[e])) v[8 * j + 2 * e] = 0.0f;
+          if (!pos16_hi(mw[e])) v[8 * j + 2 * e + 1] = 0.0f;
         }
       }
     }
@@ -119,18 +209,21 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
           uint4* o4 = reinterpret_cast<uint4*>(p.up_out + uo);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            Pack8 pm, po;
-            pm.u = __ldg(m4 + j);
+            Pack8 po;
+            const uint4 mk = __ldg(m4 + j);
+            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(pm.h2[e]);
-              po.h2[e] = __floats2bfloat162_rn(f.x > 0.0f ? 0.25f * v[8 * j + 2 * e] : 0.0f,
-                                               f.y > 0.0f ? 0.25f * v[8 * j + 2 * e + 1] : 0.0f);
+              po.h2[e] = __floats2bfloat162_rn(pos16_lo(mw[e]) ? 0.25f * v[8 * j + 2 * e] : 0.0f,
+                                               pos16_hi(mw[e]) ? 0.25f * v[8 * j + 2 * e + 1] : 0.0f);
             }
             o4[j] = po.u;
           }
         }
       }
+    } else if (FMT == 2) {
+      store_f16f8_32(v, p.out, p.out_lo, (static_cast<size_t>(n) * p.H + h) * p.W + w, p.cout, ch0);
+      if (p.aux_out) store_bf16_32(v, p.aux_out + off);
     } else {
       uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
       // the low halves are optional even in split mode: a layer that only feeds a fused pool (whose hi/lo outputs
@@ -163,7 +256,13 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
       v[j] = 0.25f * t;
     }
     const int lane = threadIdx.x & 31;
-    if (valid && (lane & 9) == 0) {
+    if (FMT == 2) {
+      if (valid && (lane & 9) == 0) {
+        const size_t ppix = (static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+        store_f16f8_32(v, p.pool_out, p.pool_out_lo, ppix, p.cout, ch0);
+        if (p.pool_aux) store_bf16_32(v, p.pool_aux + ppix * p.cout + ch0);
+      }
+    } else if (valid && (lane & 9) == 0) {
       const size_t po = ((static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * p.cout + ch0;
       uint4* o4 = reinterpret_cast<uint4*>(p.pool_out + po);
       uint4* l4 = p.pool_out_lo ? reinterpret_cast<uint4*>(p.pool_out_lo + po) : nullptr;

@@ -224,6 +224,9 @@ int launch_bn(const ConvOp& op, cudaStream_t stream) {
   p.up_out = op.up_out;
   p.up_mask = op.up_mask;
   p.export_out = op.export_out;
+  p.corr_scale = 1.0f;
+  p.aux_out = nullptr;
+  p.pool_aux = nullptr;
   dim3 grid(op.tiles_w * op.tiles_h * op.tiles_n, op.cout / BN, 1);
   STX_TRY(launch_pdl(conv_igemm_kernel<BN, SPLIT>, grid, dim3(kThreads), L::kTotal, stream, op.tmA, op.tmB,
                      SPLIT ? op.tmA2 : op.tmA, SPLIT ? op.tmB2 : op.tmB, p));
@@ -313,6 +316,9 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->up_out = nullptr;
   op->up_mask = nullptr;
   op->export_out = nullptr;
+  op->corr_scale = 1.0f;
+  op->aux_out = nullptr;
+  op->pool_aux = nullptr;
   op->split = 0;
   op->relu = 0;
   op->pad = 1;

@@ -47,7 +47,9 @@ constexpr int pow2_at_least(int v) {
 // 64-channel layers a work item is only ~1-2 us of MMA time but used to pull 72-144 KB of weights from L2 every time
 // (4x the bytes of its activation patch): 148 SMs fetching the same tiles in lock step made those layers
 // L2-delivery-bound (conv1_2 forward: 5.2 us per tile against 1.8 us of tensor work).
-template <int BN, int MT, bool SPLIT, int OCC, int RES>
+// F8 (with SPLIT): the f16 + f8 forward - the second operand pair of a stage is the e4m3 correction pair (see
+// conv_common.cuh, kF8*) and accumulates into its own TMEM columns through kind::f8f6f4.
+template <int BN, int MT, bool SPLIT, int OCC, int RES, bool F8 = false>
 struct PatchSmem {
   static constexpr int kPatchRows = (16 * MT + 2) * kPatchW;
   static constexpr int kPatchBytes = kPatchRows * 128;                        // TMA transaction bytes
@@ -73,8 +75,10 @@ struct PatchSmem {
   // epilogue adds. An M = 128, K = 16 MMA costs ~64 cycles however small N is (measured: ~70 cycles per N = 64 MMA,
   // ~72 per N = 128 MMA - the A operand streams out of shared memory at 64 B/clk), so two N = 64 MMAs on the same
   // A tile cost twice what one N = 128 MMA does.
-  static constexpr bool kMerge = SPLIT && BN == 64;
-  static constexpr int kAccCols = (kMerge ? 2 : 1) * BN * MT;
+  static constexpr bool kMerge = SPLIT && BN == 64 && !F8;
+  static constexpr bool kTwoAcc = kMerge || F8;                               // two column ranges per tile, summed by the epilogue
+  static constexpr int kAccCols = (kTwoAcc ? 2 : 1) * BN * MT;
+  static_assert(!F8 || (SPLIT && MT == 1 && RES == 0), "f16+f8 forward: split operands, one tile, ring weights");
   static constexpr int kAccStages = (2 * kAccCols * OCC <= 512) ? 2 : 1;      // TMEM accumulator buffers
   static constexpr int kTmemCols = pow2_at_least(kAccStages * kAccCols);
   static_assert(kPatchStages >= 1, "no room for a patch stage");
@@ -96,13 +100,13 @@ struct PatchSched {
   int nblocks64;     // N / 64
 };
 
-template <int BN, int MT, bool SPLIT, int OCC, int RES>
+template <int BN, int MT, bool SPLIT, int OCC, int RES, bool F8>
 __global__ void __launch_bounds__(kThreads, OCC)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                   const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmD,
                   const ConvKernelParams p, const PatchSched sched) {
-  using L = PatchSmem<BN, MT, SPLIT, OCC, RES>;
+  using L = PatchSmem<BN, MT, SPLIT, OCC, RES, F8>;
   constexpr int kPS = L::kPatchStages, kBS = L::kBStages, kAS = L::kAccStages;
   constexpr int kBB = L::kBBarriers, kDS = L::kDStages;
   extern __shared__ uint8_t smem_raw[];
@@ -258,7 +262,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // compiler wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY serialisation loop, which costs more
     // issue time than a 32-cycle N = 64 MMA takes to execute.
     {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      // operand formats: the f16+f8 forward multiplies fp16 planes (and e4m3 correction planes), everything else bf16
+      constexpr uint32_t idesc = F8 ? make_idesc(128, BN, kFmtF16, kFmtF16, 0, 0) : make_idesc_bf16(128, BN, 0, 0);
+      constexpr uint32_t idesc_f8 = make_idesc(128, BN, kFmtE4M3, kFmtE4M3, 0, 0);
+      constexpr uint32_t idesc_gram = make_idesc_bf16(128, BN, 0, 0);
       constexpr uint32_t kGroupStride = kPatchW * 128;     // bytes between consecutive 8-pixel row groups
       constexpr uint32_t kDescHiA = desc_hi_sw128(kGroupStride);   // activations: 8-row groups kGroupStride apart
       constexpr uint32_t kDescHiB = desc_hi_sw128(1024);           // weights: dense 128-byte rows
@@ -289,13 +296,20 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               const uint32_t a_lo = a_lo0 + tap_off16 + ((mt * 16 * kGroupStride) >> 4);
-              const uint32_t d = acc + mt * (L::kMerge ? 2 : 1) * BN;
+              const uint32_t d = acc + mt * (L::kTwoAcc ? 2 : 1) * BN;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint32_t accumulate = (first_chunk && tap == 0 && k == 0) ? 0u : 1u;
                 const uint64_t ad = desc_pack(a_lo + 2 * k, kDescHiA);
                 const uint64_t bd = desc_pack(b_lo0 + 2 * k, kDescHiB);
-                if (L::kMerge) {
+                if (F8) {
+                  // fp16(A) * fp16(W) into the main columns, [A8 | Alo8] * [Wlo8 ; W8] (K = 32 per instruction, the
+                  // same 32 bytes of the 128-byte rows) into the correction columns
+                  const uint64_t ad_c = desc_pack(a_lo + (L::kPatchStride >> 4) + 2 * k, kDescHiA);
+                  const uint64_t bd_c = desc_pack(b_lo0 + (L::kBBytes >> 4) + 2 * k, kDescHiB);
+                  umma_bf16(d, ad, bd, idesc, accumulate);
+                  umma_f8(d + BN, ad_c, bd_c, idesc_f8, accumulate);
+                } else if (L::kMerge) {
                   const uint64_t ad_lo = desc_pack(a_lo + (L::kPatchStride >> 4) + 2 * k, kDescHiA);
                   // [W_hi ; W_lo] are adjacent 64-row tiles of one stage: a single N = 128 operand
                   umma_bf16(d, ad, bd, make_idesc_bf16(128, 2 * BN, 0, 0), accumulate);   // A_hi * [W_hi ; W_lo]
@@ -356,7 +370,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16(acc + mt * BN, desc_pack(f_lo + mt * (16384 >> 4) + 2 * k, kDescHiB),
-                          desc_pack(g_lo + 2 * k, kDescHiB), idesc, 1);
+                          desc_pack(g_lo + 2 * k, kDescHiB), idesc_gram, 1);
             }
             umma_commit(&ring_empty[bs]);
             umma_commit(&pempty[ps]);
@@ -550,13 +564,14 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int h = h0 + mt * 16 + (r >> 3);
           const bool valid = (h < p.H) && (w < p.W);
           float v[32];
-          if (L::kMerge) {
+          if (L::kTwoAcc) {
             float u[32];
             tmem_ld_32x32(acc + mt * 2 * BN + c0, v);
             tmem_ld_32x32(acc + mt * 2 * BN + BN + c0, u);
             tmem_ld_wait();
+            const float cs = F8 ? p.corr_scale : 1.0f;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] += u[e];
+            for (int e = 0; e < 32; ++e) v[e] = fmaf(u[e], cs, v[e]);
           } else {
             tmem_ld_32x32(acc + mt * BN + c0, v);
             tmem_ld_wait();
@@ -566,7 +581,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&aempty[as]);
           }
-          conv_epilogue_store<SPLIT>(p, v, valid, n, h, w, nblk * BN + c0);
+          conv_epilogue_store<SPLIT, F8 ? 2 : 0>(p, v, valid, n, h, w, nblk * BN + c0);
         }
       }
     }
@@ -577,12 +592,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
 }
 
-template <int BN, int MT, bool SPLIT, int OCC, int RES = 0>
+template <int BN, int MT, bool SPLIT, int OCC, int RES = 0, bool F8 = false>
 int launch_patch(const ConvOp& op, cudaStream_t stream) {
-  using L = PatchSmem<BN, MT, SPLIT, OCC, RES>;
+  using L = PatchSmem<BN, MT, SPLIT, OCC, RES, F8>;
   static bool attr_set = false;
   if (!attr_set) {
-    STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT, OCC, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT, OCC, RES, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   L::kTotal));
     attr_set = true;
   }
@@ -614,9 +629,12 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.up_out = op.up_out;
   p.up_mask = op.up_mask;
   p.export_out = op.export_out;
+  p.corr_scale = op.corr_scale;
+  p.aux_out = op.aux_out;
+  p.pool_aux = op.pool_aux;
   PatchSched sched;
   sched.nblocks = op.cout / BN;
-  sched.ksplit = (op.ksplit > 1 && op.splitk_ws && op.splitk_counters && BN != 16 && !L::kMerge) ? op.ksplit : 1;
+  sched.ksplit = (op.ksplit > 1 && op.splitk_ws && op.splitk_counters && BN != 16 && !L::kTwoAcc) ? op.ksplit : 1;
   sched.wt = op.w_tiled;
   sched.wt_lo = SPLIT ? op.w_tiled_lo : nullptr;
   if (SPLIT && !op.w_tiled_lo) sched.wt = nullptr;
@@ -638,7 +656,7 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
     STX_REQUIRE(sched.nblocks == 1 && sched.ksplit == 1 && op.cin == 64 * RES,
                 "conv: resident-weight instance on a shape it does not cover");
   }
-  STX_TRY(launch_pdl(conv_patch_kernel<BN, MT, SPLIT, OCC, RES>, dim3(grid), dim3(kThreads), L::kTotal, stream, op.tmA,
+  STX_TRY(launch_pdl(conv_patch_kernel<BN, MT, SPLIT, OCC, RES, F8>, dim3(grid), dim3(kThreads), L::kTotal, stream, op.tmA,
                      op.tmB, SPLIT ? op.tmA2 : op.tmA, SPLIT ? op.tmB2 : op.tmB, sched.gram_chunks ? op.tmF : op.tmA,
                      sched.gram_chunks ? op.tmD : op.tmB, p, sched));
   count_launch();
@@ -743,6 +761,9 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->split = 0;
   op->relu = 0;
   op->pad = 1;
+  op->corr_scale = 1.0f;
+  op->aux_out = nullptr;
+  op->pool_aux = nullptr;
   return STX_OK;
 }
 
@@ -803,6 +824,12 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
   }
   STX_REQUIRE(op.out != nullptr || op.up_out != nullptr, "conv: output not set");
   STX_REQUIRE(op.pool_out == nullptr || (op.H % 2 == 0 && op.W % 2 == 0), "conv: fused pooling needs even H and W");
+  if (op.split == 2) {
+    STX_REQUIRE(op.out_lo != nullptr || op.pool_out_lo != nullptr, "conv f16+f8: correction-plane output not set");
+    STX_REQUIRE(op.res == 0 && op.mt == 1, "conv f16+f8: bad configuration");
+    if (op.bn == 128) return launch_patch<128, 1, true, 1, 0, true>(op, stream);
+    return launch_patch<64, 1, true, 1, 0, true>(op, stream);
+  }
   if (op.split) {
     STX_REQUIRE(op.out_lo != nullptr || op.pool_out_lo != nullptr, "conv split: low-half output not set");
     if (op.bn == 128) return launch_patch<128, 1, true, 1>(op, stream);

@@ -1,17 +1,12 @@
 // Bandwidth-bound pieces of the VGG19 path: the 3-channel first layer (fused with preprocessing), 2x2 average
 // pooling forward / backward (+ReLU mask), weight packing and dtype conversion. All are simple coalesced
 // 16-byte-vector kernels; none has data reuse worth staging.
+#include "conv_common.cuh"
 #include "ops.h"
-#include "ptx.cuh"
 
 namespace stx {
 
 namespace {
-
-union Pack8 {
-  uint4 u;
-  __nv_bfloat162 h2[4];
-};
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
@@ -41,7 +36,7 @@ __device__ __forceinline__ float2 unpack2(unsigned long long v) {
 __global__ void __launch_bounds__(128, 4)
 conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int is_preimage, float m0, float m1,
                    float m2, const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ out,
-                   bf16* __restrict__ out_lo) {
+                   bf16* __restrict__ out_lo, int fmt, bf16* __restrict__ aux) {
   __shared__ __align__(16) float sw[27 * 64];
   __shared__ __align__(16) float sb[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];      // constants: safe before pdl_wait
@@ -114,6 +109,18 @@ conv1_1_fwd_kernel(const float* __restrict__ image, int nimg, int H, int W, int 
       if (x + px >= W) break;
       const unsigned long long* acc = px ? acc1 : acc0;
       const long long pix = img_base + static_cast<long long>(y) * W + x + px;
+      if (fmt == 2) {      // fp16 plane + e4m3 correction plane (conv_common.cuh, kF8*)
+        float v32[32];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float2 v = unpack2(acc[k]);
+          v32[2 * k] = fmaxf(v.x, 0.0f);
+          v32[2 * k + 1] = fmaxf(v.y, 0.0f);
+        }
+        store_f16f8_32(v32, out, out_lo, static_cast<size_t>(pix), 64, half * 32);
+        if (aux) store_bf16_32(v32, aux + pix * 64 + half * 32);
+        continue;
+      }
       uint4* o4 = reinterpret_cast<uint4*>(out + pix * 64 + half * 32);
       uint4* l4 = out_lo ? reinterpret_cast<uint4*>(out_lo + pix * 64 + half * 32) : nullptr;
 #pragma unroll
@@ -273,9 +280,9 @@ avgpool2_bwd_mask_kernel(const bf16* __restrict__ g_in, const bf16* __restrict__
     f.x *= 0.25f;
     f.y *= 0.25f;
     if (act) {
-      const float2 m = __bfloat1622float2(a.h2[e]);
-      if (!(m.x > 0.0f)) f.x = 0.0f;
-      if (!(m.y > 0.0f)) f.y = 0.0f;
+      const uint32_t mw = reinterpret_cast<const uint32_t*>(&a.u)[e];     // sign test valid for bf16 and fp16 planes
+      if (!pos16_lo(mw)) f.x = 0.0f;
+      if (!pos16_hi(mw)) f.y = 0.0f;
     }
     o.h2[e] = __floats2bfloat162_rn(f.x, f.y);
   }
@@ -310,6 +317,43 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cin, int co
   if (wf) wf[(static_cast<long long>(tap) * cout + co) * cin + ci] = v;
   if (wf_lo) wf_lo[(static_cast<long long>(tap) * cout + co) * cin + ci] = __float2bfloat16_rn(w[i] - __bfloat162float(v));
   if (wd) wd[(static_cast<long long>(8 - tap) * cin + ci) * cout + co] = v;
+}
+
+// f16 + f8 forward packs (conv_common.cuh, kF8*): w16 [tap][cout][cin] fp16 and the correction rows
+// wcorr [tap][cout][cin / 64][128 B] = 64 bytes e4m3(W_lo * 4096 sw) followed by 64 bytes e4m3(W * sw), W_lo = W - fp16(W):
+// the K order matches the activations' [A8 | Alo8] rows, so that A8 * Wlo8 + Alo8 * W8 = 512 sw (A W_lo + A_lo W).
+__global__ void pack_weights_f16f8_kernel(const float* __restrict__ w, int cin, int cout, float sw,
+                                          __half* __restrict__ w16, uint8_t* __restrict__ wcorr) {
+  const long long total = 9LL * cin * cout;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % cout);
+  const int ci = static_cast<int>((i / cout) % cin);
+  const int tap = static_cast<int>(i / (static_cast<long long>(cout) * cin));
+  const float x = w[i];
+  const __half h = __float2half_rn(x);
+  const float lo = x - __half2float(h);
+  const long long row = static_cast<long long>(tap) * cout + co;
+  w16[row * cin + ci] = h;
+  uint8_t* dst = wcorr + row * cin * 2 + static_cast<long long>(ci >> 6) * 128 + (ci & 63);
+  dst[0] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(lo * 4096.0f * sw, __NV_SATFINITE, __NV_E4M3));
+  dst[64] = static_cast<uint8_t>(__nv_cvt_float_to_fp8(x * sw, __NV_SATFINITE, __NV_E4M3));
+}
+
+// fp16 plane (+ optional correction plane: the e4m3 low parts, scaled by kF8ScaleLo) -> fp32
+__global__ void f16f8_to_f32_kernel(const __half* __restrict__ hi, const uint8_t* __restrict__ corr, size_t n, int C,
+                                    float* __restrict__ out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = __half2float(hi[i]);
+  if (corr) {
+    const size_t pix = i / C;
+    const int ch = static_cast<int>(i % C);
+    const uint8_t b = corr[pix * C * 2 + static_cast<size_t>(ch >> 6) * 128 + 64 + (ch & 63)];
+    const __half_raw hr = __nv_cvt_fp8_to_halfraw(b, __NV_E4M3);
+    v += __half2float(__half(hr)) * (1.0f / kF8ScaleLo);
+  }
+  out[i] = v;
 }
 
 // The same from torch's OIHW layout [cout][cin][3][3] (the generator's nn.Parameters), with the filter bank zero-padded
@@ -387,13 +431,13 @@ inline unsigned blocks_for(long long n, int threads) { return static_cast<unsign
 }  // namespace
 
 int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3,
-                       const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream) {
+                       const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream, int fmt, bf16* aux) {
   STX_REQUIRE(image && w && b && out && mean3, "conv1_1 fwd: null operand");
   const long long threads = 2LL * nimg * H * ((W + 1) / 2);
   unsigned blocks = blocks_for(threads, 128);
   if (blocks > 148u * 4u * 4u) blocks = 148u * 4u * 4u;      // four resident blocks per SM, ~four rounds each
   STX_TRY(launch_pdl(conv1_1_fwd_kernel, dim3(blocks), dim3(128), 0, stream, image, nimg, H, W,
-                     is_preimage, mean3[0], mean3[1], mean3[2], w, b, out, out_lo));
+                     is_preimage, mean3[0], mean3[1], mean3[2], w, b, out, out_lo, fmt, aux));
   count_launch();
   return STX_OK;
 }
@@ -459,6 +503,28 @@ int pack_weights_launch(const float* w_hwio, int cin, int cout, bf16* w_fwd, bf1
   STX_REQUIRE(w_hwio, "pack_weights: null weights");
   const long long total = 9LL * cin * cout;
   pack_weights_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_hwio, cin, cout, w_fwd, w_fwd_lo, w_dgrad);
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+int pack_weights_f16f8_launch(const float* w_hwio, int cin, int cout, float sw, bf16* w16, bf16* wcorr,
+                              cudaStream_t stream) {
+  STX_REQUIRE(w_hwio && w16 && wcorr, "pack_weights_f16f8: null argument");
+  STX_REQUIRE(cin % 64 == 0 && sw > 0.0f, "pack_weights_f16f8: cin must be a multiple of 64 and the scale positive");
+  const long long total = 9LL * cin * cout;
+  pack_weights_f16f8_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(w_hwio, cin, cout, sw,
+                                                                       reinterpret_cast<__half*>(w16),
+                                                                       reinterpret_cast<uint8_t*>(wcorr));
+  STX_CUDA(cudaGetLastError());
+  count_launch();
+  return STX_OK;
+}
+
+int f16f8_to_f32_launch(const bf16* hi, const bf16* corr, size_t n, int C, float* out, cudaStream_t stream) {
+  if (n == 0) return STX_OK;
+  f16f8_to_f32_kernel<<<blocks_for(static_cast<long long>(n), 256), 256, 0, stream>>>(
+      reinterpret_cast<const __half*>(hi), reinterpret_cast<const uint8_t*>(corr), n, C, out);
   STX_CUDA(cudaGetLastError());
   count_launch();
   return STX_OK;

@@ -29,6 +29,7 @@ constexpr int kSmemTotal = kStages * kSlotBytes + 128 + 1024;
 struct GramKernelParams {
   int C, splits, iters_per_split, total_iters, tiles_per_dim;
   int cross;   // 1 = A^T B of two different maps (all T x T tiles, B operand from tmU); 0 = symmetric F^T F
+  int f16;     // the feature planes are fp16 (f16+f8 plans)
   uint32_t lbo, sbo;
   float* partial;
 };
@@ -112,7 +113,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUt
       __syncwarp();
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+    // both operands are feature planes: fp16 in the f16+f8 plans (p.f16), bf16 otherwise
+    const uint32_t idesc = p.f16 ? make_idesc(128, BN, kFmtF16, kFmtF16, 1, 1) : make_idesc_bf16(128, BN, 1, 1);
     for (int it = 0; it < iters; ++it) {
       const int s = it % kStages;
       const uint32_t ph = (it / kStages) & 1;
@@ -334,6 +336,7 @@ int gram_launch(const GramOp& op, cudaStream_t stream) {
   p.sbo = g_debug_gram_sbo ? static_cast<uint32_t>(g_debug_gram_sbo) : 1024u;
   p.partial = op.partial;
   p.cross = op.cross;
+  p.f16 = op.f16;
   dim3 grid(op.ntiles, op.splits, op.nimg);
   if (op.bn == 64)
     gram_kernel<64><<<grid, kThreads, kSmemTotal, stream>>>(op.tmF, op.cross ? op.tmU : op.tmF, p);

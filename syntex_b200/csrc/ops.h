@@ -20,7 +20,11 @@ struct ConvOp {
   int ksplit;        // split-K factor of the patch kernel (1 = off)
   float* splitk_ws;  // fp32 partial tiles (shared by all ops of a plan; launches are stream-ordered)
   int* splitk_counters;
-  int split;         // 1 = bf16x3 forward (hi/lo operands, hi/lo outputs)
+  int split;         // 1 = bf16x3 forward (hi/lo operands, hi/lo outputs); 2 = f16 + f8 forward (patch kernel only:
+                     // fp16 planes + e4m3 correction planes, conv_common.cuh kF8*)
+  float corr_scale;  // split == 2: factor of the correction accumulator (1 / (512 * weight scale) of the layer)
+  bf16* aux_out;     // split == 2: bf16 copy of the stored result (loss layers: the Gram gradient's A operand is bf16)
+  bf16* pool_aux;    // ... and of the fused pool's result
   int patch;         // 1 = halo-patch kernel (conv_patch.cu), 0 = per-tap kernel (conv_igemm.cu)
   int mt;            // patch kernel: 16x8 output tiles stacked per CTA (1 or 2)
   int occ;           // patch kernel: persistent CTAs per SM (1 or 2)
@@ -69,6 +73,7 @@ struct GramOp {
   CUtensorMap tmF;   // features viewed as [nimg][HW][C] bf16
   CUtensorMap tmU;   // cross mode: the second map (B operand)
   int cross = 0;     // 1 = A^T B of two maps, every tile computed
+  int f16 = 0;       // feature planes are fp16 (f16+f8 plans) instead of bf16
   int nimg, HW, C;
   int bn;            // N tile (64 for C == 64, else 128)
   int ntiles;        // upper-triangle 128x128 tiles
@@ -115,8 +120,16 @@ int gram_finish_batch_launch(const GramFinishBatch& fb, cudaStream_t stream);
 // conv1_1: fp32 image in [0,1] (optionally a pre-image passed through a sigmoid) -> x*255 - mean ->
 // 3x3 SAME conv (3 -> 64) + bias + ReLU -> bf16 NHWC.   w: [27][64] fp32 ((r*3+s)*3+c major), b: [64]
 // out_lo (nullable): low halves, out + out_lo carries the fp32 result to ~16 mantissa bits.
+// fmt 2: out = fp16 plane, out_lo = e4m3 correction plane (conv_common.cuh, kF8*), aux (nullable) = bf16 copy.
 int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3,
-                       const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream);
+                       const float* w, const float* b, bf16* out, bf16* out_lo, cudaStream_t stream, int fmt = 0,
+                       bf16* aux = nullptr);
+// f16 + f8 forward packs of one layer: w16 [9][cout][cin] fp16, wcorr [9][cout][cin/64][128 B] e4m3 (W_lo | W), with
+// the per-layer power-of-two weight scale sw (the layer's correction accumulator is then scaled by 1 / (512 sw)).
+int pack_weights_f16f8_launch(const float* w_hwio, int cin, int cout, float sw, bf16* w16, bf16* wcorr,
+                              cudaStream_t stream);
+// fp16 plane (+ correction plane, nullable) of a recorded layer with C channels -> fp32.
+int f16f8_to_f32_launch(const bf16* hi, const bf16* corr, size_t n, int C, float* out, cudaStream_t stream);
 // dgrad of conv1_1 chained with the preprocessing derivative: g [nimg,H,W,64] bf16 (already ReLU-masked) ->
 // dL/d(input image or pre-image) fp32 [nimg,H,W,3].
 int conv1_1_bwd_launch(const bf16* g, const float* image, int nimg, int H, int W, int is_preimage, const float* w,

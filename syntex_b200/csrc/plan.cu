@@ -3,6 +3,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace stx {
@@ -31,6 +32,8 @@ Vgg::~Vgg() {
     cudaFree(bias[i]);
     cudaFree(wf[i]);
     cudaFree(wf_lo[i]);
+    cudaFree(wf16[i]);
+    cudaFree(wcorr[i]);
     cudaFree(wd[i]);
     cudaFree(wft[i]);
     cudaFree(wft_lo[i]);
@@ -73,6 +76,19 @@ int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_
       chk(cudaMalloc(&v->wd[ci], wn * sizeof(bf16)), "cudaMalloc wd");
       if (rc == STX_OK) chk(cudaMemcpyAsync(tmp, w[ci], wn * sizeof(float), cudaMemcpyHostToDevice, stream), "copy w");
       if (rc == STX_OK) rc = pack_weights_launch(tmp, s.cin, s.cout, v->wf[ci], v->wf_lo[ci], v->wd[ci], stream);
+      {
+        // f16 + f8 packs: power-of-two weight scale from the layer's largest magnitude (e4m3 tops out at 448)
+        float wmax = 0.0f;
+        for (size_t i = 0; i < wn; ++i) wmax = std::max(wmax, std::fabs(w[ci][i]));
+        int ex = 0;
+        if (wmax > 0.0f) ex = static_cast<int>(std::floor(std::log2(224.0f / wmax)));
+        ex = std::max(-20, std::min(20, ex));
+        const float sw = std::ldexp(1.0f, ex);
+        v->corr_scale[ci] = 1.0f / (512.0f * sw);
+        chk(cudaMalloc(&v->wf16[ci], wn * sizeof(bf16)), "cudaMalloc wf16");
+        chk(cudaMalloc(&v->wcorr[ci], wn * sizeof(bf16)), "cudaMalloc wcorr");
+        if (rc == STX_OK) rc = pack_weights_f16f8_launch(tmp, s.cin, s.cout, sw, v->wf16[ci], v->wcorr[ci], stream);
+      }
       if (g_debug_tiled_weights) {
         chk(cudaMalloc(&v->wft[ci], wn * sizeof(bf16)), "cudaMalloc wft");
         chk(cudaMalloc(&v->wft_lo[ci], wn * sizeof(bf16)), "cudaMalloc wft_lo");
@@ -182,6 +198,9 @@ static int plan_layout(Plan* p, Bump& a) {
     const size_t n = static_cast<size_t>(B) * p->lh[l] * p->lw[l] * p->lc[l];
     p->act[l] = a.take<bf16>(n);
     p->act_lo[l] = p->split ? a.take<bf16>(n) : nullptr;
+    bool is_loss = false;
+    for (const LossLayer& ll : p->loss) is_loss = is_loss || ll.layer == l;
+    p->act_bf[l] = (p->split == 2 && is_loss) ? a.take<bf16>(n) : nullptr;
   }
   size_t gmax = 0;
   for (int l = 0; l <= p->topmost; ++l) gmax = std::max(gmax, static_cast<size_t>(B) * p->lh[l] * p->lw[l] * p->lc[l]);
@@ -224,7 +243,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
   p->H = H;
   p->W = W;
   p->topmost = topmost;
-  p->split = (flags & STX_PLAN_FAST_BF16) ? 0 : 1;
+  p->split = (flags & STX_PLAN_FAST_BF16) ? 0 : ((flags & STX_PLAN_F16F8) ? 2 : 1);
   p->export_grads = (flags & STX_PLAN_EXPORT_LAYER_GRADS) ? 1 : 0;
   p->full_features = (flags & STX_PLAN_FULL_FEATURES) ? 1 : 0;
   for (int l = 0; l < kNumLayers; ++l) p->lo_valid[l] = p->split != 0;
@@ -296,17 +315,29 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     const LayerSpec& s = kLayers[l];
     if (!s.is_conv) continue;
     ConvOp& op = p->fwd[l];
-    rc = conv3x3_prepare(&op, p->act[l - 1], p->split ? p->act_lo[l - 1] : nullptr, B, p->lh[l], p->lw[l], s.cin,
-                         vgg->wf[s.conv_index], p->split ? vgg->wf_lo[s.conv_index] : nullptr, s.cout, 0);
+    if (p->split == 2) {
+      // f16 + f8: fp16 planes against the fp16 pack, correction planes against the e4m3 rows (halo-patch kernel only)
+      rc = conv3x3_prepare(&op, p->act[l - 1], p->act_lo[l - 1], B, p->lh[l], p->lw[l], s.cin, vgg->wf16[s.conv_index],
+                           vgg->wcorr[s.conv_index], s.cout, 0);
+      if (rc == STX_OK && !op.patch)
+        rc = fail(STX_ERR_UNSUPPORTED, "plan_create: the f16+f8 forward needs feature maps at least 8 pixels wide");
+      op.split = 2;
+      op.corr_scale = vgg->corr_scale[s.conv_index];
+    } else {
+      rc = conv3x3_prepare(&op, p->act[l - 1], p->split ? p->act_lo[l - 1] : nullptr, B, p->lh[l], p->lw[l], s.cin,
+                           vgg->wf[s.conv_index], p->split ? vgg->wf_lo[s.conv_index] : nullptr, s.cout, 0);
+    }
     op.w_tiled = g_debug_tiled_weights ? vgg->wft[s.conv_index] : nullptr;
     op.w_tiled_lo = g_debug_tiled_weights ? vgg->wft_lo[s.conv_index] : nullptr;
     op.bias = vgg->bias[s.conv_index];
     op.relu = 1;
     op.out = p->act[l];
     op.out_lo = p->act_lo[l];
+    op.aux_out = p->act_bf[l];
     if (rc == STX_OK && op.patch && l + 1 <= topmost && !kLayers[l + 1].is_conv) {
       op.pool_out = p->act[l + 1];            // 2x2 average pool fused into this convolution's epilogue
       op.pool_out_lo = p->act_lo[l + 1];
+      op.pool_aux = p->act_bf[l + 1];
       p->pool_fused[l + 1] = true;
       if (!p->full_features) {
         // nothing on the path reads the low half of a convolution that only feeds a fused pool: the pool's own
@@ -323,6 +354,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     LossLayer& ll = p->loss[k];
     float* partial = ll.gram.partial;
     rc = gram_prepare(&ll.gram, p->act[ll.layer], B, ll.HW, ll.C, partial);
+    ll.gram.f16 = p->split == 2 ? 1 : 0;
     coef4.push_back(ll.coef * 0.25f);
     offs.push_back(ll.part_offset);
   }
@@ -334,6 +366,8 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
   }
 
   // Backward program (reverse-mode over the forward chain; see DESIGN.md "backward program").
+  // the features of a loss layer as a bf16 plane (the Gram gradient multiplies them with bf16 matrices)
+  auto feat_bf = [&](int layer) -> const bf16* { return p->split == 2 ? p->act_bf[layer] : p->act[layer]; };
   auto loss_index = [&](int layer) -> int {
     for (size_t k = 0; k < p->loss.size(); ++k)
       if (p->loss[k].layer == layer) return static_cast<int>(k);
@@ -352,19 +386,19 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       // accumulated into the same TMEM tile, then the epilogue masks (conv layers) / exports as configured.
       LossLayer& ll = p->loss[k];
       ConvOp& prod = p->bwd.back().conv;
-      rc = conv_patch_attach_gram(&prod, p->act[l], ll.dscaled);
+      rc = conv_patch_attach_gram(&prod, feat_bf(l), ll.dscaled);
       prod.mask = s.is_conv ? p->act[l] : nullptr;
       prod.export_out = ll.dfeat;
       p->bwd.back().inject_k = k;
       if (rc == STX_OK) {
-        rc = conv_prepare(&ll.layer_grad_op, p->act[l], B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
+        rc = conv_prepare(&ll.layer_grad_op, feat_bf(l), B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
         ll.layer_grad_op.out = p->gbuf[0];
       }
     } else if (k >= 0) {
       LossLayer& ll = p->loss[k];
       BwdStep st;
       st.kind = BwdStep::kGramGrad;
-      rc = conv_prepare(&st.conv, p->act[l], B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
+      rc = conv_prepare(&st.conv, feat_bf(l), B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
       st.conv.addend = have ? p->gbuf[cur] : nullptr;
       st.conv.out = p->gbuf[cur];
       st.conv.mask = s.is_conv ? p->act[l] : nullptr;
@@ -373,7 +407,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       p->bwd.push_back(st);
       have = true;
       if (rc == STX_OK) {
-        rc = conv_prepare(&ll.layer_grad_op, p->act[l], B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
+        rc = conv_prepare(&ll.layer_grad_op, feat_bf(l), B, p->lh[l], p->lw[l], ll.C, ll.dscaled, ll.C, 1, 1, 0);
         ll.layer_grad_op.out = p->gbuf[0];
       }
     }
@@ -523,12 +557,13 @@ int Plan::forward(const float* image, int is_preimage, int with_grams, bool with
     if (l == deepest) STX_TRY(launch_finish(true));
     return STX_OK;
   };
-  STX_LAUNCH(kClsConv1, conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0], act_lo[0], stream));
+  STX_LAUNCH(kClsConv1, conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0], act_lo[0], stream, split == 2 ? 2 : 0, act_bf[0]));
   STX_TRY(after_layer(0));
   for (int l = 1; l <= topmost; ++l) {
     if (kLayers[l].is_conv) {
       STX_LAUNCH(kClsConvFwd, conv_launch(fwd[l], stream));
     } else if (!pool_fused[l]) {
+      if (split == 2) return fail(STX_ERR_UNSUPPORTED, "forward: f16+f8 planes have no stand-alone pooling kernel");
       STX_LAUNCH(kClsPool, avgpool2_fwd_launch(act[l - 1], act_lo[l - 1], B, lh[l - 1], lw[l - 1], lc[l - 1], act[l], act_lo[l], stream));
     }
     STX_TRY(after_layer(l));

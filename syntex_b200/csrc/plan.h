@@ -27,6 +27,9 @@ struct Vgg {
   bf16* wf[kNumConvs] = {};       // forward pack [9][cout][cin] (conv index >= 1), high halves
   bf16* wf_lo[kNumConvs] = {};    // low halves bf16(w - bf16(w)) for the bf16x3 forward
   bf16* wd[kNumConvs] = {};       // dgrad pack   [9][cin][cout]
+  bf16* wf16[kNumConvs] = {};     // f16 + f8 forward: fp16 pack [9][cout][cin] ...
+  bf16* wcorr[kNumConvs] = {};    // ... and e4m3 correction rows [9][cout][cin/64][128 B] (conv_common.cuh, kF8*)
+  float corr_scale[kNumConvs] = {};   // 1 / (512 * weight scale): factor of the layer's correction accumulator
   bf16* wft[kNumConvs] = {};      // tiled pre-swizzled forward pack (hi), see pack_weights_tiled_kernel
   bf16* wft_lo[kNumConvs] = {};
   bf16* wdt[kNumConvs] = {};      // tiled pre-swizzled dgrad pack
@@ -79,11 +82,13 @@ struct Plan {
   int B = 0, H = 0, W = 0, topmost = 15;
   int lh[kNumLayers], lw[kNumLayers], lc[kNumLayers];
   int export_grads = 0;            // keep dL/dF_k of every loss layer (PO stage preparation)
-  int split = 1;                   // 1 = bf16x3 forward (hi/lo activations), 0 = plain bf16 forward
+  int split = 1;                   // forward precision: 0 = plain bf16, 1 = bf16x3 (hi/lo bf16 activation planes),
+                                   // 2 = f16 + f8 (fp16 planes + e4m3 correction planes: two MMAs' time per MAC)
   int full_features = 0;           // keep the low half of every recorded layer (feature export), not only those the path reads
   bool lo_valid[kNumLayers] = {};  // act_lo[l] is written by the forward
   bf16* act[kNumLayers] = {};      // recorded layers (high halves; the only halves in plain mode)
-  bf16* act_lo[kNumLayers] = {};   // low halves (split mode)
+  bf16* act_lo[kNumLayers] = {};   // low halves (split mode) / e4m3 correction planes (f16 + f8)
+  bf16* act_bf[kNumLayers] = {};   // f16 + f8: bf16 copy of the LOSS layers (A operand of the Gram gradient)
   ConvOp fwd[kNumLayers];
   bool pool_fused[kNumLayers] = {};   // pooling layer computed in the epilogue of the convolution that feeds it
   std::vector<LossLayer> loss;

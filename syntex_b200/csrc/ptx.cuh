@@ -151,6 +151,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same for 8-bit operands (e4m3 / e5m2 selected by the instruction descriptor): K = 32 per instruction, i.e. the
+// same 32 bytes of K per dispatch as kind::f16 - twice the MACs in the same tensor-pipe time.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 // (Implies tcgen05.fence::before_thread_sync.)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -209,6 +220,15 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
 //   [17,23) N >> 3         [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+// General form. Operand formats: kind::f16: 0 = f16, 1 = bf16 (A and B have separate fields and may differ);
+// kind::f8f6f4: 0 = e4m3, 1 = e5m2.
+constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1, kFmtE4M3 = 0;
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, uint32_t a_fmt, uint32_t b_fmt, int a_mn_major,
+                                                  int b_mn_major) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }

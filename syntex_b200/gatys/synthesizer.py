@@ -27,6 +27,12 @@ def get_bounds(shape=None):
     return np.tile(np.array([[0., 1.]]), (n, 1))
 
 
+import os
+
+# Forward precision of the f/g plan when args["precision"] is not given; STX_PRECISION overrides (bring-up).
+DEFAULT_PRECISION = os.environ.get("STX_PRECISION", "auto")
+
+
 class Synthesizer(object):
     DEFAULT_COEFS = OrderedDict([   # synthesizer.py:17-23
         ("conv1_1", 1e5),
@@ -52,9 +58,9 @@ class Synthesizer(object):
         if self.optimizer not in ("device", "scipy"):
             raise ValueError("optimizer must be 'device' or 'scipy'")
         self.batch = int(args.get("batch") or 1)
-        self.precision = args.get("precision") or "bf16x3"
-        if self.precision not in ("bf16x3", "bf16"):
-            raise ValueError("precision must be 'bf16x3' (accurate forward) or 'bf16' (fast forward)")
+        self.precision = args.get("precision") or DEFAULT_PRECISION
+        if self.precision not in ("auto", "f16f8", "bf16x3", "bf16"):
+            raise ValueError("precision must be 'auto', 'f16f8', 'bf16x3' (accurate forwards) or 'bf16' (fast forward)")
         self.sess = sess
         self._plan = None
         self._lbfgs = {}
@@ -76,7 +82,8 @@ class Synthesizer(object):
         # additions of this implementation
         ps.add("--optimizer", type=str, default="device", help="'device' (GPU L-BFGS) or 'scipy' (reference)")
         ps.add("--batch", type=int, default=1, help="independent jobs run side by side on one GPU")
-        ps.add("--precision", type=str, default="bf16x3", help="'bf16x3' (accurate forward) or 'bf16' (fast)")
+        ps.add("--precision", type=str, default=DEFAULT_PRECISION,
+               help="'auto' / 'f16f8' / 'bf16x3' (accurate forwards) or 'bf16' (fast)")
         return ps
 
     def build(self):
@@ -84,8 +91,12 @@ class Synthesizer(object):
         self.vgg19 = Vgg19Extractor(self.vgg19_path)
         self.shape_input = [self.batch, self.image_size, self.image_size, 3]
         coefs = OrderedDict() if self.gram_only and False else Synthesizer.DEFAULT_COEFS
+        # 'auto': the f16 + f8 forward wherever it exists (every convolution's map >= 8 pixels wide: image side a
+        # multiple of 16 and >= 64), else bf16x3 - the same accuracy class, two MMAs' time per MAC instead of three
+        f16f8 = self.precision == "f16f8" or (self.precision == "auto" and self.image_size >= 64
+                                              and self.image_size % 16 == 0)
         self._plan = self.vgg19.get_plan(self.batch, self.image_size, self.image_size, "pool4", coefs,
-                                         fast_bf16=(self.precision == "bf16"))
+                                         fast_bf16=(self.precision == "bf16"), f16f8=f16f8)
         self._have_target = False
         self.coef_names = list(coefs.keys())
 

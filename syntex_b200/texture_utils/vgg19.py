@@ -52,6 +52,7 @@ class _Plan(object):
     FAST_BF16 = 1   # STX_PLAN_FAST_BF16
     EXPORT_LAYER_GRADS = 2   # STX_PLAN_EXPORT_LAYER_GRADS
     FULL_FEATURES = 4   # STX_PLAN_FULL_FEATURES
+    F16F8 = 8   # STX_PLAN_F16F8
 
     def __init__(self, vgg_handle, batch, height, width, topmost_idx, loss_layers, coefs, flags=0):
         self.handle = ctypes.c_void_p()
@@ -167,9 +168,10 @@ class Vgg19(object):
         return self._vgg
 
     def get_plan(self, batch, height, width, topmost=None, coefs=None, fast_bf16=False, export_layer_grads=False,
-                 slot=0, full_features=None):
+                 slot=0, full_features=None, f16f8=False):
         """Cached stx_plan for this shape. coefs: OrderedDict layer name -> weight (Gram layers), or None.
         fast_bf16: single-MMA bf16 forward instead of the accurate bf16x3 forward (see include/syntex_b200.h).
+        f16f8: the f16 + f8 forward (STX_PLAN_F16F8): same accuracy class as bf16x3 at two thirds of its tensor time.
         slot: distinct slots give distinct plans of the same shape (each keeps the activations of its own last
         forward - the PO training graph evaluates VGG once per stage and back-propagates through all of them)."""
         topmost = self.topmost if topmost is None else topmost
@@ -179,14 +181,15 @@ class Vgg19(object):
         if full_features is None:       # plans without loss layers exist to export features: keep every low half
             full_features = len(coefs) == 0
         key = (batch, height, width, topmost, tuple((k, float(v)) for k, v in coefs.items()), bool(fast_bf16),
-               bool(export_layer_grads), int(slot), bool(full_features))
+               bool(export_layer_grads), int(slot), bool(full_features), bool(f16f8))
         plan = self._plans.get(key)
         if plan is None:
             plan = _Plan(self._vgg_handle(), batch, height, width, LAYER_INDEX[topmost],
                          [LAYER_INDEX[k] for k in coefs], [float(v) for v in coefs.values()],
                          (_Plan.FAST_BF16 if fast_bf16 else 0) |
                          (_Plan.EXPORT_LAYER_GRADS if export_layer_grads else 0) |
-                         (_Plan.FULL_FEATURES if full_features else 0))
+                         (_Plan.FULL_FEATURES if full_features else 0) |
+                         (_Plan.F16F8 if (f16f8 and not fast_bf16) else 0))
             plan.coef_names = list(coefs.keys())
             self._plans[key] = plan
         return plan

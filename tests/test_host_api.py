@@ -36,6 +36,52 @@ def test_signatures_match_the_reference():
     assert list(inspect.signature(SynTexModelDesc._build_extractor).parameters)[1:] == ["image_input", "calc_gram", "name"]
 
 
+REF = "/root/reference"
+
+
+def _ref_signature(relpath, qualname):
+    """(argument names, {name: default literal}) of a function in the reference's SOURCE, by `ast` (the reference
+    cannot be imported here: it needs TensorFlow 1.12 / tensorpack)."""
+    import ast
+    tree = ast.parse(open(os.path.join(REF, relpath)).read())
+    node = tree
+    for part in qualname.split("."):
+        node = next(n for n in ast.walk(node) if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name == part)
+    names = [a.arg for a in node.args.args]
+    defaults = {}
+    for a, d in zip(reversed(node.args.args), reversed(node.args.defaults)):
+        try:
+            defaults[a.arg] = ast.literal_eval(d)
+        except ValueError:
+            pass
+    return names, defaults
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present on this machine")
+@pytest.mark.parametrize("relpath,qualname,ours", [
+    ("texture_utils/vgg19_extractor.py", "Vgg19Extractor.__init__", Vgg19Extractor.__init__),
+    ("texture_utils/vgg19.py", "Vgg19.build", Vgg19.build),
+    ("texture_utils/utils.py", "build_gram", build_gram),
+    ("texture_utils/utils.py", "build_texture_loss", build_texture_loss),
+    ("gatys/synthesizer.py", "Synthesizer.compute_gram", Synthesizer.compute_gram),
+    ("gatys/synthesizer.py", "Synthesizer.step", Synthesizer.step),
+    ("gatys/synthesizer.py", "Synthesizer.synthesize", Synthesizer.synthesize),
+    ("gatys/synthesizer.py", "get_bounds", get_bounds),
+    ("gatys/synthesizer.py", "resize_crop", resize_crop),
+    ("po/model.py", "SynTexModelDesc._build_loss", SynTexModelDesc._build_loss),
+    ("po/model.py", "SynTexModelDesc._build_extractor", SynTexModelDesc._build_extractor),
+])
+def test_signatures_parsed_from_the_reference_sources(relpath, qualname, ours):
+    """Same argument names in the same order, same literal defaults - read from the reference's own files."""
+    names, defaults = _ref_signature(relpath, qualname)
+    p = inspect.signature(ours).parameters
+    assert list(p)[:len(names)] == names, (qualname, list(p), names)
+    for k, v in defaults.items():
+        if k == "name":          # TF name scopes: accepted and ignored here
+            continue
+        assert p[k].default == v, (qualname, k, p[k].default, v)
+
+
 def test_constants():
     assert VGG_MEAN == [103.939, 116.779, 123.68] and VGG_MEAN_RGB == [123.68, 116.779, 103.939]
     assert list(Synthesizer.DEFAULT_COEFS.items()) == [("conv1_1", 1e5), ("pool1", 1e5), ("pool2", 1e5),
