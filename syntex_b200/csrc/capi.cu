@@ -17,6 +17,7 @@ extern int g_debug_splitk;
 extern int g_debug_tiled_weights;
 extern int g_debug_resident;
 extern int g_lbfgs_no_graph;
+extern int g_debug_f8_single_cta;
 }  // namespace stx
 
 struct stx_vgg {
@@ -49,6 +50,7 @@ int stx_debug_set(int key, int value) {
     case 8: g_debug_resident = value; return STX_OK;
     case 9: g_pdl = value; return STX_OK;
     case 10: g_lbfgs_no_graph = value; return STX_OK;
+    case 12: g_debug_f8_single_cta = value; return STX_OK;
     default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
   }
 }
@@ -299,6 +301,10 @@ int stx_lbfgs_run(stx_lbfgs* opt, int maxiter, int max_evals, void* stream) {
 int stx_lbfgs_result(stx_lbfgs* opt, float* x, float* fun, int* nit, int* nfev, void* stream) {
   STX_REQUIRE(opt, "stx_lbfgs_result: null optimizer");
   return opt->o->result(x, fun, nit, nfev, S(stream));
+}
+int stx_lbfgs_phase_cycles(stx_lbfgs* opt, long long* host16) {
+  STX_REQUIRE(opt && host16, "stx_lbfgs_phase_cycles: null argument");
+  return opt->o->phase_cycles(host16);
 }
 int stx_lbfgs_minimize_host(stx_lbfgs* opt, const float* x0_host, int is_preimage, int maxiter, float* x_host,
                             float* fun_host, int* nit_host, int* nfev_host, void* stream) {

@@ -62,8 +62,10 @@ struct PatchSmem {
   // resident mode: a small ring for the per-image Gram-difference tiles of the fused Gram gradient
   static constexpr int kDStages = (RES > 0 && !SPLIT) ? (OCC == 2 ? 1 : 2) : 0;
   static constexpr int kResRoom = (kBudget - 9 * RES * kBStageBytes - kDStages * kBBytes) / kPatchStageBytes;
+  // (two f16+f8 CTAs per SM - the 64-channel forward, whose tiles are epilogue-bound - have room for ONE hi+corr
+  // patch stage each: the other CTA covers the refill)
   static constexpr int kPatchStages = RES > 0 ? (kResRoom > 4 ? 4 : kResRoom)
-                                              : ((SPLIT || MT == 2 || OCC == 2) ? 2 : 3);
+                                              : ((F8 && OCC == 2) ? 1 : ((SPLIT || MT == 2 || OCC == 2) ? 2 : 3));
   static constexpr int kBRoom = (kBudget - kPatchStages * kPatchStageBytes) / kBStageBytes;
   static constexpr int kBStages = RES > 0 ? 9 * RES : (kBRoom > 10 ? 10 : kBRoom);
   static constexpr int kBBarriers = RES > 0 ? 1 : kBStages;
@@ -828,6 +830,7 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
     STX_REQUIRE(op.out_lo != nullptr || op.pool_out_lo != nullptr, "conv f16+f8: correction-plane output not set");
     STX_REQUIRE(op.res == 0 && op.mt == 1, "conv f16+f8: bad configuration");
     if (op.bn == 128) return launch_patch<128, 1, true, 1, 0, true>(op, stream);
+    if (op.occ == 2) return launch_patch<64, 1, true, 2, 0, true>(op, stream);
     return launch_patch<64, 1, true, 1, 0, true>(op, stream);
   }
   if (op.split) {

@@ -55,7 +55,7 @@ constexpr int kNP = kNP0 + kNPH * kMaxM;
 constexpr int kQ = 2 * kMaxM + 2;           // rows of the active-set Gram: Y_0.. | S_0.. | y_new | s_new (chronological)
 constexpr int kSlices = 8;                  // active kernel: blocks per problem
 constexpr int kActCap = 2048;               // compacted indices held per round
-constexpr int kActRows = 32;                // rows gathered per tile
+constexpr int kActRows = 96;                // rows gathered per tile
 constexpr int kActPairs = (kQ * (kQ + 1) / 2 + kThreads - 1) / kThreads;
 constexpr int kDecideThreads = 512;
 constexpr int kKN = 2 * kMaxM;              // largest reduced system
@@ -89,12 +89,13 @@ struct Tables {
 struct Vecs {
   float *x, *xt, *g, *gt, *d, *S, *Y;   // [B][n], history [B][m][n]
   float* ft;                             // [B]
-  float* part;                           // [B][nblk][kNP]
+  float* part;                           // [B][kNP][nblk]
   float* part2;                          // [B][nblk]  g'd of a freshly built direction
   float* part3;                          // [B][nblk]  largest feasible step along it
   double* gramA;                         // [B][kSlices][kQ][kQ]
   Ctrl* ctrl;                            // [B]
   Tables* tab;                           // [B]
+  long long* dbg;                        // [16] clock64 stamps of job 0's decide kernel (diagnostic, stx_lbfgs_phase_cycles)
   int n, m, nblk, bounded;
   float lo, hi;
 };
@@ -172,20 +173,28 @@ __global__ void __launch_bounds__(kThreads) lbfgs_dots_kernel(Vecs v) {
   }
   __syncthreads();
   const int np = kNP0 + kNPH * nh;
-  float* dst = v.part + (static_cast<size_t>(b) * v.nblk + blockIdx.x) * kNP;
+  // quantity-major: the decision kernel reads one quantity of all blocks as consecutive floats
+  float* dst = v.part + static_cast<size_t>(b) * v.nblk * kNP + blockIdx.x;
   for (int k = threadIdx.x; k < np; k += kThreads) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) t += red[w][k];
-    dst[k] = t;
+    dst[static_cast<size_t>(k) * v.nblk] = t;
   }
 }
 
 // ------------------------------------------------------------------------------------------------ active set
 // Gram matrix of the history rows of the ACTIVE variables of the trial point (xt, gt): for i in A the row is
 //   u_i = (Y_0[i] .. Y_{nh-1}[i], S_0[i] .. S_{nh-1}[i], y_new[i], s_new[i])       (chronological pair order)
-// and gramA[slice] = sum over the slice's active i of u_i u_i' in fp64. Each block walks its slice in index order
-// (deterministic compaction by ballot + prefix), so the summation order depends only on the data.
+// and gramA[slice] = sum over the slice's active i of u_i u_i' in fp64.
+// Each block owns a slice of the variables and each thread a CONTIGUOUS run of it, so index order = thread order:
+// all loads of a round are issued up front (the flags of up to kActPerThread variables live in registers), ONE block
+// scan of the per-thread counts places the indices, and the rows are gathered kActRows at a time. The summation
+// order depends only on the data (deterministic, independent of the batch).
+constexpr int kActGatherUnroll = 8;
+constexpr int kActPerThread = 128;                 // variables per thread per round (4 words of flag bits)
+constexpr int kActRound = kThreads * kActPerThread;
+
 __global__ void __launch_bounds__(kThreads) lbfgs_active_kernel(Vecs v) {
   pdl_launch_dependents();
   pdl_wait();
@@ -203,7 +212,6 @@ __global__ void __launch_bounds__(kThreads) lbfgs_active_kernel(Vecs v) {
   __shared__ int list[kActCap];
   __shared__ float u[kActRows][kQ + 1];
   __shared__ int warp_tot[kThreads / 32];
-  __shared__ int count_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // this thread's (a, b) pairs, a <= b
   int pa[kActPairs], pb[kActPairs];
@@ -230,45 +238,78 @@ __global__ void __launch_bounds__(kThreads) lbfgs_active_kernel(Vecs v) {
   const int per = ((v.n / kVec + kSlices - 1) / kSlices) * kVec;
   const int i_begin = blockIdx.x * per;
   const int i_end = min(v.n, i_begin + per);
-  if (threadIdx.x == 0) count_s = 0;
-  __syncthreads();
 
+  // Gather kActRows rows at a time, then accumulate. Gather: thread (rg, a) = (tid / Q, tid % Q) takes column a of rows
+  // rg, rg + G, ...: kActGatherUnroll independent scattered loads in flight per thread (the history of all jobs is
+  // far larger than L2: every one of them is a DRAM round trip). Accumulate: fp32 products summed per tile in fp32
+  // (<= kActRows terms, four independent chains per thread), tiles added in fp64.
+  const int G = kThreads / Q;                              // row groups (Q <= 66 < kThreads)
+  const int ga = threadIdx.x % Q, grg = threadIdx.x / Q;
+  const float* gsrc;                                       // column ga of a row = gsrc[i] (history) or a difference
+  {
+    if (ga < nh) gsrc = v.Y + (static_cast<size_t>(b) * m + (head + ga) % m) * v.n;
+    else if (ga < 2 * nh) gsrc = v.S + (static_cast<size_t>(b) * m + (head + ga - nh) % m) * v.n;
+    else gsrc = nullptr;
+  }
   auto flush = [&](int count) {
     for (int r0 = 0; r0 < count; r0 += kActRows) {
       const int rows = min(kActRows, count - r0);
-      for (int e = threadIdx.x; e < rows * Q; e += kThreads) {
-        const int r = e / Q, a = e % Q;
-        const int i = list[r0 + r];
-        float val;
-        if (a < nh) val = v.Y[(static_cast<size_t>(b) * m + (head + a) % m) * v.n + i];
-        else if (a < 2 * nh) val = v.S[(static_cast<size_t>(b) * m + (head + a - nh) % m) * v.n + i];
-        else if (a == 2 * nh) val = v.gt[base + i] - v.g[base + i];
-        else val = v.xt[base + i] - v.x[base + i];
-        u[r][a] = val;
-      }
-      __syncthreads();
+      if (grg < G) {
+        for (int rb = grg; rb < rows; rb += G * kActGatherUnroll) {
+          float val[kActGatherUnroll];
 #pragma unroll
-      for (int t = 0; t < kActPairs; ++t) {
-        if (pa[t] >= 0) {
-          double a = acc[t];
-          for (int r = 0; r < rows; ++r) a += static_cast<double>(u[r][pa[t]]) * static_cast<double>(u[r][pb[t]]);
-          acc[t] = a;
+          for (int q = 0; q < kActGatherUnroll; ++q) {
+            const int r = rb + q * G;
+            val[q] = 0.f;
+            if (r < rows) {
+              const int i = list[r0 + r];
+              if (gsrc) val[q] = __ldg(gsrc + i);
+              else if (ga == 2 * nh) val[q] = v.gt[base + i] - v.g[base + i];
+              else val[q] = v.xt[base + i] - v.x[base + i];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < kActGatherUnroll; ++q) {
+            const int r = rb + q * G;
+            if (r < rows) u[r][ga] = val[q];
+          }
         }
       }
+      __syncthreads();
+      float part[kActPairs];
+#pragma unroll
+      for (int t = 0; t < kActPairs; ++t) part[t] = 0.f;
+      for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int t = 0; t < kActPairs; ++t)
+          if (pa[t] >= 0) part[t] = fmaf(u[r][pa[t]], u[r][pb[t]], part[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < kActPairs; ++t) acc[t] += static_cast<double>(part[t]);
       __syncthreads();
     }
   };
 
-  for (int t0 = i_begin; t0 < i_end; t0 += kChunk) {
-    const int i0 = t0 + threadIdx.x * kVec;
-    unsigned flags = 0;
-    if (i0 < i_end) {
-      const float4 xt = ld4(v.xt + base + i0), gt = ld4(v.gt + base + i0);
-      flags = (is_free(xt.x, gt.x, lo, hi, 1) ? 0u : 1u) | (is_free(xt.y, gt.y, lo, hi, 1) ? 0u : 2u) |
-              (is_free(xt.z, gt.z, lo, hi, 1) ? 0u : 4u) | (is_free(xt.w, gt.w, lo, hi, 1) ? 0u : 8u);
+  for (int r_begin = i_begin; r_begin < i_end; r_begin += kActRound) {
+    const int r_end = min(i_end, r_begin + kActRound);
+    // contiguous run of this thread inside the round, a multiple of 4 variables
+    const int run = (((r_end - r_begin) / kVec + kThreads - 1) / kThreads) * kVec;
+    const int t_begin = r_begin + threadIdx.x * run;
+    const int t_end = min(r_end, t_begin + run);
+    uint32_t bits[kActPerThread / 32] = {0u, 0u, 0u, 0u};
+    int mine = 0;
+#pragma unroll
+    for (int q = 0; q < kActPerThread / kVec; ++q) {
+      const int i0 = t_begin + q * kVec;
+      if (i0 < t_end) {
+        const float4 xt = ld4(v.xt + base + i0), gt = ld4(v.gt + base + i0);
+        const uint32_t f = (is_free(xt.x, gt.x, lo, hi, 1) ? 0u : 1u) | (is_free(xt.y, gt.y, lo, hi, 1) ? 0u : 2u) |
+                           (is_free(xt.z, gt.z, lo, hi, 1) ? 0u : 4u) | (is_free(xt.w, gt.w, lo, hi, 1) ? 0u : 8u);
+        bits[q / 8] |= f << (4 * (q % 8));
+        mine += __popc(f);
+      }
     }
-    const int mine = __popc(flags);
-    // exclusive prefix over the block, in thread (= index) order
+    // exclusive prefix of the per-thread counts over the block (thread order = index order)
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -277,25 +318,31 @@ __global__ void __launch_bounds__(kThreads) lbfgs_active_kernel(Vecs v) {
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    int before = count_s;
-    for (int w = 0; w < warp; ++w) before += warp_tot[w];
-    int pos = before + incl - mine;
-    for (int e = 0; e < 4; ++e)
-      if (flags & (1u << e)) list[pos++] = i0 + e;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = count_s;
-      for (int w = 0; w < kThreads / 32; ++w) tot += warp_tot[w];
-      count_s = tot;
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      if (w < warp) before += warp_tot[w];
+      total += warp_tot[w];
     }
-    __syncthreads();
-    if (count_s > kActCap - kChunk) {   // the next tile might not fit: consume the list
-      flush(count_s);
-      if (threadIdx.x == 0) count_s = 0;
+    // place the indices; when the round holds more than the list, consume it in passes of kActCap entries
+    const int first = before + incl - mine;            // this thread's first position in the round's list
+    for (int pass0 = 0; pass0 < total; pass0 += kActCap) {
+      int pos = first;
+#pragma unroll
+      for (int w = 0; w < kActPerThread / 32; ++w) {
+        uint32_t bw = bits[w];
+        while (bw) {
+          const int bit = __ffs(bw) - 1;
+          bw &= bw - 1;
+          if (pos >= pass0 && pos < pass0 + kActCap) list[pos - pass0] = t_begin + w * 32 + bit;
+          ++pos;
+        }
+      }
       __syncthreads();
+      flush(min(kActCap, total - pass0));
     }
+    __syncthreads();      // warp_tot is rewritten by the next round
   }
-  flush(count_s);
 #pragma unroll
   for (int t = 0; t < kActPairs; ++t) {
     if (pa[t] >= 0) {
@@ -569,10 +616,14 @@ __global__ void __launch_bounds__(kDecideThreads) lbfgs_decide_kernel(Vecs v) {
   __shared__ Decision dec;
   __shared__ double K[kKN][kKN + 1];     // reduced system, last column = right-hand side
   __shared__ double wv[kKN];
-  __shared__ int piv_row;
+  __shared__ double pivot_inv;
   __shared__ int singular;
   static_assert(sizeof(Ctrl) % 4 == 0, "Ctrl is copied word by word");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kDecideThreads / 32;
+  auto stamp = [&](int i) {
+    if (b == 0 && tid == 0) v.dbg[i] = clock64();
+  };
+  stamp(0);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&cg);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sc);
@@ -581,36 +632,59 @@ __global__ void __launch_bounds__(kDecideThreads) lbfgs_decide_kernel(Vecs v) {
   const int nh = cg.nh;
   const int np = kNP0 + kNPH * nh;
   // Sum the block partials in a fixed order: one warp per quantity, lane l takes blocks l, l+32, ..., then a
-  // butterfly over the lanes. Deterministic: the summation tree depends only on nblk.
-  for (int k = warp; k < np + 2; k += nwarps) {
-    double t = 0.0;
-    if (k < np) {
-      const float* src = v.part + static_cast<size_t>(b) * v.nblk * kNP + k;
-      for (int j = lane; j < v.nblk; j += 32) t += static_cast<double>(src[static_cast<size_t>(j) * kNP]);
+  // butterfly over the lanes. Deterministic: the summation tree depends only on nblk. A warp works on kSumIlp
+  // quantities at a time: a dependent chain of fp64 adds and shuffles is ~100 cycles per link on this part, and nine
+  // such chains one after the other were a third of the kernel (tests/tools/lbfgs_phases.py).
+  {
+    constexpr int kSumIlp = 3;
+    const float* pbase = v.part + static_cast<size_t>(b) * kNP * v.nblk;
+    for (int k0 = warp; k0 < np; k0 += nwarps * kSumIlp) {
+      double t[kSumIlp];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == 0) sums[k] = t;
-    } else if (k == np) {
+      for (int q = 0; q < kSumIlp; ++q) {
+        t[q] = 0.0;
+        const int k = k0 + q * nwarps;
+        if (k < np) {
+          const float* src = pbase + static_cast<size_t>(k) * v.nblk;
+          for (int j = lane; j < v.nblk; j += 32) t[q] += static_cast<double>(src[j]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < kSumIlp; ++q) t[q] += __shfl_xor_sync(0xffffffffu, t[q], o);
+      }
+#pragma unroll
+      for (int q = 0; q < kSumIlp; ++q) {
+        const int k = k0 + q * nwarps;
+        if (lane == 0 && k < np) sums[k] = t[q];
+      }
+    }
+    if (warp == nwarps - 1) {            // g'd of a freshly built direction
+      double t = 0.0;
       const float* src = v.part2 + static_cast<size_t>(b) * v.nblk;
       for (int j = lane; j < v.nblk; j += 32) t += static_cast<double>(src[j]);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
       if (lane == 0) sums[kNP] = t;
-    } else {
+    }
+    if (warp == nwarps - 2) {            // largest feasible step along it
+      float t = 3.0e38f;
       const float* src = v.part3 + static_cast<size_t>(b) * v.nblk;
-      t = STPBIG;
-      for (int j = lane; j < v.nblk; j += 32) t = fmin(t, static_cast<double>(src[j]));
+      for (int j = lane; j < v.nblk; j += 32) t = fminf(t, src[j]);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t = fmin(t, __shfl_xor_sync(0xffffffffu, t, o));
-      if (lane == 0) sums[kNP + 1] = t;
+      for (int o = 16; o > 0; o >>= 1) t = fminf(t, __shfl_xor_sync(0xffffffffu, t, o));
+      if (lane == 0) sums[kNP + 1] = static_cast<double>(t);
     }
   }
   __syncthreads();
+  stamp(1);                                   // partial sums reduced
   if (tid == 0) {
     singular = 0;
     decide_serial(sc, sums, sums[kNP], sums[kNP + 1], v, b, dec);
   }
   __syncthreads();
+  stamp(2);                                   // line search / bookkeeping decided
 
   if (dec.solve) {
     Tables& T = v.tab[b];
@@ -685,61 +759,33 @@ __global__ void __launch_bounds__(kDecideThreads) lbfgs_decide_kernel(Vecs v) {
       K[r][cc] = val;
     }
     __syncthreads();
-    // ---- Gaussian elimination with partial pivoting (K is symmetric indefinite), the whole block per step
+    stamp(3);                                 // tables updated, K built
+    // ---- Gauss-Jordan elimination in natural order, no pivoting, the whole block per step. K is quasi-definite: the
+    // first k pivots are those of -(D + Y_F'Y_F / theta) (negative definite), the last k those of the Schur complement
+    // theta S_A'S_A + B (D + Y_F'Y_F / theta)^-1 B' (positive definite) - the block LEL' factorisation formk computes -
+    // so the natural order is stable and the pivot search, the row swaps and the back-substitution go away (each was a
+    // chain of block barriers and fp64 shuffles: 105k of the kernel's 163k cycles, tests/tools/lbfgs_phases.py).
     for (int p = 0; p < N; ++p) {
-      if (warp == 0) {
-        double best = -1.0;
-        int br = p;
-        for (int r = p + lane; r < N; r += 32) {
-          const double a = fabs(K[r][p]);
-          if (a > best) {
-            best = a;
-            br = r;
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-          const int orow = __shfl_xor_sync(0xffffffffu, br, o);
-          if (ob > best || (ob == best && orow < br)) {
-            best = ob;
-            br = orow;
-          }
-        }
-        if (lane == 0) {
-          piv_row = br;
-          if (!(best > 0.0) || !isfinite(best)) singular = 1;
-        }
+      if (tid == 0) {
+        const double pv = K[p][p];
+        if (!(fabs(pv) > 0.0) || !isfinite(pv)) singular = 1;
+        pivot_inv = 1.0 / pv;
       }
       __syncthreads();
       if (singular) break;
-      const int pr = piv_row;
-      if (pr != p) {
-        for (int j = tid; j <= N; j += kDecideThreads) {
-          const double t = K[p][j];
-          K[p][j] = K[pr][j];
-          K[pr][j] = t;
-        }
-        __syncthreads();
-      }
-      const double inv = 1.0 / K[p][p];
-      const int rows = N - p - 1, cols = N - p;     // columns p+1 .. N
-      for (int e = tid; e < rows * cols; e += kDecideThreads) {
-        const int r = p + 1 + e / cols, j = p + 1 + e % cols;
+      const double inv = pivot_inv;
+      const int cols = N - p;                       // columns p+1 .. N (the right-hand side included)
+      for (int e = tid; e < (N - 1) * cols; e += kDecideThreads) {
+        int r = e / cols;
+        if (r >= p) ++r;                            // every row but the pivot row
+        const int j = p + 1 + e % cols;
         K[r][j] -= K[r][p] * inv * K[p][j];
       }
       __syncthreads();
     }
-    if (!singular && warp == 0) {
-      for (int p = N - 1; p >= 0; --p) {
-        double t = 0.0;
-        for (int j = p + 1 + lane; j < N; j += 32) t += K[p][j] * wv[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) wv[p] = (K[p][N] - t) / K[p][p];
-        __syncwarp();
-      }
-    }
+    stamp(4);                                 // eliminated
+    if (!singular)
+      for (int i = tid; i < N; i += kDecideThreads) wv[i] = K[i][N] / K[i][i];
     __syncthreads();
     if (tid == 0) {
       bool ok = !singular;
@@ -761,11 +807,13 @@ __global__ void __launch_bounds__(kDecideThreads) lbfgs_decide_kernel(Vecs v) {
     }
     __syncthreads();
   }
+  stamp(5);                                   // solved
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&sc);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&cg);
     for (int i = tid; i < static_cast<int>(sizeof(Ctrl) / 4); i += kDecideThreads) dst[i] = src[i];
   }
+  stamp(6);
 }
 
 // ------------------------------------------------------------------------------------------------ update
@@ -966,6 +1014,7 @@ Lbfgs::~Lbfgs() {
     cudaFree(im->v.ctrl);
     cudaFree(im->v.tab);
     cudaFree(im->v.gramA);
+    cudaFree(im->v.dbg);
     if (im->pinned_i) cudaFreeHost(im->pinned_i);
     if (im->pinned_f) cudaFreeHost(im->pinned_f);
     delete im;
@@ -1005,6 +1054,8 @@ int lbfgs_create(Lbfgs** out, Plan* plan, int maxcor, int bounded, float lower, 
   if (e == cudaSuccess) e = cudaMemset(v.ctrl, 0, sizeof(Ctrl) * B + 3 * sizeof(int) * B);
   if (e == cudaSuccess) e = cudaMalloc(&v.tab, sizeof(Tables) * B);
   if (e == cudaSuccess) e = cudaMemset(v.tab, 0, sizeof(Tables) * B);
+  if (e == cudaSuccess) e = cudaMalloc(&v.dbg, 16 * sizeof(long long));
+  if (e == cudaSuccess) e = cudaMemset(v.dbg, 0, 16 * sizeof(long long));
   if (e == cudaSuccess) e = cudaMalloc(&v.gramA, gram_bytes);
   if (e == cudaSuccess) e = cudaMemset(v.gramA, 0, gram_bytes);
   if (e == cudaSuccess) e = cudaMallocHost(&im->pinned_i, 3 * sizeof(int) * B);
@@ -1140,6 +1191,13 @@ int Lbfgs::run(int maxiter, int max_evals, cudaStream_t caller) {
     evals += chunk;
   }
   STX_TRY(fence_out(im, caller));
+  return STX_OK;
+}
+
+int Lbfgs::phase_cycles(long long* host16) {
+  LbfgsImpl* im = impl_of(this);
+  STX_CUDA(cudaStreamSynchronize(im->stream));
+  STX_CUDA(cudaMemcpy(host16, im->v.dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return STX_OK;
 }
 

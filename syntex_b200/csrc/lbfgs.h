@@ -15,6 +15,7 @@ struct Lbfgs {
   int reset(const float* x0, int is_preimage, cudaStream_t stream);
   int run(int maxiter, int max_evals, cudaStream_t stream);
   int result(float* x, float* fun, int* nit, int* nfev, cudaStream_t stream);
+  int phase_cycles(long long* host16);
   int minimize_host(const float* x0_host, int is_preimage, int maxiter, float* x_host, float* fun_host,
                     int* nit_host, int* nfev_host, cudaStream_t stream);
 };

@@ -14,6 +14,7 @@ int g_debug_no_gram_fusion = 0;     // 1 = stand-alone Gram-gradient launches
 int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
 int g_debug_tiled_weights = 0;      // 1 = fetch weight tiles with 1-D bulk copies from tiled pre-swizzled packs
                                     // (measured: no gain over tensor-map fetches, costs a second weight copy: off)
+int g_debug_f8_single_cta = 0;      // 1 = one CTA per SM for the 64-channel f16+f8 forward (stx_debug_set key 12)
 int g_debug_splitk = 0;             // 1 = split-K work items for small grids (measured slower at 256^2: off)
 
 static const LayerSpec kLayers[kNumLayers] = {
@@ -323,6 +324,9 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
         rc = fail(STX_ERR_UNSUPPORTED, "plan_create: the f16+f8 forward needs feature maps at least 8 pixels wide");
       op.split = 2;
       op.corr_scale = vgg->corr_scale[s.conv_index];
+      // 64-channel tiles are epilogue-bound (tensor pipe 27 % busy, profiles/r02_ncu_full_fwd_shallow.md): two CTAs per
+      // SM double the epilogue warps; each keeps a single hi+corr patch stage
+      if (op.patch && op.bn == 64 && op.tiles_w * op.tiles_h * op.nimg >= 2 * 148 && !g_debug_f8_single_cta) op.occ = 2;
     } else {
       rc = conv3x3_prepare(&op, p->act[l - 1], p->split ? p->act_lo[l - 1] : nullptr, B, p->lh[l], p->lw[l], s.cin,
                            vgg->wf[s.conv_index], p->split ? vgg->wf_lo[s.conv_index] : nullptr, s.cout, 0);
