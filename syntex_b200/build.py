@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsyntex_b200.so")
 SOURCES = ["common.cu", "conv_igemm.cu", "conv_patch.cu", "gram.cu", "elementwise.cu", "plan.cu", "lbfgs.cu", "capi.cu", "probe.cu",
-           "wgrad.cu", "gen_ops.cu"]
+           "wgrad.cu", "gen_ops.cu", "conv1_1_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-t", "0"]
 

@@ -53,6 +53,15 @@ union Pack8 {
   __nv_bfloat162 h2[4];
 };
 
+// The epilogue reads and writes 32 bytes per access (st256 / ld256 below).
+inline bool epilogue_pointers_aligned(const ConvKernelParams& p) {
+  const void* ptrs[] = {p.addend, p.mask, p.out, p.out_lo, p.export_out, p.pool_out, p.pool_out_lo, p.up_out, p.up_mask,
+                        p.aux_out, p.pool_aux};
+  for (const void* q : ptrs)
+    if (reinterpret_cast<uintptr_t>(q) & 31) return false;
+  return true;
+}
+
 // ---- f16 + f8 activation format (plan precision 2) ----------------------------------------------------------
 // A recorded layer is TWO planes of 2 bytes per element:
 //   hi   [n,H,W,C] fp16: A16 = fp16(A)                        (main MMA operand, Gram operand, ReLU mask)
@@ -78,53 +87,75 @@ union Pack8h {
   __half2 h2[4];
 };
 
+// 256-bit global accesses (sm_100: LDG/STG.E.256): one FULL 32-byte sector per lane. A thread of the epilogue owns 64
+// contiguous bytes per plane; with 128-bit accesses every instruction touched 32 half-filled sectors of 32 different
+// lines (the LSU works per sector per instruction: conv1_1 forward spent 28 M sector operations on 0.9 M requests,
+// profiles/r02_ncu_full_conv1_1_fwd_cuda_cores.md). Addresses must be 32-byte aligned (checked by the launchers).
+__device__ __forceinline__ void st256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld256_nc(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void ld256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p)
+               : "memory");
+}
+
 // 32 consecutive channels (ch0 a multiple of 32) of one pixel -> fp16 plane and correction plane.
 // pix = pixel index, C = channels of the layer; lo_plane may be null (layer whose low half nothing reads).
 __device__ __forceinline__ void store_f16f8_32(const float (&v)[32], bf16* hi_plane, bf16* corr_plane, size_t pix, int C,
                                                int ch0) {
-  uint4* o4 = reinterpret_cast<uint4*>(hi_plane + pix * C + ch0);
-  uint32_t a8[8], l8[8];
+  Pack8h pk[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    Pack8h pk;
-    float lo[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float a = fminf(v[8 * j + 2 * e], 65504.0f), b = fminf(v[8 * j + 2 * e + 1], 65504.0f);
-      pk.h2[e] = __floats2half2_rn(a, b);
-      const float2 hh = __half22float2(pk.h2[e]);
-      lo[2 * e] = (a - hh.x) * kF8ScaleLo;
-      lo[2 * e + 1] = (b - hh.y) * kF8ScaleLo;
-    }
-    o4[j] = pk.u;
-    a8[2 * j] = pack_e4m3x4(v[8 * j] * kF8ScaleA, v[8 * j + 1] * kF8ScaleA, v[8 * j + 2] * kF8ScaleA,
-                            v[8 * j + 3] * kF8ScaleA);
-    a8[2 * j + 1] = pack_e4m3x4(v[8 * j + 4] * kF8ScaleA, v[8 * j + 5] * kF8ScaleA, v[8 * j + 6] * kF8ScaleA,
-                                v[8 * j + 7] * kF8ScaleA);
-    l8[2 * j] = pack_e4m3x4(lo[0], lo[1], lo[2], lo[3]);
-    l8[2 * j + 1] = pack_e4m3x4(lo[4], lo[5], lo[6], lo[7]);
+    for (int e = 0; e < 4; ++e)
+      pk[j].h2[e] = __floats2half2_rn(fminf(v[8 * j + 2 * e], 65504.0f), fminf(v[8 * j + 2 * e + 1], 65504.0f));
   }
+  uint8_t* hb = reinterpret_cast<uint8_t*>(hi_plane + pix * C + ch0);
+  st256(hb, pk[0].u, pk[1].u);
+  st256(hb + 32, pk[2].u, pk[3].u);
   if (corr_plane) {
+    uint32_t a8[8], l8[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 hh = __half22float2(pk[j].h2[e]);
+        lo[2 * e] = (fminf(v[8 * j + 2 * e], 65504.0f) - hh.x) * kF8ScaleLo;
+        lo[2 * e + 1] = (fminf(v[8 * j + 2 * e + 1], 65504.0f) - hh.y) * kF8ScaleLo;
+      }
+      a8[2 * j] = pack_e4m3x4(v[8 * j] * kF8ScaleA, v[8 * j + 1] * kF8ScaleA, v[8 * j + 2] * kF8ScaleA,
+                              v[8 * j + 3] * kF8ScaleA);
+      a8[2 * j + 1] = pack_e4m3x4(v[8 * j + 4] * kF8ScaleA, v[8 * j + 5] * kF8ScaleA, v[8 * j + 6] * kF8ScaleA,
+                                  v[8 * j + 7] * kF8ScaleA);
+      l8[2 * j] = pack_e4m3x4(lo[0], lo[1], lo[2], lo[3]);
+      l8[2 * j + 1] = pack_e4m3x4(lo[4], lo[5], lo[6], lo[7]);
+    }
     uint8_t* cb = reinterpret_cast<uint8_t*>(corr_plane) + pix * C * 2 + static_cast<size_t>(ch0 >> 6) * 128 + (ch0 & 63);
-    uint4* c4 = reinterpret_cast<uint4*>(cb);
-    c4[0] = make_uint4(a8[0], a8[1], a8[2], a8[3]);
-    c4[1] = make_uint4(a8[4], a8[5], a8[6], a8[7]);
-    uint4* d4 = reinterpret_cast<uint4*>(cb + 64);
-    d4[0] = make_uint4(l8[0], l8[1], l8[2], l8[3]);
-    d4[1] = make_uint4(l8[4], l8[5], l8[6], l8[7]);
+    st256(cb, make_uint4(a8[0], a8[1], a8[2], a8[3]), make_uint4(a8[4], a8[5], a8[6], a8[7]));
+    st256(cb + 64, make_uint4(l8[0], l8[1], l8[2], l8[3]), make_uint4(l8[4], l8[5], l8[6], l8[7]));
   }
 }
 
 // 32 consecutive channels of one pixel -> bf16
 __device__ __forceinline__ void store_bf16_32(const float (&v)[32], bf16* dst) {
-  uint4* o4 = reinterpret_cast<uint4*>(dst);
+  Pack8 pk[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    Pack8 pk;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) pk.h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-    o4[j] = pk.u;
+    for (int e = 0; e < 4; ++e) pk[j].h2[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
   }
+  st256(dst, pk[0].u, pk[1].u);
+  st256(reinterpret_cast<uint8_t*>(dst) + 32, pk[2].u, pk[3].u);
 }
 
 // Sign test of a stored activation, valid for bf16 AND fp16 bit patterns: positive <=> the 16 bits, read as a signed
@@ -158,11 +189,13 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
       }
     }
     if (p.addend) {
-      const uint4* a4 = reinterpret_cast<const uint4*>(p.addend + off);
+      uint4 ad[4];
+      ld256(p.addend + off, ad[0], ad[1]);          // may alias `out`: not through the read-only path
+      ld256(p.addend + off + 16, ad[2], ad[3]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         Pack8 pk;
-        pk.u = a4[j];
+        pk.u = ad[j];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = __bfloat1622float2(pk.h2[e]);
@@ -186,11 +219,12 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
     }
     if (p.mask) {
-      const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off);
+      uint4 mk[4];
+      ld256_nc(p.mask + off, mk[0], mk[1]);
+      ld256_nc(p.mask + off + 16, mk[2], mk[3]);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint4 mk = __ldg(m4 + j);
-        const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+        const uint32_t mw[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           if (!pos16_lo(mw[e])) v[8 * j + 2 * e] = 0.0f;
@@ -205,44 +239,48 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx) {
           const size_t uo = ((static_cast<size_t>(n) * H2 + 2 * h + dy) * W2 + 2 * w + dx) * p.cout + ch0;
-          const uint4* m4 = reinterpret_cast<const uint4*>(p.up_mask + uo);
-          uint4* o4 = reinterpret_cast<uint4*>(p.up_out + uo);
+          uint4 mk[4];
+          ld256_nc(p.up_mask + uo, mk[0], mk[1]);
+          ld256_nc(p.up_mask + uo + 16, mk[2], mk[3]);
+          Pack8 po[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            Pack8 po;
-            const uint4 mk = __ldg(m4 + j);
-            const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+            const uint32_t mw[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              po.h2[e] = __floats2bfloat162_rn(pos16_lo(mw[e]) ? 0.25f * v[8 * j + 2 * e] : 0.0f,
-                                               pos16_hi(mw[e]) ? 0.25f * v[8 * j + 2 * e + 1] : 0.0f);
+              po[j].h2[e] = __floats2bfloat162_rn(pos16_lo(mw[e]) ? 0.25f * v[8 * j + 2 * e] : 0.0f,
+                                                  pos16_hi(mw[e]) ? 0.25f * v[8 * j + 2 * e + 1] : 0.0f);
             }
-            o4[j] = po.u;
           }
+          st256(p.up_out + uo, po[0].u, po[1].u);
+          st256(p.up_out + uo + 16, po[2].u, po[3].u);
         }
       }
     } else if (FMT == 2) {
       store_f16f8_32(v, p.out, p.out_lo, (static_cast<size_t>(n) * p.H + h) * p.W + w, p.cout, ch0);
       if (p.aux_out) store_bf16_32(v, p.aux_out + off);
     } else {
-      uint4* o4 = reinterpret_cast<uint4*>(p.out + off);
       // the low halves are optional even in split mode: a layer that only feeds a fused pool (whose hi/lo outputs
       // carry the precision forward) and the backward mask needs its high plane only
-      uint4* l4 = (SPLIT && p.out_lo) ? reinterpret_cast<uint4*>(p.out_lo + off) : nullptr;
+      bf16* lo_dst = (SPLIT && p.out_lo) ? p.out_lo + off : nullptr;
+      Pack8 pk[4], pl[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        Pack8 pk, pl;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-          pk.h2[e] = __floats2bfloat162_rn(a, b);
+          pk[j].h2[e] = __floats2bfloat162_rn(a, b);
           if (SPLIT) {
-            const float2 hh = __bfloat1622float2(pk.h2[e]);
-            pl.h2[e] = __floats2bfloat162_rn(a - hh.x, b - hh.y);
+            const float2 hh = __bfloat1622float2(pk[j].h2[e]);
+            pl[j].h2[e] = __floats2bfloat162_rn(a - hh.x, b - hh.y);
           }
         }
-        o4[j] = pk.u;
-        if (SPLIT && l4) l4[j] = pl.u;
+      }
+      st256(p.out + off, pk[0].u, pk[1].u);
+      st256(p.out + off + 16, pk[2].u, pk[3].u);
+      if (SPLIT && lo_dst) {
+        st256(lo_dst, pl[0].u, pl[1].u);
+        st256(lo_dst + 16, pl[2].u, pl[3].u);
       }
     }
   }
@@ -264,20 +302,22 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
       }
     } else if (valid && (lane & 9) == 0) {
       const size_t po = ((static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1)) * p.cout + ch0;
-      uint4* o4 = reinterpret_cast<uint4*>(p.pool_out + po);
-      uint4* l4 = p.pool_out_lo ? reinterpret_cast<uint4*>(p.pool_out_lo + po) : nullptr;
+      Pack8 pk[4], pl[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        Pack8 pk, pl;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
-          pk.h2[e] = __floats2bfloat162_rn(a, b);
-          const float2 hh = __bfloat1622float2(pk.h2[e]);
-          pl.h2[e] = __floats2bfloat162_rn(a - hh.x, b - hh.y);
+          pk[j].h2[e] = __floats2bfloat162_rn(a, b);
+          const float2 hh = __bfloat1622float2(pk[j].h2[e]);
+          pl[j].h2[e] = __floats2bfloat162_rn(a - hh.x, b - hh.y);
         }
-        o4[j] = pk.u;
-        if (l4) l4[j] = pl.u;
+      }
+      st256(p.pool_out + po, pk[0].u, pk[1].u);
+      st256(p.pool_out + po + 16, pk[2].u, pk[3].u);
+      if (p.pool_out_lo) {
+        st256(p.pool_out_lo + po, pl[0].u, pl[1].u);
+        st256(p.pool_out_lo + po + 16, pl[2].u, pl[3].u);
       }
     }
   }

@@ -227,6 +227,7 @@ int launch_bn(const ConvOp& op, cudaStream_t stream) {
   p.corr_scale = 1.0f;
   p.aux_out = nullptr;
   p.pool_aux = nullptr;
+  STX_REQUIRE(epilogue_pointers_aligned(p), "conv: epilogue tensors must be 32-byte aligned (256-bit accesses)");
   dim3 grid(op.tiles_w * op.tiles_h * op.tiles_n, op.cout / BN, 1);
   STX_TRY(launch_pdl(conv_igemm_kernel<BN, SPLIT>, grid, dim3(kThreads), L::kTotal, stream, op.tmA, op.tmB,
                      SPLIT ? op.tmA2 : op.tmA, SPLIT ? op.tmB2 : op.tmB, p));

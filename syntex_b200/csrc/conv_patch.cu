@@ -634,6 +634,7 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.corr_scale = op.corr_scale;
   p.aux_out = op.aux_out;
   p.pool_aux = op.pool_aux;
+  STX_REQUIRE(epilogue_pointers_aligned(p), "conv: epilogue tensors must be 32-byte aligned (256-bit accesses)");
   PatchSched sched;
   sched.nblocks = op.cout / BN;
   sched.ksplit = (op.ksplit > 1 && op.splitk_ws && op.splitk_counters && BN != 16 && !L::kTwoAcc) ? op.ksplit : 1;

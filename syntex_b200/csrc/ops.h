@@ -128,6 +128,11 @@ int conv1_1_fwd_launch(const float* image, int nimg, int H, int W, int is_preima
 // the per-layer power-of-two weight scale sw (the layer's correction accumulator is then scaled by 1 / (512 sw)).
 int pack_weights_f16f8_launch(const float* w_hwio, int cin, int cout, float sw, bf16* w16, bf16* wcorr,
                               cudaStream_t stream);
+// conv1_1 of the f16 + f8 plans on the tensor cores (conv1_1_tc.cu): K = 27 im2col rows built in shared memory.
+// wpack: 16 KB from pack_conv1_1_tc_launch (fp16 tile + e4m3 correction tile, pre-swizzled), sw its weight scale.
+int pack_conv1_1_tc_launch(const float* w27x64, float sw, bf16* out16k, cudaStream_t stream);
+int conv1_1_tc_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3, const bf16* wpack,
+                      float corr_scale, const float* bias, bf16* out, bf16* out_corr, bf16* aux, cudaStream_t stream);
 // fp16 plane (+ correction plane, nullable) of a recorded layer with C channels -> fp32.
 int f16f8_to_f32_launch(const bf16* hi, const bf16* corr, size_t n, int C, float* out, cudaStream_t stream);
 // dgrad of conv1_1 chained with the preprocessing derivative: g [nimg,H,W,64] bf16 (already ReLU-masked) ->

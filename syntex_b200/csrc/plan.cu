@@ -14,6 +14,7 @@ int g_debug_no_gram_fusion = 0;     // 1 = stand-alone Gram-gradient launches
 int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
 int g_debug_tiled_weights = 0;      // 1 = fetch weight tiles with 1-D bulk copies from tiled pre-swizzled packs
                                     // (measured: no gain over tensor-map fetches, costs a second weight copy: off)
+int g_debug_conv1_1_cuda_cores = 0;  // 1 = CUDA-core conv1_1 forward in the f16 + f8 plans too (stx_debug_set key 13)
 int g_debug_f8_single_cta = 0;      // 1 = one CTA per SM for the 64-channel f16+f8 forward (stx_debug_set key 12)
 int g_debug_splitk = 0;             // 1 = split-K work items for small grids (measured slower at 256^2: off)
 
@@ -29,6 +30,7 @@ const LayerSpec& layer_spec(int layer) { return kLayers[layer]; }
 Vgg::~Vgg() {
   cudaFree(w0);
   cudaFree(wd0);
+  cudaFree(wtc0);
   for (int i = 0; i < kNumConvs; ++i) {
     cudaFree(bias[i]);
     cudaFree(wf[i]);
@@ -69,6 +71,17 @@ int vgg_create(Vgg** out, const float* const* w, const float* const* b, int num_
       if (rc == STX_OK) chk(cudaMemcpyAsync(v->w0, w[ci], wn * sizeof(float), cudaMemcpyHostToDevice, stream), "copy w0");
       chk(cudaMalloc(&v->wd0, 9 * 16 * 64 * sizeof(bf16)), "cudaMalloc wd0");
       if (rc == STX_OK) rc = pack_conv1_1_dgrad_launch(v->w0, v->wd0, stream);
+      {
+        float wmax = 0.0f;
+        for (size_t i = 0; i < wn; ++i) wmax = std::max(wmax, std::fabs(w[ci][i]));
+        int ex = 0;
+        if (wmax > 0.0f) ex = static_cast<int>(std::floor(std::log2(224.0f / wmax)));
+        ex = std::max(-20, std::min(20, ex));
+        const float sw = std::ldexp(1.0f, ex);
+        v->corr_scale[0] = 1.0f / (512.0f * sw);
+        chk(cudaMalloc(&v->wtc0, 16384), "cudaMalloc wtc0");
+        if (rc == STX_OK) rc = pack_conv1_1_tc_launch(v->w0, sw, v->wtc0, stream);
+      }
     } else {
       float* tmp = nullptr;
       chk(cudaMalloc(&tmp, wn * sizeof(float)), "cudaMalloc staging");
@@ -561,7 +574,13 @@ int Plan::forward(const float* image, int is_preimage, int with_grams, bool with
     if (l == deepest) STX_TRY(launch_finish(true));
     return STX_OK;
   };
-  STX_LAUNCH(kClsConv1, conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0], act_lo[0], stream, split == 2 ? 2 : 0, act_bf[0]));
+  if (split == 2 && !g_debug_conv1_1_cuda_cores) {
+    STX_LAUNCH(kClsConv1, conv1_1_tc_launch(image, B, H, W, is_preimage, vgg->mean, vgg->wtc0, vgg->corr_scale[0],
+                                            vgg->bias[0], act[0], act_lo[0], act_bf[0], stream));
+  } else {
+    STX_LAUNCH(kClsConv1, conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0],
+                                             act_lo[0], stream, split == 2 ? 2 : 0, act_bf[0]));
+  }
   STX_TRY(after_layer(0));
   for (int l = 1; l <= topmost; ++l) {
     if (kLayers[l].is_conv) {

@@ -23,6 +23,7 @@ struct Vgg {
   float mean[3] = {0, 0, 0};
   float* w0 = nullptr;            // conv1_1 weights fp32 [27][64]
   bf16* wd0 = nullptr;            // conv1_1 dgrad pack [9][16][64] (tensor-core input-gradient path)
+  bf16* wtc0 = nullptr;           // conv1_1 forward packs of the f16 + f8 plans (conv1_1_tc.cu), 16 KB
   float* bias[kNumConvs] = {};    // fp32 [cout]
   bf16* wf[kNumConvs] = {};       // forward pack [9][cout][cin] (conv index >= 1), high halves
   bf16* wf_lo[kNumConvs] = {};    // low halves bf16(w - bf16(w)) for the bf16x3 forward

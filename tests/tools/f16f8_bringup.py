@@ -1,7 +1,7 @@
 """B200 bring-up of the f16 + f8 forward: Gram / loss / input-gradient error against the float64 oracle next to the
 bf16x3 and plain-bf16 forwards, and the per-class kernel times of one f/g evaluation.
 
-  python tests/tools/f16f8_bringup.py [batch]
+  python tests/tools/f16f8_bringup.py [batch] [sizes, comma separated]
 """
 import ctypes
 import os
@@ -23,7 +23,7 @@ def accuracy():
     raw = synthetic_vgg_weights(0)
     img = np.load(os.path.join(ROOT, "tests", "golden", "exemplar_flowerbeds0008_256.npz"))["image"]
     print("%-8s %5s %4s  %10s %10s %10s" % ("prec", "size", "seed", "gram_rel", "loss_rel", "grad_rel"))
-    for S in (64, 128, 256, 512):
+    for S in SIZES:
         tgt = so.resize_crop(img / 255.0, S)
         orc = so.SynthesizerOracle(so.load_vgg_weights(raw), S, dtype=torch.float64)
         orc.compute_gram(tgt, update=True)
@@ -72,6 +72,10 @@ def timing(batch):
         syn.close()
 
 
+SIZES = (64, 128, 256, 512)
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2:
+        SIZES = tuple(int(a) for a in sys.argv[2].split(","))
     accuracy()
     timing(int(sys.argv[1]) if len(sys.argv) > 1 else 18)
