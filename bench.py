@@ -358,21 +358,25 @@ def run_ours(args, rank, world, local_rank):
         flops = 2.0 * conv_flops_one_direction(size) * batch          # fwd + dgrad, algorithmic (2*M*N*K)
         peaks = measured_peaks()
         achieved = flops / (conv_ms * 1e-3) / 1e12
-        # the accurate forward issues three bf16 MMAs per algorithmic MAC (bf16x3): tensor-pipe work actually executed
-        exec_total = (3.0 + 1.0) * conv_flops_one_direction(size) * batch / (conv_ms * 1e-3) / 1e12
+        # tensor-pipe time actually spent, in kind::f16 MMA units per algorithmic MAC: the f16+f8 forward issues one
+        # kind::f16 and one kind::f8f6f4 MMA per K step (the latter twice the MACs in the same time) = 2 units, the
+        # input-gradient pass 1
+        fwd_units = {"auto": 2.0, "f16f8": 2.0, "bf16x3": 3.0, "bf16": 1.0}.get(syn.precision, 2.0)
+        exec_total = (fwd_units + 1.0) * conv_flops_one_direction(size) * batch / (conv_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "conv_patch_kernel (persistent tcgen05 3x3 implicit GEMM, fwd+dgrad, %d launches per f/g evaluation)" % conv_launches,
                     "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops"],
                     # dram__bytes_read + dram__bytes_write averaged over the 22 conv launches of one evaluation in the
-                    # ncu --set full captures at batch 18 (profiles/r01_ncu_full_b18.md) and batch 9
-                    # (profiles/r01_ncu_full_final_b9.md); only meaningful at those batches
-                    "traffic": {18: 139.8e6, 9: 61.8e6}.get(batch) if size == 256 else None,
-                    "traffic_note": "average DRAM bytes per conv launch, ncu --set full (profiles/r01_ncu_full_b18.md, "
-                                    "r01_ncu_full_final_b9.md): at batch 18 the deep layers move 47-80 MB per launch "
-                                    "(weights + one pass over their activations), the 64-channel layers 300-490 MB "
-                                    "(hi/lo activation planes in and out)",
+                    # ncu --set full capture at 64 jobs (profiles/r02_ncu_full_conv_b64.md: 8.52 GB read + 5.14 GB written);
+                    # only meaningful at that batch with the default (f16+f8) forward
+                    "traffic": 620.8e6 if (size == 256 and batch == 64) else None,
+                    "traffic_note": "average DRAM bytes per conv launch, ncu --set full at 64 jobs "
+                                    "(profiles/r02_ncu_full_conv_b64.md): the deep layers move 160-500 MB per launch "
+                                    "(weights + one pass over their activation planes), the 64-channel layers 1.4-2.1 GB "
+                                    "(fp16 + e4m3 planes in, gradient / mask / feature planes in and out); 13.7 GB per "
+                                    "evaluation = 2.1 ms at the measured HBM rate against 7.6 ms of conv time",
                     "executed_tflops": exec_total, "executed_frac": exec_total / peaks["bf16_tflops"],
-                    "note": "achieved counts algorithmic FLOPs (2*M*N*K once per direction); the bf16x3 forward executes 3 MMAs per MAC, executed_* counts those",
+                    "note": "achieved counts algorithmic FLOPs (2*M*N*K once per direction); the f16+f8 forward spends two kind::f16 MMA times per MAC (one f16 MMA + one f8 MMA over twice the K), executed_* counts those",
                     "avg_launch_us": 1e3 * conv_ms / max(conv_launches, 1),
                     "algorithmic_gflop_per_launch_avg": flops / 1e9 / max(conv_launches, 1),
                     "frac_of_sustained": achieved / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
@@ -387,7 +391,8 @@ def run_ours(args, rank, world, local_rank):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "warmup_cycles_run": warm_cycles, "ms_per_step": ms_max / args.steps,
            "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
-           "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+           "vs_baseline": None, "dtype": "f16+f8/bf16", "data": "synthetic",
+           "config": workload_config(args),
            "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(nit_e2e, 1),
                    "d2h_bytes_per_step": d2h / max(nit_e2e, 1),

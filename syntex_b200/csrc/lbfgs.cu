@@ -36,6 +36,7 @@
 
 namespace stx {
 int g_lbfgs_no_graph = 0;   // 1 = launch every optimiser cycle on the stream instead of replaying a CUDA graph (key 10)
+int g_lbfgs_serial_active = 0;   // 1 = active-set kernel in the main stream after the dots kernel (key 14)
 }
 
 #include <algorithm>
@@ -995,6 +996,10 @@ struct LbfgsImpl {
   // owns a stream and fences it against the caller's stream at entry and exit.
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // The active-set kernel (a latency-bound gather: ~16 k scattered 4-byte reads per block, bounded by the SM's
+  // outstanding requests x DRAM latency) runs on a side stream beside the bandwidth-bound dots kernel; both only read.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaGraphExec_t graph = nullptr;
   long long graph_nodes = 0;   // kernel launches per replay
   int graph_preimage = -1;
@@ -1008,6 +1013,9 @@ Lbfgs::~Lbfgs() {
   if (im) {
     if (im->graph) cudaGraphExecDestroy(im->graph);
     if (im->stream) cudaStreamDestroy(im->stream);
+    if (im->side) cudaStreamDestroy(im->side);
+    if (im->ev_fork) cudaEventDestroy(im->ev_fork);
+    if (im->ev_join) cudaEventDestroy(im->ev_join);
     if (im->ev_in) cudaEventDestroy(im->ev_in);
     if (im->ev_out) cudaEventDestroy(im->ev_out);
     cudaFree(im->base);
@@ -1061,6 +1069,9 @@ int lbfgs_create(Lbfgs** out, Plan* plan, int maxcor, int bounded, float lower, 
   if (e == cudaSuccess) e = cudaMallocHost(&im->pinned_i, 3 * sizeof(int) * B);
   if (e == cudaSuccess) e = cudaMallocHost(&im->pinned_f, (vec + B) * sizeof(float));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&im->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&im->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&im->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&im->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&im->ev_in, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&im->ev_out, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -1090,8 +1101,17 @@ static int launch_cycle(Lbfgs* o, cudaStream_t stream) {
   Vecs& v = im->v;
   STX_TRY(o->plan->step(v.xt, o->is_preimage, v.ft, v.gt, nullptr, stream));
   dim3 grid(v.nblk, im->B);
-  STX_TRY(launch_pdl(lbfgs_dots_kernel, grid, dim3(kThreads), 0, stream, v));
-  STX_TRY(launch_pdl(lbfgs_active_kernel, dim3(kSlices, im->B), dim3(kThreads), 0, stream, v));
+  if (g_lbfgs_serial_active) {
+    STX_TRY(launch_pdl(lbfgs_dots_kernel, grid, dim3(kThreads), 0, stream, v));
+    STX_TRY(launch_pdl(lbfgs_active_kernel, dim3(kSlices, im->B), dim3(kThreads), 0, stream, v));
+  } else {
+    STX_CUDA(cudaEventRecord(im->ev_fork, stream));
+    STX_CUDA(cudaStreamWaitEvent(im->side, im->ev_fork, 0));
+    STX_TRY(launch_pdl(lbfgs_active_kernel, dim3(kSlices, im->B), dim3(kThreads), 0, im->side, v));
+    STX_CUDA(cudaEventRecord(im->ev_join, im->side));
+    STX_TRY(launch_pdl(lbfgs_dots_kernel, grid, dim3(kThreads), 0, stream, v));
+    STX_CUDA(cudaStreamWaitEvent(stream, im->ev_join, 0));
+  }
   STX_TRY(launch_pdl(lbfgs_decide_kernel, dim3(im->B), dim3(kDecideThreads), 0, stream, v));
   STX_TRY(launch_pdl(lbfgs_update_kernel, grid, dim3(kThreads), 0, stream, v));
   count_launch(4);
