@@ -22,7 +22,8 @@ reference's own scipy L-BFGS-B call) on the host cores instead. Beside the headl
   po_config5            ProgressiveSynTex training at 512x512, per-GPU batch 1, data parallel over the N ranks (NCCL
                         gradient-mean all-reduce): images/s and the all-reduce's share of the step
   gpu_library_baseline  the same f/g evaluation through stock torch (cuDNN / cuBLAS, TF32 and bf16) on this GPU
-and N = 1 also `po_config3` (SingleSynTex inference, batch 64 of 256x256) and `cpu_baseline`.
+  po_config3            SingleSynTex inference, 64 images of 256x256 sharded 64 / N per GPU: images/s
+and N = 1 also `cpu_baseline`.
 """
 import argparse
 import ctypes
@@ -583,23 +584,30 @@ def po_config5(rank, world, local_rank):
     return out
 
 
-def po_config3():
-    """BASELINE.json config 3: SingleSynTex feed-forward synthesis, batch 64 of 256x256 (N = 1 only)."""
+def po_config3(rank, world):
+    """BASELINE.json config 3: SingleSynTex feed-forward synthesis, batch 64 of 256x256, the images sharded 64 / N per
+    GPU with no communication; images/s over all ranks, max over ranks of the device time."""
     import torch
     try:
         from syntex_b200.po.single_model import SingleSynTex
         from syntex_b200.po.trainer import SyntheticPOData
         from syntex_b200.synthetic import synthetic_vgg_weights
         torch.manual_seed(0)
+        per_rank = max(64 // max(world, 1), 1)
         single = SingleSynTex({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": 256}).cuda().eval()
-        z, t = next(iter(SyntheticPOData(64, 256, seed=0)))
+        z, t = next(iter(SyntheticPOData(per_rank, 256, seed=rank)))
 
         def infer():
             with torch.no_grad():
                 single.build_graph(z, t)
         ms = _timed_ms(infer, 2, 5)
-        return {"workload": "config3: SingleSynTex inference, batch 64 of 256x256", "images_per_s": 64e3 / ms,
-                "ms_per_batch": ms}
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+        return {"workload": "config3: SingleSynTex inference, 64 images of 256x256, %d per GPU" % per_rank,
+                "n_gpus": world, "images_per_s": per_rank * world * 1e3 / ms, "ms_per_batch": ms}
     except Exception as e:
         return {"error": "%s: %s" % (type(e).__name__, e)}
 
@@ -643,10 +651,10 @@ def main():
         out["gpu_library_baseline"] = gpu_library_baseline(args, out["fg_evals_per_iteration"])
     if extras and not args.no_po:
         po = po_config5(rank, world, local_rank)          # every rank takes part (NCCL)
+        po3 = po_config3(rank, world)
         if rank == 0:
             out["po_config5"] = po
-            if world == 1:
-                out["po_config3"] = po_config3()
+            out["po_config3"] = po3
     if out is not None:
         out["cpu_baseline"] = cpu_baseline_sample(args) if (world == 1 and not args.no_cpu_baseline) else None
         print(json.dumps(out), flush=True)

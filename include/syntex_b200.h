@@ -222,6 +222,11 @@ int stx_gram_cross_bf16(const void* a_bf16, const void* b_bf16, int n, int HW, i
 /* ---- PO generator building blocks (po/progressive_model.py:77-206) -------------
  * All tensors NHWC bf16 on the device unless noted. These replace, for the generator's trainable 3x3 layers, the
  * arithmetic of tensorpack Conv2D / InstanceNorm / tf.pad(SYMMETRIC) and of tf.gradients through them. */
+/* out[i] = x[i] * w[i]^T per image: x [n,H,W,cin] bf16, w [n][cout][cin] bf16 (one matrix per image), out
+ * [n,H,W,cout] bf16 - the d loss_k / d F_k = alpha F (G - T) product of build_texture_loss(calc_grad=True)
+ * (utils.py:50-55) and the F M products of the second-order term, for the whole batch in ONE launch. */
+int stx_conv1x1_per_image_bf16(const void* x, int n, int H, int W, int cin, const void* w, int cout, void* out,
+                               void* stream);
 /* 3x3 convolution with an explicit padding mode. H, W are the OUTPUT size; the input is
  * (H + 2 - 2 pad) x (W + 2 - 2 pad): pad 0 = VALID on an explicitly padded input (tf.pad + Conv2D("VALID"),
  * progressive_model.py:171-175), 1 = SAME (zero padding), 2 = FULL correlation (the input gradient of the VALID

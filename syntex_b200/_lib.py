@@ -38,6 +38,7 @@ def _declare(lib):
         "stx_plan_set_target_gram": (c_int, [vp, c_int, fp, c_int, vp]),
         "stx_plan_copy_target_gram": (c_int, [vp, c_int, fp, vp]),
         "stx_plan_clear_target": (c_int, [vp]),
+        "stx_conv1x1_per_image_bf16": (c_int, [vp, c_int, c_int, c_int, c_int, vp, c_int, vp, vp]),
         "stx_lbfgs_phase_cycles": (c_int, [vp, POINTER(ctypes.c_longlong)]),
         "stx_adam_tf": (c_int, [fp, fp, fp, fp, c_size_t, fp, fp, c_float, c_float, c_float, vp]),
         "stx_plan_generation": (ctypes.c_longlong, [vp]),

@@ -363,6 +363,15 @@ int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_pac
   return conv_launch(op, S(stream));
 }
 
+int stx_conv1x1_per_image_bf16(const void* x, int n, int H, int W, int cin, const void* w, int cout, void* out,
+                               void* stream) {
+  STX_REQUIRE(x && w && out, "stx_conv1x1_per_image_bf16: null argument");
+  ConvOp op;
+  STX_TRY(conv_prepare(&op, static_cast<const bf16*>(x), n, H, W, cin, static_cast<const bf16*>(w), cout, 1, 1, 0));
+  op.out = static_cast<bf16*>(out);
+  return conv_launch(op, S(stream));
+}
+
 int stx_conv_bf16_pad(const void* x, int n, int H, int W, int cin, const void* w_packed, int cout, int pad,
                       const float* bias, const void* addend, int relu, void* out, int variant, void* stream) {
   STX_REQUIRE(out, "stx_conv_bf16_pad: null output");

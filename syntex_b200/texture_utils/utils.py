@@ -73,9 +73,9 @@ def build_texture_loss(a, b, coefs, is_gram_a=False, is_gram_b=True,
         L = _lib.lib()
         _lib.check(L.stx_f32_to_bf16(diff.data_ptr(), diff.numel(), d16.data_ptr(), _lib.stream_ptr()))
         out16 = torch.empty((B, H, W, C), dtype=torch.bfloat16, device="cuda")
-        for i in range(B):   # per-image weights: one launch per image through the stand-alone conv entry point
-            _lib.check(L.stx_conv_bf16(f[i].data_ptr(), 1, H, W, C, d16[i].data_ptr(), C, 1, None, None, None, 0,
-                                       out16[i].data_ptr(), 0, _lib.stream_ptr()))
+        # per-image weights, whole batch in one launch (the matrix is symmetric: [cout][cin] = itself)
+        _lib.check(L.stx_conv1x1_per_image_bf16(f.data_ptr(), B, H, W, C, d16.data_ptr(), C, out16.data_ptr(),
+                                                _lib.stream_ptr()))
         grad_layer[k] = out16.to(torch.float32)
     return loss_overall, loss_layer, grad_layer
 
@@ -110,8 +110,7 @@ def gram_grad_double_bwd(feat, gram_diff, upstream, eps=1e-6, name="gram_grad_do
         m16 = torch.empty((B, C, C), dtype=torch.bfloat16, device="cuda")
         _lib.check(L.stx_f32_to_bf16(mat.data_ptr(), mat.numel(), m16.data_ptr(), st))
         o16 = torch.empty((B, H, W, C), dtype=torch.bfloat16, device="cuda")
-        for i in range(B):      # per-image weights: both matrices are symmetric, so [cout][cin] = the matrix itself
-            _lib.check(L.stx_conv_bf16(src[i].data_ptr(), 1, H, W, C, m16[i].data_ptr(), C, 1, None, None, None, 0,
-                                       o16[i].data_ptr(), 0, st))
+        # per-image weights, one launch for the batch: both matrices are symmetric, so [cout][cin] = the matrix itself
+        _lib.check(L.stx_conv1x1_per_image_bf16(src.data_ptr(), B, H, W, C, m16.data_ptr(), C, o16.data_ptr(), st))
         out += o16.float()
     return out

@@ -13,7 +13,7 @@ With `with_model=True` (diagnostic, `model_*` keys): the same budget run by the 
 chaotic), hence 24 seeds for config 1: the standard error of the geometric mean is then ~1.5 %.
 
   config 1: 256^2, 100 iterations, exemplar FlowerBeds0008_256, seeds 0..23      -> optimizer_config1.npz
-  config 2: 512^2, 500 iterations, the same exemplar through resize_crop(512), seeds 0..1 -> optimizer_config2.npz
+  config 2: 512^2, 500 iterations, the same exemplar through resize_crop(512), seeds 0..5 -> optimizer_config2.npz
 """
 import os
 import sys
@@ -85,4 +85,4 @@ if __name__ == "__main__":
     if "config1" in which:
         run(256, 100, list(range(24)), os.path.join(HERE, "optimizer_config1.npz"), with_model=False)
     if "config2" in which:
-        run(512, 500, [0, 1], os.path.join(HERE, "optimizer_config2.npz"), with_model=False)
+        run(512, 500, list(range(6)), os.path.join(HERE, "optimizer_config2.npz"), with_model=False)
