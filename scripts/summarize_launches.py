@@ -14,7 +14,7 @@ for r in rows[1:]:
         data.append((r[ki], float(r[vi].replace(",", ""))))
     except ValueError:
         pass
-starts = [i for i, (k, v) in enumerate(data) if "conv1_1_fwd" in k]
+starts = [i for i, (k, v) in enumerate(data) if "conv1_1_fwd" in k or "conv1_1_tc_kernel" in k]
 last = data[starts[-1]:]
 tot = sum(v for _, v in last)
 print("# ncu launch list: %s" % path)

@@ -176,7 +176,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUt
 }
 
 constexpr int kFinishThreads = 256;
-constexpr int kFinishElems = 256;                                 // Gram elements per block
+constexpr int kFinishElems = 1024;                                // Gram elements per block (4 per thread in the vector path)
 constexpr int kFinishWarps = kFinishThreads / 32;
 
 // 256 consecutive Gram elements per block, 32 per pass: `kw` warps (1, 2, 4 or 8, chosen from the slab count) share
@@ -196,6 +196,33 @@ __device__ __forceinline__ void gram_finish_block(int block, const float* __rest
   const int grp = warp / kw, sub = warp % kw;  // this warp's group and slab subset
   const int CC = C * C;
   float sq = 0.0f;
+  if (kw == 1) {
+    // Few slabs (every layer at batch >= 2): no sharing of slabs between warps, so no shared-memory pass either -
+    // four consecutive elements per thread, 128-bit accesses (C * C is a multiple of 4). The scalar path below launched
+    // one thread per Gram element: 18 k blocks of 256 threads for pool4 at 18 jobs, 53 us for 63 MB of traffic.
+    const int e = block * kFinishElems + threadIdx.x * 4;
+    if (e < CC) {
+      const float* src = partial + static_cast<size_t>(img) * splits * CC + e;
+      float4 t = *reinterpret_cast<const float4*>(src);
+      for (int k = 1; k < splits; ++k) {
+        const float4 u = *reinterpret_cast<const float4*>(src + static_cast<size_t>(k) * CC);
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+      }
+      const float4 g = make_float4(t.x / norm, t.y / norm, t.z / norm, t.w / norm);
+      if (G_out) *reinterpret_cast<float4*>(G_out + static_cast<size_t>(img) * CC + e) = g;
+      if (target) {
+        const float4 tg = *reinterpret_cast<const float4*>(target + static_cast<size_t>(img) * target_stride + e);
+        const float4 d = make_float4(g.x - tg.x, g.y - tg.y, g.z - tg.z, g.w - tg.w);
+        if (dscaled) {
+          union { uint2 u; __nv_bfloat162 h2[2]; } pk;
+          pk.h2[0] = __floats2bfloat162_rn(d.x * dscale, d.y * dscale);
+          pk.h2[1] = __floats2bfloat162_rn(d.z * dscale, d.w * dscale);
+          *reinterpret_cast<uint2*>(dscaled + static_cast<size_t>(img) * CC + e) = pk.u;
+        }
+        sq = ((d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w)) * loss_scale;
+      }
+    }
+  } else
   for (int pass = 0; pass < kFinishElems / 32; pass += groups) {
     const int e = block * kFinishElems + (pass + grp) * 32 + lane;
     float s = 0.0f;
