@@ -1,6 +1,7 @@
 """Path-level parity on the B200: Grams, per-layer loss, overall loss and input gradient of one f/g evaluation
 (Synthesizer.step) against the float64 CPU oracle and the committed golden vectors, at BASELINE.json's tolerances:
-  Gram matrices and per-layer loss   rel 1e-3 (accurate bf16x3 forward; the TF32-class bar) / 5e-3 (fast bf16)
+  Gram matrices and per-layer loss   rel 1e-3 (accurate forwards - f16+f8, the default, and bf16x3; the TF32-class bar)
+                                     / 5e-3 (fast bf16)
   input gradient                     rel 1e-2
 plus size-independent properties at the full 512^2 size, batching and run-to-run determinism."""
 import os
@@ -16,11 +17,11 @@ from gpu_util import relerr  # noqa: E402
 from syntex_b200.gatys import Synthesizer  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GRAM_TOL = {"bf16x3": 1e-3, "bf16": 5e-3}
+GRAM_TOL = {"f16f8": 1e-3, "bf16x3": 1e-3, "bf16": 5e-3}
 GRAD_TOL = 1e-2
 
 
-def make_syn(raw, S, batch=1, precision="bf16x3", **kw):
+def make_syn(raw, S, batch=1, precision="f16f8", **kw):
     args = {"vgg19_npy_path": raw, "image_size": S, "maxiter": 10, "maxcor": 20, "batch": batch,
             "precision": precision}
     args.update(kw)
@@ -29,8 +30,9 @@ def make_syn(raw, S, batch=1, precision="bf16x3", **kw):
     return syn
 
 
-@pytest.mark.parametrize("S,precision", [(64, "bf16x3"), (128, "bf16x3"), (256, "bf16x3"), (256, "bf16"),
-                                         (224, "bf16x3"), (512, "bf16x3")])     # 512: BASELINE.json config 2
+@pytest.mark.parametrize("S,precision", [(64, "f16f8"), (128, "f16f8"), (256, "f16f8"), (224, "f16f8"), (512, "f16f8"),
+                                         (64, "bf16x3"), (256, "bf16x3"), (512, "bf16x3"), (256, "bf16")])
+# f16f8 = the default forward of the Gatys plan; 256: BASELINE.json config 1, 512: config 2
 def test_step_matches_oracle(S, precision, raw_weights, exemplar):
     tgt = so.resize_crop(exemplar / 255.0, S)
     x0 = so.init_input((S, S, 3), False, 0)
@@ -46,17 +48,18 @@ def test_step_matches_oracle(S, precision, raw_weights, exemplar):
     r = syn.step(x0)
     assert r["func"].shape == (1,) and r["grad"].shape == (1, S, S, 3) and r["grad"].dtype == np.float32
     assert abs(r["func"][0] - r_ref["func"][0]) / r_ref["func"][0] < GRAM_TOL[precision]
-    if precision == "bf16x3":
+    if precision != "bf16":
         assert relerr(r["grad"], r_ref["grad"]) < GRAD_TOL
     else:   # documented limitation of the fast mode: ReLU sign flips (DESIGN.md "precision")
         assert relerr(r["grad"], r_ref["grad"]) < 6e-2
 
 
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
 @pytest.mark.parametrize("S", [64, 256])
-def test_step_matches_golden_vectors(S, raw_weights, exemplar):
+def test_step_matches_golden_vectors(S, precision, raw_weights, exemplar):
     gold = np.load(os.path.join(GOLD, "path_S%d.npz" % S))
     tgt = so.resize_crop(exemplar / 255.0, S)
-    syn = make_syn(raw_weights, S)
+    syn = make_syn(raw_weights, S, precision=precision)
     gt = syn.compute_gram(tgt)
     for k in Synthesizer.DEFAULT_COEFS:
         assert abs(np.trace(gt[k][0]) - gold["t_gram_trace_" + k]) / abs(gold["t_gram_trace_" + k]) < 1e-3
@@ -140,6 +143,58 @@ def test_large_batch_backward_has_no_cross_tile_race(raw_weights):
         # bf16-rounded Gram difference; anything beyond that is a bug
         assert relerr(rb["grad"][j], r1["grad"][0]) < 5e-3
         assert abs(rb["func"][j] - r1["func"][0]) < 1e-4 * r1["func"][0]
+
+
+def test_default_precision_is_the_f16f8_forward_with_a_bf16x3_fallback(raw_weights):
+    """'auto' (the default): f16+f8 wherever every convolution's map is at least 8 pixels wide, else bf16x3; the
+    f16+f8 planes are not bf16, so such a plan refuses the bf16 feature view."""
+    from syntex_b200 import _lib
+    from syntex_b200._lib import SyntexLibraryError
+    import ctypes
+    syn = Synthesizer({"vgg19_npy_path": raw_weights, "image_size": 64, "maxiter": 1, "maxcor": 20})
+    assert syn.precision == "auto"
+    syn.build()
+    hi, lo = ctypes.c_void_p(), ctypes.c_void_p()
+    with pytest.raises(SyntexLibraryError):
+        _lib.check(_lib.lib().stx_plan_feature_bf16(syn._plan.handle, 0, ctypes.byref(hi), ctypes.byref(lo)))
+    small = Synthesizer({"vgg19_npy_path": raw_weights, "image_size": 32, "maxiter": 1, "maxcor": 20})
+    small.build()                      # 32 / 8 = 4-pixel maps at conv4_x: bf16x3
+    _lib.check(_lib.lib().stx_plan_feature_bf16(small._plan.handle, 0, ctypes.byref(hi), ctypes.byref(lo)))
+    tgt = so.synthetic_texture(32, seed=1)
+    small.compute_gram(tgt, update=True)
+    r = small.step(so.init_input((32, 32, 3), False, 0))
+    orc = so.SynthesizerOracle(so.load_vgg_weights(raw_weights), 32, dtype=torch.float64)
+    orc.compute_gram(tgt, update=True)
+    assert relerr(r["grad"], orc.step(so.init_input((32, 32, 3), False, 0))["grad"]) < GRAD_TOL
+
+
+def test_partial_target_is_an_error_not_a_wrong_loss(raw_weights):
+    """stx_plan_set_target_gram on SOME loss layers must not arm the plan (it used to: the remaining layers silently
+    kept zeros / a stale target); stx_plan_clear_target invalidates a complete set."""
+    from syntex_b200 import _lib
+    from syntex_b200._lib import SyntexLibraryError
+    L = _lib.lib()
+    S = 64
+    syn = make_syn(raw_weights, S)
+    x0 = so.init_input((S, S, 3), False, 0)
+    grams = syn.compute_gram(so.synthetic_texture(S, seed=2))            # no update: the plan has no target yet
+    st = _lib.stream_ptr()
+    names = list(Synthesizer.DEFAULT_COEFS)
+    for k, name in enumerate(names[:-1]):
+        t = torch.as_tensor(grams[name], dtype=torch.float32).cuda().contiguous()
+        _lib.check(L.stx_plan_set_target_gram(syn._plan.handle, k, t.data_ptr(), 0, st))
+        torch.cuda.synchronize()
+    with pytest.raises(SyntexLibraryError):
+        syn.step(x0)                                                     # four of five layers set
+    t = torch.as_tensor(grams[names[-1]], dtype=torch.float32).cuda().contiguous()
+    _lib.check(L.stx_plan_set_target_gram(syn._plan.handle, len(names) - 1, t.data_ptr(), 0, st))
+    torch.cuda.synchronize()
+    r = syn.step(x0)
+    syn.compute_gram(so.synthetic_texture(S, seed=2), update=True)
+    assert abs(syn.step(x0)["func"][0] - r["func"][0]) <= 1e-6 * r["func"][0]
+    _lib.check(L.stx_plan_clear_target(syn._plan.handle))
+    with pytest.raises(SyntexLibraryError):
+        syn.step(x0)
 
 
 def test_step_is_deterministic(raw_weights):
