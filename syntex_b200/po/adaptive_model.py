@@ -64,12 +64,13 @@ def _act_arg(act_type):
 
 
 def _norm_is_native(norm, batch):
-    """InstanceNorm always; BatchNorm with batch statistics only at batch 1, where it IS InstanceNorm (the reference's
-    per-GPU batch, po/improved_model.py:24); nothing to do for Identity."""
+    """InstanceNorm always; BatchNorm with batch statistics (po/improved_model.py:353-360) at any batch: in NHWC the
+    batch folds into the pixel axis, so it is InstanceNorm of ONE image of B*H*W pixels (see _norm_native); nothing to
+    do for Identity."""
     from .layers import InstanceNormAffine
     if norm is None or isinstance(norm, (nn.Identity, InstanceNormAffine)):
         return True
-    return type(norm).__name__ == "_BatchStatsNorm" and batch == 1
+    return type(norm).__name__ == "_BatchStatsNorm"
 
 
 def _norm_native(norm, x, act=None, shortcut=None):
@@ -78,6 +79,14 @@ def _norm_native(norm, x, act=None, shortcut=None):
         if act is not None:
             x = torch.relu(x) if act is True else F.leaky_relu(x, float(act))
         return x if shortcut is None else x + shortcut
+    if type(norm).__name__ == "_BatchStatsNorm" and x.shape[0] > 1:
+        # statistics over (N, H, W) per channel, biased variance: exactly the per-image statistics of the batch viewed
+        # as one [1, N*H, W, C] image (NHWC: a reshape, no copy) - same kernels, forward and backward
+        B, H, W, C = x.shape
+        sc = None if shortcut is None else shortcut.reshape(1, B * H, W, C)
+        y = gen_ops.instance_norm(x.reshape(1, B * H, W, C), norm.weight, norm.bias, norm.eps,
+                                  act if act is not None else False, sc)
+        return y.reshape(B, H, W, C)
     return gen_ops.instance_norm(x, norm.weight, norm.bias, norm.eps, act if act is not None else False, shortcut)
 
 
@@ -222,8 +231,6 @@ def stage_native_supported(stage, batch):
         if isinstance(m, _Upsample) and (not m.nn_upsample or m.scale != 2):
             return False
         if isinstance(m, nn.BatchNorm2d):
-            return False
-        if type(m).__name__ == "_BatchStatsNorm" and batch != 1:
             return False
     return True
 

@@ -193,6 +193,38 @@ def test_instance_norm_function_matches_torch(n, h, w, c, relu, shortcut):
         assert torch.equal(sc.grad, dy)
 
 
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 64), (3, 20, 12, 128), (4, 8, 8, 256)])
+@pytest.mark.parametrize("act", [None, True, 0.2])
+def test_batch_statistics_norm_at_batch_above_one_matches_torch(n, h, w, c, act):
+    """BatchNorm with batch statistics (po/improved_model.py:353-360, training=True in every phase) on the native route
+    at batch > 1: the batch folded into the pixel axis of one NHWC image."""
+    from syntex_b200.po.adaptive_model import _norm_is_native, _norm_native
+    from syntex_b200.po.improved_model import _BatchStatsNorm
+    norm = _BatchStatsNorm(c).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(torch.linspace(0.5, 1.5, c))
+        norm.bias.copy_(torch.linspace(-0.5, 0.5, c))
+    assert _norm_is_native(norm, n)
+    x = (_rand_bf16((n, h, w, c), 17).float() * 1.5 + 0.3).to(torch.bfloat16).requires_grad_(True)
+    out = _norm_native(norm, x, act=act)
+    ref_mod = _BatchStatsNorm(c).cuda()
+    ref_mod.load_state_dict(norm.state_dict())
+    xr = _nchw(x.detach()).requires_grad_(True)
+    ref = ref_mod(xr)
+    if act is True:
+        ref = F.relu(ref)
+    elif act is not None:
+        ref = F.leaky_relu(ref, float(act))
+    assert tuple(out.shape) == (n, h, w, c)
+    assert relerr(out.float(), _nhwc(ref).detach()) < 4e-3
+    dy = _rand_bf16((n, h, w, c), 19)
+    out.backward(dy)
+    ref.backward(_nchw(dy))
+    assert relerr(x.grad.float(), _nhwc(xr.grad)) < 1e-2
+    assert relerr(norm.weight.grad, ref_mod.weight.grad) < 1e-2
+    assert relerr(norm.bias.grad, ref_mod.bias.grad) < 1e-2
+
+
 @pytest.mark.parametrize("mode,relu_in,cout", [("rep", False, 64), ("rep", True, 128), ("zero", False, 64),
                                                ("rep", True, 3)])
 def test_conv3x3_function_gradients_match_torch(mode, relu_in, cout):
