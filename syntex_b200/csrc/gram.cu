@@ -176,7 +176,8 @@ gram_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUt
 }
 
 constexpr int kFinishThreads = 256;
-constexpr int kFinishElems = 1024;                                // Gram elements per block (4 per thread in the vector path)
+constexpr int kFinishElems = 256;                                 // Gram elements per block, scalar path (= one loss partial)
+constexpr int kFinishVecElems = 1024;                             // vector path: four per thread = four loss-partial slots
 constexpr int kFinishWarps = kFinishThreads / 32;
 
 // 256 consecutive Gram elements per block, 32 per pass: `kw` warps (1, 2, 4 or 8, chosen from the slab count) share
@@ -200,7 +201,7 @@ __device__ __forceinline__ void gram_finish_block(int block, const float* __rest
     // Few slabs (every layer at batch >= 2): no sharing of slabs between warps, so no shared-memory pass either -
     // four consecutive elements per thread, 128-bit accesses (C * C is a multiple of 4). The scalar path below launched
     // one thread per Gram element: 18 k blocks of 256 threads for pool4 at 18 jobs, 53 us for 63 MB of traffic.
-    const int e = block * kFinishElems + threadIdx.x * 4;
+    const int e = block * kFinishVecElems + threadIdx.x * 4;
     if (e < CC) {
       const float* src = partial + static_cast<size_t>(img) * splits * CC + e;
       float4 t = *reinterpret_cast<const float4*>(src);
@@ -256,7 +257,15 @@ __device__ __forceinline__ void gram_finish_block(int block, const float* __rest
       float t = 0.0f;
 #pragma unroll
       for (int w = 0; w < kFinishWarps; ++w) t += sq_warp[w];
-      loss_part[static_cast<size_t>(img) * part_stride + block] = t;
+      if (kw == 1) {
+        // a vector-path block covers four slots of the per-layer partial table (gram_finish_blocks counts 256-element
+        // blocks): its sum goes to the first, zeros to the rest
+        float* lp = loss_part + static_cast<size_t>(img) * part_stride + block * (kFinishVecElems / kFinishElems);
+        const int slots = min(kFinishVecElems / kFinishElems, (CC + kFinishElems - 1) / kFinishElems - block * (kFinishVecElems / kFinishElems));
+        for (int j = 0; j < slots; ++j) lp[j] = j == 0 ? t : 0.0f;
+      } else {
+        loss_part[static_cast<size_t>(img) * part_stride + block] = t;
+      }
     }
   }
 }
@@ -374,6 +383,12 @@ int gram_launch(const GramOp& op, cudaStream_t stream) {
   return STX_OK;
 }
 
+// blocks a layer's finish occupies in a launch: the vector path (kw == 1) covers 1024 elements per block
+static int finish_grid_blocks(int C, int kw) {
+  const int per = kw == 1 ? kFinishVecElems : kFinishElems;
+  return (C * C + per - 1) / per;
+}
+
 static int finish_kw(int splits) {
   int kw = 1;
   while (kw < kFinishWarps && splits > 8 * kw) kw *= 2;      // keep the serial chain per thread <= ~8..37 slabs
@@ -397,7 +412,7 @@ int gram_finish_batch_add(GramFinishBatch* fb, const GramOp& op, float eps, floa
   f.loss_scale = loss_scale;
   f.loss_part = loss_part;
   f.block_begin = fb->total_blocks;
-  fb->total_blocks += gram_finish_blocks(op.C);
+  fb->total_blocks += finish_grid_blocks(op.C, f.kw);
   fb->nimg = op.nimg;
   fb->n += 1;
   return STX_OK;
@@ -419,8 +434,8 @@ int gram_finish_launch(const GramOp& op, float eps, float* G_out, const float* t
                        cudaStream_t stream) {
   // fp32 arithmetic as in the reference: normalizer = float32(HW) + float32(eps)  (utils.py:15, :20)
   const float norm = static_cast<float>(op.HW) + eps;
-  dim3 grid(gram_finish_blocks(op.C), op.nimg);
   const int kw = finish_kw(op.splits);
+  dim3 grid(finish_grid_blocks(op.C, kw), op.nimg);
   gram_finish_kernel<<<grid, kFinishThreads, 0, stream>>>(op.partial, op.C, op.splits, kw, op.cross, norm, G_out, target,
                                                           target_stride, dscale, dscaled, loss_scale, loss_part, part_stride);
   STX_CUDA(cudaGetLastError());
