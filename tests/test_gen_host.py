@@ -67,7 +67,7 @@ def test_native_route_selection_rules():
     from syntex_b200.po.progressive_model import _Stage as ProgressiveStage
 
     ok = ImprovedStage(2, 1, False, True, "REFLECT", "batch", "lrelu", 3)
-    assert ok.native_supported(1) and not ok.native_supported(2)          # batch statistics == instance only at batch 1
+    assert ok.native_supported(1) and ok.native_supported(2)     # batch statistics: the batch folds into the pixel axis
     assert ImprovedStage(2, 1, True, True, "CONSTANT", "instance", "relu", 3).native_supported(4)
     assert ImprovedStage(2, 1, False, True, "SYMMETRIC", "none", "relu", 3).native_supported(4)
     assert not ImprovedStage(2, 1, False, True, "REFLECT", "instance", "relu", 5).native_supported(1)   # 5x5 gradient convs
