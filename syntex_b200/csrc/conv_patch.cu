@@ -709,6 +709,13 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
     // measured 44 us against 50 us on the conv2_2 input gradient at batch 9
     // (profiles/r01_conv_variants_b9_256_occ.log), while K >= 4 chunks prefers two (35 vs 38 us).
     if (!split && bn == 128 && cin <= 128) occ = 1;
+    // Deep single-MMA layers (K >= 4 chunks, N tile 128) with plenty of work: two stacked 16x8 tiles per weight stream
+    // (one CTA per SM) halve the weight traffic that paces them; measured on the input-gradient pass at 64 / 16 jobs:
+    // 2.97 -> 2.85 ms / 0.79 -> 0.78 ms per evaluation (round 1 at 9 jobs: no difference).
+    if (!split && bn == 128 && cin >= 256 && force_mt == 0 && force_occ == 0) {
+      const int items2 = ((W + 7) / 8) * ((H + 31) / 32) * nimg * (cout / bn);
+      if (items2 >= 4 * 148) mt = 2;
+    }
     if (force_occ == 1 || force_occ == 2) occ = force_occ;
     if (split || mt == 2) occ = 1;      // only MT = 1 single-MMA instances exist with two CTAs per SM
   }

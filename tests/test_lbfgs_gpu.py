@@ -74,6 +74,27 @@ def test_final_loss_comparable_to_scipy_lbfgsb(raw_weights, exemplar):
     assert max(ratios) < 2.0, ratios
 
 
+@pytest.mark.parametrize("maxcor", [1, 3, 32])
+def test_history_sizes_from_one_pair_to_the_largest(raw_weights, maxcor):
+    """The reduced system is 2k x 2k for k = min(iterations, maxcor) pairs: one pair, a short wrapping history and the
+    largest the kernels are sized for (32) all run their budget and make progress."""
+    S, IT = 64, 40
+    tgt = so.synthetic_texture(S, seed=6)
+    x0 = so.init_input((S, S, 3), False, 2)
+    syn = make(raw_weights, S, IT, maxcor=maxcor)
+    x, fun = syn.synthesize(x0, tgt)
+    assert int(syn.last_result["nit"][0]) == IT
+    assert x.min() >= 0.0 and x.max() <= 1.0
+    f0 = syn.step(x0)["func"][0]
+    assert fun < (0.2 if maxcor == 1 else 0.05) * f0
+    if maxcor == 32:        # more memory than iterations: same trajectory as any history that never wraps
+        syn20 = make(raw_weights, S, 15, maxcor=20)
+        syn32 = make(raw_weights, S, 15, maxcor=32)
+        xa, fa = syn20.synthesize(x0, tgt)
+        xb, fb = syn32.synthesize(x0, tgt)
+        assert fa == fb and np.array_equal(xa, xb)
+
+
 def test_preimage_mode_is_unbounded(raw_weights):
     S, IT = 64, 20
     tgt = so.synthetic_texture(S, seed=4)
