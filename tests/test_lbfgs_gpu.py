@@ -55,10 +55,10 @@ def test_device_optimizer_tracks_the_numpy_model(raw_weights):
 
 
 def test_final_loss_comparable_to_scipy_lbfgsb(raw_weights, exemplar):
-    """BASELINE.json asks for the final Gram loss within 5 % of the reference path after a fixed budget. L-BFGS
-    trajectories are chaotic: scipy against ITSELF differs by far more than 5 % across seeds or under fp32 rounding of
-    f/g (DESIGN.md 'optimiser parity'), so the check is statistical: the geometric mean over seeds of
-    loss(device) / loss(scipy on the same GPU f/g) must be within 25 % of 1, and no seed may be worse than 2x."""
+    """The device optimiser against scipy L-BFGS-B driven by the SAME GPU f/g (optimizer="scipy"), small and quick: the
+    geometric mean over four seeds of loss(device) / loss(scipy) within 12 % of 1 (single seeds scatter by +-5..10 %:
+    L-BFGS trajectories are chaotic). The 5 % bar of BASELINE.json on its own configurations, against scipy over the
+    CPU oracle and with enough seeds for the mean to be a stable statistic, is tests/test_optimizer_parity_gpu.py."""
     S, IT = 64, 60
     tgt = so.resize_crop(exemplar / 255.0, S)
     dev = make(raw_weights, S, IT)
@@ -70,8 +70,8 @@ def test_final_loss_comparable_to_scipy_lbfgsb(raw_weights, exemplar):
         _, f_ref = ref.synthesize(x0, tgt)
         ratios.append(f_dev / f_ref)
     gm = float(np.exp(np.mean(np.log(ratios))))
-    assert 0.75 < gm < 1.25, ratios
-    assert max(ratios) < 2.0, ratios
+    assert 0.88 < gm < 1.12, ratios
+    assert max(ratios) < 1.4, ratios
 
 
 @pytest.mark.parametrize("maxcor", [1, 3, 32])
