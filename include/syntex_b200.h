@@ -45,8 +45,14 @@ const char* stx_last_error(void);
 int stx_abi_version(void);
 /* Kernel launches issued by this library so far in this process (CUDA-graph replays count their kernel nodes). */
 long long stx_launch_count(void);
-/* Bring-up knobs (descriptor strides etc.); key/value meanings are internal. */
+/* Bring-up knobs; key/value meanings are internal (csrc/capi.cu: descriptor strides, kernel-variant overrides, 9 =
+ * programmatic dependent launch, 10 = plain stream launches instead of the optimiser's CUDA graph, 12 = one CTA per SM
+ * for the 64-channel f16+f8 forward, 13 = CUDA-core conv1_1 in f16+f8 plans, 14 = active-set kernel in the main
+ * stream). Also read from the environment at load: STX_DEBUG="key=value,...". */
 int stx_debug_set(int key, int value);
+/* Bring-up probe of the CTA-pair MMA (tcgen05 cta_group::2): out fp32 [256][128] = a bf16 [256][64] * b bf16
+ * [128][64]^T computed by one cluster of two CTAs (each loads its 128 rows of a and 64 rows of b). */
+int stx_debug_pair_probe(const void* a_bf16, const void* b_bf16, float* out, void* stream);
 /* Descriptor-addressing probe used while bringing up the halo-patch convolution (see csrc/probe.cu). */
 int stx_debug_patch_probe(const void* patch_bf16, int rows, const void* b_bf16, int start_row, int sbo_bytes,
                           int base_mode, float* out, void* stream);

@@ -21,6 +21,7 @@ def _declare(lib):
         "stx_abi_version": (c_int, []),
         "stx_launch_count": (ctypes.c_longlong, []),
         "stx_debug_set": (c_int, [c_int, c_int]),
+        "stx_debug_pair_probe": (c_int, [vp, vp, fp, vp]),
         "stx_debug_patch_probe": (c_int, [vp, c_int, vp, c_int, c_int, c_int, fp, vp]),
         "stx_vgg_create": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int,
                                    POINTER(c_float), vp]),

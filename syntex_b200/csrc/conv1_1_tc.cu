@@ -112,7 +112,6 @@ conv1_1_tc_kernel(const float* __restrict__ image, int is_preimage, float m0, fl
       // ---- im2col row of this thread's pixel: k = (dy * 3 + dx) * 3 + colour; half 0 writes the fp16 row, half 1 the
       // correction row
       const int r = threadIdx.x & (kRows - 1), half = threadIdx.x >> 7;
-      const int h = h0 + (r >> 3), w = w0 + (r & 7);
       float xp[32];
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {

@@ -15,7 +15,7 @@
 //                dropped and the iteration restarts; the run ends when f does not decrease (factr = 0).
 // The one part of L-BFGS-B NOT here is the breakpoint walk of the generalized Cauchy point (a serial scan over up to n
 // breakpoints): the subspace step starts from x itself. Measured on the texture objective over 8 seeds, 100 iterations
-// (tests/golden/README): final loss / scipy's = 1.008 (geometric mean) with or without the walk,
+// (tests/test_lbfgsb_model.py): final loss / scipy's = 1.008 (geometric mean) with or without the walk,
 // against 1.08-1.17 for the projected L-BFGS of round 1, whose P B^-1 P step is what cost the 5 % bar.
 //
 //   cycle = [ plan.step(xt) -> ft, gt ] -> dots kernel -> active kernel -> decide kernel -> update kernel

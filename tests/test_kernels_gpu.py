@@ -252,3 +252,17 @@ def test_invalid_arguments_fail_loudly():
     assert rc == -1
     with pytest.raises(_lib.SyntexLibraryError):
         _lib.check(L().stx_gram_bf16(x.data_ptr(), 1, 64, 96, ctypes.c_float(1e-6), o.data_ptr(), o.data_ptr(), st()))
+
+
+def test_cta_pair_mma_probe():
+    """tcgen05 cta_group::2: one cluster of two CTAs computes a 256 x 128 tile - each CTA holds 128 rows of A and HALF
+    of B, the leader issues M = 256 MMAs, each CTA reads its rows of D from its own tensor memory."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.randn((256, 64), device="cuda", generator=g).to(torch.bfloat16).contiguous()
+    b = torch.randn((128, 64), device="cuda", generator=g).to(torch.bfloat16).contiguous()
+    out = torch.full((256, 128), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(L().stx_debug_pair_probe(a.data_ptr(), b.data_ptr(), out.data_ptr(), st()))
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t()
+    assert torch.isfinite(out).all()
+    assert relerr(out, ref) < 1e-6
