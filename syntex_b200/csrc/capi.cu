@@ -19,6 +19,7 @@ extern int g_debug_resident;
 extern int g_lbfgs_no_graph;
 extern int g_debug_f8_single_cta;
 extern int g_debug_conv1_1_cuda_cores;
+extern int g_debug_pair;
 extern int g_lbfgs_serial_active;
 }  // namespace stx
 
@@ -55,6 +56,7 @@ int stx_debug_set(int key, int value) {
     case 12: g_debug_f8_single_cta = value; return STX_OK;
     case 13: g_debug_conv1_1_cuda_cores = value; return STX_OK;
     case 14: g_lbfgs_serial_active = value; return STX_OK;
+    case 15: g_debug_pair = value; return STX_OK;
     default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
   }
 }

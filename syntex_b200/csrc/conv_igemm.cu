@@ -268,6 +268,7 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->taps = taps;
   op->per_image_w = per_image_w;
   op->patch = 0;
+  op->pair = 0;
   op->res = 0;
   op->mt = 1;
   op->occ = 1;
@@ -328,13 +329,15 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
 
 int conv3x3_prepare(ConvOp* op, const bf16* x, const bf16* x_lo, int nimg, int H, int W, int cin, const bf16* w,
                     const bf16* w_lo, int cout, int variant) {
+  const int want_pair = variant / 1000000;
+  variant %= 1000000;
   const int force_igemm = variant / 100000;
   const int force_mt = (variant / 1000) % 10;
   const int force_occ = (variant / 10000) % 10;
   const int force_bn = variant % 1000;
   const int split = (x_lo != nullptr) ? 1 : 0;
   if (!force_igemm) {
-    const int rc = conv_patch_prepare(op, x, nimg, H, W, cin, w, cout, split, force_bn, force_mt, force_occ);
+    const int rc = conv_patch_prepare(op, x, nimg, H, W, cin, w, cout, split, force_bn, force_mt, force_occ, want_pair);
     if (rc == STX_OK) return split ? conv_patch_prepare_split(op, x_lo, w_lo) : STX_OK;
     if (rc != STX_ERR_UNSUPPORTED) return rc;
   }

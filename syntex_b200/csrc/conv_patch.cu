@@ -49,14 +49,21 @@ constexpr int pow2_at_least(int v) {
 // L2-delivery-bound (conv1_2 forward: 5.2 us per tile against 1.8 us of tensor work).
 // F8 (with SPLIT): the f16 + f8 forward - the second operand pair of a stage is the e4m3 correction pair (see
 // conv_common.cuh, kF8*) and accumulates into its own TMEM columns through kind::f8f6f4.
-template <int BN, int MT, bool SPLIT, int OCC, int RES, bool F8 = false>
+// PAIR: two CTAs of a cluster (the two SMs of a TPC) work on two M tiles against ONE N block with tcgen05
+// cta_group::2: each CTA stages its own halo patch and HALF of every weight tile, the leader issues M = 256 MMAs, each
+// CTA receives and drains its own 128 rows. Halves the weight bytes every SM pulls through L2 and shared memory -
+// what paces the deep layers.
+template <int BN, int MT, bool SPLIT, int OCC, int RES, bool F8 = false, bool PAIR = false>
 struct PatchSmem {
   static constexpr int kPatchRows = (16 * MT + 2) * kPatchW;
   static constexpr int kPatchBytes = kPatchRows * 128;                        // TMA transaction bytes
   static constexpr int kPatchStride = (kPatchBytes + 1023) & ~1023;           // keep every buffer 1024-aligned
   static constexpr int kPatchStageBytes = (SPLIT ? 2 : 1) * kPatchStride;     // [hi | lo]
   static_assert(OCC == 1 || (OCC == 2 && (MT == 1 || BN == 16)), "two CTAs per SM: single-tile or N = 16 instances only");
-  static constexpr int kBBytes = (BN * 128 + 1023) & ~1023;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;                           // weight rows staged by this CTA
+  static constexpr int kBBytes = (kBRows * 128 + 1023) & ~1023;
+  static_assert(!PAIR || (MT == 1 && OCC == 1 && RES == 0 && BN == 128 && (!SPLIT || F8)),
+                "CTA pairs: single-tile, one CTA per SM, ring weights, N tile 128, single-MMA or f16+f8");
   static constexpr int kBStageBytes = (SPLIT ? 2 : 1) * kBBytes;              // [hi | lo]
   static constexpr int kBudget = kSmemBudget / OCC - 2048;
   // resident mode: a small ring for the per-image Gram-difference tiles of the fused Gram gradient
@@ -102,13 +109,13 @@ struct PatchSched {
   int nblocks64;     // N / 64
 };
 
-template <int BN, int MT, bool SPLIT, int OCC, int RES, bool F8>
+template <int BN, int MT, bool SPLIT, int OCC, int RES, bool F8, bool PAIR>
 __global__ void __launch_bounds__(kThreads, OCC)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                   const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmD,
                   const ConvKernelParams p, const PatchSched sched) {
-  using L = PatchSmem<BN, MT, SPLIT, OCC, RES, F8>;
+  using L = PatchSmem<BN, MT, SPLIT, OCC, RES, F8, PAIR>;
   constexpr int kPS = L::kPatchStages, kBS = L::kBStages, kAS = L::kAccStages;
   constexpr int kBB = L::kBBarriers, kDS = L::kDStages;
   extern __shared__ uint8_t smem_raw[];
@@ -126,6 +133,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair: rank in the cluster (0 = leader: issues the MMAs, owns the barriers the TMA loads complete on)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // the item list is walked per cluster in pair mode (both CTAs take the same item, two M tiles of it)
+  const int item_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -148,13 +161,18 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < kAS; ++s) {
       mbar_init(&afull[s], 1);
-      mbar_init(&aempty[s], kEpilogueWarps);
+      mbar_init(&aempty[s], (PAIR ? 2 : 1) * kEpilogueWarps);     // pair: both CTAs' epilogue warps free the leader's
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, L::kTmemCols);
+  if (PAIR) cluster_sync_all();                  // both CTAs' barriers exist before anything remote touches them
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2cta(tmem_slot, L::kTmemCols);
+    else tmem_alloc(tmem_slot, L::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Everything above overlapped the tail of the previous kernel in the stream; from here on we touch its results.
@@ -185,23 +203,31 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         __syncwarp();
       }
-      for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x) {
+      for (int item = item_first; item < sched.total_items; item += item_step) {
         const int ks = item % sched.ksplit;
         const int rest = item / sched.ksplit;
         const int nblk = rest % sched.nblocks;
-        const int tm = rest / sched.nblocks;
+        const int tm = PAIR ? 2 * (rest / sched.nblocks) + static_cast<int>(rank) : rest / sched.nblocks;
         const int w0 = (tm % p.tiles_w) * 8;
         const int h0 = ((tm / p.tiles_w) % p.tiles_h) * (16 * MT);
         const int n = tm / tiles_per_img;
         const int c_begin = ks * chunks / sched.ksplit, c_end = (ks + 1) * chunks / sched.ksplit;
         const int gram_chunks = (ks == sched.ksplit - 1) ? sched.gram_chunks : 0;
+        const int brow0 = nblk * BN + (PAIR ? static_cast<int>(rank) * (BN / 2) : 0);   // this CTA's weight rows
         for (int c = c_begin; c < c_end; ++c) {
           mbar_wait(&pempty[ps], pph ^ 1, 100 + ps);
           uint8_t* pdst = smem + ps * L::kPatchStageBytes;
           if (elect_one()) {
-            mbar_arrive_expect_tx(&pfull[ps], (SPLIT ? 2 : 1) * L::kPatchBytes);
-            tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - p.pad, h0 - p.pad, n);
-            if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - p.pad, h0 - p.pad, n);
+            if (PAIR) {
+              // both CTAs' loads complete on the LEADER's barrier: it expects the bytes of both
+              if (leader) mbar_arrive_expect_tx(&pfull[ps], 2 * (SPLIT ? 2 : 1) * L::kPatchBytes);
+              tma_load_4d_pair(pdst, &tmA, &pfull[ps], c * 64, w0 - p.pad, h0 - p.pad, n);
+              if (SPLIT) tma_load_4d_pair(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - p.pad, h0 - p.pad, n);
+            } else {
+              mbar_arrive_expect_tx(&pfull[ps], (SPLIT ? 2 : 1) * L::kPatchBytes);
+              tma_load_4d(pdst, &tmA, &pfull[ps], c * 64, w0 - p.pad, h0 - p.pad, n);
+              if (SPLIT) tma_load_4d(pdst + L::kPatchStride, &tmA2, &pfull[ps], c * 64, w0 - p.pad, h0 - p.pad, n);
+            }
           }
           if (++ps == kPS) {
             ps = 0;
@@ -211,7 +237,13 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int tap = 0; RES == 0 && tap < 9; ++tap) {
             mbar_wait(&bempty[bs], bph ^ 1, 120 + bs);
             uint8_t* bdst = smem + L::kBOffset + bs * L::kBStageBytes;
-            if (elect_one()) {
+            if (PAIR) {
+              if (elect_one()) {
+                if (leader) mbar_arrive_expect_tx(&bfull[bs], (SPLIT ? 2 : 1) * BN * 128);     // two halves
+                tma_load_3d_pair(bdst, &tmB, &bfull[bs], c * 64, brow0, tap);
+                if (SPLIT) tma_load_3d_pair(bdst + L::kBBytes, &tmB2, &bfull[bs], c * 64, brow0, tap);
+              }
+            } else if (elect_one()) {
               mbar_arrive_expect_tx(&bfull[bs], (SPLIT ? 2 : 1) * BN * 128);
               if (sched.wt != nullptr && BN >= 64) {
                 // one contiguous, pre-swizzled BN*128-byte run per weight tile
@@ -239,7 +271,16 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&ring_empty[bs], bph ^ 1, 160 + bs);
           uint8_t* pdst = smem + ps * L::kPatchStageBytes;
           uint8_t* bdst = RES > 0 ? smem + L::kDOffset + bs * L::kBBytes : smem + L::kBOffset + bs * L::kBStageBytes;
-          if (elect_one()) {
+          if (PAIR) {
+            if (elect_one()) {
+              if (leader) {
+                mbar_arrive_expect_tx(&pfull[ps], 2 * 16384);
+                mbar_arrive_expect_tx(&ring_full[bs], BN * 128);
+              }
+              tma_load_4d_pair(pdst, &tmF, &pfull[ps], cf * 64, w0, h0, n);
+              tma_load_3d_pair(bdst, &tmD, &ring_full[bs], cf * 64, brow0, n);
+            }
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(&pfull[ps], MT * 16384);
             for (int mt = 0; mt < MT; ++mt)
               tma_load_4d(pdst + mt * 16384, &tmF, &pfull[ps], cf * 64, w0, h0 + 16 * mt, n);
@@ -258,16 +299,29 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------ MMA issuer (pair: the leader's, for both CTAs)
     // The whole warp walks the loops (so every value below is provably warp-uniform and lives in uniform
     // registers); one elected lane issues the tcgen05 instructions. With `if (lane == 0)` around the loops the
     // compiler wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY serialisation loop, which costs more
     // issue time than a 32-cycle N = 64 MMA takes to execute.
-    {
+    if (!PAIR || leader) {
       // operand formats: the f16+f8 forward multiplies fp16 planes (and e4m3 correction planes), everything else bf16
-      constexpr uint32_t idesc = F8 ? make_idesc(128, BN, kFmtF16, kFmtF16, 0, 0) : make_idesc_bf16(128, BN, 0, 0);
-      constexpr uint32_t idesc_f8 = make_idesc(128, BN, kFmtE4M3, kFmtE4M3, 0, 0);
-      constexpr uint32_t idesc_gram = make_idesc_bf16(128, BN, 0, 0);
+      constexpr int kM = PAIR ? 256 : 128;     // the pair's MMA spans both CTAs' rows
+      constexpr uint32_t idesc = F8 ? make_idesc(kM, BN, kFmtF16, kFmtF16, 0, 0) : make_idesc_bf16(kM, BN, 0, 0);
+      constexpr uint32_t idesc_f8 = make_idesc(kM, BN, kFmtE4M3, kFmtE4M3, 0, 0);
+      constexpr uint32_t idesc_gram = make_idesc_bf16(kM, BN, 0, 0);
+      auto mma16 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (PAIR) umma_bf16_2cta(d, a, b, id, acc);
+        else umma_bf16(d, a, b, id, acc);
+      };
+      auto mma8 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (PAIR) umma_f8_2cta(d, a, b, id, acc);
+        else umma_f8(d, a, b, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if (PAIR) umma_commit_2cta(bar, 3);      // arrives on the barrier at this offset in BOTH CTAs
+        else umma_commit(bar);
+      };
       constexpr uint32_t kGroupStride = kPatchW * 128;     // bytes between consecutive 8-pixel row groups
       constexpr uint32_t kDescHiA = desc_hi_sw128(kGroupStride);   // activations: 8-row groups kGroupStride apart
       constexpr uint32_t kDescHiB = desc_hi_sw128(1024);           // weights: dense 128-byte rows
@@ -279,7 +333,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&bfull[0], 0, 219);     // resident weights have landed
         tc_fence_after();
       }
-      for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x) {
+      for (int item = item_first; item < sched.total_items; item += item_step) {
         mbar_wait(&aempty[as], aph ^ 1, 300 + as);    // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + as * L::kAccCols;
@@ -309,8 +363,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   // same 32 bytes of the 128-byte rows) into the correction columns
                   const uint64_t ad_c = desc_pack(a_lo + (L::kPatchStride >> 4) + 2 * k, kDescHiA);
                   const uint64_t bd_c = desc_pack(b_lo0 + (L::kBBytes >> 4) + 2 * k, kDescHiB);
-                  umma_bf16(d, ad, bd, idesc, accumulate);
-                  umma_f8(d + BN, ad_c, bd_c, idesc_f8, accumulate);
+                  mma16(d, ad, bd, idesc, accumulate);
+                  mma8(d + BN, ad_c, bd_c, idesc_f8, accumulate);
                 } else if (L::kMerge) {
                   const uint64_t ad_lo = desc_pack(a_lo + (L::kPatchStride >> 4) + 2 * k, kDescHiA);
                   // [W_hi ; W_lo] are adjacent 64-row tiles of one stage: a single N = 128 operand
@@ -323,7 +377,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   umma_bf16(d, ad, bd_lo, idesc, 1);            // A_hi * W_lo
                   umma_bf16(d, ad, bd, idesc, 1);               // A_hi * W_hi
                 } else {
-                  umma_bf16(d, ad, bd, idesc, accumulate);
+                  mma16(d, ad, bd, idesc, accumulate);
                 }
               }
             }
@@ -344,8 +398,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tc_fence_after();
               if (elect_one()) {
                 issue_tap(tap, b_ring + bs * (L::kBStageBytes >> 4), c == c_begin);
-                umma_commit(&bempty[bs]);
-                if (tap == 8) umma_commit(&pempty[ps]);
+                commit(&bempty[bs]);
+                if (tap == 8) commit(&pempty[ps]);
               }
               if (++bs == kBS) {
                 bs = 0;
@@ -371,11 +425,11 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_bf16(acc + mt * BN, desc_pack(f_lo + mt * (16384 >> 4) + 2 * k, kDescHiB),
-                          desc_pack(g_lo + 2 * k, kDescHiB), idesc_gram, 1);
+                mma16(acc + mt * BN, desc_pack(f_lo + mt * (16384 >> 4) + 2 * k, kDescHiB),
+                      desc_pack(g_lo + 2 * k, kDescHiB), idesc_gram, 1);
             }
-            umma_commit(&ring_empty[bs]);
-            umma_commit(&pempty[ps]);
+            commit(&ring_empty[bs]);
+            commit(&pempty[ps]);
           }
           if (++ps == kPS) {
             ps = 0;
@@ -386,7 +440,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             bph ^= 1;
           }
         }
-        if (elect_one()) umma_commit(&afull[as]);
+        if (elect_one()) commit(&afull[as]);
         if (++as == kAS) {
           as = 0;
           aph ^= 1;
@@ -400,11 +454,15 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int r = q * 32 + lane;
     const int ww = r & 7;
     int ait = 0;
-    for (int item = blockIdx.x; item < sched.total_items; item += gridDim.x, ++ait) {
+    auto free_acc = [&](int s) {           // hand an accumulator back to the MMA issuer (the leader's, in a pair)
+      if (PAIR) mbar_arrive_leader(&aempty[s]);
+      else mbar_arrive(&aempty[s]);
+    };
+    for (int item = item_first; item < sched.total_items; item += item_step, ++ait) {
       const int ks = item % sched.ksplit;
       const int rest = item / sched.ksplit;
       const int nblk = rest % sched.nblocks;
-      const int tm = rest / sched.nblocks;
+      const int tm = PAIR ? 2 * (rest / sched.nblocks) + static_cast<int>(rank) : rest / sched.nblocks;
       const int w = (tm % p.tiles_w) * 8 + ww;
       const int h0 = ((tm / p.tiles_w) % p.tiles_h) * (16 * MT);
       const int n = tm / tiles_per_img;
@@ -441,7 +499,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&aempty[as]);
+        if (lane == 0) free_acc(as);
         if (half == 0) {
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
@@ -483,7 +541,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&aempty[as]);
+          if (lane == 0) free_acc(as);
           __threadfence();
           asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpilogueWarps) : "memory");
           if (threadIdx.x == 64) {
@@ -556,7 +614,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (kChunks < 2 && half == 1) {       // nothing to drain for this warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&aempty[as]);
+          if (lane == 0) free_acc(as);
           released = true;
         }
 #pragma unroll 1
@@ -581,7 +639,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (j == last) {                    // accumulator fully read by this warp: hand it back before storing
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&aempty[as]);
+            if (lane == 0) free_acc(as);
           }
           conv_epilogue_store<SPLIT, F8 ? 2 : 0>(p, v, valid, n, h, w, nblk * BN + c0);
         }
@@ -590,17 +648,21 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, L::kTmemCols);
+  if (PAIR) cluster_sync_all();          // the peer may still be reading / signalling
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tmem_dealloc_2cta(tmem_base, L::kTmemCols);
+    else tmem_dealloc(tmem_base, L::kTmemCols);
+  }
 }
 
-template <int BN, int MT, bool SPLIT, int OCC, int RES = 0, bool F8 = false>
+template <int BN, int MT, bool SPLIT, int OCC, int RES = 0, bool F8 = false, bool PAIR = false>
 int launch_patch(const ConvOp& op, cudaStream_t stream) {
-  using L = PatchSmem<BN, MT, SPLIT, OCC, RES, F8>;
+  using L = PatchSmem<BN, MT, SPLIT, OCC, RES, F8, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT, OCC, RES, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  L::kTotal));
+    STX_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MT, SPLIT, OCC, RES, F8, PAIR>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
   ConvKernelParams p;
@@ -645,6 +707,11 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   sched.ws = op.splitk_ws;
   sched.counters = op.splitk_counters;
   sched.total_items = op.tiles_w * op.tiles_h * op.nimg * sched.nblocks * sched.ksplit;
+  if (PAIR) {
+    STX_REQUIRE((op.tiles_w * op.tiles_h * op.nimg) % 2 == 0 && sched.ksplit == 1, "conv: CTA pairs need an even tile count");
+    sched.total_items /= 2;            // one item = two M tiles (one per CTA of the pair) against one N block
+    sched.wt = nullptr;
+  }
   sched.gram_chunks = (!SPLIT && op.gram_chunks > 0) ? op.gram_chunks : 0;
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -652,16 +719,16 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
     STX_CUDA(cudaGetDevice(&dev));
     STX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int slots = num_sms * OCC;                                              // persistent: OCC CTAs per SM
-  const int grid = sched.total_items < slots ? sched.total_items : slots;
+  const int slots = PAIR ? num_sms / 2 : num_sms * OCC;               // persistent: OCC CTAs per SM / one pair per TPC
+  const int grid = (PAIR ? 2 : 1) * (sched.total_items < slots ? sched.total_items : slots);
   if (RES > 0) {
     sched.wt = nullptr;
     STX_REQUIRE(sched.nblocks == 1 && sched.ksplit == 1 && op.cin == 64 * RES,
                 "conv: resident-weight instance on a shape it does not cover");
   }
-  STX_TRY(launch_pdl(conv_patch_kernel<BN, MT, SPLIT, OCC, RES, F8>, dim3(grid), dim3(kThreads), L::kTotal, stream, op.tmA,
-                     op.tmB, SPLIT ? op.tmA2 : op.tmA, SPLIT ? op.tmB2 : op.tmB, sched.gram_chunks ? op.tmF : op.tmA,
-                     sched.gram_chunks ? op.tmD : op.tmB, p, sched));
+  STX_TRY(launch_pdl_cluster(PAIR ? 2 : 1, conv_patch_kernel<BN, MT, SPLIT, OCC, RES, F8, PAIR>, dim3(grid), dim3(kThreads),
+                             L::kTotal, stream, op.tmA, op.tmB, SPLIT ? op.tmA2 : op.tmA, SPLIT ? op.tmB2 : op.tmB, sched.gram_chunks ? op.tmF : op.tmA,
+                             sched.gram_chunks ? op.tmD : op.tmB, p, sched));
   count_launch();
   return STX_OK;
 }
@@ -671,7 +738,7 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
 // Geometry + tensor maps of the patch variant. Returns STX_ERR_UNSUPPORTED (without touching op) when the shape
 // does not qualify (needs W >= 8: an 8-pixel row group must be contiguous in the patch).
 int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
-                       int split, int force_bn, int force_mt, int force_occ) {
+                       int split, int force_bn, int force_mt, int force_occ, int want_pair) {
   STX_REQUIRE(x && wpacked, "conv: null operand");
   STX_REQUIRE(cin % 64 == 0 && (cout % 64 == 0 || cout == 16), "conv: channels must be multiples of 64");
   if (W < 8) return STX_ERR_UNSUPPORTED;
@@ -731,6 +798,18 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
     if (res == 1) occ = split ? 1 : 2;
     if (res == 2) occ = 1;
   }
+  // CTA pairs (cta_group::2, see PatchSmem): asked for by the caller, N tile 128, K >= 4 chunks, an even number of 16x8
+  // tiles and at least one pair item per TPC.
+  int pair = 0;
+  if (want_pair && bn == 128 && cin >= 256 && res == 0 && force_mt == 0 && force_occ == 0) {
+    const int tiles = ((W + 7) / 8) * ((H + 15) / 16) * nimg;
+    if (tiles % 2 == 0 && (tiles / 2) * (cout / bn) >= 74) {
+      pair = 1;
+      mt = 1;
+      occ = 1;
+    }
+  }
+  op->pair = pair;
   const int tiles_w = (W + 7) / 8;
   op->bn = bn;
   op->mt = mt;
@@ -747,7 +826,7 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   const uint32_t abox[4] = {64u, static_cast<uint32_t>(kPatchW), static_cast<uint32_t>(16 * mt + 2), 1u};
   STX_TRY(encode_tmap_bf16(&op->tmA, x, 4, adims, abox));
   const uint64_t bdims[3] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(cout), 9u};
-  const uint32_t bbox[3] = {64u, static_cast<uint32_t>(bn), 1u};
+  const uint32_t bbox[3] = {64u, static_cast<uint32_t>(pair ? bn / 2 : bn), 1u};    // pair: each CTA loads half the rows
   STX_TRY(encode_tmap_bf16(&op->tmB, wpacked, 3, bdims, bbox));
   op->bias = nullptr;
   op->addend = nullptr;
@@ -782,7 +861,7 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
 int conv_patch_plan_splitk(const ConvOp& op, size_t* ws_floats, size_t* counters) {
   *ws_floats = 0;
   *counters = 0;
-  if (!op.patch || op.bn == 16) return 1;
+  if (!op.patch || op.bn == 16 || op.pair) return 1;
   const int items = op.tiles_w * op.tiles_h * op.nimg * (op.cout / op.bn);
   const int slots = 148 * op.occ;
   const int chunks = op.cin / 64;
@@ -807,7 +886,7 @@ int conv_patch_attach_gram(ConvOp* op, const bf16* feat, const bf16* dscaled) {
   STX_TRY(encode_tmap_bf16(&op->tmF, feat, 4, fdims, fbox));
   const uint64_t ddims[3] = {static_cast<uint64_t>(op->cout), static_cast<uint64_t>(op->cout),
                              static_cast<uint64_t>(op->nimg)};
-  const uint32_t dbox[3] = {64u, static_cast<uint32_t>(op->bn), 1u};
+  const uint32_t dbox[3] = {64u, static_cast<uint32_t>(op->pair ? op->bn / 2 : op->bn), 1u};
   STX_TRY(encode_tmap_bf16(&op->tmD, dscaled, 3, ddims, dbox));
   op->gram_chunks = op->cout / 64;
   return STX_OK;
@@ -821,7 +900,7 @@ int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo) {
   const uint32_t abox[4] = {64u, static_cast<uint32_t>(kPatchW), 18u, 1u};
   STX_TRY(encode_tmap_bf16(&op->tmA2, x_lo, 4, adims, abox));
   const uint64_t bdims[3] = {static_cast<uint64_t>(op->cin), static_cast<uint64_t>(op->cout), 9u};
-  const uint32_t bbox[3] = {64u, static_cast<uint32_t>(op->bn), 1u};
+  const uint32_t bbox[3] = {64u, static_cast<uint32_t>(op->pair ? op->bn / 2 : op->bn), 1u};
   STX_TRY(encode_tmap_bf16(&op->tmB2, w_lo, 3, bdims, bbox));
   op->split = 1;
   return STX_OK;
@@ -837,11 +916,13 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
   if (op.split == 2) {
     STX_REQUIRE(op.out_lo != nullptr || op.pool_out_lo != nullptr, "conv f16+f8: correction-plane output not set");
     STX_REQUIRE(op.res == 0 && op.mt == 1, "conv f16+f8: bad configuration");
+    if (op.pair) return launch_patch<128, 1, true, 1, 0, true, true>(op, stream);
     if (op.bn == 128) return launch_patch<128, 1, true, 1, 0, true>(op, stream);
     if (op.occ == 2) return launch_patch<64, 1, true, 2, 0, true>(op, stream);
     return launch_patch<64, 1, true, 1, 0, true>(op, stream);
   }
   if (op.split) {
+    STX_REQUIRE(!op.pair, "conv split: no CTA-pair instance of the bf16x3 forward");
     STX_REQUIRE(op.out_lo != nullptr || op.pool_out_lo != nullptr, "conv split: low-half output not set");
     if (op.bn == 128) return launch_patch<128, 1, true, 1>(op, stream);
     if (op.res == 1) return launch_patch<64, 1, true, 1, 1>(op, stream);
@@ -852,6 +933,7 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
   const bool two = op.occ == 2;
   if (op.bn == 256) return launch_patch<256, 2, false, 1>(op, stream);
   if (op.bn == 128) {
+    if (op.pair) return launch_patch<128, 1, false, 1, 0, false, true>(op, stream);
     if (op.mt == 2) return launch_patch<128, 2, false, 1>(op, stream);
     return two ? launch_patch<128, 1, false, 2>(op, stream) : launch_patch<128, 1, false, 1>(op, stream);
   }

@@ -28,6 +28,7 @@ struct ConvOp {
   int patch;         // 1 = halo-patch kernel (conv_patch.cu), 0 = per-tap kernel (conv_igemm.cu)
   int mt;            // patch kernel: 16x8 output tiles stacked per CTA (1 or 2)
   int occ;           // patch kernel: persistent CTAs per SM (1 or 2)
+  int pair;          // patch kernel: 1 = CTA pairs (tcgen05 cta_group::2): two M tiles share each weight tile, half per SM
   int res;           // patch kernel: 64-channel input chunks whose weights stay resident in shared memory (0 = ring)
   bf16* out_lo;
   bf16* pool_out;            // fused 2x2 average pool outputs (patch kernel only)
@@ -53,13 +54,14 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
 int conv_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
 // Halo-patch variant (3x3 only, W >= 8); returns STX_ERR_UNSUPPORTED for shapes it does not cover.
 int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, const bf16* wpacked, int cout,
-                       int split, int force_bn, int force_mt, int force_occ);
+                       int split, int force_bn, int force_mt, int force_occ, int want_pair = 0);
 int conv_patch_prepare_split(ConvOp* op, const bf16* x_lo, const bf16* w_lo);
 int conv_patch_attach_gram(ConvOp* op, const bf16* feat, const bf16* dscaled);
 int conv_patch_plan_splitk(const ConvOp& op, size_t* ws_floats, size_t* counters);
 int conv_patch_launch(const ConvOp& op, cudaStream_t stream);
 // Picks the halo-patch kernel when the shape qualifies, else the per-tap kernel. x_lo / w_lo non-null = bf16x3.
-// variant: 0 = automatic; otherwise bn + 1000 * mt + 10000 * occ + 100000 * (force the per-tap kernel).
+// variant: 0 = automatic; otherwise bn + 1000 * mt + 10000 * occ + 100000 * (force the per-tap kernel)
+// + 1000000 * (use CTA pairs where the shape qualifies).
 int conv3x3_prepare(ConvOp* op, const bf16* x, const bf16* x_lo, int nimg, int H, int W, int cin, const bf16* w,
                     const bf16* w_lo, int cout, int variant);
 int conv_launch(const ConvOp& op, cudaStream_t stream);

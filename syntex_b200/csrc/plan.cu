@@ -15,6 +15,8 @@ int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
 int g_debug_tiled_weights = 0;      // 1 = fetch weight tiles with 1-D bulk copies from tiled pre-swizzled packs
                                     // (measured: no gain over tensor-map fetches, costs a second weight copy: off)
 int g_debug_conv1_1_cuda_cores = 0;  // 1 = CUDA-core conv1_1 forward in the f16 + f8 plans too (stx_debug_set key 13)
+int g_debug_pair = 0;               // bit 0: CTA pairs for the deep f16+f8 forward layers, bit 1: for the deep input-gradient
+                                    // layers (stx_debug_set key 15)
 int g_debug_f8_single_cta = 0;      // 1 = one CTA per SM for the 64-channel f16+f8 forward (stx_debug_set key 12)
 int g_debug_splitk = 0;             // 1 = split-K work items for small grids (measured slower at 256^2: off)
 
@@ -332,7 +334,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     if (p->split == 2) {
       // f16 + f8: fp16 planes against the fp16 pack, correction planes against the e4m3 rows (halo-patch kernel only)
       rc = conv3x3_prepare(&op, p->act[l - 1], p->act_lo[l - 1], B, p->lh[l], p->lw[l], s.cin, vgg->wf16[s.conv_index],
-                           vgg->wcorr[s.conv_index], s.cout, 0);
+                           vgg->wcorr[s.conv_index], s.cout, (g_debug_pair & 1) ? 1000000 : 0);
       if (rc == STX_OK && !op.patch)
         rc = fail(STX_ERR_UNSUPPORTED, "plan_create: the f16+f8 forward needs feature maps at least 8 pixels wide");
       op.split = 2;
@@ -442,7 +444,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       BwdStep st;
       st.kind = BwdStep::kDgrad;
       rc = conv3x3_prepare(&st.conv, p->gbuf[cur], nullptr, B, p->lh[l], p->lw[l], s.cout, vgg->wd[s.conv_index],
-                           nullptr, s.cin, g_debug_dgrad_variant);
+                           nullptr, s.cin, g_debug_dgrad_variant + ((g_debug_pair & 2) ? 1000000 : 0));
       st.conv.w_tiled = g_debug_tiled_weights ? vgg->wdt[s.conv_index] : nullptr;
       st.conv.out = p->gbuf[cur ^ 1];
       st.conv.mask = (kLayers[l - 1].is_conv && loss_index(l - 1) < 0) ? p->act[l - 1] : nullptr;
