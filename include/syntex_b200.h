@@ -48,7 +48,7 @@ long long stx_launch_count(void);
 /* Bring-up knobs; key/value meanings are internal (csrc/capi.cu: descriptor strides, kernel-variant overrides, 9 =
  * programmatic dependent launch, 10 = plain stream launches instead of the optimiser's CUDA graph, 12 = one CTA per SM
  * for the 64-channel f16+f8 forward, 13 = CUDA-core conv1_1 in f16+f8 plans, 14 = active-set kernel in the main
- * stream). Also read from the environment at load: STX_DEBUG="key=value,...". */
+ * stream, 15 = CTA-pair convolution instances: bit 0 forward, bit 1 input gradient, default 3). Also read from the environment at load: STX_DEBUG="key=value,...". */
 int stx_debug_set(int key, int value);
 /* Bring-up probe of the CTA-pair MMA (tcgen05 cta_group::2): out fp32 [256][128] = a bf16 [256][64] * b bf16
  * [128][64]^T computed by one cluster of two CTAs (each loads its 128 rows of a and 64 rows of b). */
@@ -201,9 +201,10 @@ int stx_conv_bf16x3(const void* x_hi, const void* x_lo, int n, int H, int W, int
                     int force_bn, void* stream);
 /* out = epilogue(conv(x, w)) with x [n,H,W,cin] bf16, w packed [taps][cout][cin] bf16, taps in {9, 1}.
  * epilogue: (+ bias[cout] fp32) (+ addend bf16) (relu) (zero where mask <= 0); any of them may be NULL/0.
- * force_bn ("variant"): 0 = automatic kernel and tile choice; otherwise bn + 1000 * mt + 100000 * per_tap, with
- *   bn in {0, 64, 128, 256} the N tile, mt in {0, 1, 2} the stacked 16x8 output tiles of the halo-patch kernel and
- *   per_tap = 1 forcing the general per-tap kernel (conv_igemm.cu) instead of the halo-patch one (conv_patch.cu). */
+ * force_bn ("variant"): 0 = automatic kernel and tile choice; otherwise bn + 1000 * mt + 100000 * per_tap + 1000000 *
+ *   pair, with bn in {0, 64, 128, 256} the N tile, mt in {0, 1, 2} the stacked 16x8 output tiles of the halo-patch
+ *   kernel, per_tap = 1 forcing the general per-tap kernel (conv_igemm.cu) instead of the halo-patch one
+ *   (conv_patch.cu) and pair = 1 asking for the CTA-pair instance (tcgen05 cta_group::2) where the shape qualifies. */
 int stx_conv_bf16(const void* x, int n, int H, int W, int cin, const void* w_packed, int cout, int taps,
                   const float* bias, const void* addend, const void* mask, int relu, void* out, int force_bn,
                   void* stream);

@@ -798,10 +798,12 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
     if (res == 1) occ = split ? 1 : 2;
     if (res == 2) occ = 1;
   }
-  // CTA pairs (cta_group::2, see PatchSmem): asked for by the caller, N tile 128, K >= 4 chunks, an even number of 16x8
-  // tiles and at least one pair item per TPC.
+  // CTA pairs (cta_group::2, see PatchSmem): asked for by the caller, N tile 128, an even number of 16x8 tiles and at
+  // least one pair item per TPC. Measured at 64 jobs of 256^2 (profiles/r02_cta_pairs.log): f16+f8 forward 4.86 -> 4.35
+  // ms, input gradient 2.90 -> 2.74 ms, every layer with 128+ output channels gains (also the short-K ones), results
+  // bit-identical; at 4 jobs no difference. They replace the two-stacked-tiles (MT = 2) instances wherever they apply.
   int pair = 0;
-  if (want_pair && bn == 128 && cin >= 256 && res == 0 && force_mt == 0 && force_occ == 0) {
+  if (want_pair && bn == 128 && res == 0 && force_mt == 0 && force_occ == 0) {
     const int tiles = ((W + 7) / 8) * ((H + 15) / 16) * nimg;
     if (tiles % 2 == 0 && (tiles / 2) * (cout / bn) >= 74) {
       pair = 1;

@@ -15,8 +15,8 @@ int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
 int g_debug_tiled_weights = 0;      // 1 = fetch weight tiles with 1-D bulk copies from tiled pre-swizzled packs
                                     // (measured: no gain over tensor-map fetches, costs a second weight copy: off)
 int g_debug_conv1_1_cuda_cores = 0;  // 1 = CUDA-core conv1_1 forward in the f16 + f8 plans too (stx_debug_set key 13)
-int g_debug_pair = 0;               // bit 0: CTA pairs for the deep f16+f8 forward layers, bit 1: for the deep input-gradient
-                                    // layers (stx_debug_set key 15)
+int g_debug_pair = 3;               // bit 0: CTA pairs (tcgen05 cta_group::2) for the f16+f8 / plain-bf16 forward layers with
+                                    // 128+ output channels, bit 1: for the input-gradient layers (stx_debug_set key 15)
 int g_debug_f8_single_cta = 0;      // 1 = one CTA per SM for the 64-channel f16+f8 forward (stx_debug_set key 12)
 int g_debug_splitk = 0;             // 1 = split-K work items for small grids (measured slower at 256^2: off)
 
@@ -344,7 +344,8 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       if (op.patch && op.bn == 64 && op.tiles_w * op.tiles_h * op.nimg >= 2 * 148 && !g_debug_f8_single_cta) op.occ = 2;
     } else {
       rc = conv3x3_prepare(&op, p->act[l - 1], p->split ? p->act_lo[l - 1] : nullptr, B, p->lh[l], p->lw[l], s.cin,
-                           vgg->wf[s.conv_index], p->split ? vgg->wf_lo[s.conv_index] : nullptr, s.cout, 0);
+                           vgg->wf[s.conv_index], p->split ? vgg->wf_lo[s.conv_index] : nullptr, s.cout,
+                           (!p->split && (g_debug_pair & 1)) ? 1000000 : 0);
     }
     op.w_tiled = g_debug_tiled_weights ? vgg->wft[s.conv_index] : nullptr;
     op.w_tiled_lo = g_debug_tiled_weights ? vgg->wft_lo[s.conv_index] : nullptr;

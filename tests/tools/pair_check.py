@@ -1,5 +1,5 @@
 """B200 check of the CTA-pair (tcgen05 cta_group::2) instances of the halo-patch convolution: one f/g evaluation with
-stx_debug_set key 15 = 0 / 1 (forward) / 2 (input gradient) / 3 (both) - results must be bit-identical (the pair's MMA
+stx_debug_set key 15 = 0 / 1 (forward) / 2 (input gradient) / 3 (both, the default) - results must be bit-identical (the pair's MMA
 accumulates the same products in the same order), per-class kernel times next to each other.
 
   python tests/tools/pair_check.py [batch] [size]
@@ -31,7 +31,7 @@ def run(batch, S, mode, prec):
         syn = Synthesizer({"vgg19_npy_path": raw, "image_size": S, "maxiter": 1, "maxcor": 20, "precision": prec, "batch": batch})
         syn.build()
     finally:
-        _lib.check(L.stx_debug_set(15, 0))
+        _lib.check(L.stx_debug_set(15, 3))
     tg = np.stack([so.synthetic_texture(S, seed=100 + j) for j in range(batch)]).astype(np.float32)
     x0 = np.stack([so.init_input((S, S, 3), False, j) for j in range(batch)]).astype(np.float32)
     syn.compute_gram(tg, update=True)
@@ -59,7 +59,7 @@ if __name__ == "__main__":
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     for prec in ("f16f8", "bf16"):
         base = run(batch, S, 0, prec)
-        for mode in ((2, 1, 3) if prec == "f16f8" else (2,)):
+        for mode in (1, 2, 3):
             got = run(batch, S, mode, prec)
             same = np.array_equal(base[0], got[0]) and np.array_equal(base[1], got[1])
             print("   identical to pair=0:", same, "" if same else
