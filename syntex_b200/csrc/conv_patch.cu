@@ -62,8 +62,8 @@ struct PatchSmem {
   static_assert(OCC == 1 || (OCC == 2 && (MT == 1 || BN == 16)), "two CTAs per SM: single-tile or N = 16 instances only");
   static constexpr int kBRows = PAIR ? BN / 2 : BN;                           // weight rows staged by this CTA
   static constexpr int kBBytes = (kBRows * 128 + 1023) & ~1023;
-  static_assert(!PAIR || (MT == 1 && OCC == 1 && RES == 0 && BN == 128 && (!SPLIT || F8)),
-                "CTA pairs: single-tile, one CTA per SM, ring weights, N tile 128, single-MMA or f16+f8");
+  static_assert(!PAIR || (MT == 1 && RES == 0 && (BN == 128 || BN == 64) && (!SPLIT || F8)),
+                "CTA pairs: single-tile, ring weights, N tile 64 / 128, single-MMA or f16+f8");
   static constexpr int kBStageBytes = (SPLIT ? 2 : 1) * kBBytes;              // [hi | lo]
   static constexpr int kBudget = kSmemBudget / OCC - 2048;
   // resident mode: a small ring for the per-image Gram-difference tiles of the fused Gram gradient
@@ -719,7 +719,7 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
     STX_CUDA(cudaGetDevice(&dev));
     STX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int slots = PAIR ? num_sms / 2 : num_sms * OCC;               // persistent: OCC CTAs per SM / one pair per TPC
+  const int slots = PAIR ? (num_sms / 2) * OCC : num_sms * OCC;       // persistent: OCC CTAs per SM / OCC pairs per TPC
   const int grid = (PAIR ? 2 : 1) * (sched.total_items < slots ? sched.total_items : slots);
   if (RES > 0) {
     sched.wt = nullptr;
@@ -798,17 +798,18 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
     if (res == 1) occ = split ? 1 : 2;
     if (res == 2) occ = 1;
   }
-  // CTA pairs (cta_group::2, see PatchSmem): asked for by the caller, N tile 128, an even number of 16x8 tiles and at
-  // least one pair item per TPC. Measured at 64 jobs of 256^2 (profiles/r02_cta_pairs.log): f16+f8 forward 4.86 -> 4.35
-  // ms, input gradient 2.90 -> 2.74 ms, every layer with 128+ output channels gains (also the short-K ones), results
-  // bit-identical; at 4 jobs no difference. They replace the two-stacked-tiles (MT = 2) instances wherever they apply.
+  // CTA pairs (cta_group::2, see PatchSmem): asked for by the caller, N tile 64 or 128, an even number of 16x8 tiles
+  // and at least one pair item per TPC. Measured at 64 jobs of 256^2 (profiles/r02_cta_pairs.log): f16+f8 forward 4.87
+  // -> 4.28 ms, input gradient 2.92 -> 2.64 ms, every layer gains (the deep ones most: half the weight bytes per SM;
+  // the 64-channel ones 2-3 %: they are bound by the shared-memory reads of the pixel operand), results bit-identical;
+  // at 4 jobs no difference. They replace the two-stacked-tiles (MT = 2) instances wherever they apply.
   int pair = 0;
-  if (want_pair && bn == 128 && res == 0 && force_mt == 0 && force_occ == 0) {
+  if (want_pair && (bn == 128 || bn == 64) && res == 0 && force_mt == 0 && force_occ == 0) {
     const int tiles = ((W + 7) / 8) * ((H + 15) / 16) * nimg;
     if (tiles % 2 == 0 && (tiles / 2) * (cout / bn) >= 74) {
       pair = 1;
       mt = 1;
-      occ = 1;
+      if (bn == 128) occ = 1;
     }
   }
   op->pair = pair;
@@ -918,7 +919,9 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
   if (op.split == 2) {
     STX_REQUIRE(op.out_lo != nullptr || op.pool_out_lo != nullptr, "conv f16+f8: correction-plane output not set");
     STX_REQUIRE(op.res == 0 && op.mt == 1, "conv f16+f8: bad configuration");
-    if (op.pair) return launch_patch<128, 1, true, 1, 0, true, true>(op, stream);
+    if (op.pair && op.bn == 128) return launch_patch<128, 1, true, 1, 0, true, true>(op, stream);
+    if (op.pair) return op.occ == 2 ? launch_patch<64, 1, true, 2, 0, true, true>(op, stream)
+                                    : launch_patch<64, 1, true, 1, 0, true, true>(op, stream);
     if (op.bn == 128) return launch_patch<128, 1, true, 1, 0, true>(op, stream);
     if (op.occ == 2) return launch_patch<64, 1, true, 2, 0, true>(op, stream);
     return launch_patch<64, 1, true, 1, 0, true>(op, stream);
@@ -940,6 +943,8 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
     return two ? launch_patch<128, 1, false, 2>(op, stream) : launch_patch<128, 1, false, 1>(op, stream);
   }
   if (op.mt == 2) return launch_patch<64, 2, false, 1>(op, stream);
+  if (op.pair) return two ? launch_patch<64, 1, false, 2, 0, false, true>(op, stream)
+                          : launch_patch<64, 1, false, 1, 0, false, true>(op, stream);
   return two ? launch_patch<64, 1, false, 2>(op, stream) : launch_patch<64, 1, false, 1>(op, stream);
 }
 

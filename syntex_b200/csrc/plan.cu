@@ -15,8 +15,8 @@ int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
 int g_debug_tiled_weights = 0;      // 1 = fetch weight tiles with 1-D bulk copies from tiled pre-swizzled packs
                                     // (measured: no gain over tensor-map fetches, costs a second weight copy: off)
 int g_debug_conv1_1_cuda_cores = 0;  // 1 = CUDA-core conv1_1 forward in the f16 + f8 plans too (stx_debug_set key 13)
-int g_debug_pair = 3;               // bit 0: CTA pairs (tcgen05 cta_group::2) for the f16+f8 / plain-bf16 forward layers with
-                                    // 128+ output channels, bit 1: for the input-gradient layers (stx_debug_set key 15)
+int g_debug_pair = 3;               // bit 0: CTA pairs (tcgen05 cta_group::2) for the f16+f8 / plain-bf16 forward layers,
+                                    // bit 1: for the input-gradient layers (stx_debug_set key 15)
 int g_debug_f8_single_cta = 0;      // 1 = one CTA per SM for the 64-channel f16+f8 forward (stx_debug_set key 12)
 int g_debug_splitk = 0;             // 1 = split-K work items for small grids (measured slower at 256^2: off)
 

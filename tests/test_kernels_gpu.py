@@ -76,7 +76,8 @@ def test_conv_kernel_variants_agree_with_reference(n, H, W, cin, cout, variant):
 
 
 @pytest.mark.parametrize("n,H,W,cin,cout", [(4, 72, 40, 64, 256),      # ragged, 25 tiles per image: a pair spans two images
-                                            (6, 64, 64, 256, 128), (2, 128, 96, 128, 128), (37, 16, 16, 512, 512)])
+                                            (6, 64, 64, 256, 128), (2, 128, 96, 128, 128), (37, 16, 16, 512, 512),
+                                            (4, 104, 120, 64, 64), (2, 128, 128, 128, 64)])   # N tile 64, two pairs per TPC
 def test_conv_cta_pairs_match_single_cta_bitwise(n, H, W, cin, cout):
     """CTA-pair instances (tcgen05 cta_group::2, variant + 1000000): two 16x8 tiles against one weight tile, half of it
     staged per SM. Same products accumulated in the same order: bit-identical to the one-CTA instance."""
@@ -87,7 +88,7 @@ def test_conv_cta_pairs_match_single_cta_bitwise(n, H, W, cin, cout):
     msk = torch.randn((n, H, W, cout), device="cuda", generator=g).to(torch.bfloat16)
     wf, _, _ = pack(w)
     outs = []
-    for variant in (1000000, 1128):
+    for variant in (1000000, 1128 if cout % 128 == 0 else 1064):
         o = torch.full((n, H, W, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
         _lib.check(L().stx_conv_bf16(x.data_ptr(), n, H, W, cin, wf.data_ptr(), cout, 9, b.data_ptr(), None,
                                      msk.data_ptr(), 0, o.data_ptr(), variant, st()))
