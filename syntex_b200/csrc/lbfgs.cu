@@ -32,6 +32,8 @@
 //            projects it, and writes the next trial point; partial sums of g'd and of the largest feasible step.
 #include "lbfgs.h"
 
+#include <cuda_fp16.h>
+
 #include "ptx.cuh"
 
 namespace stx {
@@ -76,7 +78,9 @@ struct Ctrl {
   int mode, action, push, nh, head, slot_new, nit, nfev, fresh, maxiter;
   float stp;          // step of the trial point currently in xt
   float theta_inv;    // 1 / theta
-  float cs[kMaxM], cy[kMaxM];   // step = -g / theta + sum_j cs[j] S_j + cy[j] Y_j over F (j chronological)
+  float cs[kMaxM], cy[kMaxM];   // step = -g / theta + sum_j cs[j] S_j + cy[j] Y_j over F (j chronological); the
+                                // coefficients carry the vectors' storage scales (they multiply the stored halves)
+  float hs[kMaxM], hy[kMaxM];   // storage scales of the history vectors BY SLOT: s = hs * stored, y = hy * stored
   double f, pp, stp0, theta, stpmx;
   LsState ls;
 };
@@ -87,8 +91,17 @@ struct Tables {
   double SY[kMaxM * kMaxM], SS[kMaxM * kMaxM], YY[kMaxM * kMaxM];
 };
 
+// The (s, y) history is kept as fp16 with one power-of-two scale per vector (Ctrl::hs / hy): the two passes over it
+// are the optimiser's HBM time (2 x 2 GB per cycle in fp32 at 64 jobs of 256^2 with 20 pairs). The scale maps the
+// vector's 2-norm just below 2^15, so no element overflows whatever their distribution, and elements down to 2^-29
+// of the norm keep 11 significant bits: a relative rounding of 2^-12 per element, an order of magnitude below the
+// noise the bf16 backward leaves in the gradient itself (4e-3). The S'Y / S'S / Y'Y tables are built from the pair as
+// measured (fp32 differences) against the older vectors as stored; oracle/lbfgsb_model.py (hist = "f16") does the same.
+typedef __half hist_t;
+
 struct Vecs {
-  float *x, *xt, *g, *gt, *d, *S, *Y;   // [B][n], history [B][m][n]
+  float *x, *xt, *g, *gt, *d;           // [B][n]
+  hist_t *S, *Y;                        // history [B][m][n]
   float* ft;                             // [B]
   float* part;                           // [B][kNP][nblk]
   float* part2;                          // [B][nblk]  g'd of a freshly built direction
@@ -110,6 +123,32 @@ __device__ __forceinline__ bool is_free(float x, float g, float lo, float hi, in
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// four stored history elements (unscaled)
+__device__ __forceinline__ float4 ldh4(const hist_t* p) {
+  const uint2 raw = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+// v * inv_scale rounded to storage; returns what was stored (unscaled) so that the caller can keep using it
+__device__ __forceinline__ float4 sth4(hist_t* p, float4 v, float inv_scale) {
+  const __half2 a = __floats2half2_rn(v.x * inv_scale, v.y * inv_scale);
+  const __half2 b = __floats2half2_rn(v.z * inv_scale, v.w * inv_scale);
+  uint2 raw;
+  raw.x = *reinterpret_cast<const uint32_t*>(&a);
+  raw.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = raw;
+  const float2 fa = __half22float2(a), fb = __half22float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+// power of two that maps a vector of squared 2-norm `norm2` below 2^15 in every element (lbfgsb_model.f16_scale)
+__device__ __forceinline__ float hist_scale(double norm2) {
+  const double nrm = sqrt(norm2);
+  if (!(nrm > 0.0) || !isfinite(nrm)) return 1.f;
+  int e;
+  frexp(nrm, &e);
+  return ldexpf(1.f, e - 15);
+}
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
@@ -159,8 +198,8 @@ __global__ void __launch_bounds__(kThreads) lbfgs_dots_kernel(Vecs v) {
   for (int j = 0; j < nh; ++j) {
     const int slot = (head + j) % m;
     const size_t hoff = (static_cast<size_t>(b) * m + slot) * v.n + i0;
-    const float4 sj = in ? ld4(v.S + hoff) : z4;
-    const float4 yj = in ? ld4(v.Y + hoff) : z4;
+    const float4 sj = in ? ldh4(v.S + hoff) : z4;
+    const float4 yj = in ? ldh4(v.Y + hoff) : z4;
     const float a0 = warp_sum(dot4(sj, y));
     const float a1 = warp_sum(dot4(yj, y));
     const float a2 = warp_sum(dot4(sj, pg));
@@ -169,7 +208,8 @@ __global__ void __launch_bounds__(kThreads) lbfgs_dots_kernel(Vecs v) {
     const float a5 = warp_sum(dot4(yj, s));
     if (lane == 0) {
       float* r = &red[warp][kNP0 + kNPH * j];
-      r[0] = a0; r[1] = a1; r[2] = a2; r[3] = a3; r[4] = a4; r[5] = a5;
+      const float hsj = c.hs[slot], hyj = c.hy[slot];      // powers of two: exact
+      r[0] = a0 * hsj; r[1] = a1 * hyj; r[2] = a2 * hsj; r[3] = a3 * hyj; r[4] = a4 * hsj; r[5] = a5 * hyj;
     }
   }
   __syncthreads();
@@ -246,11 +286,18 @@ __global__ void __launch_bounds__(kThreads) lbfgs_active_kernel(Vecs v) {
   // (<= kActRows terms, four independent chains per thread), tiles added in fp64.
   const int G = kThreads / Q;                              // row groups (Q <= 66 < kThreads)
   const int ga = threadIdx.x % Q, grg = threadIdx.x / Q;
-  const float* gsrc;                                       // column ga of a row = gsrc[i] (history) or a difference
+  const hist_t* gsrc;                                      // column ga of a row = gscale * gsrc[i] (history) or a difference
+  float gscale = 1.f;
   {
-    if (ga < nh) gsrc = v.Y + (static_cast<size_t>(b) * m + (head + ga) % m) * v.n;
-    else if (ga < 2 * nh) gsrc = v.S + (static_cast<size_t>(b) * m + (head + ga - nh) % m) * v.n;
-    else gsrc = nullptr;
+    if (ga < nh) {
+      gsrc = v.Y + (static_cast<size_t>(b) * m + (head + ga) % m) * v.n;
+      gscale = c.hy[(head + ga) % m];
+    } else if (ga < 2 * nh) {
+      gsrc = v.S + (static_cast<size_t>(b) * m + (head + ga - nh) % m) * v.n;
+      gscale = c.hs[(head + ga - nh) % m];
+    } else {
+      gsrc = nullptr;
+    }
   }
   auto flush = [&](int count) {
     for (int r0 = 0; r0 < count; r0 += kActRows) {
@@ -264,7 +311,7 @@ __global__ void __launch_bounds__(kThreads) lbfgs_active_kernel(Vecs v) {
             val[q] = 0.f;
             if (r < rows) {
               const int i = list[r0 + r];
-              if (gsrc) val[q] = __ldg(gsrc + i);
+              if (gsrc) val[q] = __half2float(__ldg(gsrc + i)) * gscale;
               else if (ga == 2 * nh) val[q] = v.gt[base + i] - v.g[base + i];
               else val[q] = v.xt[base + i] - v.x[base + i];
             }
@@ -555,6 +602,8 @@ __device__ void decide_serial(Ctrl& c, const double* sums, double dg0, double st
         dec.shift = 1;
       }
       c.slot_new = slot_at(c.head, k, m);
+      c.hs[c.slot_new] = hist_scale(sums[6]);
+      c.hy[c.slot_new] = hist_scale(yy);
       c.push = 1;
       dec.push = 1;
       k += 1;
@@ -794,8 +843,9 @@ __global__ void __launch_bounds__(kDecideThreads) lbfgs_decide_kernel(Vecs v) {
       if (ok) {
         // step = r / theta + W_F wv / theta^2,  W = [Y, theta S]
         for (int i = 0; i < k; ++i) {
-          sc.cy[i] = static_cast<float>(wv[i] / (theta * theta));
-          sc.cs[i] = static_cast<float>(wv[k + i] / theta);
+          const int si = slot_at(head, i, m);
+          sc.cy[i] = static_cast<float>(wv[i] / (theta * theta)) * sc.hy[si];
+          sc.cs[i] = static_cast<float>(wv[k + i] / theta) * sc.hs[si];
         }
       } else {
         // formk / formt failure in mainlb: refresh the memory; the step falls back to the projected gradient
@@ -864,8 +914,9 @@ __global__ void __launch_bounds__(kThreads) lbfgs_update_kernel(Vecs v) {
       st4(v.g + off, g);
       if (action == kAccept && c.push) {
         const size_t hoff = (static_cast<size_t>(b) * v.m + c.slot_new) * v.n + i0;
-        st4(v.S + hoff, s);
-        st4(v.Y + hoff, y);
+        // s, y continue as the STORED (unscaled) halves: the step below multiplies them by the scaled coefficients
+        s = sth4(v.S + hoff, s, 1.f / c.hs[c.slot_new]);
+        y = sth4(v.Y + hoff, y, 1.f / c.hy[c.slot_new]);
       }
     }
     if (action == kFinalAccept) return;
@@ -883,8 +934,8 @@ __global__ void __launch_bounds__(kThreads) lbfgs_update_kernel(Vecs v) {
     for (int j = 0; j < nold; ++j) {
       const int slot = (c.head + j) % v.m;
       const size_t hoff = (static_cast<size_t>(b) * v.m + slot) * v.n + i0;
-      const float4 sj = in ? ld4(v.S + hoff) : z4;
-      const float4 yj = in ? ld4(v.Y + hoff) : z4;
+      const float4 sj = in ? ldh4(v.S + hoff) : z4;
+      const float4 yj = in ? ldh4(v.Y + hoff) : z4;
       const float a = c.cs[j], bb = c.cy[j];
       acc.x = fmaf(a, sj.x, fmaf(bb, yj.x, acc.x));
       acc.y = fmaf(a, sj.y, fmaf(bb, yj.y, acc.y));
@@ -988,6 +1039,7 @@ struct LbfgsImpl {
   Vecs v;
   int B = 0;
   float* base = nullptr;
+  void* hist = nullptr;        // the (s, y) history, fp16
   float* fun_dev = nullptr;
   int* status_dev = nullptr;   // [3B] nit | nfev | mode
   int* pinned_i = nullptr;     // [3B]
@@ -1019,6 +1071,7 @@ Lbfgs::~Lbfgs() {
     if (im->ev_in) cudaEventDestroy(im->ev_in);
     if (im->ev_out) cudaEventDestroy(im->ev_out);
     cudaFree(im->base);
+    cudaFree(im->hist);
     cudaFree(im->v.ctrl);
     cudaFree(im->v.tab);
     cudaFree(im->v.gramA);
@@ -1054,10 +1107,13 @@ int lbfgs_create(Lbfgs** out, Plan* plan, int maxcor, int bounded, float lower, 
   v.lo = lower;
   v.hi = upper;
   const size_t vec = static_cast<size_t>(B) * n;
-  const size_t total = vec * 5 + vec * maxcor * 2 + B + static_cast<size_t>(B) * v.nblk * (kNP + 2) + B;
+  const size_t total = vec * 5 + B + static_cast<size_t>(B) * v.nblk * (kNP + 2) + B;
+  const size_t hist_bytes = vec * maxcor * 2 * sizeof(hist_t);
   const size_t gram_bytes = static_cast<size_t>(B) * kSlices * kQ * kQ * sizeof(double);
   cudaError_t e = cudaMalloc(&im->base, total * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(im->base, 0, total * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&im->hist, hist_bytes);
+  if (e == cudaSuccess) e = cudaMemset(im->hist, 0, hist_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&v.ctrl, sizeof(Ctrl) * B + 3 * sizeof(int) * B);
   if (e == cudaSuccess) e = cudaMemset(v.ctrl, 0, sizeof(Ctrl) * B + 3 * sizeof(int) * B);
   if (e == cudaSuccess) e = cudaMalloc(&v.tab, sizeof(Tables) * B);
@@ -1084,8 +1140,8 @@ int lbfgs_create(Lbfgs** out, Plan* plan, int maxcor, int bounded, float lower, 
   v.g = p; p += vec;
   v.gt = p; p += vec;
   v.d = p; p += vec;
-  v.S = p; p += vec * maxcor;
-  v.Y = p; p += vec * maxcor;
+  v.S = static_cast<hist_t*>(im->hist);
+  v.Y = v.S + vec * maxcor;
   v.ft = p; p += B;
   v.part = p; p += static_cast<size_t>(B) * v.nblk * kNP;
   v.part2 = p; p += static_cast<size_t>(B) * v.nblk;
