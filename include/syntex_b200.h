@@ -181,12 +181,16 @@ int stx_lbfgs_reset(stx_lbfgs* opt, const float* x0, int is_preimage, void* stre
 int stx_lbfgs_run(stx_lbfgs* opt, int maxiter, int max_evals, void* stream);
 /* Results (device -> caller's device buffers): x [batch,H,W,3], fun [batch], iterations and evaluations [batch]. */
 int stx_lbfgs_result(stx_lbfgs* opt, float* x, float* fun, int* nit, int* nfev, void* stream);
-/* Whole optimisation through host buffers: H2D of x0, run, D2H of x and fun. Synchronous. */
 /* Diagnostic: SM clock stamps (clock64) of the phases of problem 0's decision kernel in the last cycle, host array of
  * 16: entry, sums reduced, line search decided, K built, eliminated, solved, state written back. Synchronises. */
 int stx_lbfgs_phase_cycles(stx_lbfgs* opt, long long* host16);
+/* Whole optimisation through host buffers: H2D of x0, run, D2H of x and fun. Synchronous. This is what
+ * Synthesizer.synthesize() (gatys/synthesizer.py:127-151) calls; the _f64 form returns x as float64, as the reference
+ * does (scipy's result vector), widening while it copies out of the pinned staging buffer. */
 int stx_lbfgs_minimize_host(stx_lbfgs* opt, const float* x0_host, int is_preimage, int maxiter, float* x_host,
                             float* fun_host, int* nit_host, int* nfev_host, void* stream);
+int stx_lbfgs_minimize_host_f64(stx_lbfgs* opt, const float* x0_host, int is_preimage, int maxiter, double* x_host,
+                                float* fun_host, int* nit_host, int* nfev_host, void* stream);
 
 /* ---- stand-alone operators (building blocks; used by the Python texture_utils mirror and the tests) --------- */
 /* HWIO fp32 (3,3,cin,cout) -> bf16 forward pack [9][cout][cin] and dgrad pack [9][cin][cout] (device pointers). */

@@ -57,6 +57,7 @@ def _declare(lib):
         "stx_lbfgs_run": (c_int, [vp, c_int, c_int, vp]),
         "stx_lbfgs_result": (c_int, [vp, fp, fp, ip, ip, vp]),
         "stx_lbfgs_minimize_host": (c_int, [vp, fp, c_int, c_int, fp, fp, ip, ip, vp]),
+        "stx_lbfgs_minimize_host_f64": (c_int, [vp, fp, c_int, c_int, vp, fp, ip, ip, vp]),
         "stx_pack_conv_weights": (c_int, [fp, c_int, c_int, vp, vp, vp]),
         "stx_pack_conv_weights_split": (c_int, [fp, c_int, c_int, vp, vp, vp, vp]),
         "stx_conv_bf16x3": (c_int, [vp, vp, c_int, c_int, c_int, c_int, vp, vp, c_int, fp, c_int, vp, vp, c_int, vp]),

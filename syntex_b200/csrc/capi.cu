@@ -315,7 +315,12 @@ int stx_lbfgs_phase_cycles(stx_lbfgs* opt, long long* host16) {
 int stx_lbfgs_minimize_host(stx_lbfgs* opt, const float* x0_host, int is_preimage, int maxiter, float* x_host,
                             float* fun_host, int* nit_host, int* nfev_host, void* stream) {
   STX_REQUIRE(opt && x0_host && x_host && fun_host, "stx_lbfgs_minimize_host: null argument");
-  return opt->o->minimize_host(x0_host, is_preimage, maxiter, x_host, fun_host, nit_host, nfev_host, S(stream));
+  return opt->o->minimize_host(x0_host, is_preimage, maxiter, x_host, 0, fun_host, nit_host, nfev_host, S(stream));
+}
+int stx_lbfgs_minimize_host_f64(stx_lbfgs* opt, const float* x0_host, int is_preimage, int maxiter, double* x_host,
+                                float* fun_host, int* nit_host, int* nfev_host, void* stream) {
+  STX_REQUIRE(opt && x0_host && x_host && fun_host, "stx_lbfgs_minimize_host_f64: null argument");
+  return opt->o->minimize_host(x0_host, is_preimage, maxiter, x_host, 1, fun_host, nit_host, nfev_host, S(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ stand-alone ops

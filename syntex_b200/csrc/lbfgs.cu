@@ -42,6 +42,7 @@ int g_lbfgs_serial_active = 0;   // 1 = active-set kernel in the main stream aft
 }
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 namespace stx {
@@ -1291,13 +1292,31 @@ int Lbfgs::result(float* x, float* fun, int* nit, int* nfev, cudaStream_t caller
   return STX_OK;
 }
 
-int Lbfgs::minimize_host(const float* x0_host, int is_preimage_, int maxiter, float* x_host, float* fun_host,
-                         int* nit_host, int* nfev_host, cudaStream_t caller) {
+// Host-side copies between the caller's (pageable) arrays and the pinned staging buffer: 50 MB each way at 64 jobs of
+// 256^2, and the caller's fresh output array is first touched here - a few threads instead of one memcpy.
+template <typename F>
+static void parallel_ranges(size_t n, F f) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  size_t T = std::min<size_t>(8, std::max(1u, hw));
+  if (n < (size_t(1) << 20)) T = 1;
+  const size_t per = (((n + T - 1) / T) + 1023) & ~size_t(1023);
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < T; ++t) {
+    const size_t b = std::min(n, t * per), e = std::min(n, (t + 1) * per);
+    if (b < e) th.emplace_back([=] { f(b, e); });
+  }
+  f(0, std::min(n, per));
+  for (auto& t : th) t.join();
+}
+
+int Lbfgs::minimize_host(const float* x0_host, int is_preimage_, int maxiter, void* x_host, int x_is_f64,
+                         float* fun_host, int* nit_host, int* nfev_host, cudaStream_t caller) {
   LbfgsImpl* im = impl_of(this);
   Vecs& v = im->v;
   const int B = im->B;
   const size_t vec = static_cast<size_t>(B) * v.n;
-  memcpy(im->pinned_f, x0_host, vec * sizeof(float));
+  float* const stage = im->pinned_f;
+  parallel_ranges(vec, [=](size_t b, size_t e) { memcpy(stage + b, x0_host + b, (e - b) * sizeof(float)); });
   // gt doubles as the device staging buffer for x0 (it is overwritten by the first evaluation)
   STX_CUDA(cudaMemcpyAsync(v.gt, im->pinned_f, vec * sizeof(float), cudaMemcpyHostToDevice, caller));
   STX_TRY(reset(v.gt, is_preimage_, caller));
@@ -1307,7 +1326,15 @@ int Lbfgs::minimize_host(const float* x0_host, int is_preimage_, int maxiter, fl
   STX_CUDA(cudaMemcpyAsync(im->pinned_f + vec, im->fun_dev, B * sizeof(float), cudaMemcpyDeviceToHost, caller));
   STX_CUDA(cudaMemcpyAsync(im->pinned_i, im->status_dev, 2 * sizeof(int) * B, cudaMemcpyDeviceToHost, caller));
   STX_CUDA(cudaStreamSynchronize(caller));
-  memcpy(x_host, im->pinned_f, vec * sizeof(float));
+  if (x_is_f64) {     // the reference returns scipy's float64 vector: widen while copying out
+    double* const out = static_cast<double*>(x_host);
+    parallel_ranges(vec, [=](size_t b, size_t e) {
+      for (size_t i = b; i < e; ++i) out[i] = static_cast<double>(stage[i]);
+    });
+  } else {
+    float* const out = static_cast<float*>(x_host);
+    parallel_ranges(vec, [=](size_t b, size_t e) { memcpy(out + b, stage + b, (e - b) * sizeof(float)); });
+  }
   memcpy(fun_host, im->pinned_f + vec, B * sizeof(float));
   if (nit_host) memcpy(nit_host, im->pinned_i, B * sizeof(int));
   if (nfev_host) memcpy(nfev_host, im->pinned_i + B, B * sizeof(int));

@@ -16,7 +16,7 @@ struct Lbfgs {
   int run(int maxiter, int max_evals, cudaStream_t stream);
   int result(float* x, float* fun, int* nit, int* nfev, cudaStream_t stream);
   int phase_cycles(long long* host16);
-  int minimize_host(const float* x0_host, int is_preimage, int maxiter, float* x_host, float* fun_host,
+  int minimize_host(const float* x0_host, int is_preimage, int maxiter, void* x_host, int x_is_f64, float* fun_host,
                     int* nit_host, int* nfev_host, cudaStream_t stream);
 };
 int lbfgs_create(Lbfgs** out, Plan* plan, int maxcor, int bounded, float lower, float upper);

@@ -188,17 +188,18 @@ class Synthesizer(object):
         opt = self._get_lbfgs(bounded, lo, hi)
         if self.verbose:
             return self._synthesize_device_verbose(opt, x0, is_preimage)
-        x = np.empty(self.shape_input, dtype=np.float32)
+        # the reference returns scipy's float64 vector; the library widens while copying out of its staging buffer
+        x = np.empty(self.shape_input, dtype=np.float64)
         fun = np.empty((self.batch,), dtype=np.float32)
         nit = np.empty((self.batch,), dtype=np.int32)
         nfev = np.empty((self.batch,), dtype=np.int32)
-        _lib.check(_lib.lib().stx_lbfgs_minimize_host(opt, x0.ctypes.data, int(bool(is_preimage)),
-                                                      int(self.options["maxiter"]), x.ctypes.data, fun.ctypes.data,
-                                                      nit.ctypes.data, nfev.ctypes.data, _lib.stream_ptr()))
+        _lib.check(_lib.lib().stx_lbfgs_minimize_host_f64(opt, x0.ctypes.data, int(bool(is_preimage)),
+                                                          int(self.options["maxiter"]), x.ctypes.data, fun.ctypes.data,
+                                                          nit.ctypes.data, nfev.ctypes.data, _lib.stream_ptr()))
         self.last_result = {"nit": nit, "nfev": nfev, "fun": fun}
         if self.batch == 1:
-            return x.reshape(self.shape_input[1:]).astype(np.float64), float(fun[0])
-        return x.astype(np.float64), fun
+            return x.reshape(self.shape_input[1:]), float(fun[0])
+        return x, fun
 
     def _synthesize_scipy(self, x0, bounds, is_preimage):
         from scipy.optimize import minimize
