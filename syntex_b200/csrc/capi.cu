@@ -20,6 +20,7 @@ extern int g_lbfgs_no_graph;
 extern int g_debug_f8_single_cta;
 extern int g_debug_conv1_1_cuda_cores;
 extern int g_debug_pair;
+extern int g_debug_no_mask_bits;
 extern int g_lbfgs_serial_active;
 }  // namespace stx
 
@@ -57,6 +58,7 @@ int stx_debug_set(int key, int value) {
     case 13: g_debug_conv1_1_cuda_cores = value; return STX_OK;
     case 14: g_lbfgs_serial_active = value; return STX_OK;
     case 15: g_debug_pair = value; return STX_OK;
+    case 16: g_debug_no_mask_bits = value; return STX_OK;
     default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
   }
 }
@@ -111,6 +113,9 @@ int stx_plan_copy_feature_f32(stx_plan* plan, int layer, float* out, void* strea
   Plan* p = plan->p;
   STX_REQUIRE(layer >= 0 && layer <= p->topmost, "layer index out of range for this plan");
   const size_t n = static_cast<size_t>(p->B) * p->lh[layer] * p->lw[layer] * p->lc[layer];
+  if (!p->hi_valid[layer])
+    return fail(STX_ERR_STATE, "stx_plan_copy_feature_f32: this plan keeps only the ReLU sign bits of that layer "
+                               "(create it with STX_PLAN_FULL_FEATURES to record every layer)");
   if (p->split == 2)
     return f16f8_to_f32_launch(p->act[layer], p->lo_valid[layer] ? p->act_lo[layer] : nullptr, n, p->lc[layer], out,
                                S(stream));
@@ -272,6 +277,8 @@ int stx_plan_feature_bf16(stx_plan* plan, int layer, const void** hi, const void
   Plan* p = plan->p;
   STX_REQUIRE(layer >= 0 && layer <= p->topmost, "stx_plan_feature_bf16: layer out of range");
   if (p->split == 2) return fail(STX_ERR_STATE, "stx_plan_feature_bf16: an f16+f8 plan keeps fp16 / e4m3 planes, not bf16");
+  if (!p->hi_valid[layer])
+    return fail(STX_ERR_STATE, "stx_plan_feature_bf16: this plan keeps only the ReLU sign bits of that layer");
   *hi = p->act[layer];
   if (lo) *lo = p->lo_valid[layer] ? p->act_lo[layer] : nullptr;
   return STX_OK;

@@ -35,6 +35,12 @@ struct ConvKernelParams {
   // zeroed where up_mask <= 0 (the activations of the convolution that fed the pool)
   bf16* up_out;
   const bf16* up_mask;
+  // One-bit ReLU masks for a convolution whose full-resolution result is read by nobody but the AvgPoolGrad + ReluGrad
+  // scatter of the backward pass (the layers in front of a fused pool: conv1_2, conv2_2, conv3_4, conv4_4 in the
+  // Gatys plans): bit j of word [ch0 / 32][pixel] = result of channel ch0 + j > 0. The forward writes bits_out INSTEAD
+  // of `out` (which may then be null), the scatter reads up_bits instead of up_mask: 1/16 of the bytes both ways.
+  uint32_t* bits_out;          // [cout / 32][nimg * H * W]
+  const uint32_t* up_bits;     // [cout / 32][nimg * 2H * 2W]
   // conv1_1 input-gradient mode (N tile 16, channels 0..2 real): fp32 [nimg,H,W,3] = acc * 255 (* sigmoid')
   float* rgb_out;
   const float* rgb_image;
@@ -232,7 +238,38 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
         }
       }
     }
-    if (p.up_out) {
+    if (p.bits_out) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) word |= (v[j] > 0.0f ? 1u : 0u) << j;
+      p.bits_out[static_cast<size_t>(ch0 >> 5) * (static_cast<size_t>(p.nimg) * p.H * p.W) +
+                 (static_cast<size_t>(n) * p.H + h) * p.W + w] = word;
+    }
+    if (p.up_out && p.up_bits) {
+      const int H2 = 2 * p.H, W2 = 2 * p.W;
+      const size_t plane = static_cast<size_t>(p.nimg) * H2 * W2;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const size_t pix = (static_cast<size_t>(n) * H2 + 2 * h + dy) * W2 + 2 * w;      // even: the pair is 8-byte aligned
+        const uint2 wd = __ldg(reinterpret_cast<const uint2*>(p.up_bits + static_cast<size_t>(ch0 >> 5) * plane + pix));
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const uint32_t word = dx ? wd.y : wd.x;
+          Pack8 po[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              po[j].h2[e] = __floats2bfloat162_rn(((word >> (8 * j + 2 * e)) & 1u) ? 0.25f * v[8 * j + 2 * e] : 0.0f,
+                                                  ((word >> (8 * j + 2 * e + 1)) & 1u) ? 0.25f * v[8 * j + 2 * e + 1] : 0.0f);
+            }
+          }
+          const size_t uo = (pix + dx) * p.cout + ch0;
+          st256(p.up_out + uo, po[0].u, po[1].u);
+          st256(p.up_out + uo + 16, po[2].u, po[3].u);
+        }
+      }
+    } else if (p.up_out) {
       const int H2 = 2 * p.H, W2 = 2 * p.W;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
@@ -257,9 +294,9 @@ __device__ __forceinline__ void conv_epilogue_store(const ConvKernelParams& p, f
         }
       }
     } else if (FMT == 2) {
-      store_f16f8_32(v, p.out, p.out_lo, (static_cast<size_t>(n) * p.H + h) * p.W + w, p.cout, ch0);
+      if (p.out) store_f16f8_32(v, p.out, p.out_lo, (static_cast<size_t>(n) * p.H + h) * p.W + w, p.cout, ch0);
       if (p.aux_out) store_bf16_32(v, p.aux_out + off);
-    } else {
+    } else if (p.out) {
       // the low halves are optional even in split mode: a layer that only feeds a fused pool (whose hi/lo outputs
       // carry the precision forward) and the backward mask needs its high plane only
       bf16* lo_dst = (SPLIT && p.out_lo) ? p.out_lo + off : nullptr;

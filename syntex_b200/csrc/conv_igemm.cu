@@ -223,6 +223,8 @@ int launch_bn(const ConvOp& op, cudaStream_t stream) {
   p.pool_out_lo = nullptr;
   p.up_out = op.up_out;
   p.up_mask = op.up_mask;
+  p.bits_out = nullptr;
+  p.up_bits = nullptr;
   p.export_out = op.export_out;
   p.corr_scale = 1.0f;
   p.aux_out = nullptr;
@@ -317,6 +319,8 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->pool_out_lo = nullptr;
   op->up_out = nullptr;
   op->up_mask = nullptr;
+  op->bits_out = nullptr;
+  op->up_bits = nullptr;
   op->export_out = nullptr;
   op->corr_scale = 1.0f;
   op->aux_out = nullptr;

@@ -692,6 +692,8 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.pool_out_lo = op.pool_out_lo;
   p.up_out = op.up_out;
   p.up_mask = op.up_mask;
+  p.bits_out = op.bits_out;
+  p.up_bits = op.up_bits;
   p.export_out = op.export_out;
   p.corr_scale = op.corr_scale;
   p.aux_out = op.aux_out;
@@ -849,6 +851,8 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->pool_out_lo = nullptr;
   op->up_out = nullptr;
   op->up_mask = nullptr;
+  op->bits_out = nullptr;
+  op->up_bits = nullptr;
   op->export_out = nullptr;
   op->split = 0;
   op->relu = 0;
@@ -914,7 +918,9 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
     STX_REQUIRE(op.rgb_out != nullptr && op.mt == 2 && !op.split, "conv1_1 dgrad: bad configuration");
     return launch_patch<16, 2, false, 2>(op, stream);   // two CTAs per SM: the single MMA issuer is the limit
   }
-  STX_REQUIRE(op.out != nullptr || op.up_out != nullptr, "conv: output not set");
+  STX_REQUIRE(op.out != nullptr || op.up_out != nullptr || (op.bits_out != nullptr && op.pool_out != nullptr),
+              "conv: output not set");
+  STX_REQUIRE((op.bits_out == nullptr && op.up_bits == nullptr) || op.cout % 32 == 0, "conv: bit masks need 32-channel groups");
   STX_REQUIRE(op.pool_out == nullptr || (op.H % 2 == 0 && op.W % 2 == 0), "conv: fused pooling needs even H and W");
   if (op.split == 2) {
     STX_REQUIRE(op.out_lo != nullptr || op.pool_out_lo != nullptr, "conv f16+f8: correction-plane output not set");

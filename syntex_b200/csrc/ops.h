@@ -35,6 +35,8 @@ struct ConvOp {
   bf16* pool_out_lo;
   bf16* up_out;              // fused AvgPoolGrad + ReluGrad scatter (replaces `out`)
   const bf16* up_mask;
+  uint32_t* bits_out;        // one-bit ReLU mask of the result, written instead of `out` (conv_common.cuh)
+  const uint32_t* up_bits;   // ... and read by the scatter instead of up_mask
   bf16* export_out;          // copy of the value after the addend (total gradient w.r.t. this layer's features)
   float* rgb_out;            // conv1_1 input-gradient mode of the patch kernel (bn == 16)
   const float* rgb_image;

@@ -12,6 +12,7 @@ namespace stx {
 int g_debug_dgrad_variant = 0;      // variant code for the dgrad convolutions (0 = automatic)
 int g_debug_no_gram_fusion = 0;     // 1 = stand-alone Gram-gradient launches
 int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
+int g_debug_no_mask_bits = 0;       // 1 = the convolutions in front of a pool keep their full planes as ReLU masks (key 16)
 int g_debug_tiled_weights = 0;      // 1 = fetch weight tiles with 1-D bulk copies from tiled pre-swizzled packs
                                     // (measured: no gain over tensor-map fetches, costs a second weight copy: off)
 int g_debug_conv1_1_cuda_cores = 0;  // 1 = CUDA-core conv1_1 forward in the f16 + f8 plans too (stx_debug_set key 13)
@@ -145,6 +146,7 @@ Timeline::~Timeline() {
 Plan::~Plan() {
   cudaFree(arena);
   cudaFree(splitk_ws);
+  for (uint32_t* b : mask_bits) cudaFree(b);
   cudaFree(splitk_counters);
   if (pinned) cudaFreeHost(pinned);
   if (side) cudaStreamDestroy(side);
@@ -263,6 +265,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
   p->export_grads = (flags & STX_PLAN_EXPORT_LAYER_GRADS) ? 1 : 0;
   p->full_features = (flags & STX_PLAN_FULL_FEATURES) ? 1 : 0;
   for (int l = 0; l < kNumLayers; ++l) p->lo_valid[l] = p->split != 0;
+  for (int l = 0; l < kNumLayers; ++l) p->hi_valid[l] = true;
   int h = H, w = W, convs_needed = 0;
   for (int l = 0; l <= topmost; ++l) {
     const LayerSpec& s = kLayers[l];
@@ -466,6 +469,29 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
         cur ^= 1;
       }
       prod.up_mask = p->act[l - 1];
+      // The convolution in front of a fused pool: its full-resolution result is read by this scatter alone, and only
+      // for its sign - the forward writes one bit per element instead of the plane (conv_common.cuh, bits_out).
+      ConvOp& fw = p->fwd[l - 1];
+      if (!p->full_features && !g_debug_no_mask_bits && prod.patch && fw.patch && fw.pool_out != nullptr &&
+          p->lc[l - 1] % 32 == 0) {
+        const size_t words = static_cast<size_t>(B) * p->lh[l - 1] * p->lw[l - 1] * (p->lc[l - 1] / 32);
+        uint32_t* bits = nullptr;
+        e = cudaMalloc(&bits, words * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+          rc = cuda_fail(e, "plan_create: ReLU bit masks");
+        } else {
+          p->mask_bits.push_back(bits);
+          p->arena_bytes += words * sizeof(uint32_t);    // reported by stx_plan_device_bytes
+          fw.bits_out = bits;
+          fw.out = nullptr;
+          fw.out_lo = nullptr;
+          fw.aux_out = nullptr;
+          prod.up_bits = bits;
+          prod.up_mask = nullptr;
+          p->hi_valid[l - 1] = false;
+          p->lo_valid[l - 1] = false;
+        }
+      }
     } else {
       BwdStep st;
       st.kind = BwdStep::kPoolBwd;

@@ -87,6 +87,8 @@ struct Plan {
                                    // 2 = f16 + f8 (fp16 planes + e4m3 correction planes: two MMAs' time per MAC)
   int full_features = 0;           // keep the low half of every recorded layer (feature export), not only those the path reads
   bool lo_valid[kNumLayers] = {};  // act_lo[l] is written by the forward
+  bool hi_valid[kNumLayers] = {};  // act[l] is written by the forward (false: the layer only leaves a one-bit ReLU mask)
+  std::vector<uint32_t*> mask_bits;
   bf16* act[kNumLayers] = {};      // recorded layers (high halves; the only halves in plain mode)
   bf16* act_lo[kNumLayers] = {};   // low halves (split mode) / e4m3 correction planes (f16 + f8)
   bf16* act_bf[kNumLayers] = {};   // f16 + f8: bf16 copy of the LOSS layers (A operand of the Gram gradient)

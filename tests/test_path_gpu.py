@@ -217,3 +217,35 @@ def test_step_requires_target_and_shapes(raw_weights):
     from syntex_b200.texture_utils import Vgg19Extractor
     with pytest.raises(SyntexLibraryError):
         Vgg19Extractor(raw_weights).build(torch.zeros((1, 40, 40, 3)))   # odd map at pool4 (40/8 = 5)
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
+def test_one_bit_relu_masks_equal_the_recorded_planes(precision, raw_weights):
+    """The convolutions in front of a pool (conv1_2, conv2_2, conv3_4, conv4_4) leave one bit per element (result > 0)
+    instead of their full-resolution plane: the AvgPoolGrad + ReluGrad scatter of the backward reads those bits.
+    Against the plans that keep the planes (stx_debug_set key 16): same loss bit for bit (the forward values do not
+    change), same gradient except where a positive result rounds to zero in 16 bits."""
+    from syntex_b200 import _lib
+    from syntex_b200.texture_utils.vgg19 import LAYER_INDEX
+    L = _lib.lib()
+    S, B = 128, 3
+    tg = np.stack([so.synthetic_texture(S, seed=30 + j) for j in range(B)])
+    x0 = np.stack([so.init_input((S, S, 3), False, j) for j in range(B)])
+    res = []
+    try:
+        for planes in (0, 1):
+            _lib.check(L.stx_debug_set(16, planes))
+            syn = make_syn(raw_weights, S, batch=B, precision=precision)
+            syn.compute_gram(tg, update=True)
+            res.append(syn.step(x0))
+            if not planes:      # the plane of such a layer does not exist on this plan: asking for it is an error
+                h, w, c = syn._plan.layer_shape(LAYER_INDEX["conv1_2"])
+                out = torch.empty((B, h, w, c), dtype=torch.float32, device="cuda")
+                with pytest.raises(_lib.SyntexLibraryError):
+                    _lib.check(L.stx_plan_copy_feature_f32(syn._plan.handle, LAYER_INDEX["conv1_2"], out.data_ptr(),
+                                                           _lib.stream_ptr()))
+            syn.close()
+    finally:
+        _lib.check(L.stx_debug_set(16, 0))
+    np.testing.assert_array_equal(res[0]["func"], res[1]["func"])
+    assert relerr(torch.from_numpy(res[0]["grad"]), torch.from_numpy(res[1]["grad"])) < 1e-5
