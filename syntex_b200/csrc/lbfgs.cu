@@ -50,9 +50,10 @@ namespace stx {
 namespace {
 
 constexpr int kMaxM = 32;
-constexpr int kVec = 4;
+constexpr int kVec = 4;                     // granularity of the problem size and of the active kernel's loads
+constexpr int kPer = 8;                     // elements per thread in the dots / update kernels: one 16-byte load of fp16 history
 constexpr int kThreads = 256;
-constexpr int kChunk = kThreads * kVec;     // elements per block
+constexpr int kChunk = kThreads * kPer;     // elements per block
 constexpr int kNP0 = 8;                     // scalar partial sums per block (dots kernel)
 constexpr int kNPH = 6;                     // partial sums per history pair
 constexpr int kNP = kNP0 + kNPH * kMaxM;
@@ -112,6 +113,7 @@ struct Vecs {
   Tables* tab;                           // [B]
   long long* dbg;                        // [16] clock64 stamps of job 0's decide kernel (diagnostic, stx_lbfgs_phase_cycles)
   int n, m, nblk, bounded;
+  int hn;                                // elements between history vectors: n rounded up to 8 (16-byte aligned rows)
   float lo, hi;
 };
 
@@ -124,23 +126,58 @@ __device__ __forceinline__ bool is_free(float x, float g, float lo, float hi, in
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-// four stored history elements (unscaled)
-__device__ __forceinline__ float4 ldh4(const hist_t* p) {
-  const uint2 raw = *reinterpret_cast<const uint2*>(p);
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-  return make_float4(a.x, a.y, b.x, b.y);
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// eight fp32 elements of a vector, the two halves guarded separately (n is a multiple of 4, not of 8)
+__device__ __forceinline__ void ld8(const float* p, bool in_a, bool in_b, float (&v)[8]) {
+  const float4 a = in_a ? ld4(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b = in_b ? ld4(p + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-// v * inv_scale rounded to storage; returns what was stored (unscaled) so that the caller can keep using it
-__device__ __forceinline__ float4 sth4(hist_t* p, float4 v, float inv_scale) {
-  const __half2 a = __floats2half2_rn(v.x * inv_scale, v.y * inv_scale);
-  const __half2 b = __floats2half2_rn(v.z * inv_scale, v.w * inv_scale);
-  uint2 raw;
-  raw.x = *reinterpret_cast<const uint32_t*>(&a);
-  raw.y = *reinterpret_cast<const uint32_t*>(&b);
-  *reinterpret_cast<uint2*>(p) = raw;
-  const float2 fa = __half22float2(a), fb = __half22float2(b);
-  return make_float4(fa.x, fa.y, fb.x, fb.y);
+__device__ __forceinline__ void st8(float* p, bool in_a, bool in_b, const float (&v)[8]) {
+  if (in_a) st4(p, make_float4(v[0], v[1], v[2], v[3]));
+  if (in_b) st4(p + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+__device__ __forceinline__ float dot8(const float (&a)[8], const float (&b)[8]) {
+  float t = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) t = fmaf(a[e], b[e], t);
+  return t;
+}
+// eight stored history elements (unscaled), one 16-byte load; rows are padded to 8 elements, so the load is always in
+// range and the elements past n are zero (never written)
+__device__ __forceinline__ void ldh8(const hist_t* p, float (&v)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
+  }
+}
+__device__ __forceinline__ uint4 ldh8_raw(const hist_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void cvth8(const uint4& raw, float (&v)[8]) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
+  }
+}
+constexpr int kHistTrip = 4;     // history pairs per loop trip: 2 x kHistTrip 16-byte loads in flight per thread
+// v * inv_scale rounded to storage; v becomes what was stored (unscaled) so that the caller can keep using it
+__device__ __forceinline__ void sth8(hist_t* p, float (&v)[8], float inv_scale) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half2 h = __floats2half2_rn(v[2 * e] * inv_scale, v[2 * e + 1] * inv_scale);
+    w[e] = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 f = __half22float2(h);
+    v[2 * e] = f.x;
+    v[2 * e + 1] = f.y;
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 // power of two that maps a vector of squared 2-norm `norm2` below 2^15 in every element (lbfgsb_model.f16_scale)
 __device__ __forceinline__ float hist_scale(double norm2) {
@@ -150,7 +187,6 @@ __device__ __forceinline__ float hist_scale(double norm2) {
   frexp(nrm, &e);
   return ldexpf(1.f, e - 15);
 }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -159,10 +195,34 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sums of EIGHT quantities over the warp with 9 shuffles instead of 8 x 5: at every step each lane hands half of its
+// quantities to its partner and keeps (and accumulates) the other half. Lane 4q ends with the sum of quantity q.
+// Fixed order => bit-reproducible.
+__device__ __forceinline__ float warp_sum8(const float (&a)[8], int lane) {
+  float b[4], c[2];
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = u16 ? a[i] : a[i + 4], keep = u16 ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = u8 ? b[i] : b[i + 2], keep = u8 ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const float send = u4 ? c[0] : c[1], keep = u4 ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  d += __shfl_xor_sync(0xffffffffu, d, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;     // lane l (l % 4 == 0): quantity 4 * bit4 + 2 * bit3 + bit2 of l
+}
+__device__ __forceinline__ int warp_sum8_quantity(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
 // ------------------------------------------------------------------------------------------------ dots
 // scalars: 0 gt'd  1 s'y  2 y'y  3 Pg'Pg  4 s'Pg  5 y'Pg  6 s's  7 -
 // per pair j: S_j'y  Y_j'y  S_j'Pg  Y_j'Pg  S_j's  Y_j's        (s = xt - x, y = gt - g, Pg = gt on F of the trial point)
-__global__ void __launch_bounds__(kThreads) lbfgs_dots_kernel(Vecs v) {
+__global__ void __launch_bounds__(kThreads, 4) lbfgs_dots_kernel(Vecs v) {
   pdl_launch_dependents();   // programmatic dependent launch: see launch_pdl (common.h)
   pdl_wait();
   const int b = blockIdx.y;
@@ -170,47 +230,60 @@ __global__ void __launch_bounds__(kThreads) lbfgs_dots_kernel(Vecs v) {
   if (c.mode == kDone) return;
   __shared__ float red[kThreads / 32][kNP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * kChunk + threadIdx.x * kVec;
-  const bool in = i0 < v.n;
+  const int i0 = blockIdx.x * kChunk + threadIdx.x * kPer;
+  const bool in_a = i0 < v.n, in_b = i0 + 4 < v.n;
   const size_t off = static_cast<size_t>(b) * v.n + i0;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 x = in ? ld4(v.x + off) : z4;
-  const float4 xt = in ? ld4(v.xt + off) : z4;
-  const float4 g = in ? ld4(v.g + off) : z4;
-  const float4 gt = in ? ld4(v.gt + off) : z4;
-  const float4 d = in ? ld4(v.d + off) : z4;
+  float x[8], xt[8], g[8], gt[8], d[8];
+  ld8(v.x + off, in_a, in_b, x);
+  ld8(v.xt + off, in_a, in_b, xt);
+  ld8(v.g + off, in_a, in_b, g);
+  ld8(v.gt + off, in_a, in_b, gt);
+  ld8(v.d + off, in_a, in_b, d);
   const float lo = v.lo, hi = v.hi;
   const int bd = v.bounded;
 
-  float4 s, y, pg;
-  s.x = xt.x - x.x; s.y = xt.y - x.y; s.z = xt.z - x.z; s.w = xt.w - x.w;
-  y.x = gt.x - g.x; y.y = gt.y - g.y; y.z = gt.z - g.z; y.w = gt.w - g.w;
-  pg.x = (in && is_free(xt.x, gt.x, lo, hi, bd)) ? gt.x : 0.f;
-  pg.y = (in && is_free(xt.y, gt.y, lo, hi, bd)) ? gt.y : 0.f;
-  pg.z = (in && is_free(xt.z, gt.z, lo, hi, bd)) ? gt.z : 0.f;
-  pg.w = (in && is_free(xt.w, gt.w, lo, hi, bd)) ? gt.w : 0.f;
-  float vals[kNP0] = {dot4(gt, d), dot4(s, y), dot4(y, y), dot4(pg, pg), dot4(s, pg), dot4(y, pg), dot4(s, s), 0.f};
+  float s[8], y[8], pg[8];
 #pragma unroll
-  for (int k = 0; k < kNP0; ++k) {
-    const float r = warp_sum(vals[k]);
-    if (lane == 0) red[warp][k] = r;
+  for (int e = 0; e < 8; ++e) {
+    const bool in = e < 4 ? in_a : in_b;
+    s[e] = xt[e] - x[e];
+    y[e] = gt[e] - g[e];
+    pg[e] = (in && is_free(xt[e], gt[e], lo, hi, bd)) ? gt[e] : 0.f;
+  }
+  static_assert(kNP0 == 8 && kNPH <= 8, "warp_sum8 carries eight quantities");
+  const int myq = warp_sum8_quantity(lane);
+  {
+    const float vals[8] = {dot8(gt, d), dot8(s, y), dot8(y, y), dot8(pg, pg), dot8(s, pg), dot8(y, pg), dot8(s, s), 0.f};
+    const float r = warp_sum8(vals, lane);
+    if ((lane & 3) == 0) red[warp][myq] = r;
   }
   const int nh = c.nh, head = c.head, m = v.m;
-  for (int j = 0; j < nh; ++j) {
-    const int slot = (head + j) % m;
-    const size_t hoff = (static_cast<size_t>(b) * m + slot) * v.n + i0;
-    const float4 sj = in ? ldh4(v.S + hoff) : z4;
-    const float4 yj = in ? ldh4(v.Y + hoff) : z4;
-    const float a0 = warp_sum(dot4(sj, y));
-    const float a1 = warp_sum(dot4(yj, y));
-    const float a2 = warp_sum(dot4(sj, pg));
-    const float a3 = warp_sum(dot4(yj, pg));
-    const float a4 = warp_sum(dot4(sj, s));
-    const float a5 = warp_sum(dot4(yj, s));
-    if (lane == 0) {
-      float* r = &red[warp][kNP0 + kNPH * j];
-      const float hsj = c.hs[slot], hyj = c.hy[slot];      // powers of two: exact
-      r[0] = a0 * hsj; r[1] = a1 * hyj; r[2] = a2 * hsj; r[3] = a3 * hyj; r[4] = a4 * hsj; r[5] = a5 * hyj;
+  // kHistTrip pairs per trip: all their 16-byte loads are issued (and stay raw fp16, 4 registers each) before the first
+  // conversion - the kernel is bound by the bytes in flight per SM (measured: 2.6 TB/s with two 8-byte loads per trip)
+  for (int j = 0; j < nh; j += kHistTrip) {
+    uint4 rs[kHistTrip], ry[kHistTrip];
+#pragma unroll
+    for (int q = 0; q < kHistTrip; ++q) {
+      rs[q] = ry[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (in_a && j + q < nh) {
+        const size_t h = (static_cast<size_t>(b) * m + (head + j + q) % m) * v.hn + i0;
+        rs[q] = ldh8_raw(v.S + h);
+        ry[q] = ldh8_raw(v.Y + h);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kHistTrip; ++q) {
+      if (j + q >= nh) break;
+      float sj[8], yj[8];
+      cvth8(rs[q], sj);
+      cvth8(ry[q], yj);
+      const float vals[8] = {dot8(sj, y), dot8(yj, y), dot8(sj, pg), dot8(yj, pg), dot8(sj, s), dot8(yj, s), 0.f, 0.f};
+      const float r = warp_sum8(vals, lane);
+      if ((lane & 3) == 0 && myq < kNPH) {
+        const int slot = (head + j + q) % m;
+        // even quantities are products with S_j, odd ones with Y_j; the scales are powers of two: exact
+        red[warp][kNP0 + kNPH * (j + q) + myq] = r * ((myq & 1) ? c.hy[slot] : c.hs[slot]);
+      }
     }
   }
   __syncthreads();
@@ -291,10 +364,10 @@ __global__ void __launch_bounds__(kThreads) lbfgs_active_kernel(Vecs v) {
   float gscale = 1.f;
   {
     if (ga < nh) {
-      gsrc = v.Y + (static_cast<size_t>(b) * m + (head + ga) % m) * v.n;
+      gsrc = v.Y + (static_cast<size_t>(b) * m + (head + ga) % m) * v.hn;
       gscale = c.hy[(head + ga) % m];
     } else if (ga < 2 * nh) {
-      gsrc = v.S + (static_cast<size_t>(b) * m + (head + ga - nh) % m) * v.n;
+      gsrc = v.S + (static_cast<size_t>(b) * m + (head + ga - nh) % m) * v.hn;
       gscale = c.hs[(head + ga - nh) % m];
     } else {
       gsrc = nullptr;
@@ -869,7 +942,7 @@ __global__ void __launch_bounds__(kDecideThreads) lbfgs_decide_kernel(Vecs v) {
 }
 
 // ------------------------------------------------------------------------------------------------ update
-__global__ void __launch_bounds__(kThreads) lbfgs_update_kernel(Vecs v) {
+__global__ void __launch_bounds__(kThreads, 3) lbfgs_update_kernel(Vecs v) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.y;
@@ -877,101 +950,107 @@ __global__ void __launch_bounds__(kThreads) lbfgs_update_kernel(Vecs v) {
   const int action = c.action;
   if (action == kNone) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * kChunk + threadIdx.x * kVec;
-  const bool in = i0 < v.n;
+  const int i0 = blockIdx.x * kChunk + threadIdx.x * kPer;
+  const bool in_a = i0 < v.n, in_b = i0 + 4 < v.n;
   const size_t off = static_cast<size_t>(b) * v.n + i0;
   const float lo = v.lo, hi = v.hi;
   const int bd = v.bounded;
   const float stp = c.stp;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   if (action == kRetry) {
-    if (in) {
-      const float4 x = ld4(v.x + off), d = ld4(v.d + off);
-      float4 t;
-      t.x = clipf(fmaf(stp, d.x, x.x), lo, hi, bd);
-      t.y = clipf(fmaf(stp, d.y, x.y), lo, hi, bd);
-      t.z = clipf(fmaf(stp, d.z, x.z), lo, hi, bd);
-      t.w = clipf(fmaf(stp, d.w, x.w), lo, hi, bd);
-      st4(v.xt + off, t);
-    }
+    float x[8], d[8], t[8];
+    ld8(v.x + off, in_a, in_b, x);
+    ld8(v.d + off, in_a, in_b, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) t[e] = clipf(fmaf(stp, d[e], x[e]), lo, hi, bd);
+    st8(v.xt + off, in_a, in_b, t);
     return;
   }
 
-  float4 x = z4, g = z4, s = z4, y = z4;
+  float x[8], g[8], s[8], y[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = g[e] = s[e] = y[e] = 0.f;
   if (action == kRestart) {
-    if (in) {
-      x = ld4(v.x + off);
-      g = ld4(v.g + off);
-    }
+    ld8(v.x + off, in_a, in_b, x);
+    ld8(v.g + off, in_a, in_b, g);
   } else {   // kAccept, kStartAccept, kFinalAccept: the trial point becomes the iterate
-    if (in) {
-      const float4 xo = ld4(v.x + off), go = ld4(v.g + off);
-      x = ld4(v.xt + off);
-      g = ld4(v.gt + off);
-      s.x = x.x - xo.x; s.y = x.y - xo.y; s.z = x.z - xo.z; s.w = x.w - xo.w;
-      y.x = g.x - go.x; y.y = g.y - go.y; y.z = g.z - go.z; y.w = g.w - go.w;
-      st4(v.x + off, x);
-      st4(v.g + off, g);
-      if (action == kAccept && c.push) {
-        const size_t hoff = (static_cast<size_t>(b) * v.m + c.slot_new) * v.n + i0;
-        // s, y continue as the STORED (unscaled) halves: the step below multiplies them by the scaled coefficients
-        s = sth4(v.S + hoff, s, 1.f / c.hs[c.slot_new]);
-        y = sth4(v.Y + hoff, y, 1.f / c.hy[c.slot_new]);
-      }
+    float xo[8], go[8];
+    ld8(v.x + off, in_a, in_b, xo);
+    ld8(v.g + off, in_a, in_b, go);
+    ld8(v.xt + off, in_a, in_b, x);
+    ld8(v.gt + off, in_a, in_b, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s[e] = x[e] - xo[e];
+      y[e] = g[e] - go[e];
+    }
+    st8(v.x + off, in_a, in_b, x);
+    st8(v.g + off, in_a, in_b, g);
+    if (action == kAccept && c.push && in_a) {
+      const size_t hoff = (static_cast<size_t>(b) * v.m + c.slot_new) * v.hn + i0;
+      // s, y continue as the STORED (unscaled) halves: the step below multiplies them by the scaled coefficients
+      sth8(v.S + hoff, s, 1.f / c.hs[c.slot_new]);
+      sth8(v.Y + hoff, y, 1.f / c.hy[c.slot_new]);
     }
     if (action == kFinalAccept) return;
   }
 
   // New step over the free variables: -g / theta + sum_j cs_j S_j + cy_j Y_j (coefficients from the decide kernel;
   // the projected gradient step without history), projected onto the box: z = clip(x + step), d = z - x.
-  const bool f0 = is_free(x.x, g.x, lo, hi, bd), f1 = is_free(x.y, g.y, lo, hi, bd);
-  const bool f2 = is_free(x.z, g.z, lo, hi, bd), f3 = is_free(x.w, g.w, lo, hi, bd);
   const int nh = (action == kAccept) ? c.nh : 0;
   const float ti = nh > 0 ? c.theta_inv : 1.f;
-  float4 acc = make_float4(-ti * g.x, -ti * g.y, -ti * g.z, -ti * g.w);
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = -ti * g[e];
   if (nh > 0) {
     const int nold = c.push ? nh - 1 : nh;
-    for (int j = 0; j < nold; ++j) {
-      const int slot = (c.head + j) % v.m;
-      const size_t hoff = (static_cast<size_t>(b) * v.m + slot) * v.n + i0;
-      const float4 sj = in ? ldh4(v.S + hoff) : z4;
-      const float4 yj = in ? ldh4(v.Y + hoff) : z4;
-      const float a = c.cs[j], bb = c.cy[j];
-      acc.x = fmaf(a, sj.x, fmaf(bb, yj.x, acc.x));
-      acc.y = fmaf(a, sj.y, fmaf(bb, yj.y, acc.y));
-      acc.z = fmaf(a, sj.z, fmaf(bb, yj.z, acc.z));
-      acc.w = fmaf(a, sj.w, fmaf(bb, yj.w, acc.w));
+    for (int j = 0; j < nold; j += kHistTrip) {       // see the dots kernel
+      uint4 rs[kHistTrip], ry[kHistTrip];
+#pragma unroll
+      for (int q = 0; q < kHistTrip; ++q) {
+        rs[q] = ry[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (in_a && j + q < nold) {
+          const size_t h = (static_cast<size_t>(b) * v.m + (c.head + j + q) % v.m) * v.hn + i0;
+          rs[q] = ldh8_raw(v.S + h);
+          ry[q] = ldh8_raw(v.Y + h);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kHistTrip; ++q) {
+        if (j + q >= nold) break;
+        float sj[8], yj[8];
+        cvth8(rs[q], sj);
+        cvth8(ry[q], yj);
+        const float a = c.cs[j + q], bb = c.cy[j + q];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(a, sj[e], fmaf(bb, yj[e], acc[e]));
+      }
     }
     if (c.push) {
       const float a = c.cs[nh - 1], bb = c.cy[nh - 1];
-      acc.x = fmaf(a, s.x, fmaf(bb, y.x, acc.x));
-      acc.y = fmaf(a, s.y, fmaf(bb, y.y, acc.y));
-      acc.z = fmaf(a, s.z, fmaf(bb, y.z, acc.z));
-      acc.w = fmaf(a, s.w, fmaf(bb, y.w, acc.w));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(a, s[e], fmaf(bb, y[e], acc[e]));
     }
   }
-  float4 d;
-  d.x = f0 ? clipf(x.x + acc.x, lo, hi, bd) - x.x : 0.f;
-  d.y = f1 ? clipf(x.y + acc.y, lo, hi, bd) - x.y : 0.f;
-  d.z = f2 ? clipf(x.z + acc.z, lo, hi, bd) - x.z : 0.f;
-  d.w = f3 ? clipf(x.w + acc.w, lo, hi, bd) - x.w : 0.f;
+  float d[8], t[8];
   float gd = 0.f, smax = 3.0e38f;
-  if (in) {
-    st4(v.d + off, d);
-    float4 t;
-    t.x = clipf(fmaf(stp, d.x, x.x), lo, hi, bd);
-    t.y = clipf(fmaf(stp, d.y, x.y), lo, hi, bd);
-    t.z = clipf(fmaf(stp, d.z, x.z), lo, hi, bd);
-    t.w = clipf(fmaf(stp, d.w, x.w), lo, hi, bd);
-    st4(v.xt + off, t);
-    gd = dot4(g, d);
-    if (bd) {
-      // lnsrlb: the largest step that keeps x + stp d inside the box
-      auto room = [&](float xi, float di) { return di > 0.f ? (hi - xi) / di : (di < 0.f ? (lo - xi) / di : 3.0e38f); };
-      smax = fminf(fminf(room(x.x, d.x), room(x.y, d.y)), fminf(room(x.z, d.z), room(x.w, d.w)));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const bool in = e < 4 ? in_a : in_b;
+    const bool fr = is_free(x[e], g[e], lo, hi, bd);
+    d[e] = fr ? clipf(x[e] + acc[e], lo, hi, bd) - x[e] : 0.f;
+    t[e] = clipf(fmaf(stp, d[e], x[e]), lo, hi, bd);
+    if (in) {
+      gd = fmaf(g[e], d[e], gd);
+      if (bd) {
+        // lnsrlb: the largest step that keeps x + stp d inside the box
+        const float room = d[e] > 0.f ? (hi - x[e]) / d[e] : (d[e] < 0.f ? (lo - x[e]) / d[e] : 3.0e38f);
+        smax = fminf(smax, room);
+      }
     }
   }
+  st8(v.d + off, in_a, in_b, d);
+  st8(v.xt + off, in_a, in_b, t);
   __shared__ float red[kThreads / 32], redm[kThreads / 32];
   const float r = warp_sum(gd);
   float mn = smax;
@@ -1102,6 +1181,7 @@ int lbfgs_create(Lbfgs** out, Plan* plan, int maxcor, int bounded, float lower, 
   im->B = B;
   Vecs& v = im->v;
   v.n = static_cast<int>(n);
+  v.hn = static_cast<int>((n + 7) & ~static_cast<size_t>(7));
   v.m = maxcor;
   v.nblk = static_cast<int>((n + kChunk - 1) / kChunk);
   v.bounded = bounded;
@@ -1109,7 +1189,8 @@ int lbfgs_create(Lbfgs** out, Plan* plan, int maxcor, int bounded, float lower, 
   v.hi = upper;
   const size_t vec = static_cast<size_t>(B) * n;
   const size_t total = vec * 5 + B + static_cast<size_t>(B) * v.nblk * (kNP + 2) + B;
-  const size_t hist_bytes = vec * maxcor * 2 * sizeof(hist_t);
+  const size_t hvec = static_cast<size_t>(B) * v.hn;
+  const size_t hist_bytes = hvec * maxcor * 2 * sizeof(hist_t);
   const size_t gram_bytes = static_cast<size_t>(B) * kSlices * kQ * kQ * sizeof(double);
   cudaError_t e = cudaMalloc(&im->base, total * sizeof(float));
   if (e == cudaSuccess) e = cudaMemset(im->base, 0, total * sizeof(float));
@@ -1142,7 +1223,7 @@ int lbfgs_create(Lbfgs** out, Plan* plan, int maxcor, int bounded, float lower, 
   v.gt = p; p += vec;
   v.d = p; p += vec;
   v.S = static_cast<hist_t*>(im->hist);
-  v.Y = v.S + vec * maxcor;
+  v.Y = v.S + hvec * maxcor;
   v.ft = p; p += B;
   v.part = p; p += static_cast<size_t>(B) * v.nblk * kNP;
   v.part2 = p; p += static_cast<size_t>(B) * v.nblk;
