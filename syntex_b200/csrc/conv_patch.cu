@@ -62,8 +62,8 @@ struct PatchSmem {
   static_assert(OCC == 1 || (OCC == 2 && (MT == 1 || BN == 16)), "two CTAs per SM: single-tile or N = 16 instances only");
   static constexpr int kBRows = PAIR ? BN / 2 : BN;                           // weight rows staged by this CTA
   static constexpr int kBBytes = (kBRows * 128 + 1023) & ~1023;
-  static_assert(!PAIR || (MT == 1 && RES == 0 && (BN == 128 || BN == 64) && (!SPLIT || F8)),
-                "CTA pairs: single-tile, ring weights, N tile 64 / 128, single-MMA or f16+f8");
+  static_assert(!PAIR || (MT == 1 && RES == 0 && (BN == 128 || BN == 64 || (BN == 256 && !SPLIT)) && (!SPLIT || F8)),
+                "CTA pairs: single-tile, ring weights, N tile 64 / 128 (256: single-MMA only), single-MMA or f16+f8");
   static constexpr int kBStageBytes = (SPLIT ? 2 : 1) * kBBytes;              // [hi | lo]
   static constexpr int kBudget = kSmemBudget / OCC - 2048;
   // resident mode: a small ring for the per-image Gram-difference tiles of the fused Gram gradient
@@ -812,6 +812,9 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
       pair = 1;
       mt = 1;
       if (bn == 128) occ = 1;
+      // N tile 256 for the single-MMA kernels (M = 256 x N = 256 MMAs, 128 weight rows per SM): half the operand bytes
+      // read from shared memory per MMA cycle again (input gradient at 64 jobs: 2.52 -> 2.43 ms)
+      if (bn == 128 && !split && cout % 256 == 0 && (tiles / 2) * (cout / 256) >= 74) bn = 256;
     }
   }
   op->pair = pair;
@@ -942,6 +945,7 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
   if (op.res == 1) return launch_patch<64, 1, false, 2, 1>(op, stream);
   if (op.res == 2) return launch_patch<64, 1, false, 1, 2>(op, stream);
   const bool two = op.occ == 2;
+  if (op.bn == 256 && op.pair) return launch_patch<256, 1, false, 1, 0, false, true>(op, stream);
   if (op.bn == 256) return launch_patch<256, 2, false, 1>(op, stream);
   if (op.bn == 128) {
     if (op.pair) return launch_patch<128, 1, false, 1, 0, false, true>(op, stream);

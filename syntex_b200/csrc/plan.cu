@@ -448,7 +448,8 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       BwdStep st;
       st.kind = BwdStep::kDgrad;
       rc = conv3x3_prepare(&st.conv, p->gbuf[cur], nullptr, B, p->lh[l], p->lw[l], s.cout, vgg->wd[s.conv_index],
-                           nullptr, s.cin, g_debug_dgrad_variant + ((g_debug_pair & 2) ? 1000000 : 0));
+                           nullptr, s.cin,
+                           g_debug_dgrad_variant + ((g_debug_pair & 2) ? 1000000 : 0));
       st.conv.w_tiled = g_debug_tiled_weights ? vgg->wdt[s.conv_index] : nullptr;
       st.conv.out = p->gbuf[cur ^ 1];
       st.conv.mask = (kLayers[l - 1].is_conv && loss_index(l - 1) < 0) ? p->act[l - 1] : nullptr;

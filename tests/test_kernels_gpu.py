@@ -88,6 +88,7 @@ def test_conv_cta_pairs_match_single_cta_bitwise(n, H, W, cin, cout):
     msk = torch.randn((n, H, W, cout), device="cuda", generator=g).to(torch.bfloat16)
     wf, _, _ = pack(w)
     outs = []
+    # (cout a multiple of 256: the pair instance takes N tiles of 256 - 128 weight rows per SM)
     for variant in (1000000, 1128 if cout % 128 == 0 else 1064):
         o = torch.full((n, H, W, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
         _lib.check(L().stx_conv_bf16(x.data_ptr(), n, H, W, cin, wf.data_ptr(), cout, 9, b.data_ptr(), None,
