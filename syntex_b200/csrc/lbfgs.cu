@@ -740,7 +740,6 @@ __global__ void __launch_bounds__(kDecideThreads) lbfgs_decide_kernel(Vecs v) {
   __shared__ Decision dec;
   __shared__ double K[kKN][kKN + 1];     // reduced system, last column = right-hand side
   __shared__ double wv[kKN];
-  __shared__ double pivot_inv;
   __shared__ int singular;
   static_assert(sizeof(Ctrl) % 4 == 0, "Ctrl is copied word by word");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = kDecideThreads / 32;
@@ -889,24 +888,25 @@ __global__ void __launch_bounds__(kDecideThreads) lbfgs_decide_kernel(Vecs v) {
     // theta S_A'S_A + B (D + Y_F'Y_F / theta)^-1 B' (positive definite) - the block LEL' factorisation formk computes -
     // so the natural order is stable and the pivot search, the row swaps and the back-substitution go away (each was a
     // chain of block barriers and fp64 shuffles: 105k of the kernel's 163k cycles, tests/tools/lbfgs_phases.py).
+    // One barrier per step: every thread derives the pivot's reciprocal itself (the same shared-memory word, final
+    // since the previous step's barrier), and threads map to (row group, column) without integer divisions.
+    static_assert(kDecideThreads == 512 && kKN + 1 <= 2 * 64, "elimination thread map: 8 row groups x 64 columns");
+    const int ecol = tid & 63, erow = tid >> 6;
     for (int p = 0; p < N; ++p) {
-      if (tid == 0) {
-        const double pv = K[p][p];
-        if (!(fabs(pv) > 0.0) || !isfinite(pv)) singular = 1;
-        pivot_inv = 1.0 / pv;
+      const double pv = K[p][p];
+      if (!(fabs(pv) > 0.0) || !isfinite(pv)) {     // uniform: every thread reads the same value
+        if (tid == 0) singular = 1;
+        break;
       }
-      __syncthreads();
-      if (singular) break;
-      const double inv = pivot_inv;
-      const int cols = N - p;                       // columns p+1 .. N (the right-hand side included)
-      for (int e = tid; e < (N - 1) * cols; e += kDecideThreads) {
-        int r = e / cols;
-        if (r >= p) ++r;                            // every row but the pivot row
-        const int j = p + 1 + e % cols;
-        K[r][j] -= K[r][p] * inv * K[p][j];
+      const double inv = 1.0 / pv;
+      for (int j = p + 1 + ecol; j <= N; j += 64) {   // columns p+1 .. N (the right-hand side included)
+        const double pj = K[p][j] * inv;
+        for (int r = erow; r < N; r += 8)
+          if (r != p) K[r][j] -= K[r][p] * pj;
       }
       __syncthreads();
     }
+    __syncthreads();
     stamp(4);                                 // eliminated
     if (!singular)
       for (int i = tid; i < N; i += kDecideThreads) wv[i] = K[i][N] / K[i][i];
