@@ -368,14 +368,15 @@ def run_ours(args, rank, world, local_rank):
                     "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops"],
                     # dram__bytes_read + dram__bytes_write averaged over the 22 conv launches of one evaluation in the
-                    # ncu --set full capture at 64 jobs (profiles/r02_ncu_full_conv_b64.md: 8.52 GB read + 5.14 GB written);
-                    # only meaningful at that batch with the default (f16+f8) forward
-                    "traffic": 620.8e6 if (size == 256 and batch == 64) else None,
+                    # ncu --set full capture at 64 jobs (profiles/r02_ncu_full_conv_b64_final.md: 7.24 GB read + 4.56 GB
+                    # written); only meaningful at that batch with the default (f16+f8) forward
+                    "traffic": 536.3e6 if (size == 256 and batch == 64) else None,
                     "traffic_note": "average DRAM bytes per conv launch, ncu --set full at 64 jobs "
-                                    "(profiles/r02_ncu_full_conv_b64.md): the deep layers move 160-500 MB per launch "
-                                    "(weights + one pass over their activation planes), the 64-channel layers 1.4-2.1 GB "
-                                    "(fp16 + e4m3 planes in, gradient / mask / feature planes in and out); 13.7 GB per "
-                                    "evaluation = 2.1 ms at the measured HBM rate against 7.6 ms of conv time",
+                                    "(profiles/r02_ncu_full_conv_b64_final.md): the deep layers move 160-500 MB per launch "
+                                    "(weights + one pass over their activation planes), the 64-channel layers 0.9-2.1 GB "
+                                    "(fp16 + e4m3 planes in, gradient / feature planes in and out; ReLU masks are one bit "
+                                    "per element); 11.8 GB per evaluation = 1.8 ms at the measured HBM rate against 6.6 ms "
+                                    "of conv time",
                     "executed_tflops": exec_total, "executed_frac": exec_total / peaks["bf16_tflops"],
                     "note": "achieved counts algorithmic FLOPs (2*M*N*K once per direction); the f16+f8 forward spends two kind::f16 MMA times per MAC (one f16 MMA + one f8 MMA over twice the K), executed_* counts those",
                     "avg_launch_us": 1e3 * conv_ms / max(conv_launches, 1),
