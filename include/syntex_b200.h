@@ -48,7 +48,8 @@ long long stx_launch_count(void);
 /* Bring-up knobs; key/value meanings are internal (csrc/capi.cu: descriptor strides, kernel-variant overrides, 9 =
  * programmatic dependent launch, 10 = plain stream launches instead of the optimiser's CUDA graph, 12 = one CTA per SM
  * for the 64-channel f16+f8 forward, 13 = CUDA-core conv1_1 in f16+f8 plans, 14 = active-set kernel in the main
- * stream, 15 = CTA-pair convolution instances: bit 0 forward, bit 1 input gradient, default 3). Also read from the environment at load: STX_DEBUG="key=value,...". */
+ * stream, 15 = CTA-pair convolution instances: bit 0 forward, bit 1 input gradient, default 3, 16 = full ReLU mask planes
+ * instead of sign bits, 17 = keep evaluating the finished jobs of a batch). Also read from the environment at load: STX_DEBUG="key=value,...". */
 int stx_debug_set(int key, int value);
 /* Bring-up probe of the CTA-pair MMA (tcgen05 cta_group::2): out fp32 [256][128] = a bf16 [256][64] * b bf16
  * [128][64]^T computed by one cluster of two CTAs (each loads its 128 rows of a and 64 rows of b). */

@@ -21,6 +21,7 @@ extern int g_debug_f8_single_cta;
 extern int g_debug_conv1_1_cuda_cores;
 extern int g_debug_pair;
 extern int g_debug_no_mask_bits;
+extern int g_lbfgs_no_skip;
 extern int g_lbfgs_serial_active;
 }  // namespace stx
 
@@ -59,6 +60,7 @@ int stx_debug_set(int key, int value) {
     case 14: g_lbfgs_serial_active = value; return STX_OK;
     case 15: g_debug_pair = value; return STX_OK;
     case 16: g_debug_no_mask_bits = value; return STX_OK;
+    case 17: g_lbfgs_no_skip = value; return STX_OK;
     default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
   }
 }

@@ -91,6 +91,10 @@ conv1_1_tc_kernel(const float* __restrict__ image, int is_preimage, float m0, fl
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, phase ^= 1) {
     const int n = tile / tiles_per_img;
+    if (p.active && !__ldg(p.active + n)) {     // a finished job's image (uniform over the block)
+      phase ^= 1;                               // undone by the loop increment: the barriers' phase follows processed tiles
+      continue;
+    }
     const int t2 = tile % tiles_per_img;
     const int h0 = (t2 / p.tiles_w) * 16, w0 = (t2 % p.tiles_w) * 8;
     if (warp < 8) {
@@ -254,7 +258,8 @@ int pack_conv1_1_tc_launch(const float* w27x64, float sw, bf16* out16k, cudaStre
 }
 
 int conv1_1_tc_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3, const bf16* wpack,
-                      float corr_scale, const float* bias, bf16* out, bf16* out_corr, bf16* aux, cudaStream_t stream) {
+                      float corr_scale, const float* bias, bf16* out, bf16* out_corr, bf16* aux, cudaStream_t stream,
+                      const int* active) {
   STX_REQUIRE(image && wpack && bias && out && mean3, "conv1_1 (tensor cores): null operand");
   static bool attr_set = false;
   if (!attr_set) {
@@ -275,6 +280,7 @@ int conv1_1_tc_launch(const float* image, int nimg, int H, int W, int is_preimag
   p.out_lo = out_corr;
   p.aux_out = aux;
   p.corr_scale = corr_scale;
+  p.active = active;
   // store maps: one 8 x 16 pixel x 64 channel box per tile and plane (2-byte elements; the correction plane's 128
   // bytes per pixel are 64 such elements), 128-byte swizzle as staged
   const uint64_t dims[4] = {64u, static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(nimg)};

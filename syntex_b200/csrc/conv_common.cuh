@@ -52,6 +52,10 @@ struct ConvKernelParams {
   float corr_scale;
   bf16* aux_out;
   bf16* pool_aux;
+  // Per-image switch (nullable): images whose flag is 0 are skipped by the persistent work loops - their outputs keep
+  // whatever they held. The device optimiser clears the flag of a job that has finished while the other jobs of the
+  // batch still run (csrc/lbfgs.cu), so the tail of a batch costs what its remaining jobs cost.
+  const int* active;
 };
 
 union Pack8 {

@@ -225,6 +225,7 @@ int launch_bn(const ConvOp& op, cudaStream_t stream) {
   p.up_mask = op.up_mask;
   p.bits_out = nullptr;
   p.up_bits = nullptr;
+  p.active = nullptr;
   p.export_out = op.export_out;
   p.corr_scale = 1.0f;
   p.aux_out = nullptr;
@@ -321,6 +322,7 @@ int conv_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int cin, con
   op->up_mask = nullptr;
   op->bits_out = nullptr;
   op->up_bits = nullptr;
+  op->active = nullptr;
   op->export_out = nullptr;
   op->corr_scale = 1.0f;
   op->aux_out = nullptr;

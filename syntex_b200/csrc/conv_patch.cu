@@ -139,6 +139,15 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // the item list is walked per cluster in pair mode (both CTAs take the same item, two M tiles of it)
   const int item_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int item_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  // Work items of finished jobs (ConvKernelParams::active) are skipped by all three roles alike; a pair item spans two
+  // tiles (possibly of two images) and is skipped when neither is wanted - both CTAs of the pair evaluate the same test.
+  auto skipped = [&](int item) -> bool {
+    if (p.active == nullptr) return false;
+    const int per_img = p.tiles_w * p.tiles_h;
+    const int t = (item / sched.ksplit) / sched.nblocks;
+    if (PAIR) return !(__ldg(p.active + (2 * t) / per_img) | __ldg(p.active + (2 * t + 1) / per_img));
+    return !__ldg(p.active + t / per_img);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -204,6 +213,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         __syncwarp();
       }
       for (int item = item_first; item < sched.total_items; item += item_step) {
+        if (skipped(item)) continue;
         const int ks = item % sched.ksplit;
         const int rest = item / sched.ksplit;
         const int nblk = rest % sched.nblocks;
@@ -334,6 +344,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_after();
       }
       for (int item = item_first; item < sched.total_items; item += item_step) {
+        if (skipped(item)) continue;
         mbar_wait(&aempty[as], aph ^ 1, 300 + as);    // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + as * L::kAccCols;
@@ -459,6 +470,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       else mbar_arrive(&aempty[s]);
     };
     for (int item = item_first; item < sched.total_items; item += item_step, ++ait) {
+      if (skipped(item)) {
+        --ait;            // undone by the loop increment: the accumulator ring follows processed items
+        continue;
+      }
       const int ks = item % sched.ksplit;
       const int rest = item / sched.ksplit;
       const int nblk = rest % sched.nblocks;
@@ -694,6 +709,7 @@ int launch_patch(const ConvOp& op, cudaStream_t stream) {
   p.up_mask = op.up_mask;
   p.bits_out = op.bits_out;
   p.up_bits = op.up_bits;
+  p.active = op.active;
   p.export_out = op.export_out;
   p.corr_scale = op.corr_scale;
   p.aux_out = op.aux_out;
@@ -856,6 +872,7 @@ int conv_patch_prepare(ConvOp* op, const bf16* x, int nimg, int H, int W, int ci
   op->up_mask = nullptr;
   op->bits_out = nullptr;
   op->up_bits = nullptr;
+  op->active = nullptr;
   op->export_out = nullptr;
   op->split = 0;
   op->relu = 0;

@@ -39,6 +39,7 @@
 namespace stx {
 int g_lbfgs_no_graph = 0;   // 1 = launch every optimiser cycle on the stream instead of replaying a CUDA graph (key 10)
 int g_lbfgs_serial_active = 0;   // 1 = active-set kernel in the main stream after the dots kernel (key 14)
+int g_lbfgs_no_skip = 0;         // 1 = finished jobs keep being evaluated until the whole batch is done (key 17)
 }
 
 #include <algorithm>
@@ -111,6 +112,7 @@ struct Vecs {
   double* gramA;                         // [B][kSlices][kQ][kQ]
   Ctrl* ctrl;                            // [B]
   Tables* tab;                           // [B]
+  int* active;                           // [B] the plan's per-image switch (null: finished jobs keep being evaluated)
   long long* dbg;                        // [16] clock64 stamps of job 0's decide kernel (diagnostic, stx_lbfgs_phase_cycles)
   int n, m, nblk, bounded;
   int hn;                                // elements between history vectors: n rounded up to 8 (16-byte aligned rows)
@@ -937,6 +939,8 @@ __global__ void __launch_bounds__(kDecideThreads) lbfgs_decide_kernel(Vecs v) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&sc);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&cg);
     for (int i = tid; i < static_cast<int>(sizeof(Ctrl) / 4); i += kDecideThreads) dst[i] = src[i];
+    // a job that has just finished: the f/g kernels skip its image from the next cycle on (Plan::d_active)
+    if (tid == 0 && v.active && sc.mode == kDone) v.active[b] = 0;
   }
   stamp(6);
 }
@@ -1102,7 +1106,11 @@ __global__ void lbfgs_set_maxiter_kernel(Vecs v, int maxiter, int nprob) {
   }
 }
 
-__global__ void lbfgs_export_kernel(Vecs v, float* fun, int* nit, int* nfev, int* mode, int nprob) {
+// active (nullable): the plan's per-image switch - a finished job's image is skipped by the f/g kernels from the next
+// cycle on (the jobs of a batch finish at different times; without this the tail of a run costs full cycles).
+// all_on = 1: switch every image back on (end of a run: the plan is shared with other callers).
+__global__ void lbfgs_export_kernel(Vecs v, float* fun, int* nit, int* nfev, int* mode, int nprob, int* active,
+                                    int all_on) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < nprob) {
     const Ctrl& c = v.ctrl[b];
@@ -1110,6 +1118,7 @@ __global__ void lbfgs_export_kernel(Vecs v, float* fun, int* nit, int* nfev, int
     if (nit) nit[b] = c.nit;
     if (nfev) nfev[b] = c.nfev;
     if (mode) mode[b] = c.mode;
+    if (active) active[b] = (all_on || c.mode != kDone) ? 1 : 0;
   }
 }
 
@@ -1182,6 +1191,7 @@ int lbfgs_create(Lbfgs** out, Plan* plan, int maxcor, int bounded, float lower, 
   Vecs& v = im->v;
   v.n = static_cast<int>(n);
   v.hn = static_cast<int>((n + 7) & ~static_cast<size_t>(7));
+  v.active = g_lbfgs_no_skip ? nullptr : plan->d_active;
   v.m = maxcor;
   v.nblk = static_cast<int>((n + kChunk - 1) / kChunk);
   v.bounded = bounded;
@@ -1325,7 +1335,8 @@ int Lbfgs::run(int maxiter, int max_evals, cudaStream_t caller) {
   int evals = 0;
   while (evals < max_evals) {
     lbfgs_export_kernel<<<(B + 127) / 128, 128, 0, stream>>>(v, nullptr, im->status_dev, im->status_dev + B,
-                                                             im->status_dev + 2 * B, B);
+                                                             im->status_dev + 2 * B, B,
+                                                             v.active, 0);
     STX_CUDA(cudaMemcpyAsync(im->pinned_i, im->status_dev, 3 * sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
     STX_CUDA(cudaStreamSynchronize(stream));
     int min_nit = maxiter;
@@ -1348,6 +1359,8 @@ int Lbfgs::run(int maxiter, int max_evals, cudaStream_t caller) {
     }
     evals += chunk;
   }
+  lbfgs_export_kernel<<<(B + 127) / 128, 128, 0, stream>>>(v, nullptr, nullptr, nullptr, nullptr, B, plan->d_active, 1);
+  STX_CUDA(cudaGetLastError());
   STX_TRY(fence_out(im, caller));
   return STX_OK;
 }
@@ -1367,7 +1380,7 @@ int Lbfgs::result(float* x, float* fun, int* nit, int* nfev, cudaStream_t caller
   if (x)
     STX_CUDA(cudaMemcpyAsync(x, v.x, static_cast<size_t>(B) * v.n * sizeof(float), cudaMemcpyDeviceToDevice,
                              im->stream));
-  lbfgs_export_kernel<<<(B + 127) / 128, 128, 0, im->stream>>>(v, fun, nit, nfev, nullptr, B);
+  lbfgs_export_kernel<<<(B + 127) / 128, 128, 0, im->stream>>>(v, fun, nit, nfev, nullptr, B, nullptr, 0);
   STX_CUDA(cudaGetLastError());
   STX_TRY(fence_out(im, caller));
   return STX_OK;

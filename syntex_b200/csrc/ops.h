@@ -35,6 +35,7 @@ struct ConvOp {
   bf16* pool_out_lo;
   bf16* up_out;              // fused AvgPoolGrad + ReluGrad scatter (replaces `out`)
   const bf16* up_mask;
+  const int* active;         // per-image switch, nullable (conv_common.cuh)
   uint32_t* bits_out;        // one-bit ReLU mask of the result, written instead of `out` (conv_common.cuh)
   const uint32_t* up_bits;   // ... and read by the scatter instead of up_mask
   bf16* export_out;          // copy of the value after the addend (total gradient w.r.t. this layer's features)
@@ -135,8 +136,10 @@ int pack_weights_f16f8_launch(const float* w_hwio, int cin, int cout, float sw, 
 // conv1_1 of the f16 + f8 plans on the tensor cores (conv1_1_tc.cu): K = 27 im2col rows built in shared memory.
 // wpack: 16 KB from pack_conv1_1_tc_launch (fp16 tile + e4m3 correction tile, pre-swizzled), sw its weight scale.
 int pack_conv1_1_tc_launch(const float* w27x64, float sw, bf16* out16k, cudaStream_t stream);
+// active: per-image switch (nullable, see ConvKernelParams)
 int conv1_1_tc_launch(const float* image, int nimg, int H, int W, int is_preimage, const float* mean3, const bf16* wpack,
-                      float corr_scale, const float* bias, bf16* out, bf16* out_corr, bf16* aux, cudaStream_t stream);
+                      float corr_scale, const float* bias, bf16* out, bf16* out_corr, bf16* aux, cudaStream_t stream,
+                      const int* active = nullptr);
 // fp16 plane (+ correction plane, nullable) of a recorded layer with C channels -> fp32.
 int f16f8_to_f32_launch(const bf16* hi, const bf16* corr, size_t n, int C, float* out, cudaStream_t stream);
 // dgrad of conv1_1 chained with the preprocessing derivative: g [nimg,H,W,64] bf16 (already ReLU-masked) ->

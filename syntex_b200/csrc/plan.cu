@@ -242,6 +242,7 @@ static int plan_layout(Plan* p, Bump& a) {
   p->layer_loss = a.take<float>(static_cast<size_t>(B) * std::max<size_t>(p->loss.size(), 1));
   p->d_coef = a.take<float>(std::max<size_t>(p->loss.size(), 1));
   p->d_part_offsets = a.take<int>(p->loss.size() + 1);
+  p->d_active = a.take<int>(B);
   p->x_dev = a.take<float>(p->image_elems());
   p->grad_dev = a.take<float>(p->image_elems());
   p->func_dev = a.take<float>(B);
@@ -506,6 +507,17 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
       cur ^= 1;
     }
   }
+  // Per-image switch of the persistent work loops (all on; the device optimiser turns finished jobs off).
+  if (rc == STX_OK) {
+    std::vector<int> ones(B, 1);
+    e = cudaMemcpy(p->d_active, ones.data(), ones.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "plan_create: active flags");
+    for (int l = 1; l <= topmost; ++l)
+      if (kLayers[l].is_conv) p->fwd[l].active = p->d_active;
+    for (BwdStep& st : p->bwd)
+      if (st.kind == BwdStep::kDgrad || st.kind == BwdStep::kGramGrad || st.kind == BwdStep::kConv1BwdTensor)
+        st.conv.active = p->d_active;
+  }
   // Split-K for the convolutions whose grid would leave most SMs idle (deep layers at small batch). Implemented and
   // parity-tested, but off by default: at 256^2, batch 1, the per-item fixed cost (pipeline fill, partial-tile
   // round trip through L2, serial fix-up) outweighs the extra parallelism (profiles/r01_splitk_b1.md).
@@ -606,7 +618,7 @@ int Plan::forward(const float* image, int is_preimage, int with_grams, bool with
   };
   if (split == 2 && !g_debug_conv1_1_cuda_cores) {
     STX_LAUNCH(kClsConv1, conv1_1_tc_launch(image, B, H, W, is_preimage, vgg->mean, vgg->wtc0, vgg->corr_scale[0],
-                                            vgg->bias[0], act[0], act_lo[0], act_bf[0], stream));
+                                            vgg->bias[0], act[0], act_lo[0], act_bf[0], stream, d_active));
   } else {
     STX_LAUNCH(kClsConv1, conv1_1_fwd_launch(image, B, H, W, is_preimage, vgg->mean, vgg->w0, vgg->bias[0], act[0],
                                              act_lo[0], stream, split == 2 ? 2 : 0, act_bf[0]));

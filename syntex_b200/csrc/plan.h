@@ -101,6 +101,8 @@ struct Plan {
   int part_total = 0;
   float* layer_loss = nullptr;     // [nloss][B]
   float* d_coef = nullptr;         // [nloss] coef/4
+  int* d_active = nullptr;         // [B] per-image switch of the conv work loops (ConvKernelParams::active): all 1 except
+                                   // while the device optimiser runs a batch whose jobs finish at different times
   int* d_part_offsets = nullptr;   // [nloss+1]
   bool have_target = false, have_grams = false;
   long long generation = 0;        // bumped by every forward(): a backward may check that its activations are still there
