@@ -22,6 +22,7 @@ extern int g_debug_conv1_1_cuda_cores;
 extern int g_debug_pair;
 extern int g_debug_no_mask_bits;
 extern int g_lbfgs_no_skip;
+extern int g_f16_plain_layers;
 extern int g_lbfgs_serial_active;
 }  // namespace stx
 
@@ -61,6 +62,7 @@ int stx_debug_set(int key, int value) {
     case 15: g_debug_pair = value; return STX_OK;
     case 16: g_debug_no_mask_bits = value; return STX_OK;
     case 17: g_lbfgs_no_skip = value; return STX_OK;
+    case 18: g_f16_plain_layers = value; return STX_OK;
     default: return fail(STX_ERR_INVALID, "stx_debug_set: unknown key");
   }
 }

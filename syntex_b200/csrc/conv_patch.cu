@@ -85,9 +85,11 @@ struct PatchSmem {
   // ~72 per N = 128 MMA - the A operand streams out of shared memory at 64 B/clk), so two N = 64 MMAs on the same
   // A tile cost twice what one N = 128 MMA does.
   static constexpr bool kMerge = SPLIT && BN == 64 && !F8;
-  static constexpr bool kTwoAcc = kMerge || F8;                               // two column ranges per tile, summed by the epilogue
+  static constexpr bool kTwoAcc = kMerge || (F8 && SPLIT);                    // two column ranges per tile, summed by the epilogue
   static constexpr int kAccCols = (kTwoAcc ? 2 : 1) * BN * MT;
-  static_assert(!F8 || (SPLIT && MT == 1 && RES == 0), "f16+f8 forward: split operands, one tile, ring weights");
+  // F8 without SPLIT: fp16 operands, ONE MMA per K step, results stored in the f16+f8 plane format (the layers of an
+  // f16+f8 plan that go without the correction product, see plan.cu)
+  static_assert(!F8 || (MT == 1 && RES == 0), "f16+f8 forward: one tile, ring weights");
   static constexpr int kAccStages = (2 * kAccCols * OCC <= 512) ? 2 : 1;      // TMEM accumulator buffers
   static constexpr int kTmemCols = pow2_at_least(kAccStages * kAccCols);
   static_assert(kPatchStages >= 1, "no room for a patch stage");
@@ -369,7 +371,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t accumulate = (first_chunk && tap == 0 && k == 0) ? 0u : 1u;
                 const uint64_t ad = desc_pack(a_lo + 2 * k, kDescHiA);
                 const uint64_t bd = desc_pack(b_lo0 + 2 * k, kDescHiB);
-                if (F8) {
+                if (F8 && SPLIT) {
                   // fp16(A) * fp16(W) into the main columns, [A8 | Alo8] * [Wlo8 ; W8] (K = 32 per instruction, the
                   // same 32 bytes of the 128-byte rows) into the correction columns
                   const uint64_t ad_c = desc_pack(a_lo + (L::kPatchStride >> 4) + 2 * k, kDescHiA);
@@ -644,7 +646,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tmem_ld_32x32(acc + mt * 2 * BN + c0, v);
             tmem_ld_32x32(acc + mt * 2 * BN + BN + c0, u);
             tmem_ld_wait();
-            const float cs = F8 ? p.corr_scale : 1.0f;
+            const float cs = (F8 && SPLIT) ? p.corr_scale : 1.0f;
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = fmaf(u[e], cs, v[e]);
           } else {
@@ -942,6 +944,15 @@ int conv_patch_launch(const ConvOp& op, cudaStream_t stream) {
               "conv: output not set");
   STX_REQUIRE((op.bits_out == nullptr && op.up_bits == nullptr) || op.cout % 32 == 0, "conv: bit masks need 32-channel groups");
   STX_REQUIRE(op.pool_out == nullptr || (op.H % 2 == 0 && op.W % 2 == 0), "conv: fused pooling needs even H and W");
+  if (op.split == 3) {      // fp16 operands, single MMA, f16+f8-format outputs
+    STX_REQUIRE(op.res == 0 && op.mt == 1, "conv f16 (plain): bad configuration");
+    if (op.pair && op.bn == 256) return launch_patch<256, 1, false, 1, 0, true, true>(op, stream);
+    if (op.pair && op.bn == 128) return launch_patch<128, 1, false, 1, 0, true, true>(op, stream);
+    STX_REQUIRE(!op.pair, "conv f16 (plain): no CTA-pair instance for this N tile");
+    if (op.bn == 128) return launch_patch<128, 1, false, 1, 0, true>(op, stream);
+    STX_REQUIRE(op.bn == 64, "conv f16 (plain): N tile must be 64 or 128 without pairs");
+    return launch_patch<64, 1, false, 1, 0, true>(op, stream);
+  }
   if (op.split == 2) {
     STX_REQUIRE(op.out_lo != nullptr || op.pool_out_lo != nullptr, "conv f16+f8: correction-plane output not set");
     STX_REQUIRE(op.res == 0 && op.mt == 1, "conv f16+f8: bad configuration");

@@ -21,7 +21,8 @@ struct ConvOp {
   float* splitk_ws;  // fp32 partial tiles (shared by all ops of a plan; launches are stream-ordered)
   int* splitk_counters;
   int split;         // 1 = bf16x3 forward (hi/lo operands, hi/lo outputs); 2 = f16 + f8 forward (patch kernel only:
-                     // fp16 planes + e4m3 correction planes, conv_common.cuh kF8*)
+                     // fp16 planes + e4m3 correction planes, conv_common.cuh kF8*); 3 = a layer of an f16 + f8 plan that
+                     // runs without the correction product (fp16 operands, one MMA, same output planes)
   float corr_scale;  // split == 2: factor of the correction accumulator (1 / (512 * weight scale) of the layer)
   bf16* aux_out;     // split == 2: bf16 copy of the stored result (loss layers: the Gram gradient's A operand is bf16)
   bf16* pool_aux;    // ... and of the fused pool's result

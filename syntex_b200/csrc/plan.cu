@@ -12,6 +12,9 @@ namespace stx {
 int g_debug_dgrad_variant = 0;      // variant code for the dgrad convolutions (0 = automatic)
 int g_debug_no_gram_fusion = 0;     // 1 = stand-alone Gram-gradient launches
 int g_debug_no_poolbwd_fusion = 0;  // 1 = stand-alone AvgPoolGrad launches
+int g_f16_plain_layers = -1;        // f16+f8 plans: bit i = convolution i (1 = conv1_2 ... 11 = conv4_4) runs WITHOUT the e4m3
+                                    // correction product: fp16 operands, one MMA per K step; -1 = as the plan's flags
+                                    // say (STX_PLAN_F16F8_LEAN: conv4_2..conv4_4) (stx_debug_set key 18)
 int g_debug_no_mask_bits = 0;       // 1 = the convolutions in front of a pool keep their full planes as ReLU masks (key 16)
 int g_debug_tiled_weights = 0;      // 1 = fetch weight tiles with 1-D bulk copies from tiled pre-swizzled packs
                                     // (measured: no gain over tensor-map fetches, costs a second weight copy: off)
@@ -265,6 +268,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
   p->split = (flags & STX_PLAN_FAST_BF16) ? 0 : ((flags & STX_PLAN_F16F8) ? 2 : 1);
   p->export_grads = (flags & STX_PLAN_EXPORT_LAYER_GRADS) ? 1 : 0;
   p->full_features = (flags & STX_PLAN_FULL_FEATURES) ? 1 : 0;
+  p->f16_plain_layers = g_f16_plain_layers >= 0 ? g_f16_plain_layers : ((flags & STX_PLAN_F16F8_LEAN) ? 0xE00 : 0);
   for (int l = 0; l < kNumLayers; ++l) p->lo_valid[l] = p->split != 0;
   for (int l = 0; l < kNumLayers; ++l) p->hi_valid[l] = true;
   int h = H, w = W, convs_needed = 0;
@@ -335,7 +339,18 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     const LayerSpec& s = kLayers[l];
     if (!s.is_conv) continue;
     ConvOp& op = p->fwd[l];
-    if (p->split == 2) {
+    if (p->split == 2 && ((p->f16_plain_layers >> s.conv_index) & 1)) {
+      // f16 + f8 plan, a layer chosen to go without the correction product: fp16 planes against the fp16 pack, one
+      // MMA per K step (the single-MMA instances: CTA pairs, N tile 256), outputs in the plan's plane format
+      rc = conv3x3_prepare(&op, p->act[l - 1], nullptr, B, p->lh[l], p->lw[l], s.cin, vgg->wf16[s.conv_index], nullptr,
+                           s.cout, (g_debug_pair & 1) ? 1000000 : 0);
+      if (rc == STX_OK && op.patch && op.mt != 1)      // no stacked-tile instance of this flavour
+        rc = conv3x3_prepare(&op, p->act[l - 1], nullptr, B, p->lh[l], p->lw[l], s.cin, vgg->wf16[s.conv_index],
+                             nullptr, s.cout, 1000 + (s.cout % 128 == 0 ? 128 : 64));
+      if (rc == STX_OK && !op.patch)
+        rc = fail(STX_ERR_UNSUPPORTED, "plan_create: the f16+f8 forward needs feature maps at least 8 pixels wide");
+      op.split = 3;
+    } else if (p->split == 2) {
       // f16 + f8: fp16 planes against the fp16 pack, correction planes against the e4m3 rows (halo-patch kernel only)
       rc = conv3x3_prepare(&op, p->act[l - 1], p->act_lo[l - 1], B, p->lh[l], p->lw[l], s.cin, vgg->wf16[s.conv_index],
                            vgg->wcorr[s.conv_index], s.cout, (g_debug_pair & 1) ? 1000000 : 0);
@@ -353,6 +368,7 @@ int plan_create(Plan** out, const Vgg* vgg, int B, int H, int W, int topmost, in
     }
     op.w_tiled = g_debug_tiled_weights ? vgg->wft[s.conv_index] : nullptr;
     op.w_tiled_lo = g_debug_tiled_weights ? vgg->wft_lo[s.conv_index] : nullptr;
+    if (op.split == 3) op.w_tiled = op.w_tiled_lo = nullptr;     // (the tiled packs are bf16)
     op.bias = vgg->bias[s.conv_index];
     op.relu = 1;
     op.out = p->act[l];

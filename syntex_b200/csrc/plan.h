@@ -85,6 +85,7 @@ struct Plan {
   int export_grads = 0;            // keep dL/dF_k of every loss layer (PO stage preparation)
   int split = 1;                   // forward precision: 0 = plain bf16, 1 = bf16x3 (hi/lo bf16 activation planes),
                                    // 2 = f16 + f8 (fp16 planes + e4m3 correction planes: two MMAs' time per MAC)
+  int f16_plain_layers = 0;        // f16+f8 plans: convolutions (bit = conv index) without the correction product
   int full_features = 0;           // keep the low half of every recorded layer (feature export), not only those the path reads
   bool lo_valid[kNumLayers] = {};  // act_lo[l] is written by the forward
   bool hi_valid[kNumLayers] = {};  // act[l] is written by the forward (false: the layer only leaves a one-bit ReLU mask)

@@ -53,6 +53,7 @@ class _Plan(object):
     EXPORT_LAYER_GRADS = 2   # STX_PLAN_EXPORT_LAYER_GRADS
     FULL_FEATURES = 4   # STX_PLAN_FULL_FEATURES
     F16F8 = 8   # STX_PLAN_F16F8
+    F16F8_LEAN = 16   # STX_PLAN_F16F8_LEAN
 
     def __init__(self, vgg_handle, batch, height, width, topmost_idx, loss_layers, coefs, flags=0):
         self.handle = ctypes.c_void_p()
@@ -171,7 +172,8 @@ class Vgg19(object):
                  slot=0, full_features=None, f16f8=False):
         """Cached stx_plan for this shape. coefs: OrderedDict layer name -> weight (Gram layers), or None.
         fast_bf16: single-MMA bf16 forward instead of the accurate bf16x3 forward (see include/syntex_b200.h).
-        f16f8: the f16 + f8 forward (STX_PLAN_F16F8): same accuracy class as bf16x3 at two thirds of its tensor time.
+        f16f8: the f16 + f8 forward (STX_PLAN_F16F8): same accuracy class as bf16x3 at two thirds of its tensor time;
+        "lean" adds STX_PLAN_F16F8_LEAN (conv4_2..conv4_4 without the correction product).
         slot: distinct slots give distinct plans of the same shape (each keeps the activations of its own last
         forward - the PO training graph evaluates VGG once per stage and back-propagates through all of them)."""
         topmost = self.topmost if topmost is None else topmost
@@ -181,7 +183,7 @@ class Vgg19(object):
         if full_features is None:       # plans without loss layers exist to export features: keep every low half
             full_features = len(coefs) == 0
         key = (batch, height, width, topmost, tuple((k, float(v)) for k, v in coefs.items()), bool(fast_bf16),
-               bool(export_layer_grads), int(slot), bool(full_features), bool(f16f8))
+               bool(export_layer_grads), int(slot), bool(full_features), str(f16f8))
         plan = self._plans.get(key)
         if plan is None:
             plan = _Plan(self._vgg_handle(), batch, height, width, LAYER_INDEX[topmost],
@@ -189,7 +191,8 @@ class Vgg19(object):
                          (_Plan.FAST_BF16 if fast_bf16 else 0) |
                          (_Plan.EXPORT_LAYER_GRADS if export_layer_grads else 0) |
                          (_Plan.FULL_FEATURES if full_features else 0) |
-                         (_Plan.F16F8 if (f16f8 and not fast_bf16) else 0))
+                         (_Plan.F16F8 if (f16f8 and not fast_bf16) else 0) |
+                         (_Plan.F16F8_LEAN if (f16f8 == "lean" and not fast_bf16) else 0))
             plan.coef_names = list(coefs.keys())
             self._plans[key] = plan
         return plan

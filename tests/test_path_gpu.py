@@ -17,7 +17,7 @@ from gpu_util import relerr  # noqa: E402
 from syntex_b200.gatys import Synthesizer  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GRAM_TOL = {"f16f8": 1e-3, "bf16x3": 1e-3, "bf16": 5e-3}
+GRAM_TOL = {"f16f8": 1e-3, "f16f8-lean": 1e-3, "bf16x3": 1e-3, "bf16": 5e-3}
 GRAD_TOL = 1e-2
 
 
@@ -31,8 +31,10 @@ def make_syn(raw, S, batch=1, precision="f16f8", **kw):
 
 
 @pytest.mark.parametrize("S,precision", [(64, "f16f8"), (128, "f16f8"), (256, "f16f8"), (224, "f16f8"), (512, "f16f8"),
+                                         (64, "f16f8-lean"), (256, "f16f8-lean"), (512, "f16f8-lean"),
                                          (64, "bf16x3"), (256, "bf16x3"), (512, "bf16x3"), (256, "bf16")])
-# f16f8 = the default forward of the Gatys plan; 256: BASELINE.json config 1, 512: config 2
+# f16f8 = the default forward of the Gatys plan, f16f8-lean = the same with conv4_2..conv4_4 without the correction
+# product (opt-in); 256: BASELINE.json config 1, 512: config 2
 def test_step_matches_oracle(S, precision, raw_weights, exemplar):
     tgt = so.resize_crop(exemplar / 255.0, S)
     x0 = so.init_input((S, S, 3), False, 0)
@@ -166,6 +168,28 @@ def test_default_precision_is_the_f16f8_forward_with_a_bf16x3_fallback(raw_weigh
     orc = so.SynthesizerOracle(so.load_vgg_weights(raw_weights), 32, dtype=torch.float64)
     orc.compute_gram(tgt, update=True)
     assert relerr(r["grad"], orc.step(so.init_input((32, 32, 3), False, 0))["grad"]) < GRAD_TOL
+
+
+def test_lean_and_full_f16f8_forwards_differ_only_above_conv4_1(raw_weights):
+    """'f16f8-lean' (STX_PLAN_F16F8_LEAN) drops the e4m3 correction product in conv4_2..conv4_4 only: the Grams of the
+    four lower loss layers are bit-identical to 'f16f8', pool4's moves by a few 1e-4, the gradient by a few 1e-3 of its
+    norm (both forwards are within the bars against the oracle, test_step_matches_oracle)."""
+    S = 128
+    tgt = so.synthetic_texture(S, seed=8)
+    x0 = so.init_input((S, S, 3), False, 4)
+    out = {}
+    for prec in ("f16f8-lean", "f16f8"):
+        syn = make_syn(raw_weights, S, precision=prec)
+        syn.compute_gram(tgt, update=True)
+        out[prec] = (syn.compute_gram(x0), syn.step(x0))
+        syn.close()
+    ga, gb = out["f16f8-lean"][0], out["f16f8"][0]
+    for k in ("conv1_1", "pool1", "pool2", "pool3"):
+        np.testing.assert_array_equal(ga[k], gb[k])
+    d4 = relerr(ga["pool4"], gb["pool4"])
+    assert 0.0 < d4 < 1e-3, d4
+    dg = relerr(out["f16f8-lean"][1]["grad"], out["f16f8"][1]["grad"])
+    assert 0.0 < dg < 8e-3, dg
 
 
 def test_partial_target_is_an_error_not_a_wrong_loss(raw_weights):
