@@ -19,6 +19,7 @@ metric through Synthesizer.synthesize() with host buffers (H2D of x0 and exempla
 D2H of the result). `--impl reference` times the CPU oracle (torch-CPU fp32 restatement of the TF graph + the
 reference's own scipy L-BFGS-B call) on the host cores instead. Beside the headline, every N carries
   config1_b1            BASELINE.json config 1 (ONE 256x256 job, 100 iterations) on rank 0: iterations/s
+  config2_b1            BASELINE.json config 2 (ONE 512x512 job, 500 iterations) on rank 0: iterations/s
   po_config5            ProgressiveSynTex training at 512x512, per-GPU batch 1, data parallel over the N ranks (NCCL
                         gradient-mean all-reduce): images/s and the all-reduce's share of the step
   gpu_library_baseline  the same f/g evaluation through stock torch (cuDNN / cuBLAS, TF32 and bf16) on this GPU
@@ -424,9 +425,11 @@ def _timed_ms(fn, warmup, steps):
     return a.elapsed_time(b) / steps
 
 
-def config1_b1(args):
+def config1_b1(args, size=None, IT=100, label="config1"):
     """BASELINE.json config 1 on one GPU: ONE 256x256 job, 100 L-BFGS-B iterations (rank 0). Device-timed through the
-    optimiser's C entry points and end to end through Synthesizer.synthesize() with host arrays."""
+    optimiser's C entry points and end to end through Synthesizer.synthesize() with host arrays. With size = 512 and
+    IT = 500: config 2 (configs[1] of BASELINE.json: the TF32-tolerance case; the tolerance itself is checked by
+    tests/test_path_gpu.py and tests/test_optimizer_parity_gpu.py)."""
     import torch
     from syntex_b200 import _lib
     from syntex_b200.gatys import Synthesizer
@@ -434,7 +437,7 @@ def config1_b1(args):
     try:
         L = _lib.lib()
         stream = _lib.stream_ptr()
-        size, IT = args.size, 100
+        size = args.size if size is None else size
         x0, targets = make_inputs(size, 1, 0)
         syn = Synthesizer({"vgg19_npy_path": synthetic_vgg_weights(0), "image_size": size, "maxiter": IT,
                            "maxcor": args.maxcor, "batch": 1})
@@ -456,7 +459,8 @@ def config1_b1(args):
         ev1.record()
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1)
-        return {"workload": "config1: 1 job, %dx%d, %d L-BFGS-B iterations" % (size, size, IT),
+        syn.close()
+        return {"workload": "%s: 1 job, %dx%d, %d L-BFGS-B iterations" % (label, size, size, IT),
                 "iterations_per_s": nit_e2e / (ms * 1e-3), "ms_per_iteration": ms / max(nit_e2e, 1),
                 "e2e_iterations_per_s": nit_e2e / e2e_s, "nit": nit_e2e, "nfev": nfev_e2e, "final_loss": float(fun)}
     except Exception as e:
@@ -652,6 +656,8 @@ def main():
     extras = not args.no_extras
     if extras and rank == 0:
         out["config1_b1"] = config1_b1(args)
+        if args.size == 256:
+            out["config2_b1"] = config1_b1(args, size=512, IT=500, label="config2")
         out["gpu_library_baseline"] = gpu_library_baseline(args, out["fg_evals_per_iteration"])
     if extras and not args.no_po:
         po = po_config5(rank, world, local_rank)          # every rank takes part (NCCL)
