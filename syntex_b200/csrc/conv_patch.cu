@@ -11,7 +11,8 @@
 // tap (r, s) is just "start address + (r*10 + s) * 128 B, stride between 8-row groups = 10 * 128 B".
 // MT = 2 stacks two 16x8 output tiles (two TMEM accumulators) on one weight stream.
 //
-// The kernel is PERSISTENT: one CTA per SM walks a static round-robin list of (tile, N-block) work items, so the
+// The kernel is PERSISTENT: one CTA per SM (or two; or one CTA PAIR per TPC issuing cta_group::2 MMAs, see PatchSmem)
+// walks a static round-robin list of (tile, N-block) work items (minus the images switched off, see `skipped`), so the
 // prologue (barrier init, TMEM allocation, descriptor prefetch) is paid once and the whole shared memory is one deep
 // TMA ring. The TMEM accumulator is double-buffered (when 2 * BN * MT <= 512 columns): eight epilogue warps drain
 // tile i (tcgen05.ld -> bias / ReLU / mask / pooling -> bf16 hi/lo stores) while the MMA warp already accumulates

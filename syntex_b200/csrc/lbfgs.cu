@@ -20,14 +20,16 @@
 //
 //   cycle = [ plan.step(xt) -> ft, gt ] -> dots kernel -> active kernel -> decide kernel -> update kernel
 //
-//   dots   : one pass over x, xt, g, gt, d and the (s, y) history: every inner product the decision needs as
-//            per-block partial sums (warp-shuffle + shared-memory reductions, fixed order => bit-reproducible).
+//   dots   : one pass over x, xt, g, gt, d and the (s, y) history (fp16 with one power-of-two scale per vector, see
+//            hist_t): every inner product the decision needs as per-block partial sums (packed warp-shuffle +
+//            shared-memory reductions, fixed order => bit-reproducible).
 //   active : W_A'W_A over the active set of the trial point (about 1 % of the variables): each block compacts its
 //            slice of the variables in index order and accumulates the (2k+2)^2 Gram matrix of the gathered rows
 //            in fp64. W_F'W_F = W'W - W_A'W_A then needs no masked pass over the history.
 //   decide : one CTA per problem: sums the partials in fp64, advances the line search, and on acceptance updates
-//            S'Y / S'S / Y'Y, builds K, solves it (Gaussian elimination with partial pivoting, the whole block) and
-//            leaves the coefficients of the new step.
+//            S'Y / S'S / Y'Y, builds K, solves it (Gauss-Jordan in natural order - K is quasi-definite - the whole
+//            block, one barrier per step) and leaves the coefficients of the new step; a job that finishes clears
+//            its image's switch in the plan, so the f/g kernels skip it while the rest of the batch runs on.
 //   update : applies the decision: stores the new pair, moves x, builds the step in one pass over the history,
 //            projects it, and writes the next trial point; partial sums of g'd and of the largest feasible step.
 #include "lbfgs.h"
