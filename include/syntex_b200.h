@@ -45,6 +45,10 @@ const char* stx_last_error(void);
 int stx_abi_version(void);
 /* Kernel launches issued by this library so far in this process (CUDA-graph replays count their kernel nodes). */
 long long stx_launch_count(void);
+/* Host helper, no GPU involved: CRC-32C (Castagnoli) of n bytes, continuing `crc` (0 to start) - the per-tensor checksum
+ * of TensorFlow checkpoint files, which syntex_b200/po/tf_bundle.py reads and writes (reference: tensorpack's
+ * ModelSaver / SaverRestore, po/progressive_model.py:354-356). */
+unsigned int stx_crc32c(const void* data, size_t n, unsigned int crc);
 /* Bring-up knobs; key/value meanings are internal (csrc/capi.cu: descriptor strides, kernel-variant overrides, 9 =
  * programmatic dependent launch, 10 = plain stream launches instead of the optimiser's CUDA graph, 12 = one CTA per SM
  * for the 64-channel f16+f8 forward, 13 = CUDA-core conv1_1 in f16+f8 plans, 14 = active-set kernel in the main

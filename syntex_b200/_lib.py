@@ -20,6 +20,7 @@ def _declare(lib):
         "stx_last_error": (c_char_p, []),
         "stx_abi_version": (c_int, []),
         "stx_launch_count": (ctypes.c_longlong, []),
+        "stx_crc32c": (ctypes.c_uint, [c_void_p, c_size_t, ctypes.c_uint]),
         "stx_debug_set": (c_int, [c_int, c_int]),
         "stx_debug_pair_probe": (c_int, [vp, vp, fp, vp]),
         "stx_debug_patch_probe": (c_int, [vp, c_int, vp, c_int, c_int, c_int, fp, vp]),

@@ -1,11 +1,19 @@
 """PO checkpoints: tensorpack's ModelSaver writes `model-<global_step>` files into the
 log directory and `SaverRestore` / `--test-only` load them (po/progressive_model.py:354-356, po/improved_model.py:453-484).
-Same naming here, torch serialisation inside (TensorFlow checkpoint files are not readable without TensorFlow)."""
+Same file naming here. Two formats:
+  * torch serialisation (save_checkpoint / restore_checkpoint): everything, including the optimiser state;
+  * TensorFlow's own checkpoint format (export_tf_checkpoint / restore_tf_checkpoint, through po/tf_bundle.py, no
+    TensorFlow needed) under the reference's variable names, for the generator of po/progressive_model.py: a
+    checkpoint trained with the reference loads here, and one written here loads with the reference's SaverRestore.
+    restore_checkpoint() recognises such a file by its `.index` companion."""
 import glob
 import os
 import re
 
+import numpy as np
 import torch
+
+from . import tf_bundle
 
 
 def save_checkpoint(folder, model, trainer=None, global_step=None):
@@ -24,7 +32,95 @@ def save_checkpoint(folder, model, trainer=None, global_step=None):
 
 def latest_checkpoint(folder):
     files = [p for p in glob.glob(os.path.join(folder, "model-*")) if re.search(r"model-\d+$", p)]
+    files += [p[:-len(".index")] for p in glob.glob(os.path.join(folder, "model-*.index"))
+              if re.search(r"model-\d+\.index$", p)]
     return max(files, key=lambda p: int(p.rsplit("-", 1)[1])) if files else None
+
+
+# ---------------------------------------------------------------------------------------------- TensorFlow format
+# state_dict key of po/progressive_model.py's generator -> variable name in the reference's graph
+# (po/progressive_model.py:145-206: scopes syn / stage<s> / <layer> / ...; tensorpack's Conv2D names its variables W
+# and b, its InstanceNorm gamma and beta; INReLU's norm lives under the convolution's scope as `inorm`).
+_L = r"(conv\d_\d|pool\d)"
+_TF_RULES = [
+    (r"^syn\.(\d+)\.grad_conv(\d)\.%s\.conv\.weight$" % _L, "syn/stage{0}/{2}/grad_conv{1}/W"),
+    (r"^syn\.(\d+)\.grad_conv(\d)\.%s\.norm\.weight$" % _L, "syn/stage{0}/{2}/grad_conv{1}/inorm/gamma"),
+    (r"^syn\.(\d+)\.grad_conv(\d)\.%s\.norm\.bias$" % _L, "syn/stage{0}/{2}/grad_conv{1}/inorm/beta"),
+    (r"^syn\.(\d+)\.up\.%s\.conv\.conv\.weight$" % _L, "syn/stage{0}/{1}/up/W"),
+    (r"^syn\.(\d+)\.post_inorm\.%s\.weight$" % _L, "syn/stage{0}/{1}/post_inorm/gamma"),
+    (r"^syn\.(\d+)\.post_inorm\.%s\.bias$" % _L, "syn/stage{0}/{1}/post_inorm/beta"),
+    (r"^syn\.(\d+)\.pre_inorm\.%s\.weight$" % _L, "syn/stage{0}/{1}/inorm/gamma"),
+    (r"^syn\.(\d+)\.pre_inorm\.%s\.bias$" % _L, "syn/stage{0}/{1}/inorm/beta"),
+    (r"^syn\.(\d+)\.res\.%s\.(\d+)\.conv(\d)\.conv\.weight$" % _L, "syn/stage{0}/{1}/res{2}/conv{3}/W"),
+    (r"^syn\.(\d+)\.res\.%s\.(\d+)\.conv(\d)\.norm\.weight$" % _L, "syn/stage{0}/{1}/res{2}/conv{3}/inorm/gamma"),
+    (r"^syn\.(\d+)\.res\.%s\.(\d+)\.conv(\d)\.norm\.bias$" % _L, "syn/stage{0}/{1}/res{2}/conv{3}/inorm/beta"),
+    (r"^syn\.(\d+)\.res\.%s\.(\d+)\.inorm\.weight$" % _L, "syn/stage{0}/{1}/res{2}/inorm/gamma"),
+    (r"^syn\.(\d+)\.res\.%s\.(\d+)\.inorm\.bias$" % _L, "syn/stage{0}/{1}/res{2}/inorm/beta"),
+    (r"^syn\.(\d+)\.actlast_inorm\.weight$", "syn/stage{0}/inorm/gamma"),
+    (r"^syn\.(\d+)\.actlast_inorm\.bias$", "syn/stage{0}/inorm/beta"),
+    (r"^syn\.(\d+)\.convlast\.conv\.weight$", "syn/stage{0}/convlast/W"),
+    (r"^syn\.(\d+)\.convlast\.conv\.bias$", "syn/stage{0}/convlast/b"),
+]
+_TF_RULES = [(re.compile(a), b) for a, b in _TF_RULES]
+
+
+def tf_variable_name(key):
+    """Reference variable name of a state_dict key of the progressive generator; KeyError for anything else."""
+    for rx, fmt in _TF_RULES:
+        m = rx.match(key)
+        if m:
+            return fmt.format(*m.groups())
+    raise KeyError("no TensorFlow variable name known for parameter %r (only po/progressive_model.py's generator "
+                   "is mapped)" % key)
+
+
+def _to_tf(key, t):
+    a = t.detach().cpu().float().numpy()
+    return np.ascontiguousarray(a.transpose(2, 3, 1, 0)) if a.ndim == 4 else a      # OIHW -> HWIO
+
+
+def _from_tf(a, like):
+    a = np.asarray(a, dtype=np.float32)
+    if like.dim() == 4:
+        a = a.transpose(3, 2, 0, 1)                                                   # HWIO -> OIHW
+    if tuple(a.shape) != tuple(like.shape):
+        raise ValueError("shape %s in the checkpoint, %s in the model" % (a.shape, tuple(like.shape)))
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def export_tf_checkpoint(folder, model, global_step=0):
+    """Write `folder/model-<step>.index` + `.data-00000-of-00001` in TensorFlow's checkpoint format under the
+    reference's variable names (model parameters and `global_step`; no optimiser slots), plus the `checkpoint` state
+    file tf.train.latest_checkpoint reads. Returns the checkpoint prefix."""
+    if not getattr(model, "_nn_upsample", True):
+        raise NotImplementedError("export_tf_checkpoint: the deconvolution up-sampling variant is not mapped")
+    os.makedirs(folder, exist_ok=True)
+    step = int(global_step)
+    tensors = {tf_variable_name(k): _to_tf(k, v) for k, v in model.state_dict().items()}
+    tensors["global_step"] = np.array(step, dtype=np.int64)
+    prefix = os.path.join(folder, "model-%d" % step)
+    tf_bundle.write_bundle(prefix, tensors)
+    with open(os.path.join(folder, "checkpoint"), "w") as f:
+        f.write('model_checkpoint_path: "model-%d"\nall_model_checkpoint_paths: "model-%d"\n' % (step, step))
+    return prefix
+
+
+def restore_tf_checkpoint(prefix, model, strict=True):
+    """Load a TensorFlow checkpoint written by the reference (tensorpack ModelSaver) or by export_tf_checkpoint into
+    the progressive generator, in place. Optimiser slots (`.../Adam`, `beta1_power`, ...) and summaries' moving
+    averages in the file are ignored. Returns the global step (0 if the file has none)."""
+    own = model.state_dict()
+    wanted = {tf_variable_name(k): k for k in own}
+    have = tf_bundle.list_variables(prefix)
+    missing = sorted(n for n in wanted if n not in have)
+    if missing and strict:
+        raise KeyError("checkpoint %s lacks %d variables of the model, e.g. %s" % (prefix, len(missing), missing[:3]))
+    data = tf_bundle.read_bundle(prefix, names=set(wanted) | {"global_step"})
+    with torch.no_grad():
+        for name, key in wanted.items():
+            if name in data:
+                own[key].copy_(_from_tf(data[name], own[key]))
+    return int(data["global_step"]) if "global_step" in data else 0
 
 
 def restore_checkpoint(path, model, trainer=None):
@@ -34,6 +130,11 @@ def restore_checkpoint(path, model, trainer=None):
         if found is None:
             raise IOError("no model-<step> checkpoint in %s" % path)
         path = found
+    if tf_bundle.is_bundle(path) and not os.path.isfile(path):      # a TensorFlow checkpoint prefix
+        step = restore_tf_checkpoint(path, model)
+        if trainer is not None:
+            trainer.global_step = step
+        return step
     # tensors, floats and strings only: nothing in a checkpoint needs unpickling arbitrary objects
     state = torch.load(path, map_location="cpu", weights_only=True)
     with torch.no_grad():
