@@ -3,7 +3,7 @@ log directory and `SaverRestore` / `--test-only` load them (po/progressive_model
 Same file naming here. Two formats:
   * torch serialisation (save_checkpoint / restore_checkpoint): everything, including the optimiser state;
   * TensorFlow's own checkpoint format (export_tf_checkpoint / restore_tf_checkpoint, through po/tf_bundle.py, no
-    TensorFlow needed) under the reference's variable names, for the generator of po/progressive_model.py: a
+    TensorFlow needed) under the reference's variable names, for the generators of po/progressive_model.py and po/single_model.py: a
     checkpoint trained with the reference loads here, and one written here loads with the reference's SaverRestore.
     restore_checkpoint() recognises such a file by its `.index` companion."""
 import glob
@@ -38,8 +38,8 @@ def latest_checkpoint(folder):
 
 
 # ---------------------------------------------------------------------------------------------- TensorFlow format
-# state_dict key of po/progressive_model.py's generator -> variable name in the reference's graph
-# (po/progressive_model.py:145-206: scopes syn / stage<s> / <layer> / ...; tensorpack's Conv2D names its variables W
+# state_dict key of the progressive / single generator -> variable name in the reference's graph
+# (po/progressive_model.py:145-206, po/single_model.py:142-190: scopes syn / stage<s> / <layer> / ...; tensorpack's Conv2D names its variables W
 # and b, its InstanceNorm gamma and beta; INReLU's norm lives under the convolution's scope as `inorm`).
 _L = r"(conv\d_\d|pool\d)"
 _TF_RULES = [
@@ -70,8 +70,8 @@ def tf_variable_name(key):
         m = rx.match(key)
         if m:
             return fmt.format(*m.groups())
-    raise KeyError("no TensorFlow variable name known for parameter %r (only po/progressive_model.py's generator "
-                   "is mapped)" % key)
+    raise KeyError("no TensorFlow variable name known for parameter %r (only the generators of po/progressive_model.py and "
+                   "po/single_model.py are mapped)" % key)
 
 
 def _to_tf(key, t):

@@ -201,6 +201,23 @@ def test_generator_as_a_tensorflow_checkpoint(tmp_path, raw_weights, extra):
         assert torch.equal(m2.state_dict()[k], v), k
 
 
+def test_single_generator_uses_the_same_scopes(tmp_path, raw_weights):
+    """po/single_model.py:142-190 builds its one stage under the same scope names."""
+    from syntex_b200.po.model import SynTexModelDesc
+    from syntex_b200.po.single_model import SingleSynTex
+    tex = so.OracleTexture(so.load_vgg_weights(raw_weights), list(SynTexModelDesc.DEFAULT_COEFS.keys()), torch.float32)
+    torch.manual_seed(0)
+    m1 = SingleSynTex({"vgg19_npy_path": raw_weights, "image_size": 32}, texture_fn=tex)
+    prefix = checkpoint.export_tf_checkpoint(str(tmp_path), m1, 5)
+    names = tb.list_variables(prefix)
+    assert names["syn/stage0/pool3/grad_conv1/W"][1] == (3, 3, 256, 256)
+    assert names["syn/stage0/pool3/up/W"][1] == (5, 5, 512, 256)                 # HWIO: 512 channels in, 256 out
+    torch.manual_seed(1)
+    m2 = SingleSynTex({"vgg19_npy_path": raw_weights, "image_size": 32}, texture_fn=tex)
+    assert checkpoint.restore_checkpoint(prefix, m2) == 5
+    assert all(torch.equal(a, b) for a, b in zip(m1.state_dict().values(), m2.state_dict().values()))
+
+
 def test_restore_ignores_optimizer_slots_and_reports_missing_variables(tmp_path, raw_weights):
     m1 = _model(raw_weights, 0)
     tensors = {checkpoint.tf_variable_name(k): checkpoint._to_tf(k, v) for k, v in m1.state_dict().items()}
