@@ -63,15 +63,63 @@ _TF_RULES = [
 ]
 _TF_RULES = [(re.compile(a), b) for a, b in _TF_RULES]
 
+# po/improved_model.py:24-56, :131-330 and po/adaptive_model.py (same scopes): the activation's norm is `inorm`
+# (InstanceNorm) or `bnorm` (BatchNorm: gamma, beta, mean/EMA, variance/EMA) by --norm-type, the up-sampling
+# convolution lives one scope deeper (`up/conv/W`), the norm after the merge keeps the name `post_inorm` whatever its
+# type, and the pre-activation variant's extra norms sit directly under the layer / the stage scope.
+_NORM_PARAM = {"weight": "gamma", "bias": "beta", "running_mean": "mean/EMA", "running_var": "variance/EMA"}
+_TF_RULES_V2 = [
+    (r"^syn\.(\d+)\.grad_conv(\d)\.%s\.conv\.weight$" % _L, "syn/stage{0}/{2}/grad_conv{1}/W", None),
+    (r"^syn\.(\d+)\.grad_conv(\d)\.%s\.norm\.(\w+)$" % _L, "syn/stage{0}/{2}/grad_conv{1}/{N}/{P}", 3),
+    (r"^syn\.(\d+)\.up\.%s\.conv\.conv\.weight$" % _L, "syn/stage{0}/{1}/up/conv/W", None),
+    (r"^syn\.(\d+)\.post_norm\.%s\.(\w+)$" % _L, "syn/stage{0}/{1}/post_inorm/{P}", 2),
+    (r"^syn\.(\d+)\.pre_norm\.%s\.(\w+)$" % _L, "syn/stage{0}/{1}/{N}/{P}", 2),
+    (r"^syn\.(\d+)\.res\.%s\.(\d+)\.conv(\d)\.conv\.weight$" % _L, "syn/stage{0}/{1}/res{2}/conv{3}/W", None),
+    (r"^syn\.(\d+)\.res\.%s\.(\d+)\.conv(\d)\.norm\.(\w+)$" % _L, "syn/stage{0}/{1}/res{2}/conv{3}/{N}/{P}", 4),
+    (r"^syn\.(\d+)\.res\.%s\.(\d+)\.norm\.(\w+)$" % _L, "syn/stage{0}/{1}/res{2}/{N}/{P}", 3),
+    (r"^syn\.(\d+)\.last_norm\.(\w+)$", "syn/stage{0}/{N}/{P}", 1),
+    (r"^syn\.(\d+)\.convlast\.conv\.weight$", "syn/stage{0}/convlast/W", None),
+    (r"^syn\.(\d+)\.convlast\.conv\.bias$", "syn/stage{0}/convlast/b", None),
+]
+_TF_RULES_V2 = [(re.compile(a), b, c) for a, b, c in _TF_RULES_V2]
 
-def tf_variable_name(key):
-    """Reference variable name of a state_dict key of the progressive generator; KeyError for anything else."""
-    for rx, fmt in _TF_RULES:
-        m = rx.match(key)
-        if m:
-            return fmt.format(*m.groups())
-    raise KeyError("no TensorFlow variable name known for parameter %r (only the generators of po/progressive_model.py and "
-                   "po/single_model.py are mapped)" % key)
+
+def tf_variable_name(key, norm_type=None):
+    """Reference variable name of a state_dict key. norm_type None: the generators of po/progressive_model.py and
+    po/single_model.py; "instance" / "batch" / "none": those of po/improved_model.py and po/adaptive_model.py.
+    KeyError for a key that has no counterpart; None for one that TensorFlow does not store (num_batches_tracked)."""
+    if norm_type is None:
+        for rx, fmt in _TF_RULES:
+            m = rx.match(key)
+            if m:
+                return fmt.format(*m.groups())
+    else:
+        if key.endswith("num_batches_tracked"):
+            return None
+        scope = {"instance": "inorm", "batch": "bnorm"}.get(norm_type, "nonorm")
+        for rx, fmt, pidx in _TF_RULES_V2:
+            m = rx.match(key)
+            if m:
+                g = m.groups()
+                if pidx is None:
+                    return fmt.format(*g)
+                if g[pidx] not in _NORM_PARAM:
+                    break
+                return fmt.replace("{N}", scope).replace("{P}", _NORM_PARAM[g[pidx]]).format(*g)
+    raise KeyError("no TensorFlow variable name known for parameter %r" % key)
+
+
+def _names_for(model):
+    """{reference variable name: state_dict key} of a generator."""
+    norm_type = getattr(model, "_norm_type", None) if hasattr(model, "_act_type") else None
+    if not getattr(model, "_nn_upsample", True):
+        raise NotImplementedError("TensorFlow checkpoints: the deconvolution up-sampling variant is not mapped")
+    out = {}
+    for k in model.state_dict():
+        n = tf_variable_name(k, norm_type)
+        if n is not None:
+            out[n] = k
+    return out
 
 
 def _to_tf(key, t):
@@ -92,11 +140,11 @@ def export_tf_checkpoint(folder, model, global_step=0):
     """Write `folder/model-<step>.index` + `.data-00000-of-00001` in TensorFlow's checkpoint format under the
     reference's variable names (model parameters and `global_step`; no optimiser slots), plus the `checkpoint` state
     file tf.train.latest_checkpoint reads. Returns the checkpoint prefix."""
-    if not getattr(model, "_nn_upsample", True):
-        raise NotImplementedError("export_tf_checkpoint: the deconvolution up-sampling variant is not mapped")
+    names = _names_for(model)
     os.makedirs(folder, exist_ok=True)
     step = int(global_step)
-    tensors = {tf_variable_name(k): _to_tf(k, v) for k, v in model.state_dict().items()}
+    sd = model.state_dict()
+    tensors = {n: _to_tf(k, sd[k]) for n, k in names.items()}
     tensors["global_step"] = np.array(step, dtype=np.int64)
     prefix = os.path.join(folder, "model-%d" % step)
     tf_bundle.write_bundle(prefix, tensors)
@@ -110,7 +158,7 @@ def restore_tf_checkpoint(prefix, model, strict=True):
     the progressive generator, in place. Optimiser slots (`.../Adam`, `beta1_power`, ...) and summaries' moving
     averages in the file are ignored. Returns the global step (0 if the file has none)."""
     own = model.state_dict()
-    wanted = {tf_variable_name(k): k for k in own}
+    wanted = _names_for(model)
     have = tf_bundle.list_variables(prefix)
     missing = sorted(n for n in wanted if n not in have)
     if missing and strict:

@@ -218,6 +218,55 @@ def test_single_generator_uses_the_same_scopes(tmp_path, raw_weights):
     assert all(torch.equal(a, b) for a, b in zip(m1.state_dict().values(), m2.state_dict().values()))
 
 
+@pytest.mark.parametrize("which,extra", [("improved", {"norm_type": "instance"}),
+                                         ("improved", {"norm_type": "batch", "pre_act": True}),
+                                         ("improved", {"norm_type": "none"}), ("adaptive", {"norm_type": "batch"})])
+def test_improved_and_adaptive_generators(tmp_path, raw_weights, which, extra):
+    """po/improved_model.py:24-56, :131-330 (po/adaptive_model.py: the same scopes): the activation's norm is `inorm` or
+    `bnorm` by --norm-type (BatchNorm also stores mean/EMA and variance/EMA), the up-sampling convolution is
+    `up/conv/W`, the norm after the merge is called `post_inorm` whatever its type."""
+    from syntex_b200.po.model import SynTexModelDesc
+    from syntex_b200.po.adaptive_model import AdaptiveSynTex
+    from syntex_b200.po.improved_model import ImprovedSynTex
+    cls = ImprovedSynTex if which == "improved" else AdaptiveSynTex
+    tex = so.OracleTexture(so.load_vgg_weights(raw_weights), list(SynTexModelDesc.DEFAULT_COEFS.keys()), torch.float32)
+    torch.manual_seed(0)
+    m1 = cls(dict({"vgg19_npy_path": raw_weights, "image_size": 32}, **extra), texture_fn=tex)
+    with torch.no_grad():                                   # running statistics away from their initial values
+        for k, v in m1.state_dict().items():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                v.copy_(torch.rand_like(v) + 0.5)
+    prefix = checkpoint.export_tf_checkpoint(str(tmp_path), m1, 9)
+    names = tb.list_variables(prefix)
+    nt = extra["norm_type"]
+    scope = {"instance": "inorm", "batch": "bnorm"}.get(nt)
+    assert "syn/stage4/pool4/grad_conv1/W" in names or "syn/stage0/pool4/grad_conv1/W" in names
+    stage = "stage4" if "syn/stage4/pool4/grad_conv1/W" in names else "stage0"
+    assert "syn/%s/pool3/up/conv/W" % stage in names
+    if scope:
+        assert "syn/%s/pool4/grad_conv1/%s/gamma" % (stage, scope) in names
+        assert "syn/%s/pool4/res0/conv0/%s/beta" % (stage, scope) in names
+        assert ("syn/%s/pool4/res1/%s/gamma" % (stage, scope)) in names
+        if not extra.get("pre_act"):
+            assert "syn/%s/pool4/post_inorm/gamma" % stage in names
+        else:
+            assert "syn/%s/%s/gamma" % (stage, scope) in names and "syn/%s/pool3/%s/beta" % (stage, scope) in names
+    else:
+        assert not any("norm" in n for n in names)
+    if any(k.endswith("running_mean") for k in m1.state_dict()):     # (the improved model normalises with batch
+        assert "syn/%s/pool4/grad_conv1/bnorm/mean/EMA" % stage in names     # statistics only: no moving averages)
+        assert "syn/%s/pool4/grad_conv1/bnorm/variance/EMA" % stage in names
+    else:
+        assert which == "improved" or nt != "batch"
+    assert not any("num_batches_tracked" in n for n in names)
+    torch.manual_seed(1)
+    m2 = cls(dict({"vgg19_npy_path": raw_weights, "image_size": 32}, **extra), texture_fn=tex)
+    assert checkpoint.restore_checkpoint(prefix, m2) == 9
+    for (k, a), b in zip(m1.state_dict().items(), m2.state_dict().values()):
+        if not k.endswith("num_batches_tracked"):
+            assert torch.equal(a, b), k
+
+
 def test_restore_ignores_optimizer_slots_and_reports_missing_variables(tmp_path, raw_weights):
     m1 = _model(raw_weights, 0)
     tensors = {checkpoint.tf_variable_name(k): checkpoint._to_tf(k, v) for k, v in m1.state_dict().items()}
