@@ -399,3 +399,15 @@ def write_bundle(prefix, tensors):
                           encode_entry(_DTYPE_ENUM[arr.dtype], arr.shape, offset, len(raw), mask_crc(crc32c(raw)))))
             offset += len(raw)
     write_table(prefix + ".index", items)
+
+
+if __name__ == "__main__":       # python -m syntex_b200.po.tf_bundle <checkpoint prefix>: list the variables of a checkpoint
+    import sys
+    if len(sys.argv) != 2:
+        raise SystemExit("usage: python -m syntex_b200.po.tf_bundle <checkpoint prefix, e.g. train_log/model-4000>")
+    total = 0
+    for name, (dt, shape) in sorted(list_variables(sys.argv[1]).items()):
+        n = int(np.prod(shape)) if shape else 1
+        total += n * dt.itemsize
+        print("%-72s %-8s %s" % (name, dt.name, list(shape)))
+    print("%d bytes of tensors" % total)
