@@ -286,3 +286,19 @@ def test_restore_ignores_optimizer_slots_and_reports_missing_variables(tmp_path,
         checkpoint.restore_tf_checkpoint(prefix, m2)
     with pytest.raises(KeyError):
         checkpoint.tf_variable_name("some.other.parameter")
+
+
+def test_table_round_trip_property(tmp_path):
+    """Random key sets (shared prefixes, empty values, binary bytes) through writer and reader, several block sizes."""
+    from hypothesis import given, settings, strategies as st
+    path = str(tmp_path / "p.index")
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.dictionaries(st.binary(min_size=0, max_size=24), st.binary(min_size=0, max_size=200), max_size=80),
+           st.sampled_from([64, 256, 4096]))
+    def check(d, block_size):
+        items = sorted(d.items())
+        tb.write_table(path, items, block_size=block_size)
+        assert tb.read_table(path) == items
+
+    check()
